@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""Benchmark of the MPC planning hot path (BASELINE.json metric: dynamics-model
+candidate-steps/sec; CEM plan latency p50).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--engine auto|fp32|fp16|bf16]
+
+One "step" = one whole CEM plan (sample -> rollout+cost -> top-k -> refit, I iterations, then
+the chosen plan is emitted) on synthetic inputs of BASELINE config 3: cheetah-run shape
+(obs 17, act 6), dynamics MLP hidden 200 with random-init weights, N=16384 candidates per GPU,
+H=30, I=5, k=10%.  With --gpus N>1 (launched under torchrun, one rank per GPU, NCCL) the
+population is sharded: N_total = 16384*N candidates, one elite all-gather per iteration
+(weak scaling: per-GPU work fixed).
+
+Prints ONE JSON line (rank 0).  `value` is device-resident whole-job throughput (CUDA events,
+max over ranks); `e2e` is the same metric through the host-buffer C-ABI call (`mbrl_plan`:
+pinned H2D of s0 and D2H of the plan inside the timed region); `roofline` is the rollout
+kernel against the measured tensor peak; `cpu_baseline` is the oracle port of the reference's
+CPU planner timed on this box's host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "dynamics-model candidate-steps/sec (CEM plan, cheetah-run shape)"
+UNIT = "candidate-steps/s"
+WORKLOADS = {
+    # BASELINE.json configs[2]: the configuration the metric is quoted on (fits one GPU)
+    "cheetah": dict(name="cheetah-run CEM N=16384 H=30 I=5 hidden=200 (BASELINE configs[2])",
+                    O=17, A=6, U=200, N=16384, H=30, I=5, elite_frac=0.1),
+    # BASELINE.json configs[3] per-GPU shard at 8 GPUs (131072 / 8)
+    "walker": dict(name="walker-walk CEM N=16384/GPU H=30 I=5 hidden=200 (BASELINE configs[3] shard)",
+                   O=24, A=6, U=200, N=16384, H=30, I=5, elite_frac=0.1),
+    "cartpole": dict(name="cartpole-swingup CEM N=4096 H=30 I=5 hidden=50 (BASELINE configs[1])",
+                     O=5, A=1, U=50, N=4096, H=30, I=5, elite_frac=0.1),
+}
+
+
+def flops_per_cand_step(w):
+    D = w["O"] + w["A"]
+    return 2 * (D * w["U"] + w["U"] * w["U"] + w["U"] * w["O"])
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(bf16_tflops=d["bf16_tflops"], hbm_gbs=d["hbm_gbs"], source="measured")
+    return dict(bf16_tflops=1590.0, hbm_gbs=6650.0, source="fallback")
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        busy = sorted(sm)[len(sm) // 2:] if sm else []  # upper half ~ samples under load
+        return dict(sm_mhz=statistics.median(busy) if busy else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference planner (bench.py's one permitted use of oracle/)
+# ------------------------------------------------------------------------------------------
+def cpu_reference_plan_time(w, iterations, reps, warm):
+    """Times the reference-composed CEM: per iteration the reference-style
+    _generate_trajectories restatement (autograd on, one sampler call, per-candidate Python list
+    of views -- planners.py:189-216) with a Gaussian sampler closure, then stable argsort top-k
+    and mean/std refit.  Returns (seconds per `iterations`-iteration plan, threads)."""
+    import numpy as np
+    import torch
+    from oracle import planner_oracle as po
+
+    p = po.synthetic_params(w["O"], w["A"], w["U"])
+    for t in (p.W1, p.b1, p.W2, p.b2, p.W3, p.b3):
+        t.requires_grad_(True)  # reference parameters are nn.Parameters; autograd stays on
+    model, cost = po.params_as_callables(p)
+    N, H, A = w["N"], w["H"], w["A"]
+    k = max(1, int(w["elite_frac"] * N))
+    times = []
+    for rep in range(warm + reps):
+        s0 = po.synthetic_state(p, rep)
+        g = torch.Generator().manual_seed(rep)
+        t0 = time.perf_counter()
+        mu, sd = torch.zeros(H, A), torch.ones(H, A)
+        for it in range(iterations):
+            def gauss(batch_size, mu=mu, sd=sd):
+                z = torch.randn(batch_size, A, generator=g)
+                return torch.clamp(mu.repeat_interleave(N, 0) + sd.repeat_interleave(N, 0) * z, -1.0, 1.0)
+            trajs, costs = po.reference_style_generate(s0, model, cost, gauss, H, N)
+            elite = po.topk_stable(costs, k)
+            acts = torch.stack([trajs[i][1] for i in elite], dim=1)
+            mu, sd = acts.mean(1), acts.std(1, unbiased=False)
+        dt = time.perf_counter() - t0
+        if rep >= warm:
+            times.append(dt)
+    return statistics.median(times), torch.get_num_threads()
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the
+    reference is pure Python and cannot travel to the GPU box) on this box's host cores."""
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    iters = w["I"] if (args.steps + args.warmup) <= 40 else 1
+    sec, threads = cpu_reference_plan_time(w, iters, args.steps, args.warmup)
+    value = w["N"] * w["H"] * iters / sec
+    sample = (f"each step = one reference-composed CEM plan restricted to {iters} iteration(s) of "
+              f"N={w['N']} H={w['H']} (oracle port of planners.py:189-216, torch CPU fp32, autograd on, list build included)")
+    line = dict(
+        impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+        ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+        config=dict(workload=w["name"], l2="n/a (CPU)"),
+        cpu_baseline=dict(value=value, unit=UNIT, cores=threads, kind="port", sample=sample),
+        e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+        gpu_launches=0,
+    )
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------
+def pick_engine(native, w, requested):
+    if requested != "auto":
+        return requested
+    for eng in ("fp16", "bf16"):
+        try:
+            native.NativePlanner(w["O"], w["A"], w["U"], w["H"], 256, engine=eng).close()
+            return eng
+        except native.MbrlError:
+            continue
+    return "fp32"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "fp32", "fp16", "bf16"])
+    ap.add_argument("--workload", default="cheetah", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from mbrl_b200 import PlanningProblem, native
+    from mbrl_b200.sharding import NativeOps, PopulationShardedCEM
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback)")
+    args.warmup = max(args.warmup, 3)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    w = WORKLOADS[args.workload]
+    O, A, U, N, H, I = w["O"], w["A"], w["U"], w["N"], w["H"], w["I"]
+    n_total = N * world
+    k = max(1, int(w["elite_frac"] * n_total))
+    engine = pick_engine(native, w, args.engine)
+
+    # synthetic problem; the CPU arm's oracle generates the identical values
+    from mbrl_b200.synthetic import synthetic_problem, synthetic_state
+    prob = p = synthetic_problem(O, A, U)
+    h = native.NativePlanner(O, A, U, H, N, 1, I, min(k, N), engine, local_rank)
+    h.load_problem(prob)
+    states0 = torch.stack([synthetic_state(p, c) for c in range(args.warmup + args.steps)]).float()
+    d_states0 = states0.to(dev)
+    d_out_s = torch.empty(1, H, O, device=dev)
+    d_out_a = torch.empty(1, H, A, device=dev)
+    d_info = torch.zeros(1, 4, dtype=torch.int32, device=dev)
+    sharded = PopulationShardedCEM(NativeOps(h), N, H, A, rank, world, lo=p.act_lo, hi=p.act_hi) if world > 1 else None
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+
+    def plan_resident(i):
+        if sharded is None:
+            h.plan_device(d_states0[i:i + 1], d_out_s, d_out_a, d_info, iterations=I, elites=k,
+                          mode=native.SAMPLE_GAUSSIAN, seed=i)
+        else:
+            sharded.plan(d_states0[i:i + 1], I, k, seed=i)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ----
+    for i in range(args.warmup):
+        plan_resident(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = []
+    barrier()
+    for i in range(args.steps):
+        flush.zero_()  # L2 flush between timed iterations (outside the event pair)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        plan_resident(args.warmup + i)
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    clocks = sampler.stop() if rank == 0 else None
+    cand_steps_per_plan = n_total * H * I
+    value = cand_steps_per_plan * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI call ----
+    e2e_lat = []
+    if sharded is None:
+        for i in range(args.warmup + args.steps):
+            s0 = states0[i].numpy()
+            t0 = time.perf_counter()
+            out = h.plan(s0, iterations=I, elites=k, mode=native.SAMPLE_GAUSSIAN, seed=i)
+            dt = time.perf_counter() - t0
+            if i >= args.warmup:
+                e2e_lat.append(dt)
+    else:
+        pin = states0.pin_memory()
+        for i in range(args.warmup + args.steps):
+            barrier()
+            t0 = time.perf_counter()
+            d = pin[i:i + 1].to(dev, non_blocking=True)
+            res = sharded.plan(d, I, k, seed=i)
+            _ = res["actions"].cpu(), res["states"].cpu()
+            dt = time.perf_counter() - t0
+            if i >= args.warmup:
+                e2e_lat.append(dt)
+    e2e_total = torch.tensor([sum(e2e_lat)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
+    e2e_value = cand_steps_per_plan * args.steps / float(e2e_total.item())
+
+    # ---- dominant kernel alone: rollout + cost (tensor-bound) ----
+    mu = torch.zeros(1, H, A, device=dev)
+    sd = torch.ones(1, H, A, device=dev)
+    for _ in range(3):
+        h.rollout(d_states0[:1], native.SAMPLE_GAUSSIAN, 1, 0, d_mu=mu, d_sd=sd)
+    torch.cuda.synchronize()
+    kev = []
+    for i in range(20):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        h.rollout(d_states0[:1], native.SAMPLE_GAUSSIAN, 1, i % I, d_mu=mu, d_sd=sd)
+        e1.record()
+        kev.append((e0, e1))
+    torch.cuda.synchronize()
+    k_ms = statistics.mean(a.elapsed_time(b) for a, b in kev)
+    peaks = measured_peaks()
+    alg_flops = N * H * flops_per_cand_step(w)
+    achieved = alg_flops / (k_ms * 1e-3) / 1e12
+    roofline = dict(bound="tensor", kernel="rollout+cost (%s engine)" % engine, achieved=achieved,
+                    peak=peaks["bf16_tflops"], unit="TFLOP/s", frac=achieved / peaks["bf16_tflops"], traffic=None,
+                    peak_source=peaks["source"] + " cuBLAS bf16 burst", kernel_ms=k_ms,
+                    algorithmic_flops_per_launch=alg_flops)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        sec, threads = cpu_reference_plan_time(w, I, reps=3, warm=1)
+        cpu = dict(value=N * H * I / sec, unit=UNIT, cores=threads, kind="port",
+                   sample=f"3 timed reference-composed CEM plans (I={I}, N={N}, H={H}) after 1 warm-up, "
+                          f"oracle port of planners.py:189-216 incl. autograd + Python list build; {sec * 1e3:.0f} ms/plan",
+                   ms_per_plan=sec * 1e3)
+
+    launches_per_plan = 1 + 2 * I + (I - 1) + 1
+    line = dict(
+        metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+        ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+        dtype={"fp32": "f32", "fp16": "f16 operands / f32 accumulate", "bf16": "bf16 operands / f32 accumulate"}[engine],
+        data="synthetic",
+        config=dict(workload=w["name"] + (f" x{world} GPUs population-sharded, N_total={n_total}" if world > 1 else ""),
+                    engine=engine, elites=k, l2="flushed between timed plans (256 MiB write)",
+                    parallelism=("population-sharded x%d, NCCL elite all-gather" % world) if world > 1 else "single GPU"),
+        plan_latency_ms_p50=statistics.median(step_ms),
+        clocks=clocks,
+        e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=4 * O, d2h_bytes_per_step=4 * H * (O + A) + 16,
+                 latency_ms_p50=statistics.median(e2e_lat) * 1e3, api="mbrl_plan (host buffers)" if world == 1 else "PopulationShardedCEM.plan (pinned s0 -> plan -> host)"),
+        gpu_launches=launches_per_plan * args.steps,
+        roofline=roofline,
+        cpu_baseline=cpu,
+    )
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,187 @@
+/*
+ * mbrl_b200.h -- C ABI of the B200-native MPC planning hot path.
+ *
+ * Drop-in boundary for the planning path of Khodeir/mujoco-mbrl.  The reference has no
+ * native layer at all (pure Python/PyTorch-CPU), so there is no existing FFI to mirror;
+ * each entry point below names the reference Python interface it replaces (paths are
+ * relative to the reference root).  INTEGRATION.md shows the ctypes binding a maintainer
+ * of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative MBRL_E_* code on failure;
+ *     mbrl_last_error() returns a thread-local human-readable message;
+ *   - plain pointers and sizes only; `h_` = host pointer, `d_` = device pointer
+ *     (same CUDA primary context, e.g. torch tensor.data_ptr());
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the handle's own stream);
+ *   - caller owns every buffer it passes; the handle owns device weights and scratch;
+ *   - one handle per (device, shape); a handle is not thread-safe;
+ *   - all fp32 matrices are row-major; nn.Linear weights are [out, in];
+ *   - trajectories use the reference's flat step-major layout: row h*R + r is row r at
+ *     step h (src/mbrl/planners.py:199-209) with R = num_envs * num_candidates and
+ *     r = env * num_candidates + candidate;
+ *   - there is NO CPU fallback: every entry point that computes requires a CUDA device
+ *     and fails with MBRL_E_CUDA otherwise.
+ */
+#ifndef MBRL_B200_H_
+#define MBRL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MBRL_ABI_VERSION 1
+
+/* error codes */
+#define MBRL_OK 0
+#define MBRL_E_INVALID (-1)   /* bad argument / unsupported shape */
+#define MBRL_E_CUDA (-2)      /* CUDA runtime error (message has the cudaError string) */
+#define MBRL_E_STATE (-3)     /* call order: weights / norm / cost not set yet */
+#define MBRL_E_UNSUPPORTED (-4)
+
+/* rollout engines */
+#define MBRL_ENGINE_SIMT_FP32 0 /* fp32 CUDA-core kernel: 1e-5 parity cross-check      */
+#define MBRL_ENGINE_TC_BF16 1   /* tcgen05 tensor cores, bf16 operands, fp32 accumulate */
+#define MBRL_ENGINE_TC_FP16 2   /* tcgen05 tensor cores, fp16 operands, fp32 accumulate */
+
+/* where a candidate's actions come from */
+#define MBRL_SAMPLE_INJECT_ACTIONS 0 /* d_injected holds final actions [H*R, A]                */
+#define MBRL_SAMPLE_INJECT_NOISE 1   /* d_injected holds N(0,1) draws; a = clip(mu + sd*z)      */
+#define MBRL_SAMPLE_GAUSSIAN 2       /* Philox4x32-10 + Box-Muller; a = clip(mu + sd*z)         */
+#define MBRL_SAMPLE_UNIFORM 3        /* Philox4x32-10; a = lo + (hi-lo)*u   (reference sampler
+                                        distribution, src/mbrl/env_wrappers.py:50-62)          */
+
+/* cost kinds (epilogue of the rollout kernel) */
+#define MBRL_COST_SMOOTHABS_COSH 0 /* state_action_cost = SmoothAbsLoss + CoshLoss
+                                      (src/mbrl/agents.py:182-183, models.py:244-272)          */
+
+typedef struct MbrlPlanner MbrlPlanner;
+
+typedef struct MbrlConfig {
+  int32_t obs_dim;        /* O: state_dim of Model (src/mbrl/models.py:96)                     */
+  int32_t act_dim;        /* A                                                                  */
+  int32_t hidden;         /* U: hidden_units (src/mbrl/models.py:97)                            */
+  int32_t horizon;        /* H: MPCPolicy.horizon (src/mbrl/agents.py:33)                       */
+  int32_t num_candidates; /* N on this GPU: num_trajectories (src/mbrl/planners.py:141,153)    */
+  int32_t num_envs;       /* E independent planning problems batched on this GPU (>= 1)        */
+  int32_t max_iterations; /* I_max: CEM iterations a plan may use (1 = random shooting only)   */
+  int32_t max_elites;     /* k_max                                                              */
+  int32_t engine;         /* MBRL_ENGINE_*                                                      */
+  int32_t device;         /* CUDA device ordinal                                                */
+} MbrlConfig;
+
+typedef struct MbrlPlanArgs {
+  int32_t iterations;   /* 1 = random shooting (argmin); >1 = CEM                              */
+  int32_t elites;       /* k (ties -> lower index); forced to 1 when iterations == 1           */
+  int32_t sample_mode;  /* MBRL_SAMPLE_*                                                        */
+  int32_t return_mean;  /* 0: return best-ever candidate; 1: return final mean sequence        */
+  uint64_t seed;        /* Philox key                                                           */
+  uint32_t cand_offset; /* global index of this shard's first candidate (population sharding)  */
+  uint32_t env_offset;  /* global index of this shard's first environment (env sharding)       */
+  const float* h_injected; /* [iterations, H*R, A] host (INJECT_* modes) or NULL               */
+  const float* h_mu0;      /* [E, H, A] host initial mean, NULL -> (lo+hi)/2                    */
+  const float* h_sd0;      /* [E, H, A] host initial std,  NULL -> (hi-lo)/2                    */
+} MbrlPlanArgs;
+
+typedef struct MbrlPlanInfo {
+  float best_cost;
+  int32_t best_iteration;
+  int32_t best_index; /* candidate index within the environment (local to this shard)          */
+  int32_t reserved;
+} MbrlPlanInfo;
+
+int mbrl_abi_version(void);
+const char* mbrl_last_error(void);
+
+/* Life cycle.  Replaces constructing Model(...) + MPCPolicy(...) state
+ * (src/mbrl/models.py:96-104, src/mbrl/agents.py:29-36). */
+int mbrl_create(const MbrlConfig* cfg, MbrlPlanner** out);
+int mbrl_destroy(MbrlPlanner* p);
+
+/* Model.linear{1,2,3}.{weight,bias} (src/mbrl/models.py:99-101); host fp32, [out,in].
+ * Call again whenever the host retrains the model (src/mbrl/models.py:84-86). */
+int mbrl_set_weights(MbrlPlanner* p, const float* h_W1, const float* h_b1, const float* h_W2,
+                     const float* h_b2, const float* h_W3, const float* h_b3);
+/* stats["observations"|"actions"]["mean"|"std"] used by normalize_field /
+ * unnormalize_field (src/mbrl/data.py:255-269).  NULL pointers mean identity (0 / 1). */
+int mbrl_set_norm(MbrlPlanner* p, const float* h_mu_s, const float* h_sd_s, const float* h_mu_a,
+                  const float* h_sd_a);
+/* SmoothAbsLoss(weights, goal_state, alpha) + CoshLoss(beta)
+ * (src/mbrl/models.py:244-272; goal mutates via set_goal_state, models.py:240-241). */
+int mbrl_set_cost(MbrlPlanner* p, int32_t kind, const float* h_weights, const float* h_goal,
+                  double alpha, double beta); /* doubles: the reference squares the Python
+                                                 floats in fp64 before the fp32 tensor op */
+/* bounds EnvWrapper._sample_action derives from the action spec
+ * (src/mbrl/env_wrappers.py:52-55: dimension 0's bounds for every dim, clipped to +-3). */
+int mbrl_set_action_bounds(MbrlPlanner* p, float lo, float hi);
+
+/* One whole plan with HOST buffers: replaces RandomShootingPlanner.plan
+ * (src/mbrl/planners.py:143-187) for iterations == 1 and adds CEM for iterations > 1.
+ *   h_s0          [E, O]      initial_state
+ *   h_out_states  [E, H, O]   predicted s_1..s_H of the chosen sequence (s_0 excluded,
+ *                             as the reference returns them, planners.py:212-215)
+ *   h_out_actions [E, H, A]
+ *   h_info        [E]         nullable
+ *   h_out_mu/sd   [E, H, A]   nullable: final sampling distribution (warm start)
+ * H2D of s0 and D2H of the plan happen inside; returns after the plan is on the host. */
+int mbrl_plan(MbrlPlanner* p, const MbrlPlanArgs* args, const float* h_s0, float* h_out_states,
+              float* h_out_actions, MbrlPlanInfo* h_info, float* h_out_mu, float* h_out_sd);
+
+/* Same plan with everything resident in HBM, enqueued on `stream` without host sync
+ * (inputs/outputs are device pointers; d_injected replaces args->h_injected). */
+int mbrl_plan_device(MbrlPlanner* p, const MbrlPlanArgs* args, const float* d_s0,
+                     const float* d_injected, float* d_out_states, float* d_out_actions,
+                     MbrlPlanInfo* d_info, void* stream);
+
+/* ---- building blocks on device buffers (parity tests, sharded host loops) ---- */
+
+/* The hot loop of _generate_trajectories (src/mbrl/planners.py:199-210) fused with
+ * DynamicsModel.forward (models.py:13-29) and the cost (agents.py:182-183):
+ *   d_s0 [E,O]; d_injected [H*R,A] or NULL; d_mu/d_sd [E,H,A] (Gaussian / noise modes);
+ *   d_costs [R] out; d_states_out [H*R,O] / d_actions_out [H*R,A] nullable (debug/parity:
+ *   production plans never materialise trajectories). */
+int mbrl_rollout(MbrlPlanner* p, int32_t sample_mode, uint64_t seed, uint32_t iteration,
+                 uint32_t cand_offset, uint32_t env_offset, const float* d_s0,
+                 const float* d_injected, const float* d_mu, const float* d_sd, float* d_costs,
+                 float* d_states_out, float* d_actions_out, void* stream);
+
+/* Materialise the sampler's output: d_out [H*R, A] (Gaussian / uniform Philox modes). */
+int mbrl_sample(MbrlPlanner* p, int32_t sample_mode, uint64_t seed, uint32_t iteration,
+                uint32_t cand_offset, uint32_t env_offset, const float* d_mu, const float* d_sd,
+                float* d_out, void* stream);
+/* Raw Philox4x32-10 words for known-answer tests: d_ctr [n,4], d_key [n,2] -> d_out [n,4]. */
+int mbrl_philox_raw(const uint32_t* d_ctr, const uint32_t* d_key, uint32_t* d_out, int64_t n,
+                    void* stream);
+
+/* Segmented elite select: for each of `segments` cost arrays of length n pick the k
+ * smallest, ties toward the lower index (consistent with np.argmin, planners.py:184).
+ *   d_elite_idx  [segments, k] int32, ascending index order
+ *   d_elite_cost [segments, k] nullable
+ *   d_best       [segments] nullable: (cost, -, index) of the minimum                  */
+int mbrl_topk(const float* d_costs, int32_t segments, int32_t n, int32_t k, int32_t* d_elite_idx,
+              float* d_elite_cost, MbrlPlanInfo* d_best, void* stream);
+
+/* Mean / population-std refit of the sampling distribution from the elite candidates'
+ * action sequences (regenerated from the sampler, or gathered from d_injected):
+ *   d_mu_new/d_sd_new [E,H,A]. */
+int mbrl_refit(MbrlPlanner* p, int32_t sample_mode, uint64_t seed, uint32_t iteration,
+               uint32_t cand_offset, uint32_t env_offset, const float* d_injected,
+               const float* d_mu, const float* d_sd, const int32_t* d_elite_idx, int32_t k,
+               float* d_mu_new, float* d_sd_new, void* stream);
+
+/* Emit chosen plans: regenerate the action sequence of candidate d_best[e].best_index drawn
+ * in iteration d_best[e].best_iteration (from d_mu_hist/d_sd_hist [iterations+1, E, H, A],
+ * slot i = distribution sampled in iteration i) -- or the final mean when return_mean -- and
+ * replay it through the fp32 model: d_out_states [E,H,O], d_out_actions [E,H,A].  This is
+ * the (states, actions) pair RandomShootingPlanner.plan returns (planners.py:184-187). */
+int mbrl_emit(MbrlPlanner* p, int32_t sample_mode, uint64_t seed, uint32_t cand_offset,
+              uint32_t env_offset, const float* d_s0, const float* d_injected,
+              const float* d_mu_hist, const float* d_sd_hist, int32_t iterations,
+              int32_t return_mean, const MbrlPlanInfo* d_best, float* d_out_states,
+              float* d_out_actions, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MBRL_B200_H_ */

@@ -1,0 +1,132 @@
+"""Turns the reference's opaque planner callables into an explicit problem description.
+
+``ModelPlanner.plan`` receives ``model``, ``cost`` and ``sample_action`` as callables
+(src/mbrl/planners.py:16-25).  In the reference they are ``functools.partial`` objects built
+by ``GoalStateAgent.__init__`` (src/mbrl/agents.py:219-235):
+
+    model         = partial(<Model nn.Module>, normalize_state=partial(normalize_field, field_name="observations",
+                            stats=D), normalize_action=partial(..."actions"...), unnormalize_state=partial(...))
+    cost          = partial(state_action_cost, state_cost=<SmoothAbsLoss>, action_cost=<CoshLoss>)
+    sample_action = partial(EnvWrapper._sample_action, action_spec=spec)
+
+A GPU planner cannot call Python callables per candidate, so this module introspects those
+partials (or accepts an explicit ``PlanningProblem``).  Anything it does not recognise raises
+``TypeError`` -- there is deliberately no fallback to calling the callables on the CPU.
+"""
+from __future__ import annotations
+
+import functools
+from dataclasses import dataclass
+from typing import Any, Optional, Tuple
+
+import numpy as np
+
+
+@dataclass
+class PlanningProblem:
+    """Explicit description of one planning problem (host arrays / tensors)."""
+
+    W1: Any
+    b1: Any
+    W2: Any
+    b2: Any
+    W3: Any
+    b3: Any
+    mu_s: Any = None
+    sd_s: Any = None
+    mu_a: Any = None
+    sd_a: Any = None
+    cost_w: Any = None
+    goal: Any = None
+    alpha: float = 0.4
+    beta: float = 0.25
+    act_lo: float = -1.0
+    act_hi: float = 1.0
+
+    @property
+    def obs_dim(self) -> int:
+        return int(self.W3.shape[0])
+
+    @property
+    def act_dim(self) -> int:
+        return int(self.W1.shape[1]) - self.obs_dim
+
+    @property
+    def hidden(self) -> int:
+        return int(self.W1.shape[0])
+
+
+def _stats_of(norm_partial, what: str) -> Tuple[Any, Any, Any]:
+    """(mean, std, identity-token) from a partial(normalize_field|unnormalize_field, field_name=, stats=)."""
+    if norm_partial is None:
+        return None, None, None
+    if not isinstance(norm_partial, functools.partial):
+        raise TypeError(f"{what}: expected functools.partial(normalize_field, field_name=..., stats=...), got {type(norm_partial)!r}")
+    kw = norm_partial.keywords or {}
+    if "stats" not in kw or "field_name" not in kw:
+        raise TypeError(f"{what}: partial lacks 'stats'/'field_name' keywords (src/mbrl/agents.py:215-217)")
+    entry = kw["stats"][kw["field_name"]]
+    return entry["mean"], entry["std"], entry
+
+
+def _linear_layers(module):
+    names = ("linear1", "linear2", "linear3")
+    if not all(hasattr(module, n) for n in names):
+        raise TypeError(
+            f"{type(module).__name__}: unsupported dynamics model (need linear1/linear2/linear3 as in "
+            "src/mbrl/models.py:96-110); pass an explicit PlanningProblem instead")
+    if hasattr(module, "linear4"):
+        raise TypeError("ModelWithReward (reward-head cost, src/mbrl/models.py:125-163) is not supported yet")
+    if getattr(module, "noise", None) is not None:
+        raise TypeError("Model(noise=...) adds fresh Gaussian noise per forward (src/mbrl/models.py:110); unsupported")
+    return [getattr(module, n) for n in names]
+
+
+def problem_from_callables(model, cost, sample_action) -> Tuple[PlanningProblem, tuple]:
+    """Introspect the reference's partials.  Returns (problem, fingerprint); the fingerprint
+    changes whenever the host retrains the model in place (param._version), replaces the
+    statistics entries (src/mbrl/data.py:244-249) or moves the goal (models.py:240-241)."""
+    if isinstance(model, PlanningProblem):
+        return model, ("explicit", id(model))
+    if not isinstance(model, functools.partial) or not hasattr(model.func, "parameters"):
+        raise TypeError(
+            "model must be functools.partial(<nn.Module>, normalize_state=..., normalize_action=..., "
+            "unnormalize_state=...) as built in src/mbrl/agents.py:225-230, or a PlanningProblem; "
+            "opaque callables cannot run on the GPU and there is no CPU fallback")
+    module = model.func
+    l1, l2, l3 = _linear_layers(module)
+    kw = model.keywords or {}
+    mu_s, sd_s, tok_s = _stats_of(kw.get("normalize_state"), "normalize_state")
+    mu_u, sd_u, tok_u = _stats_of(kw.get("unnormalize_state"), "unnormalize_state")
+    mu_a, sd_a, tok_a = _stats_of(kw.get("normalize_action"), "normalize_action")
+    if (tok_s is None) != (tok_u is None) or (tok_s is not None and tok_s is not tok_u):
+        raise TypeError("normalize_state and unnormalize_state must use the same statistics entry")
+
+    if not isinstance(cost, functools.partial):
+        raise TypeError("cost must be functools.partial(state_action_cost, state_cost=SmoothAbsLoss, action_cost=CoshLoss) "
+                        "(src/mbrl/agents.py:231)")
+    ckw = cost.keywords or {}
+    sc, ac = ckw.get("state_cost"), ckw.get("action_cost")
+    if sc is None or ac is None or not all(hasattr(sc, a) for a in ("weights", "goal_state", "alpha")) or not hasattr(ac, "alpha"):
+        raise TypeError("cost partial must carry state_cost (weights, goal_state, alpha) and action_cost (alpha)")
+
+    lo, hi = -1.0, 1.0
+    if isinstance(sample_action, functools.partial) and "action_spec" in (sample_action.keywords or {}):
+        spec = sample_action.keywords["action_spec"]
+        # EnvWrapper._sample_action: dimension 0's bounds for every dim, clipped to +-3
+        # (src/mbrl/env_wrappers.py:52-55)
+        lo, hi = max(float(spec.minimum[0]), -3.0), min(float(spec.maximum[0]), 3.0)
+
+    prob = PlanningProblem(
+        W1=l1.weight, b1=l1.bias, W2=l2.weight, b2=l2.bias, W3=l3.weight, b3=l3.bias,
+        mu_s=mu_s, sd_s=sd_s, mu_a=mu_a, sd_a=sd_a,
+        cost_w=sc.weights, goal=sc.goal_state, alpha=float(sc.alpha), beta=float(ac.alpha),
+        act_lo=lo, act_hi=hi,
+    )
+    params = [l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias]
+    fp = (
+        tuple((id(t), int(getattr(t, "_version", 0))) for t in params),
+        tuple((id(t), int(getattr(t, "_version", 0))) for t in (mu_s, sd_s, mu_a, sd_a, sc.weights, sc.goal_state) if t is not None),
+        float(sc.alpha), float(ac.alpha), lo, hi,
+    )
+    return prob, fp

@@ -1,0 +1,71 @@
+// Shared device-side definitions for the planning kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mbrl_b200.h"
+
+namespace mbrl {
+
+constexpr int kMaxObs = 128;
+constexpr int kMaxAct = 32;
+constexpr int kMaxHidden = 1024;
+
+// Device view of the dynamics model, normalisers and cost
+// (DynamicsModel.forward src/mbrl/models.py:13-29; data.py:255-260; models.py:244-272).
+struct ModelDev {
+  int O, A, D, U;
+  const float* W1t;  // [D][U]  transposed nn.Linear weights (K-major: coalesced over outputs)
+  const float* b1;   // [U]
+  const float* W2t;  // [U][U]
+  const float* b2;   // [U]
+  const float* W3t;  // [U][O]
+  const float* b3;   // [O]
+  const float* mu_s;  // [O]
+  const float* sd_s;  // [O]
+  const float* mu_a;  // [A]
+  const float* sd_a;  // [A]
+  const float* cost_w;  // [O]
+  const float* goal;    // [O]
+  float alpha, alpha2;  // alpha2 = (float)(alpha_fp64^2), as torch folds the Python scalar
+  float beta, beta2;
+  int cost_kind;
+};
+
+// Problem extents on this GPU: R = E*N rows, row r = env*N + cand.
+struct Shape {
+  int H, N, E;
+  __host__ __device__ long long rows() const { return (long long)N * E; }
+};
+
+// Where actions come from (MBRL_SAMPLE_*).
+struct ActionSource {
+  int mode;
+  const float* buf;  // injected actions or N(0,1) noise, [H*R, A] step-major
+  const float* mu;   // [E, H, A]
+  const float* sd;   // [E, H, A]
+  uint32_t seed_lo, seed_hi;
+  uint32_t iteration;
+  uint32_t cand_offset;  // global index of local candidate 0
+  uint32_t env_offset;   // global index of local env 0
+  float lo, hi;
+};
+
+__device__ __forceinline__ float clipf(float x, float lo, float hi) {
+  return fminf(fmaxf(x, lo), hi);
+}
+
+// SmoothAbsLoss term for one state dim: sqrt(((s-g)*w)^2 + alpha^2) - alpha
+// (src/mbrl/models.py:255-259), separate roundings like the torch op chain.
+__device__ __forceinline__ float smooth_abs_term(float s, float g, float w, float alpha,
+                                                 float alpha2) {
+  float x = __fmul_rn(__fsub_rn(s, g), w);
+  return __fsub_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(x, x), alpha2)), alpha);
+}
+
+// CoshLoss term for one action dim: cosh(a/beta) - 1   (src/mbrl/models.py:271-272)
+__device__ __forceinline__ float cosh_term(float a, float beta) {
+  return __fsub_rn(coshf(__fdiv_rn(a, beta)), 1.0f);
+}
+
+}  // namespace mbrl

@@ -1,0 +1,542 @@
+// C-ABI implementation (see include/mbrl_b200.h).  Host-side orchestration only: every
+// byte of planning arithmetic happens in the kernels included below.  There is no CPU
+// fallback: without a CUDA device every computing entry point returns MBRL_E_CUDA.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "philox.cuh"
+#include "replay.cuh"
+#include "rollout_simt.cuh"
+#include "rollout_tc.cuh"
+#include "select.cuh"
+
+using namespace mbrl;
+
+// --------------------------------------------------------------------------------------
+// errors
+// --------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define MBRL_CUDA(expr)                                                                   \
+  do {                                                                                    \
+    cudaError_t e__ = (expr);                                                             \
+    if (e__ != cudaSuccess) {                                                             \
+      return fail(MBRL_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));      \
+    }                                                                                     \
+  } while (0)
+#define MBRL_REQUIRE(cond, msg) \
+  do {                          \
+    if (!(cond)) return fail(MBRL_E_INVALID, std::string("invalid argument: ") + (msg)); \
+  } while (0)
+
+// --------------------------------------------------------------------------------------
+// handle
+// --------------------------------------------------------------------------------------
+struct MbrlPlanner {
+  MbrlConfig cfg{};
+  int O = 0, A = 0, D = 0, U = 0, H = 0, N = 0, E = 0;
+  long long R = 0;
+  // device model (fp32, K-major transposed weights)
+  float *W1t = nullptr, *b1 = nullptr, *W2t = nullptr, *b2 = nullptr, *W3t = nullptr, *b3 = nullptr;
+  float *mu_s = nullptr, *sd_s = nullptr, *mu_a = nullptr, *sd_a = nullptr, *cost_w = nullptr, *goal = nullptr;
+  float alpha = 0.4f, alpha2 = 0.16f, beta = 0.25f, beta2 = 0.0625f, lo = -1.f, hi = 1.f;
+  int cost_kind = MBRL_COST_SMOOTHABS_COSH;
+  bool have_weights = false, have_cost = false;
+  // tensor-core engine state (packed 16-bit operand images), owned by rollout_tc.cuh
+  TcModel tc{};
+  // scratch
+  float* d_s0 = nullptr;        // [E,O]
+  float* d_costs = nullptr;     // [R]
+  float* d_mu_hist = nullptr;   // [(Imax+1), E, H, A]
+  float* d_sd_hist = nullptr;
+  int* d_elite = nullptr;       // [E, kmax]
+  BestEver* d_best_ever = nullptr;  // [E]
+  float* d_out_states = nullptr;    // [E,H,O]
+  float* d_out_actions = nullptr;   // [E,H,A]
+  MbrlPlanInfo* d_info = nullptr;   // [E]
+  float* d_injected = nullptr;
+  size_t injected_cap = 0;
+  // pinned host staging
+  float *h_s0 = nullptr, *h_out_states = nullptr, *h_out_actions = nullptr, *h_mu = nullptr, *h_sd = nullptr;
+  MbrlPlanInfo* h_info = nullptr;
+  cudaStream_t stream = nullptr;
+  int num_sms = 0;
+  size_t max_smem = 0;
+};
+
+static ModelDev model_view(const MbrlPlanner* p) {
+  ModelDev m;
+  m.O = p->O; m.A = p->A; m.D = p->D; m.U = p->U;
+  m.W1t = p->W1t; m.b1 = p->b1; m.W2t = p->W2t; m.b2 = p->b2; m.W3t = p->W3t; m.b3 = p->b3;
+  m.mu_s = p->mu_s; m.sd_s = p->sd_s; m.mu_a = p->mu_a; m.sd_a = p->sd_a;
+  m.cost_w = p->cost_w; m.goal = p->goal;
+  m.alpha = p->alpha; m.alpha2 = p->alpha2; m.beta = p->beta; m.beta2 = p->beta2;
+  m.cost_kind = p->cost_kind;
+  return m;
+}
+
+static ActionSource action_source(const MbrlPlanner* p, int mode, uint64_t seed, uint32_t iteration,
+                                  uint32_t cand_offset, uint32_t env_offset, const float* buf,
+                                  const float* mu, const float* sd) {
+  ActionSource s;
+  s.mode = mode; s.buf = buf; s.mu = mu; s.sd = sd;
+  s.seed_lo = (uint32_t)(seed & 0xFFFFFFFFull); s.seed_hi = (uint32_t)(seed >> 32);
+  s.iteration = iteration; s.cand_offset = cand_offset; s.env_offset = env_offset;
+  s.lo = p->lo; s.hi = p->hi;
+  return s;
+}
+
+template <class T>
+static cudaError_t dev_alloc(T** ptr, size_t count) {
+  return cudaMalloc((void**)ptr, sizeof(T) * (count ? count : 1));
+}
+
+extern "C" int mbrl_abi_version(void) { return MBRL_ABI_VERSION; }
+extern "C" const char* mbrl_last_error(void) { return g_err.c_str(); }
+
+extern "C" int mbrl_destroy(MbrlPlanner* p) {
+  if (!p) return MBRL_OK;
+  cudaSetDevice(p->cfg.device);
+  float* dev[] = {p->W1t, p->b1, p->W2t, p->b2, p->W3t, p->b3, p->mu_s, p->sd_s, p->mu_a, p->sd_a,
+                  p->cost_w, p->goal, p->d_s0, p->d_costs, p->d_mu_hist, p->d_sd_hist,
+                  p->d_out_states, p->d_out_actions, p->d_injected};
+  for (float* q : dev) if (q) cudaFree(q);
+  if (p->d_elite) cudaFree(p->d_elite);
+  if (p->d_best_ever) cudaFree(p->d_best_ever);
+  if (p->d_info) cudaFree(p->d_info);
+  tc_free(&p->tc);
+  float* pinned[] = {p->h_s0, p->h_out_states, p->h_out_actions, p->h_mu, p->h_sd};
+  for (float* q : pinned) if (q) cudaFreeHost(q);
+  if (p->h_info) cudaFreeHost(p->h_info);
+  if (p->stream) cudaStreamDestroy(p->stream);
+  delete p;
+  return MBRL_OK;
+}
+
+extern "C" int mbrl_create(const MbrlConfig* cfg, MbrlPlanner** out) {
+  if (!cfg || !out) return fail(MBRL_E_INVALID, "mbrl_create: null argument");
+  *out = nullptr;
+  MBRL_REQUIRE(cfg->obs_dim >= 1 && cfg->obs_dim <= kMaxObs, "obs_dim out of range [1,128]");
+  MBRL_REQUIRE(cfg->act_dim >= 1 && cfg->act_dim <= kMaxAct, "act_dim out of range [1,32]");
+  MBRL_REQUIRE(cfg->hidden >= 1 && cfg->hidden <= kMaxHidden, "hidden out of range [1,1024]");
+  MBRL_REQUIRE(cfg->horizon >= 1 && cfg->horizon <= 4096, "horizon out of range");
+  MBRL_REQUIRE(cfg->num_candidates >= 1, "num_candidates must be >= 1");
+  MBRL_REQUIRE(cfg->num_envs >= 1, "num_envs must be >= 1");
+  MBRL_REQUIRE((long long)cfg->num_envs * cfg->num_candidates < (1ll << 31), "E*N too large");
+  MBRL_REQUIRE(cfg->max_iterations >= 1 && cfg->max_iterations <= 1024, "max_iterations out of range");
+  MBRL_REQUIRE(cfg->max_elites >= 1 && cfg->max_elites <= cfg->num_candidates, "max_elites out of range [1,N]");
+  MBRL_REQUIRE(cfg->engine >= MBRL_ENGINE_SIMT_FP32 && cfg->engine <= MBRL_ENGINE_TC_FP16, "unknown engine");
+  int ndev = 0;
+  MBRL_CUDA(cudaGetDeviceCount(&ndev));
+  MBRL_REQUIRE(cfg->device >= 0 && cfg->device < ndev, "no such CUDA device");
+  MBRL_CUDA(cudaSetDevice(cfg->device));
+
+  MbrlPlanner* p = new (std::nothrow) MbrlPlanner();
+  if (!p) return fail(MBRL_E_INVALID, "out of host memory");
+  p->cfg = *cfg;
+  p->O = cfg->obs_dim; p->A = cfg->act_dim; p->D = p->O + p->A; p->U = cfg->hidden;
+  p->H = cfg->horizon; p->N = cfg->num_candidates; p->E = cfg->num_envs;
+  p->R = (long long)p->N * p->E;
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, cfg->device);
+  if (e != cudaSuccess) { delete p; return fail(MBRL_E_CUDA, cudaGetErrorString(e)); }
+  p->num_sms = prop.multiProcessorCount;
+  p->max_smem = prop.sharedMemPerBlockOptin;
+  if (cfg->engine != MBRL_ENGINE_SIMT_FP32 && prop.major != 10) {
+    delete p;
+    return fail(MBRL_E_UNSUPPORTED, "tcgen05 engines need an sm_100 device");
+  }
+
+  const int O = p->O, A = p->A, D = p->D, U = p->U, H = p->H, E = p->E;
+  const size_t EHA = (size_t)E * H * A;
+  bool ok = true;
+  auto A_ = [&](cudaError_t err) { if (err != cudaSuccess) { ok = false; g_err = cudaGetErrorString(err); } };
+  A_(dev_alloc(&p->W1t, (size_t)D * U)); A_(dev_alloc(&p->b1, U));
+  A_(dev_alloc(&p->W2t, (size_t)U * U)); A_(dev_alloc(&p->b2, U));
+  A_(dev_alloc(&p->W3t, (size_t)U * O)); A_(dev_alloc(&p->b3, O));
+  A_(dev_alloc(&p->mu_s, O)); A_(dev_alloc(&p->sd_s, O)); A_(dev_alloc(&p->mu_a, A)); A_(dev_alloc(&p->sd_a, A));
+  A_(dev_alloc(&p->cost_w, O)); A_(dev_alloc(&p->goal, O));
+  A_(dev_alloc(&p->d_s0, (size_t)E * O)); A_(dev_alloc(&p->d_costs, (size_t)p->R));
+  A_(dev_alloc(&p->d_mu_hist, EHA * (cfg->max_iterations + 1)));
+  A_(dev_alloc(&p->d_sd_hist, EHA * (cfg->max_iterations + 1)));
+  A_(dev_alloc(&p->d_elite, (size_t)E * cfg->max_elites));
+  A_(dev_alloc(&p->d_best_ever, E)); A_(dev_alloc(&p->d_info, E));
+  A_(dev_alloc(&p->d_out_states, (size_t)E * H * O)); A_(dev_alloc(&p->d_out_actions, EHA));
+  A_(cudaMallocHost((void**)&p->h_s0, sizeof(float) * E * O));
+  A_(cudaMallocHost((void**)&p->h_out_states, sizeof(float) * E * H * O));
+  A_(cudaMallocHost((void**)&p->h_out_actions, sizeof(float) * EHA));
+  A_(cudaMallocHost((void**)&p->h_mu, sizeof(float) * EHA));
+  A_(cudaMallocHost((void**)&p->h_sd, sizeof(float) * EHA));
+  A_(cudaMallocHost((void**)&p->h_info, sizeof(MbrlPlanInfo) * E));
+  A_(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  if (ok) {
+    // identity normalisers until mbrl_set_norm is called
+    std::vector<float> zeros(kMaxObs, 0.f), ones(kMaxObs, 1.f);
+    A_(cudaMemcpy(p->mu_s, zeros.data(), sizeof(float) * O, cudaMemcpyHostToDevice));
+    A_(cudaMemcpy(p->sd_s, ones.data(), sizeof(float) * O, cudaMemcpyHostToDevice));
+    A_(cudaMemcpy(p->mu_a, zeros.data(), sizeof(float) * A, cudaMemcpyHostToDevice));
+    A_(cudaMemcpy(p->sd_a, ones.data(), sizeof(float) * A, cudaMemcpyHostToDevice));
+  }
+  if (ok && cfg->engine != MBRL_ENGINE_SIMT_FP32) {
+    std::string why;
+    if (!tc_init(&p->tc, O, A, U, cfg->engine == MBRL_ENGINE_TC_FP16, p->max_smem, &why)) {
+      mbrl_destroy(p);
+      return fail(MBRL_E_UNSUPPORTED, "tensor-core engine: " + why);
+    }
+  }
+  if (!ok) {
+    std::string msg = g_err;
+    mbrl_destroy(p);
+    return fail(MBRL_E_CUDA, "mbrl_create: " + msg);
+  }
+  *out = p;
+  return MBRL_OK;
+}
+
+// nn.Linear [out,in] row-major  ->  K-major [in][out]
+static void transpose_to(std::vector<float>& dst, const float* W, int out_f, int in_f) {
+  dst.resize((size_t)out_f * in_f);
+  for (int o = 0; o < out_f; ++o)
+    for (int i = 0; i < in_f; ++i) dst[(size_t)i * out_f + o] = W[(size_t)o * in_f + i];
+}
+
+extern "C" int mbrl_set_weights(MbrlPlanner* p, const float* W1, const float* b1, const float* W2,
+                                const float* b2, const float* W3, const float* b3) {
+  if (!p) return fail(MBRL_E_INVALID, "null planner");
+  MBRL_REQUIRE(W1 && b1 && W2 && b2 && W3 && b3, "null weight pointer");
+  MBRL_CUDA(cudaSetDevice(p->cfg.device));
+  MBRL_CUDA(cudaStreamSynchronize(p->stream));
+  std::vector<float> t;
+  transpose_to(t, W1, p->U, p->D);
+  MBRL_CUDA(cudaMemcpy(p->W1t, t.data(), sizeof(float) * t.size(), cudaMemcpyHostToDevice));
+  transpose_to(t, W2, p->U, p->U);
+  MBRL_CUDA(cudaMemcpy(p->W2t, t.data(), sizeof(float) * t.size(), cudaMemcpyHostToDevice));
+  transpose_to(t, W3, p->O, p->U);
+  MBRL_CUDA(cudaMemcpy(p->W3t, t.data(), sizeof(float) * t.size(), cudaMemcpyHostToDevice));
+  MBRL_CUDA(cudaMemcpy(p->b1, b1, sizeof(float) * p->U, cudaMemcpyHostToDevice));
+  MBRL_CUDA(cudaMemcpy(p->b2, b2, sizeof(float) * p->U, cudaMemcpyHostToDevice));
+  MBRL_CUDA(cudaMemcpy(p->b3, b3, sizeof(float) * p->O, cudaMemcpyHostToDevice));
+  if (p->cfg.engine != MBRL_ENGINE_SIMT_FP32) {
+    std::string why;
+    if (!tc_set_weights(&p->tc, W1, b1, W2, b2, W3, b3, &why)) return fail(MBRL_E_CUDA, why);
+  }
+  p->have_weights = true;
+  return MBRL_OK;
+}
+
+extern "C" int mbrl_set_norm(MbrlPlanner* p, const float* mu_s, const float* sd_s, const float* mu_a,
+                             const float* sd_a) {
+  if (!p) return fail(MBRL_E_INVALID, "null planner");
+  MBRL_CUDA(cudaSetDevice(p->cfg.device));
+  MBRL_CUDA(cudaStreamSynchronize(p->stream));
+  std::vector<float> zeros(kMaxObs, 0.f), ones(kMaxObs, 1.f);
+  MBRL_CUDA(cudaMemcpy(p->mu_s, mu_s ? mu_s : zeros.data(), sizeof(float) * p->O, cudaMemcpyHostToDevice));
+  MBRL_CUDA(cudaMemcpy(p->sd_s, sd_s ? sd_s : ones.data(), sizeof(float) * p->O, cudaMemcpyHostToDevice));
+  MBRL_CUDA(cudaMemcpy(p->mu_a, mu_a ? mu_a : zeros.data(), sizeof(float) * p->A, cudaMemcpyHostToDevice));
+  MBRL_CUDA(cudaMemcpy(p->sd_a, sd_a ? sd_a : ones.data(), sizeof(float) * p->A, cudaMemcpyHostToDevice));
+  return MBRL_OK;
+}
+
+extern "C" int mbrl_set_cost(MbrlPlanner* p, int32_t kind, const float* w, const float* goal, double alpha,
+                             double beta) {
+  if (!p) return fail(MBRL_E_INVALID, "null planner");
+  MBRL_REQUIRE(kind == MBRL_COST_SMOOTHABS_COSH, "unknown cost kind");
+  MBRL_REQUIRE(w && goal, "null cost pointer");
+  MBRL_REQUIRE(beta != 0.0, "beta must be non-zero");
+  MBRL_CUDA(cudaSetDevice(p->cfg.device));
+  MBRL_CUDA(cudaStreamSynchronize(p->stream));
+  MBRL_CUDA(cudaMemcpy(p->cost_w, w, sizeof(float) * p->O, cudaMemcpyHostToDevice));
+  MBRL_CUDA(cudaMemcpy(p->goal, goal, sizeof(float) * p->O, cudaMemcpyHostToDevice));
+  p->cost_kind = kind;
+  p->alpha = (float)alpha; p->alpha2 = (float)(alpha * alpha);
+  p->beta = (float)beta; p->beta2 = (float)(beta * beta);
+  p->have_cost = true;
+  return MBRL_OK;
+}
+
+extern "C" int mbrl_set_action_bounds(MbrlPlanner* p, float lo, float hi) {
+  if (!p) return fail(MBRL_E_INVALID, "null planner");
+  MBRL_REQUIRE(lo <= hi, "lo > hi");
+  p->lo = lo; p->hi = hi;
+  return MBRL_OK;
+}
+
+// --------------------------------------------------------------------------------------
+// kernel launchers
+// --------------------------------------------------------------------------------------
+template <int TM, int CPT>
+static cudaError_t launch_simt_t(const MbrlPlanner* p, const ActionSource& src, const float* d_s0,
+                                 float* d_costs, float* d_states, float* d_actions, cudaStream_t st) {
+  const size_t smem = simt_smem_bytes<TM>(p->O, p->A, p->U);
+  auto kern = rollout_simt_kernel<TM, CPT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  Shape sh{p->H, p->N, p->E};
+  const unsigned grid = (unsigned)((p->R + TM - 1) / TM);
+  kern<<<grid, TM * 4, smem, st>>>(model_view(p), src, sh, d_s0, d_costs, d_states, d_actions);
+  return cudaGetLastError();
+}
+
+template <int TM>
+static cudaError_t launch_simt_cpt(const MbrlPlanner* p, const ActionSource& src, const float* d_s0,
+                                   float* d_costs, float* d_states, float* d_actions, cudaStream_t st) {
+  const int U = p->U;
+  if (U <= 64) return launch_simt_t<TM, 2>(p, src, d_s0, d_costs, d_states, d_actions, st);
+  if (U <= 128) return launch_simt_t<TM, 4>(p, src, d_s0, d_costs, d_states, d_actions, st);
+  if (U <= 224) return launch_simt_t<TM, 7>(p, src, d_s0, d_costs, d_states, d_actions, st);
+  return launch_simt_t<TM, 8>(p, src, d_s0, d_costs, d_states, d_actions, st);
+}
+
+static int launch_rollout(MbrlPlanner* p, const ActionSource& src, const float* d_s0, float* d_costs,
+                          float* d_states, float* d_actions, cudaStream_t st) {
+  if (!p->have_weights || !p->have_cost)
+    return fail(MBRL_E_STATE, "mbrl_set_weights and mbrl_set_cost must be called before planning");
+  if ((src.mode == MBRL_SAMPLE_INJECT_ACTIONS || src.mode == MBRL_SAMPLE_INJECT_NOISE) && !src.buf)
+    return fail(MBRL_E_INVALID, "injected sample mode without an injected buffer");
+  if ((src.mode == MBRL_SAMPLE_INJECT_NOISE || src.mode == MBRL_SAMPLE_GAUSSIAN) && (!src.mu || !src.sd))
+    return fail(MBRL_E_INVALID, "Gaussian sample mode without mu/sd");
+  if (src.mode < MBRL_SAMPLE_INJECT_ACTIONS || src.mode > MBRL_SAMPLE_UNIFORM)
+    return fail(MBRL_E_INVALID, "unknown sample mode");
+  cudaError_t e;
+  if (p->cfg.engine == MBRL_ENGINE_SIMT_FP32) {
+    if (simt_smem_bytes<64>(p->O, p->A, p->U) <= p->max_smem)
+      e = launch_simt_cpt<64>(p, src, d_s0, d_costs, d_states, d_actions, st);
+    else if (simt_smem_bytes<32>(p->O, p->A, p->U) <= p->max_smem)
+      e = launch_simt_cpt<32>(p, src, d_s0, d_costs, d_states, d_actions, st);
+    else if (simt_smem_bytes<16>(p->O, p->A, p->U) <= p->max_smem)
+      e = launch_simt_cpt<16>(p, src, d_s0, d_costs, d_states, d_actions, st);
+    else
+      return fail(MBRL_E_UNSUPPORTED, "model too large for the fp32 engine's shared-memory tiling");
+  } else {
+    Shape sh{p->H, p->N, p->E};
+    e = tc_launch_rollout(&p->tc, model_view(p), src, sh, d_s0, d_costs, d_states, d_actions, p->num_sms, st);
+  }
+  if (e != cudaSuccess) return fail(MBRL_E_CUDA, std::string("rollout launch: ") + cudaGetErrorString(e));
+  return MBRL_OK;
+}
+
+static int launch_topk(const float* d_costs, int segments, int n, int k, int* d_idx, float* d_cost,
+                       MbrlPlanInfo* d_best, BestEver* d_best_ever, int iteration, cudaStream_t st) {
+  MBRL_REQUIRE(segments >= 1 && n >= 1, "topk: empty input");
+  MBRL_REQUIRE(k >= 1 && k <= n, "topk: k out of range [1,n]");
+  topk_select_kernel<<<segments, kSelectThreads, 0, st>>>(d_costs, n, k, d_idx, d_cost, d_best, d_best_ever, iteration);
+  MBRL_CUDA(cudaGetLastError());
+  return MBRL_OK;
+}
+
+static int launch_refit(const MbrlPlanner* p, const ActionSource& src, const int* d_elite, int k,
+                        float* d_mu_new, float* d_sd_new, cudaStream_t st) {
+  MBRL_REQUIRE(k >= 1, "refit: k must be >= 1");
+  const int G = (p->A + 3) / 4;
+  Shape sh{p->H, p->N, p->E};
+  dim3 grid(p->H * G, p->E);
+  refit_kernel<<<grid, kRefitThreads, 0, st>>>(src, sh, p->A, d_elite, k, d_mu_new, d_sd_new);
+  MBRL_CUDA(cudaGetLastError());
+  return MBRL_OK;
+}
+
+static int launch_replay(MbrlPlanner* p, int mode, uint64_t seed, uint32_t cand_offset, uint32_t env_offset,
+                         const float* d_s0, const float* d_injected, const float* d_mu_hist,
+                         const float* d_sd_hist, int iterations, int return_mean, const BestEver* d_best,
+                         float* d_out_states, float* d_out_actions, MbrlPlanInfo* d_info, cudaStream_t st) {
+  if (!p->have_weights) return fail(MBRL_E_STATE, "mbrl_set_weights must be called before planning");
+  ActionSource src = action_source(p, mode, seed, 0, cand_offset, env_offset, d_injected, d_mu_hist, d_sd_hist);
+  Shape sh{p->H, p->N, p->E};
+  const size_t smem = replay_smem_bytes(p->O, p->A, p->U, p->H);
+  MBRL_REQUIRE(smem <= p->max_smem, "horizon too long for the replay kernel's shared memory");
+  MBRL_CUDA(cudaFuncSetAttribute(replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  replay_kernel<<<p->E, kReplayThreads, smem, st>>>(model_view(p), src, sh, d_s0, d_mu_hist, d_sd_hist, d_best,
+                                                   iterations, return_mean, d_out_states, d_out_actions, d_info);
+  MBRL_CUDA(cudaGetLastError());
+  return MBRL_OK;
+}
+
+// --------------------------------------------------------------------------------------
+// building-block entry points
+// --------------------------------------------------------------------------------------
+extern "C" int mbrl_rollout(MbrlPlanner* p, int32_t mode, uint64_t seed, uint32_t iteration,
+                            uint32_t cand_offset, uint32_t env_offset, const float* d_s0,
+                            const float* d_injected, const float* d_mu, const float* d_sd, float* d_costs,
+                            float* d_states_out, float* d_actions_out, void* stream) {
+  if (!p) return fail(MBRL_E_INVALID, "null planner");
+  MBRL_REQUIRE(d_s0 && d_costs, "null s0/costs");
+  MBRL_CUDA(cudaSetDevice(p->cfg.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+  ActionSource src = action_source(p, mode, seed, iteration, cand_offset, env_offset, d_injected, d_mu, d_sd);
+  return launch_rollout(p, src, d_s0, d_costs, d_states_out, d_actions_out, st);
+}
+
+extern "C" int mbrl_sample(MbrlPlanner* p, int32_t mode, uint64_t seed, uint32_t iteration,
+                           uint32_t cand_offset, uint32_t env_offset, const float* d_mu, const float* d_sd,
+                           float* d_out, void* stream) {
+  if (!p) return fail(MBRL_E_INVALID, "null planner");
+  MBRL_REQUIRE(mode == MBRL_SAMPLE_GAUSSIAN || mode == MBRL_SAMPLE_UNIFORM, "sample: Philox modes only");
+  MBRL_REQUIRE(d_out, "null output");
+  MBRL_REQUIRE(mode == MBRL_SAMPLE_UNIFORM || (d_mu && d_sd), "Gaussian mode needs mu/sd");
+  MBRL_CUDA(cudaSetDevice(p->cfg.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+  ActionSource src = action_source(p, mode, seed, iteration, cand_offset, env_offset, nullptr, d_mu, d_sd);
+  Shape sh{p->H, p->N, p->E};
+  const long long total = p->R * p->H;
+  sample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, sh, p->A, d_out);
+  MBRL_CUDA(cudaGetLastError());
+  return MBRL_OK;
+}
+
+extern "C" int mbrl_philox_raw(const uint32_t* d_ctr, const uint32_t* d_key, uint32_t* d_out, int64_t n,
+                               void* stream) {
+  MBRL_REQUIRE(d_ctr && d_key && d_out && n >= 0, "philox_raw: bad argument");
+  if (n == 0) return MBRL_OK;
+  philox_raw_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_ctr, d_key, d_out, n);
+  MBRL_CUDA(cudaGetLastError());
+  return MBRL_OK;
+}
+
+extern "C" int mbrl_topk(const float* d_costs, int32_t segments, int32_t n, int32_t k, int32_t* d_elite_idx,
+                         float* d_elite_cost, MbrlPlanInfo* d_best, void* stream) {
+  MBRL_REQUIRE(d_costs && d_elite_idx, "topk: null pointer");
+  return launch_topk(d_costs, segments, n, k, d_elite_idx, d_elite_cost, d_best, nullptr, 0, (cudaStream_t)stream);
+}
+
+extern "C" int mbrl_refit(MbrlPlanner* p, int32_t mode, uint64_t seed, uint32_t iteration,
+                          uint32_t cand_offset, uint32_t env_offset, const float* d_injected,
+                          const float* d_mu, const float* d_sd, const int32_t* d_elite_idx, int32_t k,
+                          float* d_mu_new, float* d_sd_new, void* stream) {
+  if (!p) return fail(MBRL_E_INVALID, "null planner");
+  MBRL_REQUIRE(d_elite_idx && d_mu_new && d_sd_new, "refit: null pointer");
+  MBRL_REQUIRE(mode >= MBRL_SAMPLE_INJECT_ACTIONS && mode <= MBRL_SAMPLE_UNIFORM, "unknown sample mode");
+  MBRL_REQUIRE((mode != MBRL_SAMPLE_INJECT_ACTIONS && mode != MBRL_SAMPLE_INJECT_NOISE) || d_injected,
+               "injected mode without buffer");
+  MBRL_REQUIRE((mode != MBRL_SAMPLE_INJECT_NOISE && mode != MBRL_SAMPLE_GAUSSIAN) || (d_mu && d_sd),
+               "Gaussian mode needs mu/sd");
+  MBRL_CUDA(cudaSetDevice(p->cfg.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+  ActionSource src = action_source(p, mode, seed, iteration, cand_offset, env_offset, d_injected, d_mu, d_sd);
+  return launch_refit(p, src, d_elite_idx, k, d_mu_new, d_sd_new, st);
+}
+
+static_assert(sizeof(BestEver) == sizeof(MbrlPlanInfo), "BestEver and MbrlPlanInfo share one layout");
+
+extern "C" int mbrl_emit(MbrlPlanner* p, int32_t mode, uint64_t seed, uint32_t cand_offset, uint32_t env_offset,
+                         const float* d_s0, const float* d_injected, const float* d_mu_hist,
+                         const float* d_sd_hist, int32_t iterations, int32_t return_mean,
+                         const MbrlPlanInfo* d_best, float* d_out_states, float* d_out_actions, void* stream) {
+  if (!p) return fail(MBRL_E_INVALID, "null planner");
+  MBRL_REQUIRE(d_s0 && d_best && d_out_states && d_out_actions, "emit: null pointer");
+  MBRL_REQUIRE(d_mu_hist && d_sd_hist, "emit: null mu/sd history");
+  MBRL_REQUIRE(iterations >= 1, "emit: iterations must be >= 1");
+  MBRL_CUDA(cudaSetDevice(p->cfg.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+  return launch_replay(p, mode, seed, cand_offset, env_offset, d_s0, d_injected, d_mu_hist, d_sd_hist, iterations,
+                       return_mean, reinterpret_cast<const BestEver*>(d_best), d_out_states, d_out_actions, nullptr, st);
+}
+
+// --------------------------------------------------------------------------------------
+// whole plans
+// --------------------------------------------------------------------------------------
+static int enqueue_plan(MbrlPlanner* p, const MbrlPlanArgs* a, const float* d_s0, const float* d_injected,
+                        float* d_out_states, float* d_out_actions, MbrlPlanInfo* d_info, bool need_final_dist,
+                        cudaStream_t st) {
+  const int I = a->iterations;
+  MBRL_REQUIRE(I >= 1 && I <= p->cfg.max_iterations, "iterations out of range [1, max_iterations]");
+  const int k = (I == 1 && !need_final_dist) ? 1 : a->elites;
+  MBRL_REQUIRE(k >= 1 && k <= p->cfg.max_elites, "elites out of range [1, max_elites]");
+  const size_t EHA = (size_t)p->E * p->H * p->A;
+  const long long HRA = (long long)p->H * p->R * p->A;
+
+  if (a->h_mu0 && a->h_sd0) {
+    MBRL_CUDA(cudaMemcpyAsync(p->d_mu_hist, a->h_mu0, sizeof(float) * EHA, cudaMemcpyHostToDevice, st));
+    MBRL_CUDA(cudaMemcpyAsync(p->d_sd_hist, a->h_sd0, sizeof(float) * EHA, cudaMemcpyHostToDevice, st));
+    init_plan_kernel<<<(unsigned)((p->E + 255) / 256), 256, 0, st>>>(nullptr, nullptr, 0, p->lo, p->hi, p->d_best_ever, p->E);
+  } else {
+    MBRL_REQUIRE(!a->h_mu0 && !a->h_sd0, "mu0 and sd0 must be given together");
+    const long long n = (long long)EHA > p->E ? (long long)EHA : p->E;
+    init_plan_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p->d_mu_hist, p->d_sd_hist, (long long)EHA, p->lo, p->hi, p->d_best_ever, p->E);
+  }
+  MBRL_CUDA(cudaGetLastError());
+
+  for (int it = 0; it < I; ++it) {
+    const float* inj = d_injected ? d_injected + (long long)it * HRA : nullptr;
+    ActionSource src = action_source(p, a->sample_mode, a->seed, (uint32_t)it, a->cand_offset, a->env_offset, inj,
+                                     p->d_mu_hist + it * EHA, p->d_sd_hist + it * EHA);
+    int rc = launch_rollout(p, src, d_s0, p->d_costs, nullptr, nullptr, st);
+    if (rc) return rc;
+    rc = launch_topk(p->d_costs, p->E, p->N, k, p->d_elite, nullptr, nullptr, p->d_best_ever, it, st);
+    if (rc) return rc;
+    if (it + 1 < I || need_final_dist) {
+      rc = launch_refit(p, src, p->d_elite, k, p->d_mu_hist + (it + 1) * EHA, p->d_sd_hist + (it + 1) * EHA, st);
+      if (rc) return rc;
+    }
+  }
+  return launch_replay(p, a->sample_mode, a->seed, a->cand_offset, a->env_offset, d_s0, d_injected, p->d_mu_hist,
+                       p->d_sd_hist, I, a->return_mean, p->d_best_ever, d_out_states, d_out_actions, d_info, st);
+}
+
+extern "C" int mbrl_plan_device(MbrlPlanner* p, const MbrlPlanArgs* args, const float* d_s0,
+                                const float* d_injected, float* d_out_states, float* d_out_actions,
+                                MbrlPlanInfo* d_info, void* stream) {
+  if (!p || !args) return fail(MBRL_E_INVALID, "null planner/args");
+  MBRL_REQUIRE(d_s0 && d_out_states && d_out_actions, "null device buffer");
+  MBRL_CUDA(cudaSetDevice(p->cfg.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+  return enqueue_plan(p, args, d_s0, d_injected, d_out_states, d_out_actions, d_info,
+                      args->return_mean != 0, st);
+}
+
+extern "C" int mbrl_plan(MbrlPlanner* p, const MbrlPlanArgs* args, const float* h_s0, float* h_out_states,
+                         float* h_out_actions, MbrlPlanInfo* h_info, float* h_out_mu, float* h_out_sd) {
+  if (!p || !args) return fail(MBRL_E_INVALID, "null planner/args");
+  MBRL_REQUIRE(h_s0 && h_out_states && h_out_actions, "null host buffer");
+  MBRL_REQUIRE((h_out_mu == nullptr) == (h_out_sd == nullptr), "out_mu and out_sd must be given together");
+  MBRL_CUDA(cudaSetDevice(p->cfg.device));
+  cudaStream_t st = p->stream;
+  const int O = p->O, A = p->A, H = p->H, E = p->E;
+  const size_t EHA = (size_t)E * H * A;
+  const float* d_inj = nullptr;
+  const bool inject = args->sample_mode == MBRL_SAMPLE_INJECT_ACTIONS || args->sample_mode == MBRL_SAMPLE_INJECT_NOISE;
+  if (inject) {
+    MBRL_REQUIRE(args->h_injected, "injected sample mode without h_injected");
+    MBRL_REQUIRE(args->iterations >= 1, "iterations must be >= 1");
+    const size_t need = (size_t)args->iterations * H * (size_t)p->R * A;
+    if (need > p->injected_cap) {
+      if (p->d_injected) MBRL_CUDA(cudaFree(p->d_injected));
+      p->d_injected = nullptr; p->injected_cap = 0;
+      MBRL_CUDA(dev_alloc(&p->d_injected, need));
+      p->injected_cap = need;
+    }
+    MBRL_CUDA(cudaMemcpyAsync(p->d_injected, args->h_injected, sizeof(float) * need, cudaMemcpyHostToDevice, st));
+    d_inj = p->d_injected;
+  }
+  std::memcpy(p->h_s0, h_s0, sizeof(float) * E * O);
+  MBRL_CUDA(cudaMemcpyAsync(p->d_s0, p->h_s0, sizeof(float) * E * O, cudaMemcpyHostToDevice, st));
+  const bool need_dist = h_out_mu != nullptr || args->return_mean != 0;
+  int rc = enqueue_plan(p, args, p->d_s0, d_inj, p->d_out_states, p->d_out_actions, p->d_info, need_dist, st);
+  if (rc) return rc;
+  MBRL_CUDA(cudaMemcpyAsync(p->h_out_actions, p->d_out_actions, sizeof(float) * EHA, cudaMemcpyDeviceToHost, st));
+  MBRL_CUDA(cudaMemcpyAsync(p->h_out_states, p->d_out_states, sizeof(float) * E * H * O, cudaMemcpyDeviceToHost, st));
+  MBRL_CUDA(cudaMemcpyAsync(p->h_info, p->d_info, sizeof(MbrlPlanInfo) * E, cudaMemcpyDeviceToHost, st));
+  if (h_out_mu) {
+    MBRL_CUDA(cudaMemcpyAsync(p->h_mu, p->d_mu_hist + (size_t)args->iterations * EHA, sizeof(float) * EHA, cudaMemcpyDeviceToHost, st));
+    MBRL_CUDA(cudaMemcpyAsync(p->h_sd, p->d_sd_hist + (size_t)args->iterations * EHA, sizeof(float) * EHA, cudaMemcpyDeviceToHost, st));
+  }
+  MBRL_CUDA(cudaStreamSynchronize(st));
+  std::memcpy(h_out_actions, p->h_out_actions, sizeof(float) * EHA);
+  std::memcpy(h_out_states, p->h_out_states, sizeof(float) * E * H * O);
+  if (h_info) std::memcpy(h_info, p->h_info, sizeof(MbrlPlanInfo) * E);
+  if (h_out_mu) {
+    std::memcpy(h_out_mu, p->h_mu, sizeof(float) * EHA);
+    std::memcpy(h_out_sd, p->h_sd, sizeof(float) * EHA);
+  }
+  return MBRL_OK;
+}

@@ -1,0 +1,149 @@
+"""Drop-in planners with the reference's API (src/mbrl/planners.py:14-25, 140-187).
+
+    states, actions = RandomShootingPlanner.plan(initial_state, model, cost, sample_action, horizon,
+                                                 initial_trajectory=None, num_trajectories=1000)
+    states, actions = CEMPlanner.plan(initial_state, model, cost, sample_action, horizon,
+                                      initial_trajectory=None, num_trajectories=16384,
+                                      num_iterations=5, elite_frac=0.1)
+
+Planners are passed around as classes with static methods and pickled with the policy
+(src/mbrl/experiment.py:22-26, src/mbrl/parallel.py:23-38), so no CUDA handle lives on them:
+handles sit in a lazily built module-level cache keyed by model identity and shape.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+from . import native
+from .adaptor import PlanningProblem, problem_from_callables
+
+_HANDLES: Dict[tuple, dict] = {}
+
+
+def _as_torch(x):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(x))
+
+
+def _get_handle(model, cost, sample_action, horizon, n, max_iters, engine, device):
+    prob, fp = problem_from_callables(model, cost, sample_action)
+    owner = model.func if hasattr(model, "func") else model
+    key = (id(owner), prob.obs_dim, prob.act_dim, prob.hidden, horizon, n, max_iters, engine, device)
+    ent = _HANDLES.get(key)
+    if ent is None:
+        h = native.NativePlanner(prob.obs_dim, prob.act_dim, prob.hidden, horizon, n, 1, max_iters, n, engine, device)
+        ent = dict(handle=h, fingerprint=None, calls=0, keepalive=None)
+        _HANDLES[key] = ent
+    if ent["fingerprint"] != fp:
+        ent["handle"].load_problem(prob)
+        ent["fingerprint"] = fp
+        ent["keepalive"] = (owner, prob)  # keeps ids in the fingerprint from being recycled
+    return ent, prob
+
+
+def clear_handles():
+    """Destroy every cached native handle (frees device memory)."""
+    for ent in _HANDLES.values():
+        ent["handle"].close()
+    _HANDLES.clear()
+
+
+class ModelPlanner:
+    """Interface of src/mbrl/planners.py:14-25."""
+
+    @staticmethod
+    def plan(initial_state, model, cost, sample_action, horizon, initial_trajectory=None, **kwargs):
+        raise NotImplementedError
+
+
+def _host_sample(sample_action, n, horizon, act_dim):
+    """One sampler call for all H*N rows, exactly as the reference makes it
+    (src/mbrl/planners.py:200); the result is injected into the device rollout."""
+    acts = sample_action(batch_size=n * horizon)
+    acts = native._f32(acts)
+    if acts.shape != (n * horizon, act_dim):
+        raise ValueError(f"sample_action returned shape {acts.shape}, expected {(n * horizon, act_dim)}")
+    return acts
+
+
+class RandomShootingPlanner(ModelPlanner):
+    """GPU random shooting: N candidate sequences rolled through the dynamics MLP for
+    `horizon` steps, scored, argmin (first minimum) returned -- src/mbrl/planners.py:140-216.
+
+    kwargs: num_trajectories (default 1000, planners.py:141); sampler="device" (Philox uniform
+    on the GPU with the reference sampler's bounds) or "host" (call `sample_action` once on the
+    host like the reference and inject the draws: bit-faithful to a given numpy stream);
+    engine="fp32"|"bf16"|"fp16"; seed; device."""
+
+    defaults = dict(num_trajectories=1000, sampler="device", engine="fp32", seed=None, device=0)
+
+    @staticmethod
+    def plan(initial_state, model, cost, sample_action, horizon, initial_trajectory=None, **kwargs):
+        d = RandomShootingPlanner.defaults
+        n = int(kwargs.get("num_trajectories", d["num_trajectories"]))
+        sampler = kwargs.get("sampler", d["sampler"])
+        ent, prob = _get_handle(model, cost, sample_action, horizon, n, 1, kwargs.get("engine", d["engine"]),
+                                kwargs.get("device", d["device"]))
+        h = ent["handle"]
+        seed = kwargs.get("seed", d["seed"])
+        if seed is None:
+            seed = ent["calls"]
+        ent["calls"] += 1
+        if sampler == "host":
+            out = h.plan(initial_state, 1, 1, native.SAMPLE_INJECT_ACTIONS, seed,
+                         injected=_host_sample(sample_action, n, horizon, prob.act_dim))
+        elif sampler == "device":
+            out = h.plan(initial_state, 1, 1, native.SAMPLE_UNIFORM, seed)
+        else:
+            raise ValueError("sampler must be 'device' or 'host'")
+        return _as_torch(out["states"][0]), _as_torch(out["actions"][0])
+
+
+class CEMPlanner(ModelPlanner):
+    """Cross-entropy-method planner (not in the reference; SURVEY.md section 8a last row):
+    per iteration sample a ~ clip(N(mu[h], sd[h])), roll out + score (same fused kernel as
+    random shooting), keep the k = int(elite_frac*N) cheapest (ties -> lower index), refit
+    mu/sd per (h, a) with the population std; return the best-ever candidate.
+
+    `initial_trajectory` (the warm start MPCPolicy passes, src/mbrl/agents.py:41-47) seeds the
+    mean with its action sequence when given."""
+
+    defaults = dict(num_trajectories=16384, num_iterations=5, elite_frac=0.1, engine="fp32", seed=None, device=0,
+                    return_mean=False, init_std=None)
+
+    @staticmethod
+    def plan(initial_state, model, cost, sample_action, horizon, initial_trajectory=None, **kwargs):
+        d = CEMPlanner.defaults
+        n = int(kwargs.get("num_trajectories", d["num_trajectories"]))
+        iters = int(kwargs.get("num_iterations", d["num_iterations"]))
+        k = int(kwargs.get("num_elites", max(1, int(kwargs.get("elite_frac", d["elite_frac"]) * n))))
+        ent, prob = _get_handle(model, cost, sample_action, horizon, n, iters, kwargs.get("engine", d["engine"]),
+                                kwargs.get("device", d["device"]))
+        h = ent["handle"]
+        seed = kwargs.get("seed", d["seed"])
+        if seed is None:
+            seed = ent["calls"]
+        ent["calls"] += 1
+        mu0 = sd0 = None
+        if initial_trajectory is not None:
+            acts = native._f32(_stack(initial_trajectory[1])).reshape(-1, prob.act_dim)
+            mu0 = np.zeros((horizon, prob.act_dim), np.float32) + 0.5 * (prob.act_lo + prob.act_hi)
+            m = min(horizon, acts.shape[0])
+            mu0[:m] = acts[:m]
+            init_std = kwargs.get("init_std", d["init_std"])
+            sd0 = np.full((horizon, prob.act_dim), 0.5 * (prob.act_hi - prob.act_lo) if init_std is None else init_std,
+                          np.float32)
+        noise = kwargs.get("noise")  # [I, H*N, A] recorded N(0,1) draws (parity runs)
+        mode = native.SAMPLE_GAUSSIAN if noise is None else native.SAMPLE_INJECT_NOISE
+        out = h.plan(initial_state, iters, k, mode, seed, injected=noise, mu0=mu0, sd0=sd0,
+                     return_mean=kwargs.get("return_mean", d["return_mean"]))
+        return _as_torch(out["states"][0]), _as_torch(out["actions"][0])
+
+
+def _stack(seq):
+    import torch
+    if isinstance(seq, (list, tuple)):
+        return torch.stack([torch.as_tensor(s).reshape(-1) for s in seq])
+    return seq

@@ -1,0 +1,105 @@
+"""CPU-side checks: the C-ABI library builds/loads and exports every symbol the header
+declares (no compute calls -- there is no GPU here), the host adaptor recognises the
+reference's partials, and misuse fails loudly instead of falling back."""
+import ctypes
+import functools
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    from mbrl_b200 import native
+    lib = native.load_library()
+    header = open(os.path.join(ROOT, "include", "mbrl_b200.h")).read()
+    declared = set(re.findall(r"^\s*(?:int|const char\*)\s+(mbrl_\w+)\s*\(", header, re.M))
+    assert declared == set(native.ABI_SYMBOLS), declared ^ set(native.ABI_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.mbrl_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    from mbrl_b200 import native
+    assert ctypes.sizeof(native.MbrlConfig) == 40
+    assert ctypes.sizeof(native.MbrlPlanInfo) == 16 == native.PLAN_INFO_DTYPE.itemsize
+    assert ctypes.sizeof(native.MbrlPlanArgs) == 56
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    from mbrl_b200 import native
+    with pytest.raises(native.MbrlError):
+        native.NativePlanner(5, 1, 50, 20, 1000)
+
+
+def test_invalid_arguments_are_rejected_before_cuda():
+    from mbrl_b200 import native
+    lib = native.load_library()
+    cfg = native.MbrlConfig(0, 1, 50, 20, 1000, 1, 1, 1, 0, 0)
+    handle = ctypes.c_void_p()
+    assert lib.mbrl_create(ctypes.byref(cfg), ctypes.byref(handle)) == -1
+    assert b"obs_dim" in lib.mbrl_last_error()
+    assert lib.mbrl_topk(None, 1, 1, 1, None, None, None, None) == -1
+
+
+def test_adaptor_introspects_reference_partials():
+    from mbrl_b200.adaptor import PlanningProblem, problem_from_callables
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.linear1, self.linear2, self.linear3 = torch.nn.Linear(7, 12), torch.nn.Linear(12, 12), torch.nn.Linear(12, 5)
+            self.noise = None
+
+    def norm(field_value, field_name, stats):
+        return field_value
+
+    stats = {"observations": {"mean": torch.zeros(5), "std": torch.ones(5)},
+             "actions": {"mean": torch.zeros(2), "std": torch.ones(2)}}
+    net = Net()
+    model = functools.partial(net, normalize_state=functools.partial(norm, field_name="observations", stats=stats),
+                              normalize_action=functools.partial(norm, field_name="actions", stats=stats),
+                              unnormalize_state=functools.partial(norm, field_name="observations", stats=stats))
+    sc = type("SC", (), dict(weights=torch.ones(5), goal_state=torch.zeros(5), alpha=0.4))()
+    ac = type("AC", (), dict(alpha=0.25))()
+    cost = functools.partial(lambda s, a, state_cost, action_cost: 0, state_cost=sc, action_cost=ac)
+    spec = type("Spec", (), dict(minimum=np.array([-5.0, -1.0]), maximum=np.array([0.5, 1.0]), shape=(2,)))()
+    sampler = functools.partial(lambda action_spec, batch_size=None: None, action_spec=spec)
+    prob, fp = problem_from_callables(model, cost, sampler)
+    assert (prob.obs_dim, prob.act_dim, prob.hidden) == (5, 2, 12)
+    assert (prob.act_lo, prob.act_hi) == (-3.0, 0.5)  # dim-0 bounds, clipped to +-3 (env_wrappers.py:52-55)
+    _, fp_same = problem_from_callables(model, cost, sampler)
+    assert fp == fp_same
+    with torch.no_grad():
+        net.linear2.weight.mul_(0.5)  # in-place training step
+    assert problem_from_callables(model, cost, sampler)[1] != fp
+    stats["observations"] = {"mean": torch.ones(5), "std": torch.ones(5)}  # add_rollouts replaces entries
+    assert problem_from_callables(model, cost, sampler)[1][1] != fp[1]
+    with pytest.raises(TypeError):
+        problem_from_callables(lambda s, a: s, cost, sampler)
+    with pytest.raises(TypeError):
+        problem_from_callables(model, lambda s, a: 0, sampler)
+    assert isinstance(problem_from_callables(prob, None, None)[0], PlanningProblem)
+
+
+def test_planner_classes_pickle():
+    import pickle
+    import mbrl_b200
+    for cls in (mbrl_b200.RandomShootingPlanner, mbrl_b200.CEMPlanner):
+        assert pickle.loads(pickle.dumps(cls)) is cls
+        assert isinstance(cls.__dict__["plan"], staticmethod)
+
+
+def test_synthetic_inputs_identical_for_product_and_oracle():
+    from mbrl_b200.synthetic import synthetic_problem, synthetic_state
+    from oracle import planner_oracle as po
+    a, b = synthetic_problem(17, 6, 200), po.synthetic_params(17, 6, 200)
+    for name in ("W1", "b1", "W2", "b2", "W3", "b3", "mu_s", "sd_s", "mu_a", "sd_a", "cost_w", "goal"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    assert torch.equal(synthetic_state(a, 3), po.synthetic_state(b, 3))

@@ -1,0 +1,344 @@
+"""GPU parity tests (run on the B200 with ``-m gpu``).  Every computation goes through the
+C ABI (libmbrl_b200.so); the oracle (oracle/) is only the checker."""
+import functools
+
+import numpy as np
+import pytest
+import torch
+
+from mbrl_helpers import load_golden, params_from_golden
+from oracle import philox as ophilox
+from oracle import planner_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+# fp32 engine tolerances: per-step predicted states and trajectory costs against the fp32
+# CPU planner (only the GEMM summation order differs from MKL).
+FP32_STATE_RTOL, FP32_STATE_ATOL = 2e-5, 2e-5
+FP32_COST_RTOL = 2e-5
+
+
+@pytest.fixture(scope="module")
+def native():
+    from mbrl_b200 import native as n
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    n.load_library()
+    return n
+
+
+def _planner(native, p, horizon, n, envs=1, iters=1, engine="fp32", max_elites=None):
+    h = native.NativePlanner(p.obs_dim, p.act_dim, p.hidden, horizon, n, envs, iters, max_elites, engine)
+    h.set_weights(p.W1, p.b1, p.W2, p.b2, p.W3, p.b3)
+    h.set_norm(p.mu_s, p.sd_s, p.mu_a, p.sd_a)
+    h.set_cost(p.cost_w, p.goal, p.alpha, p.beta)
+    h.set_action_bounds(p.act_lo, p.act_hi)
+    return h
+
+
+def _cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ---------------------------------------------------------------------------------------
+# sampler
+# ---------------------------------------------------------------------------------------
+def test_philox_known_answers_and_random_counters(native):
+    rng = np.random.default_rng(0)
+    ctr = rng.integers(0, 2 ** 32, size=(4099, 4), dtype=np.uint64).astype(np.uint32)
+    key = rng.integers(0, 2 ** 32, size=(4099, 2), dtype=np.uint64).astype(np.uint32)
+    ctr[0], key[0] = 0, 0
+    ctr[1], key[1] = 0xFFFFFFFF, 0xFFFFFFFF
+    ctr[2], key[2] = [0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0]
+    out = native.philox_raw(_cuda(ctr.view(np.int32)), _cuda(key.view(np.int32))).cpu().numpy().view(np.uint32)
+    assert out[0].tolist() == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert out[1].tolist() == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    assert out[2].tolist() == [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+    np.testing.assert_array_equal(out, ophilox.philox4x32_10(ctr, key))
+
+
+@pytest.mark.parametrize("act_dim,n,envs", [(6, 300, 1), (1, 257, 2), (21, 64, 3)])
+def test_sampler_matches_oracle(native, act_dim, n, envs):
+    p = po.synthetic_params(7, act_dim, 16)
+    H = 5
+    h = _planner(native, p, H, n, envs)
+    h.set_action_bounds(-0.8, 0.9)
+    seed, it, coff, eoff = 0x1234567890ABCDEF, 3, 1000, 5
+    u = h.sample(native.SAMPLE_UNIFORM, seed, it, cand_offset=coff, env_offset=eoff).cpu().numpy()
+    ref_u = np.concatenate(
+        [ophilox.uniform(seed, it, H, n, act_dim, -0.8, 0.9, coff, eoff + e).reshape(H, n, act_dim) for e in range(envs)],
+        axis=1).reshape(H * n * envs, act_dim)
+    np.testing.assert_array_equal(u, ref_u)  # integer generator + exact fp32 affine map
+    mu = torch.zeros(envs, H, act_dim, device="cuda")
+    sd = torch.ones(envs, H, act_dim, device="cuda")
+    h.set_action_bounds(-100.0, 100.0)
+    z = h.sample(native.SAMPLE_GAUSSIAN, seed, it, mu, sd, coff, eoff).cpu().numpy()
+    ref_z = np.concatenate(
+        [ophilox.standard_normal(seed, it, H, n, act_dim, coff, eoff + e).reshape(H, n, act_dim) for e in range(envs)],
+        axis=1).reshape(H * n * envs, act_dim)
+    # log / sincospi differ from numpy's libm in the last ulps only
+    np.testing.assert_allclose(z, ref_z, rtol=0, atol=4e-6)
+    # clip + affine
+    mu2 = torch.rand(envs, H, act_dim, device="cuda") - 0.5
+    sd2 = torch.rand(envs, H, act_dim, device="cuda") + 0.1
+    h.set_action_bounds(-0.5, 0.5)
+    a = h.sample(native.SAMPLE_GAUSSIAN, seed, it, mu2, sd2, coff, eoff).cpu()
+    zz = torch.from_numpy(z).view(H, envs, n, act_dim)
+    want = torch.clamp(mu2.cpu().permute(1, 0, 2)[:, :, None, :] + sd2.cpu().permute(1, 0, 2)[:, :, None, :] * zz, -0.5, 0.5)
+    np.testing.assert_allclose(a.view(H, envs, n, act_dim).numpy(), want.numpy(), rtol=0, atol=1e-5)
+    assert a.min() >= -0.5 and a.max() <= 0.5 and (a == 0.5).any() and (a == -0.5).any()
+
+
+# ---------------------------------------------------------------------------------------
+# rollout + cost
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["rs_cartpole.npz", "rs_cheetah_small.npz"])
+def test_rollout_matches_reference_golden(native, name):
+    g = load_golden(name)
+    p = params_from_golden(g)
+    n, H = int(g["n"]), int(g["horizon"])
+    h = _planner(native, p, H, n)
+    costs, states, actions = h.rollout(_cuda(g["s0"][None]), native.SAMPLE_INJECT_ACTIONS, d_injected=_cuda(g["actions"]),
+                                       want_states=True, want_actions=True)
+    np.testing.assert_array_equal(actions.cpu().numpy(), g["actions"])
+    np.testing.assert_allclose(costs.cpu().numpy(), g["costs"], rtol=FP32_COST_RTOL)
+    keep = g["states_first"].shape[1]
+    got = states.cpu().numpy().reshape(H, n, -1)[:, :keep]
+    np.testing.assert_allclose(got, g["states_first"], rtol=FP32_STATE_RTOL, atol=FP32_STATE_ATOL)
+    assert int(torch.argmin(costs)) == int(g["idx"])
+
+
+@pytest.mark.parametrize("name", ["rs_cartpole.npz", "rs_cheetah_small.npz"])
+def test_rs_plan_matches_reference_golden(native, name):
+    g = load_golden(name)
+    p = params_from_golden(g)
+    n, H = int(g["n"]), int(g["horizon"])
+    h = _planner(native, p, H, n)
+    out = h.plan(g["s0"], 1, 1, native.SAMPLE_INJECT_ACTIONS, injected=g["actions"])
+    assert int(out["info"]["best_index"][0]) == int(g["idx"])
+    np.testing.assert_allclose(out["info"]["best_cost"][0], g["costs"].min(), rtol=FP32_COST_RTOL)
+    np.testing.assert_array_equal(out["actions"][0], g["plan_actions"])
+    np.testing.assert_array_equal(out["actions"][0][0], g["first_action"])
+    np.testing.assert_allclose(out["states"][0], g["plan_states"], rtol=FP32_STATE_RTOL, atol=FP32_STATE_ATOL)
+
+
+def test_rollout_ragged_rows_and_batched_envs(native):
+    """N not a multiple of the row tile, several environments with distinct s0."""
+    p = po.synthetic_params(9, 3, 40, seed=5)
+    H, n, E = 7, 77, 3
+    h = _planner(native, p, H, n, E)
+    g = torch.Generator().manual_seed(1)
+    s0 = p.mu_s + p.sd_s * torch.randn(E, 9, generator=g)
+    acts = torch.rand(H * E * n, 3, generator=g) * 2 - 1  # rows r = env*n + cand, step-major
+    costs, states, _ = h.rollout(s0.cuda(), native.SAMPLE_INJECT_ACTIONS, d_injected=acts.cuda(), want_states=True)
+    a4 = acts.view(H, E, n, 3)
+    for e in range(E):
+        st, c = po.rollout_costs(p, s0[e], a4[:, e].reshape(H * n, 3), H, n)
+        np.testing.assert_allclose(costs.cpu().numpy()[e * n:(e + 1) * n], c, rtol=FP32_COST_RTOL)
+        np.testing.assert_allclose(states.cpu().view(H, E, n, 9)[:, e].numpy(), st.view(H, n, 9).numpy(),
+                                   rtol=FP32_STATE_RTOL, atol=FP32_STATE_ATOL)
+
+
+# ---------------------------------------------------------------------------------------
+# elite select
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,k,segments", [(1, 1, 1), (5, 5, 1), (1000, 1, 1), (1024, 100, 2), (4096, 409, 1),
+                                           (16384, 1638, 1), (2048, 204, 7), (131072, 13107, 1), (3001, 3000, 2)])
+def test_topk_bit_exact_with_ties(native, n, k, segments):
+    rng = np.random.default_rng(n + k)
+    # coarse quantisation -> many exact ties, including at the k-th value
+    costs = np.round(rng.normal(size=(segments, n)) * 20).astype(np.float32) / 4
+    costs[:, rng.integers(0, n, size=max(1, n // 50))] *= -1
+    idx, cost, best = native.topk(_cuda(costs), k, segments)
+    idx, cost, best = idx.cpu().numpy(), cost.cpu().numpy(), best.cpu().numpy()
+    for s in range(segments):
+        want = po.topk_stable(costs[s], k)
+        np.testing.assert_array_equal(idx[s], np.sort(want))  # same set, ascending index order
+        np.testing.assert_array_equal(cost[s], costs[s][idx[s]])
+        assert best[s, 2] == np.argmin(costs[s])  # first minimum, like np.argmin (planners.py:184)
+        assert best[s, 0].view(np.float32) == costs[s].min()
+
+
+def test_topk_special_values(native):
+    c = np.array([[3.0, -0.0, 0.0, np.inf, -np.inf, np.nan, 1e-45, -1e-45, 2.0, np.nan, -np.inf, 0.0]], np.float32)
+    for k in range(1, c.shape[1] + 1):
+        idx, _, best = native.topk(_cuda(c), k, 1)
+        np.testing.assert_array_equal(idx.cpu().numpy()[0], np.sort(po.topk_stable(c[0], k)))
+    assert best.cpu().numpy()[0, 2] == 4
+
+
+def test_topk_costs_from_reference(native):
+    """Elite indices on the reference's own cost arrays (north_star: bit-exact)."""
+    for name in ("cem_cheetah_small.npz", "cem_cartpole_small.npz"):
+        g = load_golden(name)
+        k = int(g["k"])
+        for it in range(int(g["iters"])):
+            idx, _, best = native.topk(_cuda(g[f"costs_{it}"]), k, 1)
+            np.testing.assert_array_equal(idx.cpu().numpy()[0], np.sort(g[f"elite_{it}"]))
+            assert best.cpu().numpy()[0, 2] == g[f"elite_{it}"][0]
+
+
+# ---------------------------------------------------------------------------------------
+# refit + CEM
+# ---------------------------------------------------------------------------------------
+def test_refit_matches_oracle(native):
+    p = po.synthetic_params(6, 5, 16)
+    H, n, E, k = 4, 500, 2, 50
+    h = _planner(native, p, H, n, E)
+    g = torch.Generator().manual_seed(3)
+    acts = torch.rand(H * E * n, 5, generator=g) * 2 - 1
+    elite = torch.stack([torch.randperm(n, generator=g)[:k].sort().values for _ in range(E)]).int()
+    mu, sd = h.refit(elite.cuda(), k, native.SAMPLE_INJECT_ACTIONS, d_injected=acts.cuda())
+    a4 = acts.view(H, E, n, 5)
+    for e in range(E):
+        m, s = po.refit(a4[:, e], elite[e].numpy())
+        np.testing.assert_allclose(mu[e].cpu().numpy(), m.numpy(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(sd[e].cpu().numpy(), s.numpy(), rtol=1e-5, atol=1e-6)
+    # regenerated-from-Philox path == materialised sampler path
+    mu0 = (torch.rand(E, H, 5, generator=g) - 0.5).cuda()
+    sd0 = (torch.rand(E, H, 5, generator=g) + 0.2).cuda()
+    mat = h.sample(native.SAMPLE_GAUSSIAN, 11, 2, mu0, sd0)
+    m1, s1 = h.refit(elite.cuda(), k, native.SAMPLE_GAUSSIAN, 11, 2, d_mu=mu0, d_sd=sd0)
+    m2, s2 = h.refit(elite.cuda(), k, native.SAMPLE_INJECT_ACTIONS, d_injected=mat)
+    assert torch.equal(m1, m2) and torch.equal(s1, s2)
+
+
+@pytest.mark.parametrize("name", ["cem_cheetah_small.npz", "cem_cartpole_small.npz"])
+def test_cem_plan_matches_reference_composition(native, name):
+    g = load_golden(name)
+    p = params_from_golden(g)
+    n, H, k, I = int(g["n"]), int(g["horizon"]), int(g["k"]), int(g["iters"])
+    h = _planner(native, p, H, n, 1, I)
+    out = h.plan(g["s0"], I, k, native.SAMPLE_INJECT_NOISE, injected=g["noise"], want_dist=True)
+    info = out["info"][0]
+    assert (int(info["best_iteration"]), int(info["best_index"])) == (int(g["best_it"]), int(g["best_idx"]))
+    np.testing.assert_allclose(info["best_cost"], g["best_cost"], rtol=FP32_COST_RTOL)
+    np.testing.assert_allclose(out["actions"][0], g["best_actions"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(out["states"][0], g["best_states"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(out["mu"][0], g[f"mu_{I - 1}"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(out["sd"][0], g[f"sd_{I - 1}"], rtol=1e-3, atol=2e-5)
+
+
+# ---------------------------------------------------------------------------------------
+# reference-facing Python API
+# ---------------------------------------------------------------------------------------
+class _Lin:
+    def __init__(self, W, b):
+        self.weight, self.bias = torch.nn.Parameter(W.clone()), torch.nn.Parameter(b.clone())
+
+
+class _Net(torch.nn.Module):  # stands in for src/mbrl/models.py:96 Model
+    def __init__(self, p):
+        super().__init__()
+        self.linear1, self.linear2, self.linear3 = (torch.nn.Linear(1, 1) for _ in range(3))
+        for lin, (W, b) in zip((self.linear1, self.linear2, self.linear3), ((p.W1, p.b1), (p.W2, p.b2), (p.W3, p.b3))):
+            lin.weight, lin.bias = torch.nn.Parameter(W.clone()), torch.nn.Parameter(b.clone())
+        self.noise = None
+
+
+def _norm(field_value, field_name, stats):
+    return (field_value - stats[field_name]["mean"]) / stats[field_name]["std"]
+
+
+def _unnorm(field_value, field_name, stats):
+    return field_value * stats[field_name]["std"] + stats[field_name]["mean"]
+
+
+class _StateCost:
+    def __init__(self, p):
+        self.weights, self.goal_state, self.alpha = p.cost_w, p.goal, p.alpha
+
+
+class _ActCost:
+    def __init__(self, p):
+        self.alpha = p.beta
+
+
+class _Spec:
+    def __init__(self, a):
+        self.minimum, self.maximum, self.shape = np.full(a, -1.0), np.full(a, 1.0), (a,)
+
+
+def _reference_style_callables(p, recorded):
+    stats = {"observations": {"mean": p.mu_s, "std": p.sd_s}, "actions": {"mean": p.mu_a, "std": p.sd_a}}
+    model = functools.partial(
+        _Net(p),
+        normalize_state=functools.partial(_norm, field_name="observations", stats=stats),
+        normalize_action=functools.partial(_norm, field_name="actions", stats=stats),
+        unnormalize_state=functools.partial(_unnorm, field_name="observations", stats=stats))
+    cost = functools.partial(lambda s, a, state_cost, action_cost: None, state_cost=_StateCost(p), action_cost=_ActCost(p))
+
+    def _sample(action_spec, batch_size=None):
+        return recorded.clone()
+
+    return model, cost, functools.partial(_sample, action_spec=_Spec(p.act_dim)), stats
+
+
+def test_python_planner_api_drop_in(native):
+    import mbrl_b200
+    g = load_golden("rs_cartpole.npz")
+    p = params_from_golden(g)
+    n, H = int(g["n"]), int(g["horizon"])
+    model, cost, sampler, stats = _reference_style_callables(p, torch.from_numpy(g["actions"]))
+    s, a = mbrl_b200.RandomShootingPlanner.plan(torch.from_numpy(g["s0"]), model, cost, sampler, H, None,
+                                                num_trajectories=n, sampler="host")
+    assert s.shape == (H, p.obs_dim) and a.shape == (H, p.act_dim)
+    np.testing.assert_array_equal(a.numpy(), g["plan_actions"])
+    np.testing.assert_array_equal(a[0].flatten().numpy(), g["first_action"])  # what MPCPolicy returns (agents.py:56)
+    np.testing.assert_allclose(s.numpy(), g["plan_states"], rtol=FP32_STATE_RTOL, atol=FP32_STATE_ATOL)
+    # host retrains in place -> weights re-uploaded on the next call
+    with torch.no_grad():
+        model.func.linear3.bias.add_(0.25)
+    p2 = params_from_golden(g)
+    p2.b3 = p2.b3 + 0.25
+    want = po.rs_plan(p2, torch.from_numpy(g["s0"]), torch.from_numpy(g["actions"]), H, n)
+    s2, a2 = mbrl_b200.RandomShootingPlanner.plan(torch.from_numpy(g["s0"]), model, cost, sampler, H, None,
+                                                  num_trajectories=n, sampler="host")
+    np.testing.assert_array_equal(a2.numpy(), want["actions"].numpy())
+    np.testing.assert_allclose(s2.numpy(), want["states"].numpy(), rtol=FP32_STATE_RTOL, atol=FP32_STATE_ATOL)
+    # device sampler + CEM run and respect the action bounds
+    s3, a3 = mbrl_b200.CEMPlanner.plan(torch.from_numpy(g["s0"]), model, cost, sampler, H, None,
+                                       num_trajectories=2048, num_iterations=3)
+    assert a3.abs().max() <= 1.0 and torch.isfinite(s3).all()
+    with pytest.raises(TypeError):
+        mbrl_b200.RandomShootingPlanner.plan(torch.from_numpy(g["s0"]), lambda s, a: s, cost, sampler, H)
+    mbrl_b200.planners.clear_handles()
+
+
+# ---------------------------------------------------------------------------------------
+# BASELINE.json full sizes: size-independent properties
+# ---------------------------------------------------------------------------------------
+def test_full_size_cem_properties(native):
+    """cfg 3 (cheetah-run shape, N=16384 H=30 I=5, k=1638) on the device sampler:
+    spot-check rollout costs against the oracle on a candidate subset, elite-set invariants,
+    and monotone best-ever cost."""
+    O, A, U, H, N, I, k = 17, 6, 200, 30, 16384, 5, 1638
+    p = po.synthetic_params(O, A, U)
+    s0 = po.synthetic_state(p, 0)
+    h = _planner(native, p, H, N, 1, I)
+    mu = torch.zeros(1, H, A, device="cuda")
+    sd = torch.ones(1, H, A, device="cuda")
+    d_s0 = s0[None].cuda()
+    best_prev = np.inf
+    for it in range(I):
+        costs, _, acts = h.rollout(d_s0, native.SAMPLE_GAUSSIAN, 42, it, d_mu=mu, d_sd=sd, want_actions=True)
+        # oracle on 96 candidates spread over the population, with the device's own draws injected
+        sub = torch.arange(0, N, N // 96)[:96]
+        a_sub = acts.cpu().view(H, N, A)[:, sub].reshape(H * 96, A)
+        _, c_ref = po.rollout_costs(p, s0, a_sub, H, 96)
+        np.testing.assert_allclose(costs.cpu().numpy()[sub.numpy()], c_ref, rtol=FP32_COST_RTOL)
+        idx, ecost, best = native.topk(costs, k, 1)
+        e = idx.cpu().numpy()[0]
+        assert len(np.unique(e)) == k and (np.diff(e) > 0).all()
+        c = costs.cpu().numpy()
+        np.testing.assert_array_equal(e, np.sort(po.topk_stable(c, k)))
+        assert c[e].max() <= np.delete(c, e).min()
+        mu, sd = h.refit(idx, k, native.SAMPLE_GAUSSIAN, 42, it, d_mu=mu, d_sd=sd)
+        m_ref, s_ref = po.refit(acts.cpu().view(H, N, A), e)
+        np.testing.assert_allclose(mu[0].cpu().numpy(), m_ref.numpy(), rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(sd[0].cpu().numpy(), s_ref.numpy(), rtol=1e-4, atol=1e-5)
+        best_prev = min(best_prev, float(c.min()))
+    out = h.plan(s0.numpy(), I, k, native.SAMPLE_GAUSSIAN, 42)
+    np.testing.assert_allclose(out["info"]["best_cost"][0], best_prev, rtol=1e-6)
+    # replayed plan reproduces its own cost under the oracle
+    _, c_plan = po.rollout_costs(p, s0, torch.from_numpy(out["actions"][0]), H, 1)
+    np.testing.assert_allclose(c_plan[0], out["info"]["best_cost"][0], rtol=FP32_COST_RTOL)
