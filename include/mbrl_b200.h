@@ -12,7 +12,9 @@
  *     mbrl_last_error() returns a thread-local human-readable message;
  *   - plain pointers and sizes only; `h_` = host pointer, `d_` = device pointer
  *     (same CUDA primary context, e.g. torch tensor.data_ptr());
- *   - `stream` is a cudaStream_t passed as void* (NULL = the handle's own stream);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the CUDA default stream); work is
+ *     only enqueued, never synchronised, except in mbrl_plan which runs on the handle's own
+ *     stream and returns after the plan has reached the host;
  *   - caller owns every buffer it passes; the handle owns device weights and scratch;
  *   - one handle per (device, shape); a handle is not thread-safe;
  *   - all fp32 matrices are row-major; nn.Linear weights are [out, in];

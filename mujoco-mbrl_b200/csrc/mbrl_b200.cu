@@ -372,7 +372,7 @@ extern "C" int mbrl_rollout(MbrlPlanner* p, int32_t mode, uint64_t seed, uint32_
   if (!p) return fail(MBRL_E_INVALID, "null planner");
   MBRL_REQUIRE(d_s0 && d_costs, "null s0/costs");
   MBRL_CUDA(cudaSetDevice(p->cfg.device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+  cudaStream_t st = (cudaStream_t)stream;  // NULL = the CUDA default stream, as everywhere in CUDA
   ActionSource src = action_source(p, mode, seed, iteration, cand_offset, env_offset, d_injected, d_mu, d_sd);
   return launch_rollout(p, src, d_s0, d_costs, d_states_out, d_actions_out, st);
 }
@@ -385,7 +385,7 @@ extern "C" int mbrl_sample(MbrlPlanner* p, int32_t mode, uint64_t seed, uint32_t
   MBRL_REQUIRE(d_out, "null output");
   MBRL_REQUIRE(mode == MBRL_SAMPLE_UNIFORM || (d_mu && d_sd), "Gaussian mode needs mu/sd");
   MBRL_CUDA(cudaSetDevice(p->cfg.device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+  cudaStream_t st = (cudaStream_t)stream;  // NULL = the CUDA default stream, as everywhere in CUDA
   ActionSource src = action_source(p, mode, seed, iteration, cand_offset, env_offset, nullptr, d_mu, d_sd);
   Shape sh{p->H, p->N, p->E};
   const long long total = p->R * p->H;
@@ -421,7 +421,7 @@ extern "C" int mbrl_refit(MbrlPlanner* p, int32_t mode, uint64_t seed, uint32_t 
   MBRL_REQUIRE((mode != MBRL_SAMPLE_INJECT_NOISE && mode != MBRL_SAMPLE_GAUSSIAN) || (d_mu && d_sd),
                "Gaussian mode needs mu/sd");
   MBRL_CUDA(cudaSetDevice(p->cfg.device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+  cudaStream_t st = (cudaStream_t)stream;  // NULL = the CUDA default stream, as everywhere in CUDA
   ActionSource src = action_source(p, mode, seed, iteration, cand_offset, env_offset, d_injected, d_mu, d_sd);
   return launch_refit(p, src, d_elite_idx, k, d_mu_new, d_sd_new, st);
 }
@@ -437,7 +437,7 @@ extern "C" int mbrl_emit(MbrlPlanner* p, int32_t mode, uint64_t seed, uint32_t c
   MBRL_REQUIRE(d_mu_hist && d_sd_hist, "emit: null mu/sd history");
   MBRL_REQUIRE(iterations >= 1, "emit: iterations must be >= 1");
   MBRL_CUDA(cudaSetDevice(p->cfg.device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+  cudaStream_t st = (cudaStream_t)stream;  // NULL = the CUDA default stream, as everywhere in CUDA
   return launch_replay(p, mode, seed, cand_offset, env_offset, d_s0, d_injected, d_mu_hist, d_sd_hist, iterations,
                        return_mean, reinterpret_cast<const BestEver*>(d_best), d_out_states, d_out_actions, nullptr, st);
 }
@@ -489,7 +489,7 @@ extern "C" int mbrl_plan_device(MbrlPlanner* p, const MbrlPlanArgs* args, const 
   if (!p || !args) return fail(MBRL_E_INVALID, "null planner/args");
   MBRL_REQUIRE(d_s0 && d_out_states && d_out_actions, "null device buffer");
   MBRL_CUDA(cudaSetDevice(p->cfg.device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+  cudaStream_t st = (cudaStream_t)stream;  // NULL = the CUDA default stream, as everywhere in CUDA
   return enqueue_plan(p, args, d_s0, d_injected, d_out_states, d_out_actions, d_info,
                       args->return_mean != 0, st);
 }
