@@ -183,6 +183,11 @@ int mbrl_emit(MbrlPlanner* p, int32_t sample_mode, uint64_t seed, uint32_t cand_
               int32_t return_mean, const MbrlPlanInfo* d_best, float* d_out_states,
               float* d_out_actions, void* stream);
 
+/* Diagnostic for the tensor-core engines (tests only): enable != 0 arms a dump of the raw
+ * fp32 accumulators of row tile 0 at step 0 ([3 layers][128 rows][256 cols]) by the next
+ * mbrl_rollout; h_out != NULL copies the dump to the host (after synchronising). */
+int mbrl_tc_debug(MbrlPlanner* p, int32_t enable, float* h_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -442,6 +442,27 @@ extern "C" int mbrl_emit(MbrlPlanner* p, int32_t mode, uint64_t seed, uint32_t c
                        return_mean, reinterpret_cast<const BestEver*>(d_best), d_out_states, d_out_actions, nullptr, st);
 }
 
+extern "C" int mbrl_tc_debug(MbrlPlanner* p, int32_t enable, float* h_out) {
+  if (!p) return fail(MBRL_E_INVALID, "null planner");
+  MBRL_REQUIRE(p->cfg.engine != MBRL_ENGINE_SIMT_FP32, "tc_debug: not a tensor-core engine");
+  MBRL_CUDA(cudaSetDevice(p->cfg.device));
+  const size_t bytes = sizeof(float) * 3 * 128 * 256;
+  if (h_out) {
+    MBRL_REQUIRE(p->tc.d_dbg, "tc_debug: dump was never armed");
+    MBRL_CUDA(cudaDeviceSynchronize());
+    MBRL_CUDA(cudaMemcpy(h_out, p->tc.d_dbg, bytes, cudaMemcpyDeviceToHost));
+  }
+  if (enable && !p->tc.d_dbg) {
+    MBRL_CUDA(cudaMalloc((void**)&p->tc.d_dbg, bytes));
+    MBRL_CUDA(cudaMemset(p->tc.d_dbg, 0, bytes));
+  } else if (!enable && p->tc.d_dbg) {
+    MBRL_CUDA(cudaDeviceSynchronize());
+    MBRL_CUDA(cudaFree(p->tc.d_dbg));
+    p->tc.d_dbg = nullptr;
+  }
+  return MBRL_OK;
+}
+
 // --------------------------------------------------------------------------------------
 // whole plans
 // --------------------------------------------------------------------------------------

@@ -88,7 +88,8 @@ __global__ void __launch_bounds__(TM * 4)
 rollout_simt_kernel(ModelDev m, ActionSource src, Shape sh, const float* __restrict__ s0,
                     float* __restrict__ costs, float* __restrict__ states_out,
                     float* __restrict__ actions_out) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(16) float simt_smem[];
+  float* const smem = simt_smem;
   const int O = m.O, A = m.A, D = m.D, U = m.U;
   const int KA = D > U ? D : U;
   const int KB = U > O ? U : O;

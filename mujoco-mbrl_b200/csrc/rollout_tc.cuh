@@ -1,29 +1,561 @@
-// tcgen05 tensor-core rollout engine (placeholder until the kernel lands).
+// tcgen05 tensor-core rollout + cost engine (MBRL_ENGINE_TC_FP16 / MBRL_ENGINE_TC_BF16).
+//
+// Same fused computation as rollout_simt.cuh -- the hot loop of
+// RandomShootingPlanner._generate_trajectories (src/mbrl/planners.py:199-210) with
+// DynamicsModel.forward (src/mbrl/models.py:13-29), the 3-layer ReLU MLP (models.py:106-110),
+// the normalisers (src/mbrl/data.py:255-260) and SmoothAbs+Cosh cost (models.py:244-272) --
+// but the three layer GEMMs of every step run on the 5th-generation tensor cores:
+//
+//   * one CTA owns a tile of 128 candidate rows for all H steps (row r <-> TMEM lane r);
+//   * the three weight matrices are packed once on the host into the UMMA canonical K-major
+//     (no-swizzle, 8x16B core matrices) layout as 16-bit operands and TMA-bulk-copied
+//     (cp.async.bulk) into shared memory at kernel start, where they stay for the whole
+//     rollout;
+//   * layer 1: SS-mode tcgen05.mma, A = the 128 x Kx input tile in shared memory
+//     ([action section | 1 | state section], written by the epilogue threads),
+//     D1 -> TMEM columns [0, Np);
+//   * epilogue 1: tcgen05.ld D1 chunk -> cvt.rn.relu.{f16,bf16}x2 -> tcgen05.st the packed
+//     activations back IN PLACE (columns [0, Np/2)); each finished 32-column chunk releases
+//     the next layer's K-steps through an mbarrier, so the layer-2 MMAs (TS mode: A straight
+//     from TMEM, D2 -> columns [256, 256+Np)) overlap the rest of the epilogue;
+//   * epilogue 2 / layer 3 the same way (h2 in place at [256, 256+Np/2), D3 -> [0, Op));
+//   * epilogue 3: D3 + b3 in fp32 -> un-normalise -> accumulate the cost -> the normalised
+//     prediction is the next step's input tile.  b1/b2 ride in the GEMMs through a constant-1
+//     input column (K padding that exists anyway), so the hidden epilogues are pure
+//     load/convert/store.
+//   * actions come from the Philox sampler (or injected buffers) one step ahead, hidden
+//     behind the layer-1 MMA.
+//
+// Nothing but costs[R] leaves the SM (debug trajectory outputs are optional).
+// Operand precision: fp16 or bf16 operands, fp32 accumulation (TMEM), fp32 bias-3,
+// un-normalisation and cost.  Tolerances are stated in tests/test_gpu_tc.py.
 #pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include <string>
+#include <vector>
 
 #include "common.cuh"
 #include "philox.cuh"
 
 namespace mbrl {
 
-struct TcModel {
-  int ready = 0;
+constexpr int kTcRows = 128;           // MMA M
+constexpr int kTcEpiThreads = 128;     // warps 0-3: one thread per row / TMEM lane
+constexpr int kTcThreads = 160;        // + warp 4: TMEM alloc, weight TMA, MMA issue
+constexpr int kTcD2Col = 256;          // TMEM column of the layer-2 accumulator
+constexpr int kTcMaxChunks = 8;        // ceil(256 / 32)
+
+struct TcGeom {
+  int O, A, U;
+  int Ka;  // action section of the input tile: A actions, the constant 1, zero pad (multiple of 8)
+  int Kx;  // layer-1 K (multiple of 16): Ka + O rounded up
+  int Np;  // padded hidden width (multiple of 16, > U: column U carries the constant 1)
+  int Op;  // layer-3 N (multiple of 32)
+  int w1_off, w2_off, w3_off, w_bytes;  // packed operand image
+  int x_bytes;                           // one input tile
+  int tab_off, x_off, bar_off, smem_bytes;
 };
 
-inline bool tc_init(TcModel*, int, int, int, bool, size_t, std::string* why) {
-  *why = "not built yet";
-  return false;
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+inline bool tc_geometry(int O, int A, int U, size_t max_smem, TcGeom* g, std::string* why) {
+  g->O = O; g->A = A; g->U = U;
+  g->Ka = round_up(A + 1, 8);
+  g->Kx = round_up(g->Ka + O, 16);
+  g->Np = round_up(U + 1, 16);
+  g->Op = round_up(O, 32);
+  if (g->Np > 256) { *why = "hidden > 255 needs the N-split / weight-streaming kernel (not built yet)"; return false; }
+  if (g->Op > 128) { *why = "obs_dim > 128 unsupported"; return false; }
+  g->w1_off = 0;
+  g->w2_off = g->w1_off + g->Kx * g->Np * 2;
+  g->w3_off = g->w2_off + g->Np * g->Np * 2;
+  g->w_bytes = g->w3_off + g->Np * g->Op * 2;
+  g->x_bytes = g->Kx * kTcRows * 2;
+  g->tab_off = g->w_bytes;                       // 5 fp32 tables of Op entries
+  g->x_off = round_up(g->tab_off + 5 * g->Op * 4, 128);
+  g->bar_off = g->x_off + 2 * g->x_bytes;
+  g->smem_bytes = g->bar_off + 8 * (5 + 2 * kTcMaxChunks) + 16;
+  if ((size_t)g->smem_bytes > max_smem) { *why = "weights do not fit shared memory (streaming kernel not built yet)"; return false; }
+  return true;
 }
-inline bool tc_set_weights(TcModel*, const float*, const float*, const float*, const float*, const float*,
-                           const float*, std::string* why) {
-  *why = "not built yet";
-  return false;
+
+struct TcModel {
+  int ready = 0;
+  bool fp16 = true;
+  TcGeom g{};
+  uint8_t* d_wimg = nullptr;
+  float* d_dbg = nullptr;  // optional [3][128][256] accumulator dump of tile 0 / step 0 (tests)
+};
+
+// ---- host-side packing -----------------------------------------------------------------
+// Canonical K-major no-swizzle operand: element (row n, k) at byte
+//   (k/8) * rows*16 + n*16 + (k%8)*2          (8x16B core matrices, LBO = rows*16, SBO = 128)
+inline void tc_put(std::vector<uint16_t>& img, int off_bytes, int rows, int n, int k, float v, bool fp16) {
+  uint16_t bits;
+  if (fp16) { __half h = __float2half_rn(v); std::memcpy(&bits, &h, 2); }
+  else { __nv_bfloat16 h = __float2bfloat16_rn(v); std::memcpy(&bits, &h, 2); }
+  img[(size_t)off_bytes / 2 + (size_t)(k / 8) * rows * 8 + (size_t)n * 8 + (k % 8)] = bits;
 }
-inline void tc_free(TcModel*) {}
-inline cudaError_t tc_launch_rollout(TcModel*, const ModelDev&, const ActionSource&, const Shape&, const float*,
-                                     float*, float*, float*, int, cudaStream_t) {
-  return cudaErrorNotSupported;
+
+inline bool tc_init(TcModel* t, int O, int A, int U, bool fp16, size_t max_smem, std::string* why) {
+  if (!tc_geometry(O, A, U, max_smem, &t->g, why)) return false;
+  t->fp16 = fp16;
+  if (cudaMalloc((void**)&t->d_wimg, t->g.w_bytes) != cudaSuccess) { *why = "cudaMalloc failed"; return false; }
+  t->ready = 1;
+  return true;
+}
+
+inline void tc_free(TcModel* t) {
+  if (t->d_wimg) cudaFree(t->d_wimg);
+  if (t->d_dbg) cudaFree(t->d_dbg);
+  t->d_wimg = nullptr; t->d_dbg = nullptr; t->ready = 0;
+}
+
+// W1 [U, O+A], W2 [U, U], W3 [O, U] in nn.Linear layout (src/mbrl/models.py:99-101).
+inline bool tc_set_weights(TcModel* t, const float* W1, const float* b1, const float* W2, const float* b2,
+                           const float* W3, const float* b3, std::string* why) {
+  (void)b3;  // added in fp32 in the last epilogue
+  const TcGeom& g = t->g;
+  const int O = g.O, A = g.A, U = g.U, D = O + A;
+  std::vector<uint16_t> img((size_t)g.w_bytes / 2, 0);
+  // layer 1: input column e:  e < A -> action e;  e == A -> constant 1;  Ka <= e < Ka+O -> state e-Ka
+  for (int n = 0; n < U; ++n) {
+    for (int a = 0; a < A; ++a) tc_put(img, g.w1_off, g.Np, n, a, W1[(size_t)n * D + O + a], t->fp16);
+    tc_put(img, g.w1_off, g.Np, n, A, b1[n], t->fp16);
+    for (int o = 0; o < O; ++o) tc_put(img, g.w1_off, g.Np, n, g.Ka + o, W1[(size_t)n * D + o], t->fp16);
+  }
+  tc_put(img, g.w1_off, g.Np, U, A, 1.0f, t->fp16);  // hidden unit U == relu(1) == 1 carries b2
+  for (int n = 0; n < U; ++n) {
+    for (int k = 0; k < U; ++k) tc_put(img, g.w2_off, g.Np, n, k, W2[(size_t)n * U + k], t->fp16);
+    tc_put(img, g.w2_off, g.Np, n, U, b2[n], t->fp16);
+  }
+  for (int o = 0; o < O; ++o)
+    for (int k = 0; k < U; ++k) tc_put(img, g.w3_off, g.Op, o, k, W3[(size_t)o * U + k], t->fp16);
+  if (cudaMemcpy(t->d_wimg, img.data(), g.w_bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+    *why = "cudaMemcpy of packed operands failed";
+    return false;
+  }
+  return true;
+}
+
+// ---- PTX wrappers ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// K-major, no swizzle, descriptor version 1 (Blackwell).  Fields are in 16-byte units.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
+         ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+// kind::f16 instruction descriptor: fp32 accumulate, A/B K-major, M=128.
+__host__ __device__ inline uint32_t umma_idesc(int n, bool fp16) {
+  const uint32_t fmt = fp16 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
+}
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+
+#define MBRL_R8(v, o) "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]), "=r"(v[o + 7])
+#define MBRL_I8(v, o) "r"(v[o + 0]), "r"(v[o + 1]), "r"(v[o + 2]), "r"(v[o + 3]), "r"(v[o + 4]), "r"(v[o + 5]), "r"(v[o + 6]), "r"(v[o + 7])
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,"
+      "%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : MBRL_R8(v, 0), MBRL_R8(v, 8), MBRL_R8(v, 16), MBRL_R8(v, 24)
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : MBRL_R8(v, 0), MBRL_R8(v, 8)
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      MBRL_I8(v, 0), MBRL_I8(v, 8) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), MBRL_I8(v, 0) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// relu + round-to-nearest + pack: lo -> bits [0,16) (even k), hi -> bits [16,32) (odd k)
+template <bool FP16>
+__device__ __forceinline__ uint32_t pack_relu(uint32_t lo_bits, uint32_t hi_bits) {
+  uint32_t d;
+  if (FP16)
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi_bits)), "f"(__uint_as_float(lo_bits)));
+  else
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi_bits)), "f"(__uint_as_float(lo_bits)));
+  return d;
+}
+template <bool FP16>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  uint32_t d;
+  if (FP16)
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
+// ---- action sampling, 4 raw actions for dims 4g..4g+3 (0 beyond A) --------------------------
+__device__ __forceinline__ void raw_action4(const ActionSource& s, int A, int H, int h, int env_l, int cand_l,
+                                            long long row, long long R, int g, float (&out)[4]) {
+  const long long ms = ((long long)env_l * H + h) * A;
+  if (s.mode == MBRL_SAMPLE_INJECT_ACTIONS || s.mode == MBRL_SAMPLE_INJECT_NOISE) {
+    const float* p = s.buf + ((long long)h * R + row) * A;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int a = 4 * g + j;
+      float v = 0.f;
+      if (a < A) {
+        v = __ldg(p + a);
+        if (s.mode == MBRL_SAMPLE_INJECT_NOISE)
+          v = clipf(__fadd_rn(__ldg(s.mu + ms + a), __fmul_rn(__ldg(s.sd + ms + a), v)), s.lo, s.hi);
+      }
+      out[j] = v;
+    }
+  } else {
+    const int G = (A + 3) >> 2;
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)(h * G + g), s.iteration, s.cand_offset + (uint32_t)cand_l,
+                                             s.env_offset + (uint32_t)env_l),
+                                  make_uint2(s.seed_lo, s.seed_hi));
+    float z[4];
+    if (s.mode == MBRL_SAMPLE_GAUSSIAN) {
+      const float4 q = box_muller4(r);
+      z[0] = q.x; z[1] = q.y; z[2] = q.z; z[3] = q.w;
+    } else {
+      z[0] = u32_to_uniform(r.x); z[1] = u32_to_uniform(r.y); z[2] = u32_to_uniform(r.z); z[3] = u32_to_uniform(r.w);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int a = 4 * g + j;
+      float v = 0.f;
+      if (a < A)
+        v = s.mode == MBRL_SAMPLE_GAUSSIAN
+                ? clipf(__fadd_rn(__ldg(s.mu + ms + a), __fmul_rn(__ldg(s.sd + ms + a), z[j])), s.lo, s.hi)
+                : __fadd_rn(s.lo, __fmul_rn(__fsub_rn(s.hi, s.lo), z[j]));
+      out[j] = v;
+    }
+  }
+}
+
+// ---- the kernel ----------------------------------------------------------------------------
+template <bool FP16>
+__global__ void __launch_bounds__(kTcThreads, 1)
+rollout_tc_kernel(TcGeom g, const uint8_t* __restrict__ wimg, ModelDev m, ActionSource src, Shape sh,
+                  const float* __restrict__ s0, float* __restrict__ costs, float* __restrict__ states_out,
+                  float* __restrict__ actions_out, float* __restrict__ dbg) {
+  extern __shared__ __align__(128) uint8_t tc_smem[];
+  uint8_t* const smem = tc_smem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int O = g.O, A = g.A, H = sh.H;
+  const int NC = (g.Np + 31) >> 5;       // hidden epilogue chunks (32 columns, last may be 16)
+  const int KS_H = g.Np >> 4;            // K-steps of layers 2 and 3
+  const int KS_X = g.Kx >> 4;            // K-steps of layer 1
+
+  float* tab = reinterpret_cast<float*>(smem + g.tab_off);  // [5][Op]: b3, sd_s, mu_s, goal, cost_w
+  uint8_t* xbuf = smem + g.x_off;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.bar_off);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + g.bar_off + 8 * (5 + 2 * kTcMaxChunks));
+  const uint32_t bar0 = smem_u32(bars);
+  // barrier map: 0 weights, 1 x-ready, 2 d1, 3 d2, 4 d3, 5.. a1[c], 5+8.. a2[c]
+  const uint32_t bar_w = bar0, bar_x = bar0 + 8, bar_d1 = bar0 + 16, bar_d2 = bar0 + 24, bar_d3 = bar0 + 32;
+  const uint32_t bar_a1 = bar0 + 40, bar_a2 = bar0 + 40 + 8 * kTcMaxChunks;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_init(bar_w, 1);
+      mbar_init(bar_x, kTcEpiThreads);
+      mbar_init(bar_d1, 1); mbar_init(bar_d2, 1); mbar_init(bar_d3, 1);
+      for (int c = 0; c < kTcMaxChunks; ++c) { mbar_init(bar_a1 + 8 * c, kTcEpiThreads); mbar_init(bar_a2 + 8 * c, kTcEpiThreads); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = tid; i < g.Op; i += kTcThreads) {
+    const bool in = i < O;
+    tab[0 * g.Op + i] = in ? __ldg(m.b3 + i) : 0.f;
+    tab[1 * g.Op + i] = in ? __ldg(m.sd_s + i) : 1.f;
+    tab[2 * g.Op + i] = in ? __ldg(m.mu_s + i) : 0.f;
+    tab[3 * g.Op + i] = in ? __ldg(m.goal + i) : 0.f;
+    tab[4 * g.Op + i] = in ? __ldg(m.cost_w + i) : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    // ================= MMA issuer (one thread) =================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_w, (uint32_t)g.w_bytes);
+      bulk_g2s(smem_u32(smem), wimg, (uint32_t)g.w_bytes, bar_w);
+      const uint32_t idesc_h = umma_idesc(g.Np, FP16), idesc_o = umma_idesc(g.Op, FP16);
+      const uint32_t w1 = smem_u32(smem + g.w1_off), w2 = smem_u32(smem + g.w2_off), w3 = smem_u32(smem + g.w3_off);
+      const uint32_t lbo_h = (uint32_t)g.Np * 16, lbo_o = (uint32_t)g.Op * 16, lbo_x = kTcRows * 16;
+      mbar_wait(bar_w, 0);
+      for (int h = 0; h < H; ++h) {
+        const uint32_t ph = h & 1;
+        const uint32_t xs = smem_u32(xbuf + (h & 1) * g.x_bytes);
+        mbar_wait(bar_x, ph);
+        tc_fence_after();
+        for (int ks = 0; ks < KS_X; ++ks)
+          mma_ss(tmem, umma_desc(xs + ks * 2 * lbo_x, lbo_x, 128), umma_desc(w1 + ks * 2 * lbo_h, lbo_h, 128), idesc_h, ks > 0);
+        tc_commit(bar_d1);
+        for (int c = 0; c < NC; ++c) {
+          mbar_wait(bar_a1 + 8 * c, ph);
+          tc_fence_after();
+          for (int ks = 2 * c; ks < min(2 * c + 2, KS_H); ++ks)
+            mma_ts(tmem + kTcD2Col, tmem + 8 * ks, umma_desc(w2 + ks * 2 * lbo_h, lbo_h, 128), idesc_h, ks > 0);
+        }
+        tc_commit(bar_d2);
+        for (int c = 0; c < NC; ++c) {
+          mbar_wait(bar_a2 + 8 * c, ph);
+          tc_fence_after();
+          for (int ks = 2 * c; ks < min(2 * c + 2, KS_H); ++ks)
+            mma_ts(tmem, tmem + kTcD2Col + 8 * ks, umma_desc(w3 + ks * 2 * lbo_o, lbo_o, 128), idesc_o, ks > 0);
+        }
+        tc_commit(bar_d3);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue / row threads =================
+    const long long R = sh.rows();
+    const long long row = (long long)blockIdx.x * kTcRows + tid;
+    const bool valid = row < R;
+    const int env_l = valid ? (int)(row / sh.N) : 0;
+    const int cand_l = valid ? (int)(row - (long long)env_l * sh.N) : 0;
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
+    const int QA = g.Ka >> 3;               // action chunks of the input tile
+    const int SC = (g.Kx - g.Ka) >> 3;      // state chunks of the input tile
+    float cost = 0.f, act_cur = 0.f;
+
+    // writes the action section of input tile `buf` for step h; returns sum_a(cosh(a/beta)-1)
+    auto stage_actions = [&](int h, int buf) -> float {
+      float acc = 0.f;
+      float* aout = (actions_out && valid) ? actions_out + ((long long)h * R + row) * A : nullptr;
+      for (int q = 0; q < QA; ++q) {
+        float v[8];
+        {
+          float t4[4];
+          raw_action4(src, A, H, h, env_l, cand_l, row, R, 2 * q, t4);
+          v[0] = t4[0]; v[1] = t4[1]; v[2] = t4[2]; v[3] = t4[3];
+          if (8 * q + 4 < A) raw_action4(src, A, H, h, env_l, cand_l, row, R, 2 * q + 1, t4);
+          else { t4[0] = t4[1] = t4[2] = t4[3] = 0.f; }
+          v[4] = t4[0]; v[5] = t4[1]; v[6] = t4[2]; v[7] = t4[3];
+        }
+        float xn[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int a = 8 * q + i;
+          if (a < A && valid) {
+            acc = __fadd_rn(acc, cosh_term(v[i], m.beta));
+            xn[i] = __fdiv_rn(__fsub_rn(v[i], __ldg(m.mu_a + a)), __ldg(m.sd_a + a));
+            if (aout) aout[a] = v[i];
+          } else {
+            xn[i] = (a == A) ? 1.0f : 0.0f;
+          }
+        }
+        uint4 pk;
+        pk.x = pack2<FP16>(xn[0], xn[1]); pk.y = pack2<FP16>(xn[2], xn[3]);
+        pk.z = pack2<FP16>(xn[4], xn[5]); pk.w = pack2<FP16>(xn[6], xn[7]);
+        *reinterpret_cast<uint4*>(xbuf + buf * g.x_bytes + q * (kTcRows * 16) + tid * 16) = pk;
+      }
+      return acc;
+    };
+
+    // ---- step 0 input: actions + normalised s0 ----
+    act_cur = stage_actions(0, 0);
+    for (int j = 0; j < SC; ++j) {
+      float xn[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int o = 8 * j + i;
+        xn[i] = (o < O && valid) ? __fdiv_rn(__fsub_rn(__ldg(s0 + (long long)env_l * O + o), tab[2 * g.Op + o]), tab[1 * g.Op + o]) : 0.f;
+      }
+      uint4 pk;
+      pk.x = pack2<FP16>(xn[0], xn[1]); pk.y = pack2<FP16>(xn[2], xn[3]);
+      pk.z = pack2<FP16>(xn[4], xn[5]); pk.w = pack2<FP16>(xn[6], xn[7]);
+      *reinterpret_cast<uint4*>(xbuf + (QA + j) * (kTcRows * 16) + tid * 16) = pk;
+    }
+    fence_proxy_async();
+    mbar_arrive(bar_x);
+
+    for (int h = 0; h < H; ++h) {
+      const uint32_t ph = h & 1;
+      // (a) actions of the next step, hidden behind the layer-1 MMA
+      float act_next = 0.f;
+      if (h + 1 < H) act_next = stage_actions(h + 1, (h + 1) & 1);
+
+      // (b),(c) hidden epilogues: TMEM fp32 -> relu -> 16-bit, in place; chunk-wise release
+#pragma unroll 1
+      for (int layer = 0; layer < 2; ++layer) {
+        const uint32_t dcol = layer == 0 ? 0u : (uint32_t)kTcD2Col;
+        mbar_wait(layer == 0 ? bar_d1 : bar_d2, ph);
+        tc_fence_after();
+        const uint32_t bar_a = layer == 0 ? bar_a1 : bar_a2;
+#pragma unroll 1
+        for (int c = 0; c < NC; ++c) {
+          uint32_t v[32], pk[16];
+          const bool full = 32 * c + 32 <= g.Np;
+          if (full) tmem_ld32(lane_base + dcol + 32 * c, v);
+          else tmem_ld16(lane_base + dcol + 32 * c, v);
+          tmem_ld_wait();
+          if (dbg && blockIdx.x == 0 && h == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (full || i < 16) dbg[(layer * kTcRows + tid) * 256 + 32 * c + i] = __uint_as_float(v[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = pack_relu<FP16>(v[2 * i], v[2 * i + 1]);
+          if (full) tmem_st16(lane_base + dcol + 16 * c, pk);
+          else tmem_st8(lane_base + dcol + 16 * c, pk);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(bar_a + 8 * c);
+        }
+      }
+
+      // (d) output epilogue: y = D3 + b3 (fp32), un-normalise, cost, next input tile
+      mbar_wait(bar_d3, ph);
+      tc_fence_after();
+      float st_cost = 0.f;
+      float* sout = (states_out && valid) ? states_out + ((long long)h * R + row) * O : nullptr;
+      uint8_t* xnext = xbuf + ((h + 1) & 1) * g.x_bytes;
+      const int CC = max(g.Op >> 5, (SC + 3) >> 2);
+#pragma unroll 1
+      for (int cc = 0; cc < CC; ++cc) {
+        uint32_t v[32];
+        if (32 * cc < g.Op) {
+          tmem_ld32(lane_base + 32 * cc, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0u;
+        }
+        if (dbg && blockIdx.x == 0 && h == 0 && 32 * cc < g.Op) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) dbg[(2 * kTcRows + tid) * 256 + 32 * cc + i] = __uint_as_float(v[i]);
+        }
+        float y[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int o = 32 * cc + i;
+          y[i] = 0.f;
+          if (o < O) {
+            y[i] = __fadd_rn(__uint_as_float(v[i]), tab[0 * g.Op + o]);
+            // unnormalize_state: y * std + mean   (data.py:255-257)
+            const float s = __fadd_rn(__fmul_rn(y[i], tab[1 * g.Op + o]), tab[2 * g.Op + o]);
+            st_cost = __fadd_rn(st_cost, smooth_abs_term(s, tab[3 * g.Op + o], tab[4 * g.Op + o], m.alpha, m.alpha2));
+            if (sout) sout[o] = s;
+          }
+        }
+        if (h + 1 < H) {
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int j = 4 * cc + jj;
+            if (j < SC) {
+              uint4 pk;
+              pk.x = pack2<FP16>(y[8 * jj + 0], y[8 * jj + 1]); pk.y = pack2<FP16>(y[8 * jj + 2], y[8 * jj + 3]);
+              pk.z = pack2<FP16>(y[8 * jj + 4], y[8 * jj + 5]); pk.w = pack2<FP16>(y[8 * jj + 6], y[8 * jj + 7]);
+              *reinterpret_cast<uint4*>(xnext + (QA + j) * (kTcRows * 16) + tid * 16) = pk;
+            }
+          }
+        }
+      }
+      // CoshLoss: beta^2 * mean_a(cosh(a/beta) - 1); row cost pairs s_{h+1} with a_h
+      cost = __fadd_rn(cost, __fadd_rn(st_cost, __fmul_rn(m.beta2, __fdiv_rn(act_cur, (float)A))));
+      act_cur = act_next;
+      if (h + 1 < H) {
+        fence_proxy_async();   // generic-proxy writes of the input tile -> visible to the MMA
+        tc_fence_before();     // our tcgen05.ld of D3 is ordered before the next layer-1 MMA
+        mbar_arrive(bar_x);
+      }
+    }
+    if (valid) costs[row] = cost;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
+}
+
+inline cudaError_t tc_launch_rollout(TcModel* t, const ModelDev& m, const ActionSource& src, const Shape& sh,
+                                     const float* d_s0, float* d_costs, float* d_states, float* d_actions, int num_sms,
+                                     cudaStream_t st) {
+  (void)num_sms;
+  if (!t->ready) return cudaErrorNotReady;
+  const unsigned grid = (unsigned)((sh.rows() + kTcRows - 1) / kTcRows);
+  cudaError_t e;
+  if (t->fp16) {
+    e = cudaFuncSetAttribute(rollout_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, t->g.smem_bytes);
+    if (e != cudaSuccess) return e;
+    rollout_tc_kernel<true><<<grid, kTcThreads, t->g.smem_bytes, st>>>(t->g, t->d_wimg, m, src, sh, d_s0, d_costs, d_states,
+                                                                      d_actions, t->d_dbg);
+  } else {
+    e = cudaFuncSetAttribute(rollout_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, t->g.smem_bytes);
+    if (e != cudaSuccess) return e;
+    rollout_tc_kernel<false><<<grid, kTcThreads, t->g.smem_bytes, st>>>(t->g, t->d_wimg, m, src, sh, d_s0, d_costs, d_states,
+                                                                       d_actions, t->d_dbg);
+  }
+  return cudaGetLastError();
 }
 
 }  // namespace mbrl

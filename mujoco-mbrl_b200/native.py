@@ -25,6 +25,7 @@ ABI_SYMBOLS = [
     "mbrl_abi_version", "mbrl_last_error", "mbrl_create", "mbrl_destroy", "mbrl_set_weights",
     "mbrl_set_norm", "mbrl_set_cost", "mbrl_set_action_bounds", "mbrl_plan", "mbrl_plan_device",
     "mbrl_rollout", "mbrl_sample", "mbrl_philox_raw", "mbrl_topk", "mbrl_refit", "mbrl_emit",
+    "mbrl_tc_debug",
 ]
 
 
@@ -92,6 +93,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         "mbrl_topk": [vp, i32, i32, i32, vp, vp, vp, vp],
         "mbrl_refit": [p, i32, u64, u32, u32, u32, vp, vp, vp, vp, i32, vp, vp, vp],
         "mbrl_emit": [p, i32, u64, u32, u32, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp],
+        "mbrl_tc_debug": [p, i32, vp],
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)
@@ -262,6 +264,12 @@ class NativePlanner:
                                    _dp(d_mu), _dp(d_sd), _dp(d_elite_idx), k, _dp(mu), _dp(sd), _stream_ptr()))
         return mu, sd
 
+
+    def tc_debug(self, enable=True, fetch=False):
+        """Diagnostic: arm / fetch the raw accumulator dump of tile 0, step 0 ([3,128,256])."""
+        out = np.zeros((3, 128, 256), np.float32) if fetch else None
+        _check(self.lib.mbrl_tc_debug(self._h, int(enable), _hp(out)))
+        return out
 
     def emit(self, d_s0, d_best, d_mu_hist, d_sd_hist, iterations, mode, seed=0, d_injected=None, return_mean=False,
              cand_offset=0, env_offset=0):

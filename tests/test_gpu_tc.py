@@ -1,0 +1,158 @@
+"""GPU tests of the tcgen05 tensor-core engines (fp16 / bf16 operands, fp32 accumulate).
+
+Tolerances (stated here, per north_star): the reference is fp32; 16-bit operands are rounded
+once per layer input.  Against the fp32 oracle on the same injected actions:
+  * per-step predicted states: relative error <= STATE_RTOL of the state scale per step
+    (fp16: 2e-3, bf16: 1.5e-2), checked on every step of the horizon;
+  * trajectory costs: relative error <= COST_RTOL (fp16: 2e-3, bf16: 1.5e-2).
+Elite indices are only required to be bit-exact on identical cost arrays (test_gpu_parity.py);
+here the elite SETS of the two precisions are compared by overlap.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from mbrl_helpers import load_golden, params_from_golden
+from oracle import planner_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp16": dict(state=2e-3, cost=2e-3), "bf16": dict(state=1.5e-2, cost=1.5e-2)}
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+
+
+@pytest.fixture(scope="module")
+def native():
+    from mbrl_b200 import native as n
+    assert torch.cuda.is_available()
+    n.load_library()
+    return n
+
+
+def _planner(native, p, horizon, n, envs=1, iters=1, engine="fp16"):
+    h = native.NativePlanner(p.obs_dim, p.act_dim, p.hidden, horizon, n, envs, iters, None, engine)
+    h.set_weights(p.W1, p.b1, p.W2, p.b2, p.W3, p.b3)
+    h.set_norm(p.mu_s, p.sd_s, p.mu_a, p.sd_a)
+    h.set_cost(p.cost_w, p.goal, p.alpha, p.beta)
+    h.set_action_bounds(p.act_lo, p.act_hi)
+    return h
+
+
+def _round16(x, engine):
+    t = torch.as_tensor(x, dtype=torch.float32)
+    return (t.half() if engine == "fp16" else t.bfloat16()).float()
+
+
+@pytest.mark.parametrize("engine", ["fp16", "bf16"])
+@pytest.mark.parametrize("dims", [(17, 6, 200), (5, 1, 50), (24, 6, 200), (33, 9, 100)])
+def test_layer_accumulators_match_16bit_emulation(native, engine, dims):
+    """Raw TMEM accumulators of tile 0 / step 0 against a numpy emulation that rounds the
+    operands exactly where the kernel does -- pins the UMMA descriptors, the operand packing,
+    the in-place TMEM A operand and the bias-through-ones-column trick layer by layer."""
+    O, A, U = dims
+    p = po.synthetic_params(O, A, U, seed=11)
+    n, H = 128, 2
+    h = _planner(native, p, H, n, engine=engine)
+    g = torch.Generator().manual_seed(5)
+    s0 = p.mu_s + p.sd_s * torch.randn(O, generator=g)
+    acts = torch.rand(H * n, A, generator=g) * 2 - 1
+    h.tc_debug(True)
+    costs, states, _ = h.rollout(s0[None].cuda(), native.SAMPLE_INJECT_ACTIONS, d_injected=acts.cuda(), want_states=True)
+    torch.cuda.synchronize()
+    dump = h.tc_debug(True, fetch=True)
+    h.tc_debug(False)
+    Np = (U + 1 + 15) // 16 * 16
+    # emulation
+    xs = _round16(((s0 - p.mu_s) / p.sd_s)[None].repeat(n, 1), engine)
+    xa = _round16((acts[:n] - p.mu_a) / p.sd_a, engine)
+    W1, b1 = _round16(p.W1, engine), _round16(p.b1, engine)
+    W2, b2 = _round16(p.W2, engine), _round16(p.b2, engine)
+    W3 = _round16(p.W3, engine)
+    d1 = (torch.cat([xs, xa], 1).double() @ W1.double().t() + b1.double()).float()
+    h1 = _round16(torch.relu(d1), engine)
+    d2 = (h1.double() @ W2.double().t() + b2.double()).float()
+    h2 = _round16(torch.relu(d2), engine)
+    d3 = (h2.double() @ W3.double().t()).float()
+    report = []
+    ok = True
+    for name, got, want in (("D1", dump[0][:, :U], d1.numpy()), ("D2", dump[1][:, :U], d2.numpy()), ("D3", dump[2][:, :O], d3.numpy())):
+        err = np.abs(got - want).max()
+        scale = np.abs(want).max()
+        report.append(f"{engine} {dims} {name}: max|err|={err:.3e} scale={scale:.3e} got[0,:4]={got[0,:4]} want[0,:4]={want[0,:4]}")
+        ok &= bool(err <= 2e-3 * scale + 1e-4)
+    report.append(f"ones column D1[:,U]={dump[0][:3, U]} (want 1) pad={dump[0][0, U + 1:Np]}")
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, "tc_probe.txt"), "a") as f:
+        f.write("\n".join(report) + "\n")
+    print("\n".join(report))
+    assert ok, "\n".join(report)
+    np.testing.assert_allclose(dump[0][:, U], 1.0, atol=1e-6)
+    # and the end-to-end predicted state of step 0
+    want_s = (d3 + p.b3) * p.sd_s + p.mu_s
+    np.testing.assert_allclose(states.cpu().numpy()[:n], want_s.numpy(), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("engine", ["fp16", "bf16"])
+@pytest.mark.parametrize("name", ["rs_cartpole.npz", "rs_cheetah_small.npz"])
+def test_tc_rollout_within_tolerance_of_reference(native, engine, name):
+    g = load_golden(name)
+    p = params_from_golden(g)
+    n, H = int(g["n"]), int(g["horizon"])
+    h = _planner(native, p, H, n, engine=engine)
+    costs, states, actions = h.rollout(torch.from_numpy(g["s0"][None]).cuda(), native.SAMPLE_INJECT_ACTIONS,
+                                       d_injected=torch.from_numpy(g["actions"]).cuda(), want_states=True, want_actions=True)
+    np.testing.assert_array_equal(actions.cpu().numpy(), g["actions"])
+    keep = g["states_first"].shape[1]
+    got = states.cpu().numpy().reshape(H, n, -1)[:, :keep]
+    want = g["states_first"]
+    scale = np.abs(want).max(axis=(1, 2), keepdims=True)
+    step_err = (np.abs(got - want) / scale).max(axis=(1, 2))
+    cost_err = np.abs(costs.cpu().numpy() - g["costs"]) / np.abs(g["costs"])
+    msg = f"{engine} {name}: per-step state rel err max={step_err.max():.3e} (first {step_err[0]:.3e}, last {step_err[-1]:.3e}); cost rel err max={cost_err.max():.3e}"
+    print(msg)
+    with open(os.path.join(OUT, "tc_probe.txt"), "a") as f:
+        f.write(msg + "\n")
+    assert step_err.max() <= TOL[engine]["state"], msg
+    assert cost_err.max() <= TOL[engine]["cost"], msg
+
+
+@pytest.mark.parametrize("engine", ["fp16", "bf16"])
+def test_tc_matches_fp32_engine_on_device_sampler(native, engine):
+    """Same Philox stream on both engines: identical actions, costs within tolerance, large
+    elite overlap; ragged tile (N not a multiple of 128) and 2 environments."""
+    p = po.synthetic_params(17, 6, 200)
+    H, n, E, k = 30, 1000, 2, 100
+    s0 = torch.stack([po.synthetic_state(p, c) for c in range(E)]).cuda()
+    mu = (torch.rand(E, H, 6) * 0.2 - 0.1).cuda()
+    sd = (torch.rand(E, H, 6) * 0.5 + 0.5).cuda()
+    ref = _planner(native, p, H, n, E, engine="fp32")
+    tc = _planner(native, p, H, n, E, engine=engine)
+    c0, _, a0 = ref.rollout(s0, native.SAMPLE_GAUSSIAN, 9, 2, d_mu=mu, d_sd=sd, want_actions=True)
+    c1, _, a1 = tc.rollout(s0, native.SAMPLE_GAUSSIAN, 9, 2, d_mu=mu, d_sd=sd, want_actions=True)
+    assert torch.equal(a0, a1)
+    rel = ((c0 - c1).abs() / c0.abs()).max().item()
+    assert rel <= TOL[engine]["cost"], rel
+    i0, _, _ = native.topk(c0, k, E)
+    i1, _, _ = native.topk(c1, k, E)
+    for e in range(E):
+        overlap = len(set(i0[e].tolist()) & set(i1[e].tolist())) / k
+        assert overlap >= (0.9 if engine == "fp16" else 0.7), overlap
+
+
+@pytest.mark.parametrize("engine", ["fp16", "bf16"])
+def test_tc_cem_plan_consistent(native, engine):
+    """Whole CEM plan on the tensor-core engine: the reported best cost is reproduced by the
+    fp32 oracle on the emitted action sequence within the engine's cost tolerance, and the
+    first action is inside the bounds."""
+    p = po.synthetic_params(17, 6, 200)
+    H, n, I, k = 30, 4096, 4, 409
+    h = _planner(native, p, H, n, 1, I, engine=engine)
+    s0 = po.synthetic_state(p, 3)
+    out = h.plan(s0.numpy(), I, k, native.SAMPLE_GAUSSIAN, seed=5)
+    acts = torch.from_numpy(out["actions"][0])
+    states, c = po.rollout_costs(p, s0, acts, H, 1)
+    np.testing.assert_allclose(out["info"]["best_cost"][0], c[0], rtol=TOL[engine]["cost"])
+    np.testing.assert_allclose(out["states"][0], states.numpy(), rtol=1e-4, atol=1e-4)  # replay is fp32
+    assert np.abs(out["actions"]).max() <= 1.0
