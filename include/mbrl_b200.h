@@ -184,8 +184,9 @@ int mbrl_emit(MbrlPlanner* p, int32_t sample_mode, uint64_t seed, uint32_t cand_
               float* d_out_actions, void* stream);
 
 /* Diagnostic for the tensor-core engines (tests only): enable != 0 arms a dump of the raw
- * fp32 accumulators of row tile 0 at step 0 ([3 layers][128 rows][256 cols]) by the next
- * mbrl_rollout; h_out != NULL copies the dump to the host (after synchronising). */
+ * fp32 accumulators of row tile 0 at step 0 ([3 layers][128 rows][256 cols] floats) followed
+ * by a clock64() timeline of tile 1 ([64 steps][32 events] int64) by the next mbrl_rollout;
+ * h_out != NULL copies the dump (3*128*256*4 + 64*32*8 bytes) to the host after a sync. */
 int mbrl_tc_debug(MbrlPlanner* p, int32_t enable, float* h_out);
 
 #ifdef __cplusplus

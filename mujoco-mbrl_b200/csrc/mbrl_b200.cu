@@ -15,6 +15,7 @@
 #include "replay.cuh"
 #include "rollout_simt.cuh"
 #include "rollout_tc.cuh"
+#include "rollout_tcf.cuh"
 #include "select.cuh"
 
 using namespace mbrl;
@@ -330,7 +331,13 @@ static int launch_topk(const float* d_costs, int segments, int n, int k, int* d_
                        MbrlPlanInfo* d_best, BestEver* d_best_ever, int iteration, cudaStream_t st) {
   MBRL_REQUIRE(segments >= 1 && n >= 1, "topk: empty input");
   MBRL_REQUIRE(k >= 1 && k <= n, "topk: k out of range [1,n]");
-  topk_select_kernel<<<segments, kSelectThreads, 0, st>>>(d_costs, n, k, d_idx, d_cost, d_best, d_best_ever, iteration);
+  if (n <= kSelectStageMax) {
+    const size_t smem = sizeof(uint32_t) * (size_t)n;
+    MBRL_CUDA(cudaFuncSetAttribute(topk_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    topk_select_kernel<true><<<segments, kSelectThreads, smem, st>>>(d_costs, n, k, d_idx, d_cost, d_best, d_best_ever, iteration);
+  } else {
+    topk_select_kernel<false><<<segments, kSelectThreads, 0, st>>>(d_costs, n, k, d_idx, d_cost, d_best, d_best_ever, iteration);
+  }
   MBRL_CUDA(cudaGetLastError());
   return MBRL_OK;
 }
@@ -353,11 +360,18 @@ static int launch_replay(MbrlPlanner* p, int mode, uint64_t seed, uint32_t cand_
   if (!p->have_weights) return fail(MBRL_E_STATE, "mbrl_set_weights must be called before planning");
   ActionSource src = action_source(p, mode, seed, 0, cand_offset, env_offset, d_injected, d_mu_hist, d_sd_hist);
   Shape sh{p->H, p->N, p->E};
-  const size_t smem = replay_smem_bytes(p->O, p->A, p->U, p->H);
-  MBRL_REQUIRE(smem <= p->max_smem, "horizon too long for the replay kernel's shared memory");
-  MBRL_CUDA(cudaFuncSetAttribute(replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  replay_kernel<<<p->E, kReplayThreads, smem, st>>>(model_view(p), src, sh, d_s0, d_mu_hist, d_sd_hist, d_best,
-                                                   iterations, return_mean, d_out_states, d_out_actions, d_info);
+  const size_t smem_w = replay_smem_bytes(p->O, p->A, p->U, p->H, true);
+  if (smem_w <= p->max_smem) {
+    MBRL_CUDA(cudaFuncSetAttribute(replay_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+    replay_kernel<true><<<p->E, kReplayThreads, smem_w, st>>>(model_view(p), src, sh, d_s0, d_mu_hist, d_sd_hist, d_best,
+                                                             iterations, return_mean, d_out_states, d_out_actions, d_info);
+  } else {
+    const size_t smem = replay_smem_bytes(p->O, p->A, p->U, p->H, false);
+    MBRL_REQUIRE(smem <= p->max_smem, "horizon too long for the replay kernel's shared memory");
+    MBRL_CUDA(cudaFuncSetAttribute(replay_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    replay_kernel<false><<<p->E, kReplayThreads, smem, st>>>(model_view(p), src, sh, d_s0, d_mu_hist, d_sd_hist, d_best,
+                                                            iterations, return_mean, d_out_states, d_out_actions, d_info);
+  }
   MBRL_CUDA(cudaGetLastError());
   return MBRL_OK;
 }
@@ -446,7 +460,7 @@ extern "C" int mbrl_tc_debug(MbrlPlanner* p, int32_t enable, float* h_out) {
   if (!p) return fail(MBRL_E_INVALID, "null planner");
   MBRL_REQUIRE(p->cfg.engine != MBRL_ENGINE_SIMT_FP32, "tc_debug: not a tensor-core engine");
   MBRL_CUDA(cudaSetDevice(p->cfg.device));
-  const size_t bytes = sizeof(float) * 3 * 128 * 256;
+  const size_t bytes = sizeof(float) * kTcDbgFloats + sizeof(long long) * kTcTimelineSteps * kTcTimelineEvents;
   if (h_out) {
     MBRL_REQUIRE(p->tc.d_dbg, "tc_debug: dump was never armed");
     MBRL_CUDA(cudaDeviceSynchronize());

@@ -15,7 +15,8 @@
 //     ([action section | 1 | state section], written by the epilogue threads),
 //     D1 -> TMEM columns [0, Np);
 //   * epilogue 1: tcgen05.ld D1 chunk -> cvt.rn.relu.{f16,bf16}x2 -> tcgen05.st the packed
-//     activations back IN PLACE (columns [0, Np/2)); each finished 32-column chunk releases
+//     activations back into the first half of the chunk's OWN columns (no cross-warp overlap);
+//     each finished 32-column chunk releases
 //     the next layer's K-steps through an mbarrier, so the layer-2 MMAs (TS mode: A straight
 //     from TMEM, D2 -> columns [256, 256+Np)) overlap the rest of the epilogue;
 //   * epilogue 2 / layer 3 the same way (h2 in place at [256, 256+Np/2), D3 -> [0, Op));
@@ -42,8 +43,10 @@
 namespace mbrl {
 
 constexpr int kTcRows = 128;           // MMA M
-constexpr int kTcEpiThreads = 128;     // warps 0-3: one thread per row / TMEM lane
-constexpr int kTcThreads = 160;        // + warp 4: TMEM alloc, weight TMA, MMA issue
+constexpr int kTcEpiWarps = 8;         // warps 0-7: two warpgroups share the 128 TMEM lanes
+constexpr int kTcSampWarps = 4;        // warps 8-11: one sampler thread per row
+constexpr int kTcMmaWarp = 12;         // warp 12: TMEM alloc, weight TMA, MMA issue
+constexpr int kTcThreads = 13 * 32;
 constexpr int kTcD2Col = 256;          // TMEM column of the layer-2 accumulator
 constexpr int kTcMaxChunks = 8;        // ceil(256 / 32)
 
@@ -73,21 +76,13 @@ inline bool tc_geometry(int O, int A, int U, size_t max_smem, TcGeom* g, std::st
   g->w3_off = g->w2_off + g->Np * g->Np * 2;
   g->w_bytes = g->w3_off + g->Np * g->Op * 2;
   g->x_bytes = g->Kx * kTcRows * 2;
-  g->tab_off = g->w_bytes;                       // 5 fp32 tables of Op entries
-  g->x_off = round_up(g->tab_off + 5 * g->Op * 4, 128);
+  g->tab_off = g->w_bytes;  // fp32: 5 tables of Op, 2 of kMaxAct, 3 x 128 cost partials
+  g->x_off = round_up(g->tab_off + (5 * g->Op + 2 * kMaxAct + 3 * kTcRows) * 4, 128);
   g->bar_off = g->x_off + 2 * g->x_bytes;
   g->smem_bytes = g->bar_off + 8 * (5 + 2 * kTcMaxChunks) + 16;
   if ((size_t)g->smem_bytes > max_smem) { *why = "weights do not fit shared memory (streaming kernel not built yet)"; return false; }
   return true;
 }
-
-struct TcModel {
-  int ready = 0;
-  bool fp16 = true;
-  TcGeom g{};
-  uint8_t* d_wimg = nullptr;
-  float* d_dbg = nullptr;  // optional [3][128][256] accumulator dump of tile 0 / step 0 (tests)
-};
 
 // ---- host-side packing -----------------------------------------------------------------
 // Canonical K-major no-swizzle operand: element (row n, k) at byte
@@ -99,45 +94,25 @@ inline void tc_put(std::vector<uint16_t>& img, int off_bytes, int rows, int n, i
   img[(size_t)off_bytes / 2 + (size_t)(k / 8) * rows * 8 + (size_t)n * 8 + (k % 8)] = bits;
 }
 
-inline bool tc_init(TcModel* t, int O, int A, int U, bool fp16, size_t max_smem, std::string* why) {
-  if (!tc_geometry(O, A, U, max_smem, &t->g, why)) return false;
-  t->fp16 = fp16;
-  if (cudaMalloc((void**)&t->d_wimg, t->g.w_bytes) != cudaSuccess) { *why = "cudaMalloc failed"; return false; }
-  t->ready = 1;
-  return true;
-}
-
-inline void tc_free(TcModel* t) {
-  if (t->d_wimg) cudaFree(t->d_wimg);
-  if (t->d_dbg) cudaFree(t->d_dbg);
-  t->d_wimg = nullptr; t->d_dbg = nullptr; t->ready = 0;
-}
-
 // W1 [U, O+A], W2 [U, U], W3 [O, U] in nn.Linear layout (src/mbrl/models.py:99-101).
-inline bool tc_set_weights(TcModel* t, const float* W1, const float* b1, const float* W2, const float* b2,
-                           const float* W3, const float* b3, std::string* why) {
-  (void)b3;  // added in fp32 in the last epilogue
-  const TcGeom& g = t->g;
+inline void tc_pack(const TcGeom& g, bool fp16, const float* W1, const float* b1, const float* W2, const float* b2,
+                    const float* W3, std::vector<uint16_t>* out) {
   const int O = g.O, A = g.A, U = g.U, D = O + A;
-  std::vector<uint16_t> img((size_t)g.w_bytes / 2, 0);
+  std::vector<uint16_t>& img = *out;
+  img.assign((size_t)g.w_bytes / 2, 0);
   // layer 1: input column e:  e < A -> action e;  e == A -> constant 1;  Ka <= e < Ka+O -> state e-Ka
   for (int n = 0; n < U; ++n) {
-    for (int a = 0; a < A; ++a) tc_put(img, g.w1_off, g.Np, n, a, W1[(size_t)n * D + O + a], t->fp16);
-    tc_put(img, g.w1_off, g.Np, n, A, b1[n], t->fp16);
-    for (int o = 0; o < O; ++o) tc_put(img, g.w1_off, g.Np, n, g.Ka + o, W1[(size_t)n * D + o], t->fp16);
+    for (int a = 0; a < A; ++a) tc_put(img, g.w1_off, g.Np, n, a, W1[(size_t)n * D + O + a], fp16);
+    tc_put(img, g.w1_off, g.Np, n, A, b1[n], fp16);
+    for (int o = 0; o < O; ++o) tc_put(img, g.w1_off, g.Np, n, g.Ka + o, W1[(size_t)n * D + o], fp16);
   }
-  tc_put(img, g.w1_off, g.Np, U, A, 1.0f, t->fp16);  // hidden unit U == relu(1) == 1 carries b2
+  tc_put(img, g.w1_off, g.Np, U, A, 1.0f, fp16);  // hidden unit U == relu(1) == 1 carries b2
   for (int n = 0; n < U; ++n) {
-    for (int k = 0; k < U; ++k) tc_put(img, g.w2_off, g.Np, n, k, W2[(size_t)n * U + k], t->fp16);
-    tc_put(img, g.w2_off, g.Np, n, U, b2[n], t->fp16);
+    for (int k = 0; k < U; ++k) tc_put(img, g.w2_off, g.Np, n, k, W2[(size_t)n * U + k], fp16);
+    tc_put(img, g.w2_off, g.Np, n, U, b2[n], fp16);
   }
   for (int o = 0; o < O; ++o)
-    for (int k = 0; k < U; ++k) tc_put(img, g.w3_off, g.Op, o, k, W3[(size_t)o * U + k], t->fp16);
-  if (cudaMemcpy(t->d_wimg, img.data(), g.w_bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
-    *why = "cudaMemcpy of packed operands failed";
-    return false;
-  }
-  return true;
+    for (int k = 0; k < U; ++k) tc_put(img, g.w3_off, g.Op, o, k, W3[(size_t)o * U + k], fp16);
 }
 
 // ---- PTX wrappers ------------------------------------------------------------------------
@@ -251,46 +226,64 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 // ---- action sampling, 4 raw actions for dims 4g..4g+3 (0 beyond A) --------------------------
 __device__ __forceinline__ void raw_action4(const ActionSource& s, int A, int H, int h, int env_l, int cand_l,
                                             long long row, long long R, int g, float (&out)[4]) {
+  // branch-free per element: indices are clamped into range and the result is masked, so the four
+  // independent load -> fma -> clip chains can overlap
   const long long ms = ((long long)env_l * H + h) * A;
+  float z[4];
   if (s.mode == MBRL_SAMPLE_INJECT_ACTIONS || s.mode == MBRL_SAMPLE_INJECT_NOISE) {
     const float* p = s.buf + ((long long)h * R + row) * A;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int a = 4 * g + j;
-      float v = 0.f;
-      if (a < A) {
-        v = __ldg(p + a);
-        if (s.mode == MBRL_SAMPLE_INJECT_NOISE)
-          v = clipf(__fadd_rn(__ldg(s.mu + ms + a), __fmul_rn(__ldg(s.sd + ms + a), v)), s.lo, s.hi);
-      }
-      out[j] = v;
-    }
+    for (int j = 0; j < 4; ++j) z[j] = __ldg(p + min(4 * g + j, A - 1));
   } else {
     const int G = (A + 3) >> 2;
     const uint4 r = philox4x32_10(make_uint4((uint32_t)(h * G + g), s.iteration, s.cand_offset + (uint32_t)cand_l,
                                              s.env_offset + (uint32_t)env_l),
                                   make_uint2(s.seed_lo, s.seed_hi));
-    float z[4];
     if (s.mode == MBRL_SAMPLE_GAUSSIAN) {
       const float4 q = box_muller4(r);
       z[0] = q.x; z[1] = q.y; z[2] = q.z; z[3] = q.w;
     } else {
       z[0] = u32_to_uniform(r.x); z[1] = u32_to_uniform(r.y); z[2] = u32_to_uniform(r.z); z[3] = u32_to_uniform(r.w);
     }
+  }
+  const bool affine = s.mode == MBRL_SAMPLE_INJECT_NOISE || s.mode == MBRL_SAMPLE_GAUSSIAN;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int a = 4 * g + j;
-      float v = 0.f;
-      if (a < A)
-        v = s.mode == MBRL_SAMPLE_GAUSSIAN
-                ? clipf(__fadd_rn(__ldg(s.mu + ms + a), __fmul_rn(__ldg(s.sd + ms + a), z[j])), s.lo, s.hi)
-                : __fadd_rn(s.lo, __fmul_rn(__fsub_rn(s.hi, s.lo), z[j]));
-      out[j] = v;
-    }
+  for (int j = 0; j < 4; ++j) {
+    const int a = 4 * g + j, ac = min(a, A - 1);
+    float v = z[j];
+    if (affine) v = clipf(__fadd_rn(__ldg(s.mu + ms + ac), __fmul_rn(__ldg(s.sd + ms + ac), v)), s.lo, s.hi);
+    else if (s.mode == MBRL_SAMPLE_UNIFORM) v = __fadd_rn(s.lo, __fmul_rn(__fsub_rn(s.hi, s.lo), v));
+    out[j] = a < A ? v : 0.f;
   }
 }
 
 // ---- the kernel ----------------------------------------------------------------------------
+// Warp roles (416 threads, 1 CTA per SM):
+//   warps 0-7   epilogue: thread <-> TMEM lane (warp%4)*32+lane; the two warpgroups split the
+//               accumulator columns (even / odd 32-column chunks; 16-column halves of D3)
+//   warps 8-11  sampler: one thread per row draws the next step's actions (Philox + Box-Muller
+//               + clip), normalises them into the input tile and accumulates the action cost --
+//               entirely off the GEMM critical path
+//   warp 12     one elected thread: weight TMA, all tcgen05.mma issue, commits
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float cosh_m1_fast(float t) {
+  const float e = __expf(t);
+  return 0.5f * (e + __fdividef(1.0f, e)) - 1.0f;
+}
+
+// Diagnostic timeline (tests/profiling only): when the debug buffer is armed, tile 1 records
+// clock64() at the hand-over points of every step: slot [h][e], e = 0..15.
+constexpr int kTcDbgFloats = 3 * kTcRows * 256;
+constexpr int kTcTimelineSteps = 64, kTcTimelineEvents = 32;
+__device__ __forceinline__ void tc_stamp(float* dbg, int h, int e) {
+  if (dbg && blockIdx.x == 1 && h < kTcTimelineSteps)
+    reinterpret_cast<long long*>(dbg + kTcDbgFloats)[h * kTcTimelineEvents + e] = clock64();
+}
+
 template <bool FP16>
 __global__ void __launch_bounds__(kTcThreads, 1)
 rollout_tc_kernel(TcGeom g, const uint8_t* __restrict__ wimg, ModelDev m, ActionSource src, Shape sh,
@@ -303,8 +296,14 @@ rollout_tc_kernel(TcGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Action
   const int NC = (g.Np + 31) >> 5;       // hidden epilogue chunks (32 columns, last may be 16)
   const int KS_H = g.Np >> 4;            // K-steps of layers 2 and 3
   const int KS_X = g.Kx >> 4;            // K-steps of layer 1
+  const int QA = g.Ka >> 3;              // action chunks of the input tile
+  const int SC = (g.Kx - g.Ka) >> 3;     // state chunks of the input tile
 
-  float* tab = reinterpret_cast<float*>(smem + g.tab_off);  // [5][Op]: b3, sd_s, mu_s, goal, cost_w
+  // fp32 tables: per output o: b3, P = sd*w, Q = (b3*sd + mu - goal)*w, sd, mu; per action a:
+  // 1/sd_a, mu_a/sd_a; then the three per-row cost partials
+  float* tab = reinterpret_cast<float*>(smem + g.tab_off);
+  float* t_b3 = tab, *t_P = tab + g.Op, *t_Q = tab + 2 * g.Op, *t_sd = tab + 3 * g.Op, *t_mu = tab + 4 * g.Op;
+  float* t_ainv = tab + 5 * g.Op, *t_aoff = t_ainv + kMaxAct, *costp = t_aoff + kMaxAct;
   uint8_t* xbuf = smem + g.x_off;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.bar_off);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + g.bar_off + 8 * (5 + 2 * kTcMaxChunks));
@@ -313,12 +312,12 @@ rollout_tc_kernel(TcGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Action
   const uint32_t bar_w = bar0, bar_x = bar0 + 8, bar_d1 = bar0 + 16, bar_d2 = bar0 + 24, bar_d3 = bar0 + 32;
   const uint32_t bar_a1 = bar0 + 40, bar_a2 = bar0 + 40 + 8 * kTcMaxChunks;
 
-  if (warp == 4) {
+  if (warp == kTcMmaWarp) {
     if (lane == 0) {
       mbar_init(bar_w, 1);
-      mbar_init(bar_x, kTcEpiThreads);
+      mbar_init(bar_x, kTcEpiWarps + 1);  // 8 epilogue warps (state section) + the sampler group
       mbar_init(bar_d1, 1); mbar_init(bar_d2, 1); mbar_init(bar_d3, 1);
-      for (int c = 0; c < kTcMaxChunks; ++c) { mbar_init(bar_a1 + 8 * c, kTcEpiThreads); mbar_init(bar_a2 + 8 * c, kTcEpiThreads); }
+      for (int c = 0; c < kTcMaxChunks; ++c) { mbar_init(bar_a1 + 8 * c, 4); mbar_init(bar_a2 + 8 * c, 4); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -327,74 +326,112 @@ rollout_tc_kernel(TcGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Action
   }
   for (int i = tid; i < g.Op; i += kTcThreads) {
     const bool in = i < O;
-    tab[0 * g.Op + i] = in ? __ldg(m.b3 + i) : 0.f;
-    tab[1 * g.Op + i] = in ? __ldg(m.sd_s + i) : 1.f;
-    tab[2 * g.Op + i] = in ? __ldg(m.mu_s + i) : 0.f;
-    tab[3 * g.Op + i] = in ? __ldg(m.goal + i) : 0.f;
-    tab[4 * g.Op + i] = in ? __ldg(m.cost_w + i) : 0.f;
+    const float b3 = in ? __ldg(m.b3 + i) : 0.f, sd = in ? __ldg(m.sd_s + i) : 1.f, mu = in ? __ldg(m.mu_s + i) : 0.f;
+    const float w = in ? __ldg(m.cost_w + i) : 0.f, goal = in ? __ldg(m.goal + i) : 0.f;
+    t_b3[i] = b3; t_sd[i] = sd; t_mu[i] = mu;
+    t_P[i] = sd * w;
+    t_Q[i] = (b3 * sd + mu - goal) * w;
+  }
+  for (int i = tid; i < kMaxAct; i += kTcThreads) {
+    const float inv = i < A ? 1.0f / __ldg(m.sd_a + i) : 0.f;
+    t_ainv[i] = inv;
+    t_aoff[i] = i < A ? __ldg(m.mu_a + i) * inv : 0.f;
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  const long long R = sh.rows();
 
-  if (warp == 4) {
+  if (warp == kTcMmaWarp) {
     // ================= MMA issuer (one thread) =================
     if (lane == 0) {
       mbar_arrive_expect_tx(bar_w, (uint32_t)g.w_bytes);
       bulk_g2s(smem_u32(smem), wimg, (uint32_t)g.w_bytes, bar_w);
       const uint32_t idesc_h = umma_idesc(g.Np, FP16), idesc_o = umma_idesc(g.Op, FP16);
-      const uint32_t w1 = smem_u32(smem + g.w1_off), w2 = smem_u32(smem + g.w2_off), w3 = smem_u32(smem + g.w3_off);
       const uint32_t lbo_h = (uint32_t)g.Np * 16, lbo_o = (uint32_t)g.Op * 16, lbo_x = kTcRows * 16;
+      // Descriptors are loop invariant; a K-step advances the 14-bit start-address field by
+      // 2*LBO/16 (smem addresses stay below 256 KB, so the add never carries out of the field).
+      const uint64_t d_w1 = umma_desc(smem_u32(smem + g.w1_off), lbo_h, 128);
+      const uint64_t d_w2 = umma_desc(smem_u32(smem + g.w2_off), lbo_h, 128);
+      const uint64_t d_w3 = umma_desc(smem_u32(smem + g.w3_off), lbo_o, 128);
+      const uint64_t d_x0 = umma_desc(smem_u32(xbuf), lbo_x, 128);
+      const uint64_t d_x1 = umma_desc(smem_u32(xbuf + g.x_bytes), lbo_x, 128);
+      const uint64_t step_h = (2 * lbo_h) >> 4, step_o = (2 * lbo_o) >> 4, step_x = (2 * lbo_x) >> 4;
       mbar_wait(bar_w, 0);
       for (int h = 0; h < H; ++h) {
         const uint32_t ph = h & 1;
-        const uint32_t xs = smem_u32(xbuf + (h & 1) * g.x_bytes);
         mbar_wait(bar_x, ph);
         tc_fence_after();
-        for (int ks = 0; ks < KS_X; ++ks)
-          mma_ss(tmem, umma_desc(xs + ks * 2 * lbo_x, lbo_x, 128), umma_desc(w1 + ks * 2 * lbo_h, lbo_h, 128), idesc_h, ks > 0);
+        tc_stamp(dbg, h, 0);
+        {
+          uint64_t ad = (h & 1) ? d_x1 : d_x0, bd = d_w1;
+          mma_ss(tmem, ad, bd, idesc_h, 0);
+          tc_stamp(dbg, h, 20);
+          for (int ks = 1; ks < KS_X; ++ks) { ad += step_x; bd += step_h; mma_ss(tmem, ad, bd, idesc_h, 1); }
+        }
+        tc_stamp(dbg, h, 21);
         tc_commit(bar_d1);
-        for (int c = 0; c < NC; ++c) {
-          mbar_wait(bar_a1 + 8 * c, ph);
-          tc_fence_after();
-          for (int ks = 2 * c; ks < min(2 * c + 2, KS_H); ++ks)
-            mma_ts(tmem + kTcD2Col, tmem + 8 * ks, umma_desc(w2 + ks * 2 * lbo_h, lbo_h, 128), idesc_h, ks > 0);
+        tc_stamp(dbg, h, 1);
+        {
+          uint64_t bd = d_w2;
+          uint32_t a = tmem, acc = 0;
+          int left = KS_H;
+          for (int c = 0; c < NC; ++c) {
+            mbar_wait(bar_a1 + 8 * c, ph);
+            tc_fence_after();
+            mma_ts(tmem + kTcD2Col, a, bd, idesc_h, acc);
+            acc = 1; bd += step_h;
+            if (left > 1) { mma_ts(tmem + kTcD2Col, a + 8, bd, idesc_h, 1); bd += step_h; }
+            a += 32; left -= 2;  // packed chunk c sits in the first half of its own 32 columns
+          }
         }
         tc_commit(bar_d2);
-        for (int c = 0; c < NC; ++c) {
-          mbar_wait(bar_a2 + 8 * c, ph);
-          tc_fence_after();
-          for (int ks = 2 * c; ks < min(2 * c + 2, KS_H); ++ks)
-            mma_ts(tmem, tmem + kTcD2Col + 8 * ks, umma_desc(w3 + ks * 2 * lbo_o, lbo_o, 128), idesc_o, ks > 0);
+        tc_stamp(dbg, h, 2);
+        {
+          // layer 3 (N = Op) is issue-bound, not tensor-bound: chunk-wise release hides the
+          // issue cost behind the rest of epilogue 2
+          uint64_t bd = d_w3;
+          uint32_t a = tmem + kTcD2Col, acc = 0;
+          int left = KS_H;
+          for (int c = 0; c < NC; ++c) {
+            mbar_wait(bar_a2 + 8 * c, ph);
+            tc_fence_after();
+            mma_ts(tmem, a, bd, idesc_o, acc);
+            acc = 1; bd += step_o;
+            if (left > 1) { mma_ts(tmem, a + 8, bd, idesc_o, 1); bd += step_o; }
+            a += 32; left -= 2;
+          }
         }
         tc_commit(bar_d3);
+        tc_stamp(dbg, h, 3);
       }
     }
     __syncwarp();
-  } else {
-    // ================= epilogue / row threads =================
-    const long long R = sh.rows();
-    const long long row = (long long)blockIdx.x * kTcRows + tid;
+  } else if (warp >= kTcEpiWarps) {
+    // ================= sampler threads (one per row) =================
+    const int srow = tid - kTcEpiWarps * 32;
+    const long long row = (long long)blockIdx.x * kTcRows + srow;
     const bool valid = row < R;
     const int env_l = valid ? (int)(row / sh.N) : 0;
     const int cand_l = valid ? (int)(row - (long long)env_l * sh.N) : 0;
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
-    const int QA = g.Ka >> 3;               // action chunks of the input tile
-    const int SC = (g.Kx - g.Ka) >> 3;      // state chunks of the input tile
-    float cost = 0.f, act_cur = 0.f;
-
-    // writes the action section of input tile `buf` for step h; returns sum_a(cosh(a/beta)-1)
-    auto stage_actions = [&](int h, int buf) -> float {
+    const float inv_beta = 1.0f / m.beta, cscale = m.beta2 / (float)A;
+    float act_total = 0.f;
+    for (int hs = 0; hs < H; ++hs) {
+      // the layer-1 MMA of step hs-1 has finished reading the tiles: buffer hs&1 is free and
+      // the x-ready barrier has moved on to phase hs
+      if (hs >= 1) mbar_wait(bar_d1, (hs - 1) & 1);
+      if (srow == 0) tc_stamp(dbg, hs, 12);
       float acc = 0.f;
-      float* aout = (actions_out && valid) ? actions_out + ((long long)h * R + row) * A : nullptr;
+      float* aout = (actions_out && valid) ? actions_out + ((long long)hs * R + row) * A : nullptr;
+      uint8_t* xt = xbuf + (hs & 1) * g.x_bytes;
       for (int q = 0; q < QA; ++q) {
         float v[8];
         {
           float t4[4];
-          raw_action4(src, A, H, h, env_l, cand_l, row, R, 2 * q, t4);
+          raw_action4(src, A, H, hs, env_l, cand_l, row, R, 2 * q, t4);
           v[0] = t4[0]; v[1] = t4[1]; v[2] = t4[2]; v[3] = t4[3];
-          if (8 * q + 4 < A) raw_action4(src, A, H, h, env_l, cand_l, row, R, 2 * q + 1, t4);
+          if (8 * q + 4 < A) raw_action4(src, A, H, hs, env_l, cand_l, row, R, 2 * q + 1, t4);
           else { t4[0] = t4[1] = t4[2] = t4[3] = 0.f; }
           v[4] = t4[0]; v[5] = t4[1]; v[6] = t4[2]; v[7] = t4[3];
         }
@@ -403,8 +440,8 @@ rollout_tc_kernel(TcGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Action
         for (int i = 0; i < 8; ++i) {
           const int a = 8 * q + i;
           if (a < A && valid) {
-            acc = __fadd_rn(acc, cosh_term(v[i], m.beta));
-            xn[i] = __fdiv_rn(__fsub_rn(v[i], __ldg(m.mu_a + a)), __ldg(m.sd_a + a));
+            acc += cosh_m1_fast(v[i] * inv_beta);
+            xn[i] = fmaf(v[i], t_ainv[a], -t_aoff[a]);
             if (aout) aout[a] = v[i];
           } else {
             xn[i] = (a == A) ? 1.0f : 0.0f;
@@ -413,149 +450,177 @@ rollout_tc_kernel(TcGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Action
         uint4 pk;
         pk.x = pack2<FP16>(xn[0], xn[1]); pk.y = pack2<FP16>(xn[2], xn[3]);
         pk.z = pack2<FP16>(xn[4], xn[5]); pk.w = pack2<FP16>(xn[6], xn[7]);
-        *reinterpret_cast<uint4*>(xbuf + buf * g.x_bytes + q * (kTcRows * 16) + tid * 16) = pk;
+        *reinterpret_cast<uint4*>(xt + q * (kTcRows * 16) + srow * 16) = pk;
       }
-      return acc;
-    };
+      act_total = fmaf(cscale, acc, act_total);  // CoshLoss: beta^2 * mean_a(cosh(a/beta) - 1)
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four sampler warps
+      if (srow == 0) { mbar_arrive(bar_x); tc_stamp(dbg, hs, 13); }
+    }
+    costp[2 * kTcRows + srow] = act_total;
+  } else {
+    // ================= epilogue threads =================
+    const int wg = warp >> 2, quarter = warp & 3;
+    const int trow = quarter * 32 + lane;                 // row in the tile == TMEM lane
+    const long long row = (long long)blockIdx.x * kTcRows + trow;
+    const bool valid = row < R;
+    const int env_l = valid ? (int)(row / sh.N) : 0;
+    const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
+    float st_total = 0.f;
 
-    // ---- step 0 input: actions + normalised s0 ----
-    act_cur = stage_actions(0, 0);
+    // step 0: normalised s0 into this warpgroup's state chunks
     for (int j = 0; j < SC; ++j) {
+      if (((j >> 1) & 1) != wg) continue;
       float xn[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int o = 8 * j + i;
-        xn[i] = (o < O && valid) ? __fdiv_rn(__fsub_rn(__ldg(s0 + (long long)env_l * O + o), tab[2 * g.Op + o]), tab[1 * g.Op + o]) : 0.f;
+        xn[i] = (o < O && valid) ? (__ldg(s0 + (long long)env_l * O + o) - t_mu[o]) / t_sd[o] : 0.f;
       }
       uint4 pk;
       pk.x = pack2<FP16>(xn[0], xn[1]); pk.y = pack2<FP16>(xn[2], xn[3]);
       pk.z = pack2<FP16>(xn[4], xn[5]); pk.w = pack2<FP16>(xn[6], xn[7]);
-      *reinterpret_cast<uint4*>(xbuf + (QA + j) * (kTcRows * 16) + tid * 16) = pk;
+      *reinterpret_cast<uint4*>(xbuf + (QA + j) * (kTcRows * 16) + trow * 16) = pk;
     }
     fence_proxy_async();
-    mbar_arrive(bar_x);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_x);
 
     for (int h = 0; h < H; ++h) {
       const uint32_t ph = h & 1;
-      // (a) actions of the next step, hidden behind the layer-1 MMA
-      float act_next = 0.f;
-      if (h + 1 < H) act_next = stage_actions(h + 1, (h + 1) & 1);
-
-      // (b),(c) hidden epilogues: TMEM fp32 -> relu -> 16-bit, in place; chunk-wise release
+      // hidden epilogues: TMEM fp32 -> relu -> 16-bit, in place; chunk-wise release
 #pragma unroll 1
       for (int layer = 0; layer < 2; ++layer) {
         const uint32_t dcol = layer == 0 ? 0u : (uint32_t)kTcD2Col;
         mbar_wait(layer == 0 ? bar_d1 : bar_d2, ph);
         tc_fence_after();
-        const uint32_t bar_a = layer == 0 ? bar_a1 : bar_a2;
+        if (tid == 0) tc_stamp(dbg, h, 4 + 2 * layer);
 #pragma unroll 1
-        for (int c = 0; c < NC; ++c) {
-          uint32_t v[32], pk[16];
-          const bool full = 32 * c + 32 <= g.Np;
+        for (int c = wg; c < NC; c += 4) {
+          // this warpgroup's chunks c and c+2: both TMEM loads in flight before converting
+          const int c2 = c + 2;
+          const bool has2 = c2 < NC;
+          const bool full = 32 * c + 32 <= g.Np, full2 = has2 && 32 * c2 + 32 <= g.Np;
+          uint32_t v[32], v2[32], pk[16];
           if (full) tmem_ld32(lane_base + dcol + 32 * c, v);
           else tmem_ld16(lane_base + dcol + 32 * c, v);
+          if (has2) {
+            if (full2) tmem_ld32(lane_base + dcol + 32 * c2, v2);
+            else tmem_ld16(lane_base + dcol + 32 * c2, v2);
+          }
           tmem_ld_wait();
+          if (tid == 0 && layer == 0 && c == 0) tc_stamp(dbg, h, 16);
           if (dbg && blockIdx.x == 0 && h == 0) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (full || i < 16) dbg[(layer * kTcRows + tid) * 256 + 32 * c + i] = __uint_as_float(v[i]);
+            for (int i = 0; i < 32; ++i) {
+              if (full || i < 16) dbg[(layer * kTcRows + trow) * 256 + 32 * c + i] = __uint_as_float(v[i]);
+              if (has2 && (full2 || i < 16)) dbg[(layer * kTcRows + trow) * 256 + 32 * c2 + i] = __uint_as_float(v2[i]);
+            }
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) pk[i] = pack_relu<FP16>(v[2 * i], v[2 * i + 1]);
-          if (full) tmem_st16(lane_base + dcol + 16 * c, pk);
-          else tmem_st8(lane_base + dcol + 16 * c, pk);
+          if (full) tmem_st16(lane_base + dcol + 32 * c, pk);
+          else tmem_st8(lane_base + dcol + 32 * c, pk);
+          if (has2) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[i] = pack_relu<FP16>(v2[2 * i], v2[2 * i + 1]);
+            if (full2) tmem_st16(lane_base + dcol + 32 * c2, pk);
+            else tmem_st8(lane_base + dcol + 32 * c2, pk);
+          }
+          if (tid == 0 && layer == 0 && c == 0) tc_stamp(dbg, h, 17);
           tmem_st_wait();
           tc_fence_before();
-          mbar_arrive(bar_a + 8 * c);
+          if (tid == 0 && layer == 0 && c == 0) tc_stamp(dbg, h, 18);
+          __syncwarp();
+          if (lane == 0) {
+            const uint32_t bar_a = layer == 0 ? bar_a1 : bar_a2;
+            mbar_arrive(bar_a + 8 * c);
+            if (has2) mbar_arrive(bar_a + 8 * c2);
+          }
+          if (tid == 0 && layer == 0 && c == 0) tc_stamp(dbg, h, 19);
         }
+        if (tid == 0) tc_stamp(dbg, h, 5 + 2 * layer);
       }
 
-      // (d) output epilogue: y = D3 + b3 (fp32), un-normalise, cost, next input tile
+      // output epilogue on this warpgroup's 16-column halves of D3
       mbar_wait(bar_d3, ph);
       tc_fence_after();
-      float st_cost = 0.f;
+      if (tid == 0) tc_stamp(dbg, h, 8);
       float* sout = (states_out && valid) ? states_out + ((long long)h * R + row) * O : nullptr;
       uint8_t* xnext = xbuf + ((h + 1) & 1) * g.x_bytes;
       const int CC = max(g.Op >> 5, (SC + 3) >> 2);
 #pragma unroll 1
       for (int cc = 0; cc < CC; ++cc) {
+        const int col0 = 32 * cc + 16 * wg;
         uint32_t v[32];
-        if (32 * cc < g.Op) {
-          tmem_ld32(lane_base + 32 * cc, v);
+        if (col0 < g.Op) {
+          tmem_ld16(lane_base + col0, v);
           tmem_ld_wait();
+          if (tid == 0 && cc == 0) tc_stamp(dbg, h, 10);
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0u;
+          for (int i = 0; i < 16; ++i) v[i] = 0u;
         }
-        if (dbg && blockIdx.x == 0 && h == 0 && 32 * cc < g.Op) {
+        if (dbg && blockIdx.x == 0 && h == 0 && col0 < g.Op) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) dbg[(2 * kTcRows + tid) * 256 + 32 * cc + i] = __uint_as_float(v[i]);
+          for (int i = 0; i < 16; ++i) dbg[(2 * kTcRows + trow) * 256 + col0 + i] = __uint_as_float(v[i]);
         }
-        float y[32];
+        // branch-free: padded table entries are zero, padded outputs are masked by select
+        float y[16], term[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int o = 32 * cc + i;
-          y[i] = 0.f;
-          if (o < O) {
-            y[i] = __fadd_rn(__uint_as_float(v[i]), tab[0 * g.Op + o]);
-            // unnormalize_state: y * std + mean   (data.py:255-257)
-            const float s = __fadd_rn(__fmul_rn(y[i], tab[1 * g.Op + o]), tab[2 * g.Op + o]);
-            st_cost = __fadd_rn(st_cost, smooth_abs_term(s, tab[3 * g.Op + o], tab[4 * g.Op + o], m.alpha, m.alpha2));
-            if (sout) sout[o] = s;
+        for (int i = 0; i < 16; ++i) {
+          const int o = col0 + i;        // o < Op always when col0 < Op; tables are Op long
+          const int oc = o < g.Op ? o : 0;
+          const float raw = __uint_as_float(v[i]);
+          y[i] = o < O ? raw + t_b3[oc] : 0.f;              // normalised prediction == next input
+          const float x = fmaf(raw, t_P[oc], t_Q[oc]);      // (s - goal) * w with s = y*sd + mu
+          term[i] = o < O ? fast_sqrt(fmaf(x, x, m.alpha2)) - m.alpha : 0.f;
+        }
+        st_total += ((term[0] + term[1]) + (term[2] + term[3])) + ((term[4] + term[5]) + (term[6] + term[7])) +
+                    (((term[8] + term[9]) + (term[10] + term[11])) + ((term[12] + term[13]) + (term[14] + term[15])));
+        if (sout) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int o = col0 + i;
+            if (o < O) sout[o] = fmaf(y[i], t_sd[o], t_mu[o]);  // unnormalize_state (data.py:255-257)
           }
         }
         if (h + 1 < H) {
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const int j = 4 * cc + jj;
+          for (int jj = 0; jj < 2; ++jj) {
+            const int j = 4 * cc + 2 * wg + jj;
             if (j < SC) {
               uint4 pk;
               pk.x = pack2<FP16>(y[8 * jj + 0], y[8 * jj + 1]); pk.y = pack2<FP16>(y[8 * jj + 2], y[8 * jj + 3]);
               pk.z = pack2<FP16>(y[8 * jj + 4], y[8 * jj + 5]); pk.w = pack2<FP16>(y[8 * jj + 6], y[8 * jj + 7]);
-              *reinterpret_cast<uint4*>(xnext + (QA + j) * (kTcRows * 16) + tid * 16) = pk;
+              *reinterpret_cast<uint4*>(xnext + (QA + j) * (kTcRows * 16) + trow * 16) = pk;
             }
           }
         }
       }
-      // CoshLoss: beta^2 * mean_a(cosh(a/beta) - 1); row cost pairs s_{h+1} with a_h
-      cost = __fadd_rn(cost, __fadd_rn(st_cost, __fmul_rn(m.beta2, __fdiv_rn(act_cur, (float)A))));
-      act_cur = act_next;
+      if (tid == 0) tc_stamp(dbg, h, 11);
       if (h + 1 < H) {
         fence_proxy_async();   // generic-proxy writes of the input tile -> visible to the MMA
         tc_fence_before();     // our tcgen05.ld of D3 is ordered before the next layer-1 MMA
-        mbar_arrive(bar_x);
+        if (tid == 0) tc_stamp(dbg, h, 14);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_x);
       }
+      if (tid == 0) tc_stamp(dbg, h, 9);
     }
-    if (valid) costs[row] = cost;
+    costp[wg * kTcRows + trow] = st_total;
   }
 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 4) {
+  if (tid < kTcRows) {
+    const long long row = (long long)blockIdx.x * kTcRows + tid;
+    if (row < R) costs[row] = (costp[tid] + costp[kTcRows + tid]) + costp[2 * kTcRows + tid];
+  }
+  if (warp == kTcMmaWarp) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
   }
-}
-
-inline cudaError_t tc_launch_rollout(TcModel* t, const ModelDev& m, const ActionSource& src, const Shape& sh,
-                                     const float* d_s0, float* d_costs, float* d_states, float* d_actions, int num_sms,
-                                     cudaStream_t st) {
-  (void)num_sms;
-  if (!t->ready) return cudaErrorNotReady;
-  const unsigned grid = (unsigned)((sh.rows() + kTcRows - 1) / kTcRows);
-  cudaError_t e;
-  if (t->fp16) {
-    e = cudaFuncSetAttribute(rollout_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, t->g.smem_bytes);
-    if (e != cudaSuccess) return e;
-    rollout_tc_kernel<true><<<grid, kTcThreads, t->g.smem_bytes, st>>>(t->g, t->d_wimg, m, src, sh, d_s0, d_costs, d_states,
-                                                                      d_actions, t->d_dbg);
-  } else {
-    e = cudaFuncSetAttribute(rollout_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, t->g.smem_bytes);
-    if (e != cudaSuccess) return e;
-    rollout_tc_kernel<false><<<grid, kTcThreads, t->g.smem_bytes, st>>>(t->g, t->d_wimg, m, src, sh, d_s0, d_costs, d_states,
-                                                                       d_actions, t->d_dbg);
-  }
-  return cudaGetLastError();
 }
 
 }  // namespace mbrl

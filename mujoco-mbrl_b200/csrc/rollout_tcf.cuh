@@ -1,0 +1,515 @@
+// Fused-recurrence tcgen05 rollout engine (default for MBRL_ENGINE_TC_*; rollout_tc.cuh is
+// the unfused fallback for shapes whose fused operands do not fit shared memory).
+//
+// The reference recurrence per step (src/mbrl/models.py:13-29, 106-110) is
+//     x = [norm(s), norm(a)],  h1 = relu(W1 x + b1),  h2 = relu(W2 h1 + b2),  y = W3 h2 + b3,
+//     s' = unnorm(y),  next x = [y, norm(a')]        (normalise o unnormalise == identity)
+// There is no nonlinearity between layer 3 of step h and layer 1 of step h+1, so
+//     h1' = relu(W1s y + W1a a' + b1) = relu((W1s W3) h2 + W1a a' + (b1 + W1s b3)).
+// The host packs W13 = W1s*W3 (U x U) and b13 = b1 + W1s*b3 once, and every step becomes TWO
+// chained GEMMs on the tensor cores instead of three plus a serial small-GEMM/epilogue chain:
+//     GEMM-A(h+1): D_A[128 x (Np+Oy)] = a'(h+1) . [W1a|b13|0]^T  (SS, 1 K-step, actions + const 1)
+//                                     + h2(h)   . [W13 ; W3]^T   (TS, A operand from TMEM)
+//                  columns [0,Np)      -> pre-activation of h1(h+1)
+//                  columns [Np,Np+Oy)  -> y(h) = W3 h2(h): consumed OFF the critical path by the
+//                                         cost threads (fp32: + b3, un-normalise, SmoothAbs cost)
+//     GEMM-B(h):   D_B[128 x Np] = h1(h) . W2p^T                  (TS)
+// Both hidden epilogues (TMEM fp32 -> relu -> 16 bit -> TMEM, each 32-column chunk packed into the
+// first half of its own columns, so no warp ever overwrites data another warp still has to read)
+// release the next GEMM's
+// K-steps chunk by chunk through mbarriers, so the tensor pipe only idles for the first-chunk
+// latency of each epilogue.  Step 0 uses a state tile (x0 - b3, so that b13 gives exactly b1)
+// with W1s as extra SS K-steps.
+//
+// Warp roles (544 threads, 1 CTA/SM): warps 0-7 hidden epilogues (two warpgroups, even/odd
+// 32-column chunks); warps 8-11 cost epilogue, one thread per candidate row (fp32: y + b3,
+// un-normalise, SmoothAbs); warps 12-15 action sampler, one thread per row (Philox + Box-Muller
+// + clip, one step ahead, Cosh cost); warp 16 one thread: weight TMA + all tcgen05.mma issue.
+// The per-element epilogue math is written branch-free (zero-padded tables and masks): per-element
+// branches serialise the load -> fma -> sqrt chains and cost ~10x (measured).
+#pragma once
+#include <cstdlib>
+
+#include "rollout_tc.cuh"
+
+namespace mbrl {
+
+struct TcfGeom {
+  int O, A, U;
+  int Ka;  // action K-range (multiple of 16): A actions, constant 1, zero pad
+  int Ks;  // state K-range of the step-0 tile (multiple of 16)
+  int Np;  // padded hidden width (multiple of 16, > U)
+  int Oy;  // y columns (multiple of 16)
+  int Na;  // Np + Oy: N of GEMM-A
+  int wa_off, waa_off, w1s_off, w2_off, w_bytes;
+  int tab_off, xs_off, xa_off, bar_off, smem_bytes;
+};
+
+constexpr int kTcfBarriers = 5 + 2 * kTcMaxChunks;  // w, xa, dA, dB, y, hA[8], hB[8]
+constexpr int kTcfCostWarp0 = 8;    // warps 8-11: cost epilogue (TMEM lane quarter = warp - 8)
+constexpr int kTcfSampWarp0 = 12;   // warps 12-15: action sampler
+constexpr int kTcfMmaWarp = 16;     // warp 16: TMEM alloc, weight TMA, MMA issue
+constexpr int kTcfThreads = 17 * 32;
+
+inline bool tcf_geometry(int O, int A, int U, size_t max_smem, TcfGeom* g, std::string* why) {
+  g->O = O; g->A = A; g->U = U;
+  g->Ka = round_up(A + 1, 16);
+  g->Ks = round_up(O, 16);
+  g->Np = round_up(U + 1, 16);
+  g->Oy = round_up(O, 16);
+  g->Na = g->Np + g->Oy;
+  if (g->Na > 256) { *why = "hidden + obs too wide for the fused GEMM (N > 256)"; return false; }
+  g->wa_off = 0;
+  g->waa_off = g->wa_off + g->Np * g->Na * 2;
+  g->w1s_off = g->waa_off + g->Ka * g->Na * 2;
+  g->w2_off = g->w1s_off + g->Ks * g->Np * 2;
+  g->w_bytes = g->w2_off + g->Np * g->Np * 2;
+  g->tab_off = g->w_bytes;  // fp32: 6 tables of Oy, 2 of kMaxAct, 2 x 128 cost partials
+  g->xs_off = round_up(g->tab_off + (6 * g->Oy + 2 * kMaxAct + 2 * kTcRows) * 4, 128);
+  g->xa_off = g->xs_off + g->Ks * kTcRows * 2;
+  g->bar_off = g->xa_off + 2 * g->Ka * kTcRows * 2;
+  g->smem_bytes = g->bar_off + 8 * kTcfBarriers + 16;
+  if ((size_t)g->smem_bytes > max_smem) { *why = "fused operands do not fit shared memory"; return false; }
+  return true;
+}
+
+// Packs [W13;W3], [W1a|b13], W1s, W2p as 16-bit canonical K-major operands (see tc_put).
+inline void tcf_pack(const TcfGeom& g, bool fp16, const float* W1, const float* b1, const float* W2, const float* b2,
+                     const float* W3, const float* b3, std::vector<uint16_t>* out) {
+  const int O = g.O, A = g.A, U = g.U, D = O + A;
+  std::vector<uint16_t>& img = *out;
+  img.assign((size_t)g.w_bytes / 2, 0);
+  std::vector<double> w13((size_t)U * U), b13(U);
+  for (int n = 0; n < U; ++n) {
+    double b = b1[n];
+    for (int o = 0; o < O; ++o) b += (double)W1[(size_t)n * D + o] * b3[o];
+    b13[n] = b;
+    for (int k = 0; k < U; ++k) {
+      double acc = 0.0;
+      for (int o = 0; o < O; ++o) acc += (double)W1[(size_t)n * D + o] * W3[(size_t)o * U + k];
+      w13[(size_t)n * U + k] = acc;
+    }
+  }
+  for (int n = 0; n < U; ++n)
+    for (int k = 0; k < U; ++k) tc_put(img, g.wa_off, g.Na, n, k, (float)w13[(size_t)n * U + k], fp16);
+  for (int o = 0; o < O; ++o)
+    for (int k = 0; k < U; ++k) tc_put(img, g.wa_off, g.Na, g.Np + o, k, W3[(size_t)o * U + k], fp16);
+  for (int n = 0; n < U; ++n) {
+    for (int a = 0; a < A; ++a) tc_put(img, g.waa_off, g.Na, n, a, W1[(size_t)n * D + O + a], fp16);
+    tc_put(img, g.waa_off, g.Na, n, A, (float)b13[n], fp16);
+  }
+  tc_put(img, g.waa_off, g.Na, U, A, 1.0f, fp16);  // hidden unit U == relu(1) == 1 carries b2
+  for (int n = 0; n < U; ++n)
+    for (int o = 0; o < O; ++o) tc_put(img, g.w1s_off, g.Np, n, o, W1[(size_t)n * D + o], fp16);
+  for (int n = 0; n < U; ++n) {
+    for (int k = 0; k < U; ++k) tc_put(img, g.w2_off, g.Np, n, k, W2[(size_t)n * U + k], fp16);
+    tc_put(img, g.w2_off, g.Np, n, U, b2[n], fp16);
+  }
+}
+
+template <bool FP16>
+__global__ void __launch_bounds__(kTcfThreads, 1)
+rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, ActionSource src, Shape sh,
+                   const float* __restrict__ s0, float* __restrict__ costs, float* __restrict__ states_out,
+                   float* __restrict__ actions_out, float* __restrict__ dbg) {
+  extern __shared__ __align__(128) uint8_t tcf_smem[];
+  uint8_t* const smem = tcf_smem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int O = g.O, A = g.A, H = sh.H;
+  const int NC = (g.Np + 31) >> 5;   // hidden epilogue chunks (32 columns, last may be 16)
+  const int KS_H = g.Np >> 4;        // K-steps over a hidden operand
+  const int KS_A = g.Ka >> 4, KS_S = g.Ks >> 4;
+
+  float* tab = reinterpret_cast<float*>(smem + g.tab_off);
+  float *t_b3 = tab, *t_P = tab + g.Oy, *t_Q = tab + 2 * g.Oy, *t_sd = tab + 3 * g.Oy, *t_mu = tab + 4 * g.Oy;
+  float *t_M = tab + 5 * g.Oy;  // 1 for real outputs, 0 for padding
+  float *t_ainv = tab + 6 * g.Oy, *t_aoff = t_ainv + kMaxAct, *costp = t_aoff + kMaxAct;
+  uint8_t* xs = smem + g.xs_off;
+  uint8_t* xa = smem + g.xa_off;
+  const int xa_bytes = g.Ka * kTcRows * 2;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.bar_off);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + g.bar_off + 8 * kTcfBarriers);
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t bar_w = bar0, bar_xa = bar0 + 8, bar_dA = bar0 + 16, bar_dB = bar0 + 24, bar_y = bar0 + 32;
+  const uint32_t bar_hA = bar0 + 40, bar_hB = bar0 + 40 + 8 * kTcMaxChunks;
+
+  if (warp == kTcfMmaWarp) {
+    if (lane == 0) {
+      mbar_init(bar_w, 1); mbar_init(bar_xa, 1); mbar_init(bar_dA, 1); mbar_init(bar_dB, 1); mbar_init(bar_y, 1);
+      for (int c = 0; c < kTcMaxChunks; ++c) { mbar_init(bar_hA + 8 * c, 4); mbar_init(bar_hB + 8 * c, 4); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = tid; i < g.Oy; i += kTcfThreads) {
+    const bool in = i < O;
+    t_M[i] = in ? 1.f : 0.f;
+    const float b3 = in ? __ldg(m.b3 + i) : 0.f, sd = in ? __ldg(m.sd_s + i) : 1.f, mu = in ? __ldg(m.mu_s + i) : 0.f;
+    const float w = in ? __ldg(m.cost_w + i) : 0.f, goal = in ? __ldg(m.goal + i) : 0.f;
+    t_b3[i] = b3; t_sd[i] = sd; t_mu[i] = mu;
+    t_P[i] = sd * w;
+    t_Q[i] = (b3 * sd + mu - goal) * w;
+  }
+  for (int i = tid; i < kMaxAct; i += kTcfThreads) {
+    // normalised action = a * inv - off; the constant-1 column (i == A) is 0 * 0 - (-1)
+    const float inv = i < A ? 1.0f / __ldg(m.sd_a + i) : 0.f;
+    t_ainv[i] = inv;
+    t_aoff[i] = i < A ? __ldg(m.mu_a + i) * inv : (i == A ? -1.f : 0.f);
+  }
+  // zero the action tiles once: chunks beyond the sampled ones stay zero for the whole rollout
+  for (int i = tid; i < 2 * xa_bytes / 16; i += kTcfThreads) reinterpret_cast<uint4*>(xa)[i] = make_uint4(0, 0, 0, 0);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const long long R = sh.rows();
+
+  if (warp == kTcfMmaWarp) {
+    // ================= MMA issuer (one thread) =================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_w, (uint32_t)g.w_bytes);
+      bulk_g2s(smem_u32(smem), wimg, (uint32_t)g.w_bytes, bar_w);
+      const uint32_t idesc_a = umma_idesc(g.Na, FP16), idesc_h = umma_idesc(g.Np, FP16), idesc_y = umma_idesc(g.Oy, FP16);
+      const uint32_t lbo_a = (uint32_t)g.Na * 16, lbo_h = (uint32_t)g.Np * 16, lbo_x = kTcRows * 16;
+      const uint64_t d_wa = umma_desc(smem_u32(smem + g.wa_off), lbo_a, 128);
+      const uint64_t d_wy = umma_desc(smem_u32(smem + g.wa_off) + (uint32_t)g.Np * 16, lbo_a, 128);  // rows Np.. of [W13;W3]
+      const uint64_t d_waa = umma_desc(smem_u32(smem + g.waa_off), lbo_a, 128);
+      const uint64_t d_w1s = umma_desc(smem_u32(smem + g.w1s_off), lbo_h, 128);
+      const uint64_t d_w2 = umma_desc(smem_u32(smem + g.w2_off), lbo_h, 128);
+      const uint64_t d_xs = umma_desc(smem_u32(xs), lbo_x, 128);
+      const uint64_t d_xa0 = umma_desc(smem_u32(xa), lbo_x, 128), d_xa1 = umma_desc(smem_u32(xa + xa_bytes), lbo_x, 128);
+      const uint64_t step_a = (2 * lbo_a) >> 4, step_h = (2 * lbo_h) >> 4, step_x = (2 * lbo_x) >> 4;
+      const uint32_t tm_a = tmem, tm_b = tmem + kTcD2Col;
+      mbar_wait(bar_w, 0);
+
+      // ---- step 0: D_A = a(0).[W1a|b13]^T + (x0 - b3).W1s^T ----
+      mbar_wait(bar_xa, 0);
+      tc_fence_after();
+      {
+        uint64_t ad = d_xa0, bd = d_waa;
+        mma_ss(tm_a, ad, bd, idesc_a, 0);
+        for (int ks = 1; ks < KS_A; ++ks) { ad += step_x; bd += step_a; mma_ss(tm_a, ad, bd, idesc_a, 1); }
+        ad = d_xs; bd = d_w1s;
+        for (int ks = 0; ks < KS_S; ++ks) { mma_ss(tm_a, ad, bd, idesc_h, 1); ad += step_x; bd += step_h; }
+      }
+      tc_commit(bar_dA);
+
+      for (int h = 0; h < H; ++h) {
+        const uint32_t ph = h & 1;
+        tc_stamp(dbg, h, 0);
+        // ---- GEMM-B(h): D_B = h1(h) . W2p^T, K-steps released by epilogue A ----
+        {
+          // packed chunk c of h1 lives in the first half of its own 32 fp32 columns:
+          // K-step 2c at column 32c, K-step 2c+1 at column 32c+8
+          uint64_t bd = d_w2;
+          uint32_t a = tm_a, acc = 0;
+          int left = KS_H;
+          for (int c = 0; c < NC; ++c) {
+            mbar_wait(bar_hA + 8 * c, ph);
+            tc_fence_after();
+            mma_ts(tm_b, a, bd, idesc_h, acc);
+            acc = 1; bd += step_h;
+            if (left > 1) { mma_ts(tm_b, a + 8, bd, idesc_h, 1); bd += step_h; }
+            a += 32; left -= 2;
+          }
+        }
+        tc_commit(bar_dB);
+        tc_stamp(dbg, h, 1);
+        // ---- GEMM-A(h+1) (or, after the last step, only the y columns) ----
+        const bool last = h + 1 == H;
+        if (h >= 1) { mbar_wait(bar_y, (h - 1) & 1); }  // y(h-1) in D_A has been consumed
+        uint32_t acc = 0;
+        if (!last) {
+          mbar_wait(bar_xa, (h + 1) & 1);
+          tc_fence_after();
+          uint64_t ad = ((h + 1) & 1) ? d_xa1 : d_xa0, bd = d_waa;
+          for (int ks = 0; ks < KS_A; ++ks) { mma_ss(tm_a, ad, bd, idesc_a, acc); acc = 1; ad += step_x; bd += step_a; }
+        }
+        {
+          uint64_t bd = last ? d_wy : d_wa;
+          const uint32_t d = last ? tm_a + (uint32_t)g.Np : tm_a;
+          const uint32_t idesc = last ? idesc_y : idesc_a;
+          uint32_t a = tm_b;
+          int left = KS_H;
+          for (int c = 0; c < NC; ++c) {
+            mbar_wait(bar_hB + 8 * c, ph);
+            tc_fence_after();
+            mma_ts(d, a, bd, idesc, acc);
+            acc = 1; bd += step_a;
+            if (left > 1) { mma_ts(d, a + 8, bd, idesc, 1); bd += step_a; }
+            a += 32; left -= 2;
+          }
+        }
+        tc_commit(bar_dA);
+        tc_stamp(dbg, h, 2);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= kTcfSampWarp0) {
+    // ================= sampler threads (one per row) =================
+    const int srow = tid - kTcfSampWarp0 * 32;
+    const long long row = (long long)blockIdx.x * kTcRows + srow;
+    const bool valid = row < R;
+    const int env_l = valid ? (int)(row / sh.N) : 0;
+    const int cand_l = valid ? (int)(row - (long long)env_l * sh.N) : 0;
+    const float inv_beta = 1.0f / m.beta, cscale = valid ? m.beta2 / (float)A : 0.f;
+    const int QA = (A + 8) >> 3;  // 8-wide chunks holding the actions and the constant 1
+    float act_total = 0.f;
+
+    auto stage_actions = [&](int hs) {
+      float acc = 0.f;
+      float* aout = (actions_out && valid) ? actions_out + ((long long)hs * R + row) * A : nullptr;
+      uint8_t* xt = xa + (hs & 1) * xa_bytes;
+      for (int q = 0; q < QA; ++q) {
+        float v[8];
+        {
+          float t4[4], u4[4];
+          raw_action4(src, A, H, hs, env_l, cand_l, row, R, 2 * q, t4);
+          if (8 * q + 4 < A) raw_action4(src, A, H, hs, env_l, cand_l, row, R, 2 * q + 1, u4);
+          else { u4[0] = u4[1] = u4[2] = u4[3] = 0.f; }
+          v[0] = t4[0]; v[1] = t4[1]; v[2] = t4[2]; v[3] = t4[3];
+          v[4] = u4[0]; v[5] = u4[1]; v[6] = u4[2]; v[7] = u4[3];
+        }
+        // branch-free: raw_action4 returns 0 beyond A (cosh(0) - 1 == 0), tables are zero-padded
+        float xn[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc += cosh_m1_fast(v[i] * inv_beta);
+          xn[i] = fmaf(v[i], t_ainv[8 * q + i], -t_aoff[8 * q + i]);
+        }
+        if (aout) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (8 * q + i < A) aout[8 * q + i] = v[i];
+        }
+        uint4 pk;
+        pk.x = pack2<FP16>(xn[0], xn[1]); pk.y = pack2<FP16>(xn[2], xn[3]);
+        pk.z = pack2<FP16>(xn[4], xn[5]); pk.w = pack2<FP16>(xn[6], xn[7]);
+        *reinterpret_cast<uint4*>(xt + q * (kTcRows * 16) + srow * 16) = pk;
+      }
+      act_total = fmaf(cscale, acc, act_total);  // CoshLoss: beta^2 * mean_a(cosh(a/beta) - 1)
+    };
+
+    // step-0 tiles: actions(0) and the state tile x0 - b3 (so that b13 reduces to b1)
+    for (int j = 0; j < (g.Ks >> 3); ++j) {
+      float xn[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int o = 8 * j + i;
+        xn[i] = (o < O && valid) ? (__ldg(s0 + (long long)env_l * O + o) - t_mu[o]) / t_sd[o] - t_b3[o] : 0.f;
+      }
+      uint4 pk;
+      pk.x = pack2<FP16>(xn[0], xn[1]); pk.y = pack2<FP16>(xn[2], xn[3]);
+      pk.z = pack2<FP16>(xn[4], xn[5]); pk.w = pack2<FP16>(xn[6], xn[7]);
+      *reinterpret_cast<uint4*>(xs + j * (kTcRows * 16) + srow * 16) = pk;
+    }
+    stage_actions(0);
+    fence_proxy_async();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (srow == 0) mbar_arrive(bar_xa);
+    for (int hs = 1; hs < H; ++hs) {
+      // D_A(hs-1) complete: the MMA thread is past its wait on x-ready #(hs-1) (never two phases
+      // ahead) and GEMM-A(hs-2), the last reader of tile hs&1, has finished
+      mbar_wait(bar_dA, (hs - 1) & 1);
+      if (srow == 0) tc_stamp(dbg, hs - 1, 12);
+      stage_actions(hs);
+      fence_proxy_async();   // generic-proxy tile writes -> visible to the MMA (async proxy)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (srow == 0) { mbar_arrive(bar_xa); tc_stamp(dbg, hs - 1, 13); }
+    }
+    costp[kTcRows + srow] = act_total;
+  } else if (warp >= kTcfCostWarp0) {
+    // ================= cost threads (one per row) =================
+    const int crow = tid - kTcfCostWarp0 * 32;
+    const long long row = (long long)blockIdx.x * kTcRows + crow;
+    const bool valid = row < R;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp - kTcfCostWarp0) * 32) << 16);
+    float st_total = 0.f;
+    // Phases must be observed in order: a parity wait on phase #1 issued before phase #0 has
+    // completed would fall through at once (it cannot tell "not yet" from "one phase ago").
+    mbar_wait(bar_dA, 0);
+    for (int j = 1; j <= H; ++j) {
+      // D_A(j) carries y(j-1) = W3 h2(j-1) in columns [Np, Np+Oy)  (j == H: the y-only GEMM)
+      mbar_wait(bar_dA, j & 1);
+      tc_fence_after();
+      if (crow == 0) tc_stamp(dbg, j - 1, 14);
+      float* sout = (states_out && valid) ? states_out + ((long long)(j - 1) * R + row) * O : nullptr;
+#pragma unroll 1
+      for (int cc = 0; cc < (g.Oy >> 4); ++cc) {
+        uint32_t v[32];
+        tmem_ld16(lane_base + (uint32_t)(g.Np + 16 * cc), v);
+        tmem_ld_wait();
+        if (dbg && blockIdx.x == 0 && j == 1) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) dbg[(2 * kTcRows + crow) * 256 + 16 * cc + i] = __uint_as_float(v[i]);
+        }
+        float term[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int o = 16 * cc + i;  // < Oy: tables are Oy long; padded entries are zero / masked
+          const float x = fmaf(__uint_as_float(v[i]), t_P[o], t_Q[o]);  // (s - goal) * w, s = (y_raw + b3)*sd + mu
+          term[i] = (fast_sqrt(fmaf(x, x, m.alpha2)) - m.alpha) * t_M[o];
+        }
+        st_total += ((term[0] + term[1]) + (term[2] + term[3])) + ((term[4] + term[5]) + (term[6] + term[7])) +
+                    (((term[8] + term[9]) + (term[10] + term[11])) + ((term[12] + term[13]) + (term[14] + term[15])));
+        if (sout) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int o = 16 * cc + i;
+            // unnormalize_state: y * std + mean   (data.py:255-257)
+            if (o < O) sout[o] = fmaf(__uint_as_float(v[i]) + t_b3[o], t_sd[o], t_mu[o]);
+          }
+        }
+      }
+      if (j < H) {
+        tc_fence_before();  // our tcgen05.ld of y is ordered before GEMM-A(j+1) overwrites it
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (crow == 0) { mbar_arrive(bar_y); tc_stamp(dbg, j - 1, 15); }  // completion #(j-1)
+      }
+    }
+    costp[crow] = valid ? st_total : 0.f;
+  } else {
+    // ================= hidden-epilogue threads =================
+    const int wg = warp >> 2, quarter = warp & 3;
+    const int trow = quarter * 32 + lane;
+    const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
+    for (int h = 0; h < H; ++h) {
+      const uint32_t ph = h & 1;
+#pragma unroll 1
+      for (int layer = 0; layer < 2; ++layer) {
+        const uint32_t dcol = layer == 0 ? 0u : (uint32_t)kTcD2Col;
+        mbar_wait(layer == 0 ? bar_dA : bar_dB, ph);
+        tc_fence_after();
+        if (tid == 0) tc_stamp(dbg, h, 4 + 2 * layer);
+        const uint32_t bar_rel = layer == 0 ? bar_hA : bar_hB;
+        // first round: one chunk per warpgroup (fast first release), then two chunks in flight
+        bool first = true;
+#pragma unroll 1
+        for (int c = wg; c < NC;) {
+          const int c2 = c + 2;
+          const bool has2 = !first && c2 < NC;
+          const bool full = 32 * c + 32 <= g.Np, full2 = has2 && 32 * c2 + 32 <= g.Np;
+          uint32_t v[32], v2[32], pk[16];
+          if (full) tmem_ld32(lane_base + dcol + 32 * c, v);
+          else tmem_ld16(lane_base + dcol + 32 * c, v);
+          if (has2) {
+            if (full2) tmem_ld32(lane_base + dcol + 32 * c2, v2);
+            else tmem_ld16(lane_base + dcol + 32 * c2, v2);
+          }
+          tmem_ld_wait();
+          if (dbg && blockIdx.x == 0 && h == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (full || i < 16) dbg[(layer * kTcRows + trow) * 256 + 32 * c + i] = __uint_as_float(v[i]);
+              if (has2 && (full2 || i < 16)) dbg[(layer * kTcRows + trow) * 256 + 32 * c2 + i] = __uint_as_float(v2[i]);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = pack_relu<FP16>(v[2 * i], v[2 * i + 1]);
+          if (full) tmem_st16(lane_base + dcol + 32 * c, pk);
+          else tmem_st8(lane_base + dcol + 32 * c, pk);
+          if (has2) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[i] = pack_relu<FP16>(v2[2 * i], v2[2 * i + 1]);
+            if (full2) tmem_st16(lane_base + dcol + 32 * c2, pk);
+            else tmem_st8(lane_base + dcol + 32 * c2, pk);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(bar_rel + 8 * c);
+            if (has2) mbar_arrive(bar_rel + 8 * c2);
+          }
+          c += first ? 2 : 4;
+          first = false;
+        }
+        if (tid == 0) tc_stamp(dbg, h, 5 + 2 * layer);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid < kTcRows) {
+    const long long row = (long long)blockIdx.x * kTcRows + tid;
+    if (row < R) costs[row] = costp[tid] + costp[kTcRows + tid];
+  }
+  if (warp == kTcfMmaWarp) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
+}
+
+// ---- host side of the tensor-core engines ---------------------------------------------------
+struct TcModel {
+  int ready = 0;
+  bool fp16 = true;
+  bool fused = true;   // rollout_tcf_kernel; false -> rollout_tc_kernel (unfused fallback)
+  TcGeom g{};
+  TcfGeom fg{};
+  int w_bytes = 0;
+  uint8_t* d_wimg = nullptr;
+  float* d_dbg = nullptr;  // optional accumulator dump + timeline (tests / profiling)
+};
+
+inline bool tc_init(TcModel* t, int O, int A, int U, bool fp16, size_t max_smem, std::string* why) {
+  t->fp16 = fp16;
+  const char* force = getenv("MBRL_TC_UNFUSED");
+  std::string why_f;
+  t->fused = !(force && force[0] == '1') && tcf_geometry(O, A, U, max_smem, &t->fg, &why_f);
+  if (!t->fused && !tc_geometry(O, A, U, max_smem, &t->g, why)) {
+    if (!why_f.empty()) *why += "; fused: " + why_f;
+    return false;
+  }
+  t->w_bytes = t->fused ? t->fg.w_bytes : t->g.w_bytes;
+  if (cudaMalloc((void**)&t->d_wimg, t->w_bytes) != cudaSuccess) { *why = "cudaMalloc failed"; return false; }
+  t->ready = 1;
+  return true;
+}
+
+inline void tc_free(TcModel* t) {
+  if (t->d_wimg) cudaFree(t->d_wimg);
+  if (t->d_dbg) cudaFree(t->d_dbg);
+  t->d_wimg = nullptr; t->d_dbg = nullptr; t->ready = 0;
+}
+
+inline bool tc_set_weights(TcModel* t, const float* W1, const float* b1, const float* W2, const float* b2,
+                           const float* W3, const float* b3, std::string* why) {
+  std::vector<uint16_t> img;
+  if (t->fused) tcf_pack(t->fg, t->fp16, W1, b1, W2, b2, W3, b3, &img);
+  else tc_pack(t->g, t->fp16, W1, b1, W2, b2, W3, &img);  // b3 is added in fp32 in the last epilogue
+  if (cudaMemcpy(t->d_wimg, img.data(), t->w_bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+    *why = "cudaMemcpy of packed operands failed";
+    return false;
+  }
+  return true;
+}
+
+template <class Kern, class Geom>
+inline cudaError_t tc_launch_one(Kern kern, const Geom& g, int smem_bytes, int threads, TcModel* t, const ModelDev& m,
+                                 const ActionSource& src, const Shape& sh, const float* d_s0, float* d_costs,
+                                 float* d_states, float* d_actions, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (e != cudaSuccess) return e;
+  const unsigned grid = (unsigned)((sh.rows() + kTcRows - 1) / kTcRows);
+  kern<<<grid, threads, smem_bytes, st>>>(g, t->d_wimg, m, src, sh, d_s0, d_costs, d_states, d_actions, t->d_dbg);
+  return cudaGetLastError();
+}
+
+inline cudaError_t tc_launch_rollout(TcModel* t, const ModelDev& m, const ActionSource& src, const Shape& sh,
+                                     const float* d_s0, float* d_costs, float* d_states, float* d_actions, int num_sms,
+                                     cudaStream_t st) {
+  (void)num_sms;
+  if (!t->ready) return cudaErrorNotReady;
+  if (t->fused) {
+    if (t->fp16) return tc_launch_one(rollout_tcf_kernel<true>, t->fg, t->fg.smem_bytes, kTcfThreads, t, m, src, sh, d_s0, d_costs, d_states, d_actions, st);
+    return tc_launch_one(rollout_tcf_kernel<false>, t->fg, t->fg.smem_bytes, kTcfThreads, t, m, src, sh, d_s0, d_costs, d_states, d_actions, st);
+  }
+  if (t->fp16) return tc_launch_one(rollout_tc_kernel<true>, t->g, t->g.smem_bytes, kTcThreads, t, m, src, sh, d_s0, d_costs, d_states, d_actions, st);
+  return tc_launch_one(rollout_tc_kernel<false>, t->g, t->g.smem_bytes, kTcThreads, t, m, src, sh, d_s0, d_costs, d_states, d_actions, st);
+}
+
+}  // namespace mbrl

@@ -28,19 +28,31 @@ struct BestEver {  // per environment, device resident
   int pad;
 };
 
-// One CTA per segment (environment).  4 radix passes of 8 bits find the k-th smallest key
-// T and the number of keys strictly below it; a final index-ordered compaction emits every
-// key < T plus the first (k - count_less) keys == T.  Warp-shuffle/ballot scans, shared
-// memory only for the 256-bin histogram and per-warp carries.
+// One CTA per segment (environment).  The float costs are mapped to monotone uint32 keys and
+// staged once in shared memory (coalesced, loads in flight together) while the block min/max is
+// reduced.  The k-th smallest key T is then found by an ADAPTIVE radix select: every round
+// histograms the keys that are still in range into 1024 equal-width buckets of the CURRENT key
+// range [lo, hi] (so the candidates spread over the bins instead of piling onto the few leading
+// bit patterns that the costs of one population share), a block scan locates the bucket holding
+// the k-th key, and the range shrinks 1024x; it ends when the bucket width is 1 (<= 4 rounds).
+// A final index-ordered compaction (ballot + warp-shuffle scans) emits every key < T plus the
+// first `take_eq` keys == T.
 //   best (nullable):      (min cost, ., argmin) of this launch per segment
 //   best_ever (nullable): updated when this launch's minimum is strictly smaller
 //                         (earlier iteration wins ties)
+// STAGED=false re-reads the costs from global memory (segments too long for shared memory).
+constexpr int kSelectStageMax = 49152;  // keys staged in shared memory: 192 KB
+constexpr int kSelectBins = 1024;
+
+template <bool STAGED>
 __global__ void __launch_bounds__(kSelectThreads)
 topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restrict__ elite_idx,
                    float* __restrict__ elite_cost, MbrlPlanInfo* __restrict__ best,
                    BestEver* __restrict__ best_ever, int iteration) {
-  __shared__ uint32_t hist[256];
-  __shared__ uint32_t s_prefix, s_mask, s_remaining;
+  extern __shared__ __align__(16) uint32_t sel_smem[];
+  uint32_t* keys = sel_smem;  // [n] when STAGED
+  __shared__ uint32_t hist[kSelectBins];
+  __shared__ uint32_t s_lo, s_hi, s_remaining;
   __shared__ uint32_t warp_less[32], warp_eq[32];
   __shared__ unsigned long long warp_min[32];
   __shared__ uint32_t s_base_less, s_base_eq;
@@ -48,76 +60,92 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
   const int seg = blockIdx.x;
   const float* c = costs + (long long)seg * n;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  auto key_at = [&](int i) -> uint32_t { return STAGED ? keys[i] : cost_key(__ldg(c + i)); };
 
-  if (t == 0) { s_prefix = 0; s_mask = 0; s_remaining = (uint32_t)k; }
-
-  // ---- radix select, MSB first ----
-  for (int pass = 0; pass < 4; ++pass) {
-    const int shift = 24 - 8 * pass;
-    if (t < 256) hist[t] = 0;
-    __syncthreads();
-    const uint32_t prefix = s_prefix, mask = s_mask;
-    for (int base = 0; base < n; base += kSelectThreads) {  // warp-uniform trip count
-      const int i = base + t;
-      uint32_t key = 0, bin = 0;
-      bool in = false;
-      if (i < n) {
-        key = cost_key(__ldg(c + i));
-        in = (key & mask) == prefix;
-        bin = (key >> shift) & 0xFFu;
-      }
-      // warp-aggregated histogram update: one shared-memory atomic per distinct bin
-      const unsigned active = __ballot_sync(0xFFFFFFFFu, in);
-      if (in) {
-        const unsigned peers = __match_any_sync(active, bin);
-        if (lane == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
-      }
-      __syncwarp();
+  // ---- stage + min/max ----
+  uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
+#pragma unroll 8
+  for (int i = t; i < n; i += kSelectThreads) {
+    const uint32_t key = cost_key(__ldg(c + i));
+    if (STAGED) keys[i] = key;
+    kmin = min(kmin, key);
+    kmax = max(kmax, key);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    kmin = min(kmin, __shfl_xor_sync(0xFFFFFFFFu, kmin, d));
+    kmax = max(kmax, __shfl_xor_sync(0xFFFFFFFFu, kmax, d));
+  }
+  if (lane == 0) { warp_less[warp] = kmin; warp_eq[warp] = kmax; }
+  __syncthreads();
+  if (warp == 0) {
+    kmin = warp_less[lane]; kmax = warp_eq[lane];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      kmin = min(kmin, __shfl_xor_sync(0xFFFFFFFFu, kmin, d));
+      kmax = max(kmax, __shfl_xor_sync(0xFFFFFFFFu, kmax, d));
     }
+    if (lane == 0) { s_lo = kmin; s_hi = kmax; s_remaining = (uint32_t)k; s_base_less = 0; s_base_eq = 0; }
+  }
+  __syncthreads();
+
+  // ---- adaptive radix select ----
+  for (int round = 0; round < 5; ++round) {
+    const uint32_t lo = s_lo, hi = s_hi, rem = s_remaining;
+    const uint32_t width = (uint32_t)(((unsigned long long)(hi - lo)) / kSelectBins) + 1u;  // bucket width
+    hist[t] = 0;
+    __syncthreads();
+#pragma unroll 4
+    for (int i = t; i < n; i += kSelectThreads) {
+      const uint32_t key = key_at(i);
+      if (key >= lo && key <= hi) atomicAdd(&hist[(key - lo) / width], 1u);
+    }
+    __syncthreads();
+    // block-wide inclusive scan of the 1024 bins (one bin per thread)
+    const uint32_t mine = hist[t];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    if (lane == 31) warp_less[warp] = incl;
     __syncthreads();
     if (warp == 0) {
-      // 8 bins per lane, exclusive scan across the warp, locate the bin holding the
-      // remaining-th smallest
-      uint32_t local[8], sum = 0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { local[j] = hist[lane * 8 + j]; sum += local[j]; }
-      uint32_t incl = sum;
+      const uint32_t tot = warp_less[lane];
+      uint32_t wi = tot;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-        if (lane >= d) incl += v;
+        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+        if (lane >= d) wi += v;
       }
-      uint32_t run = incl - sum;
-      const uint32_t rem = s_remaining;
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (rem > run && rem <= run + local[j]) {
-          s_prefix = prefix | ((uint32_t)(lane * 8 + j) << shift);
-          s_mask = mask | (0xFFu << shift);
-          s_remaining = rem - run;  // rank inside the chosen bin
-        }
-        run += local[j];
-      }
+      warp_eq[lane] = wi - tot;  // exclusive prefix of the warp totals
     }
     __syncthreads();
+    incl += warp_eq[warp];
+    const uint32_t excl = incl - mine;
+    if (rem > excl && rem <= incl) {  // exactly one bin holds the rem-th smallest in-range key
+      const uint32_t nlo = lo + (uint32_t)t * width;
+      const unsigned long long nhi = (unsigned long long)nlo + width - 1ull;
+      s_lo = nlo;
+      s_hi = nhi < (unsigned long long)hi ? (uint32_t)nhi : hi;
+      s_remaining = rem - excl;
+    }
+    __syncthreads();
+    if (width == 1u) break;  // uniform: the bucket is a single key value
   }
-  const uint32_t T = s_prefix;         // k-th smallest key
+  const uint32_t T = s_lo;               // k-th smallest key
   const uint32_t take_eq = s_remaining;  // how many keys == T belong to the elite set
-  if (t == 0) { s_base_less = 0; s_base_eq = 0; }
-  __syncthreads();
 
   // ---- index-ordered compaction + argmin ----
   unsigned long long my_min = ~0ull;
   const int rounds = (n + kSelectThreads - 1) / kSelectThreads;
   for (int r = 0; r < rounds; ++r) {
     const int i = r * kSelectThreads + t;
-    float cv = 0.f;
     uint32_t key = 0xFFFFFFFFu;
     bool less = false, eq = false;
     if (i < n) {
-      cv = __ldg(c + i);
-      key = cost_key(cv);
+      key = key_at(i);
       less = key < T;
       eq = key == T;
       const unsigned long long packed = ((unsigned long long)key << 32) | (uint32_t)i;
@@ -127,22 +155,30 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
     const unsigned lt_mask = (1u << lane) - 1u;
     if (lane == 0) { warp_less[warp] = __popc(bl); warp_eq[warp] = __popc(be); }
     __syncthreads();
-    uint32_t less_before = s_base_less, eq_before = s_base_eq;
-    for (int w = 0; w < warp; ++w) { less_before += warp_less[w]; eq_before += warp_eq[w]; }
-    less_before += __popc(bl & lt_mask);
-    eq_before += __popc(be & lt_mask);
-    const bool sel = less || (eq && eq_before < take_eq);
-    if (sel) {
+    if (warp == 0) {
+      // exclusive scan of the 32 per-warp counts; carry the running base across rounds
+      const uint32_t cl = warp_less[lane], ce = warp_eq[lane];
+      uint32_t il = cl, ie = ce;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t vl = __shfl_up_sync(0xFFFFFFFFu, il, d), ve = __shfl_up_sync(0xFFFFFFFFu, ie, d);
+        if (lane >= d) { il += vl; ie += ve; }
+      }
+      const uint32_t bl0 = s_base_less, be0 = s_base_eq;
+      __syncwarp();
+      warp_less[lane] = bl0 + il - cl;
+      warp_eq[lane] = be0 + ie - ce;
+      if (lane == 31) { s_base_less = bl0 + il; s_base_eq = be0 + ie; }
+    }
+    __syncthreads();
+    const uint32_t less_before = warp_less[warp] + __popc(bl & lt_mask);
+    const uint32_t eq_before = warp_eq[warp] + __popc(be & lt_mask);
+    if (less || (eq && eq_before < take_eq)) {
       const uint32_t pos = less_before + (eq_before < take_eq ? eq_before : take_eq);
       elite_idx[(long long)seg * k + pos] = i;
-      if (elite_cost) elite_cost[(long long)seg * k + pos] = cv;
+      if (elite_cost) elite_cost[(long long)seg * k + pos] = __ldg(c + i);
     }
-    __syncthreads();
-    if (t == kSelectThreads - 1) {
-      s_base_less = less_before + (less ? 1u : 0u);
-      s_base_eq = eq_before + (eq ? 1u : 0u);
-    }
-    __syncthreads();
+    __syncthreads();  // warp_less / warp_eq are rewritten next round
   }
 
   // ---- block argmin (lowest index among equal minima) ----
@@ -173,75 +209,45 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
 }
 
 // ---- refit ---------------------------------------------------------------------------
-// Welford accumulator with Chan's pairwise merge: single pass, deterministic tree order.
-struct Moments {
-  float n, mean, m2;
-};
-__device__ __forceinline__ void moments_push(Moments& m, float x) {
-  m.n += 1.0f;
-  const float d = x - m.mean;
-  m.mean += d / m.n;
-  m.m2 += d * (x - m.mean);
-}
-__device__ __forceinline__ Moments moments_merge(const Moments& a, const Moments& b) {
-  if (b.n == 0.f) return a;
-  if (a.n == 0.f) return b;
-  Moments r;
-  r.n = a.n + b.n;
-  const float d = b.mean - a.mean;
-  r.mean = a.mean + d * (b.n / r.n);
-  r.m2 = a.m2 + b.m2 + d * d * (a.n * b.n / r.n);
-  return r;
-}
-__device__ __forceinline__ Moments moments_shfl_xor(const Moments& m, int d) {
-  Moments o;
-  o.n = __shfl_xor_sync(0xFFFFFFFFu, m.n, d);
-  o.mean = __shfl_xor_sync(0xFFFFFFFFu, m.mean, d);
-  o.m2 = __shfl_xor_sync(0xFFFFFFFFu, m.m2, d);
-  return o;
-}
-
-constexpr int kRefitThreads = 256;
+constexpr int kRefitThreads = 1024;
 
 // grid = (H * G, E): one CTA per (step, 4-wide action group, env).  Each thread regenerates
-// (or gathers) the 4 actions of its elites, then a shuffle tree merges the moments.
-// mean = sum/k, std = sqrt(sum((a-mean)^2)/k)  (population std, unbiased=False).
+// (or gathers) the 4 actions of its elites and accumulates shifted sums sum(d), sum(d^2) with
+// d = a - c, c = the old mean of that (h, a) (the draws are centred there, so the shifted
+// second moment does not cancel); a fixed shuffle tree + one shared-memory stage reduces them.
+// mean = c + sum(d)/k, std = sqrt(sum(d^2)/k - (sum(d)/k)^2)   (population std, unbiased=False).
 __global__ void __launch_bounds__(kRefitThreads)
 refit_kernel(ActionSource src, Shape sh, int A, const int* __restrict__ elite_idx, int k,
              float* __restrict__ mu_new, float* __restrict__ sd_new) {
-  __shared__ Moments red[kRefitThreads / 32][4];
+  __shared__ float red[kRefitThreads / 32][8];
   const int G = (A + 3) >> 2;
   const int h = blockIdx.x / G, g = blockIdx.x % G;
   const int env_l = blockIdx.y;
   const long long R = sh.rows();
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  Moments acc[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) acc[j] = Moments{0.f, 0.f, 0.f};
-
   const long long ms = ((long long)env_l * sh.H + h) * A;
+  const bool inject = src.mode == MBRL_SAMPLE_INJECT_ACTIONS || src.mode == MBRL_SAMPLE_INJECT_NOISE;
+  const bool affine = src.mode == MBRL_SAMPLE_INJECT_NOISE || src.mode == MBRL_SAMPLE_GAUSSIAN;
+  float mu_old[4], sd_old[4], s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int ac = min(4 * g + j, A - 1);
+    mu_old[j] = affine ? __ldg(src.mu + ms + ac) : 0.f;
+    sd_old[j] = affine ? __ldg(src.sd + ms + ac) : 0.f;
+  }
   const uint2 key = make_uint2(src.seed_lo, src.seed_hi);
   for (int e = t; e < k; e += kRefitThreads) {
     const int cand_l = __ldg(elite_idx + (long long)env_l * k + e);
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (src.mode == MBRL_SAMPLE_INJECT_ACTIONS || src.mode == MBRL_SAMPLE_INJECT_NOISE) {
+    float z[4];
+    if (inject) {
       const long long row = (long long)env_l * sh.N + cand_l;
       const float* p = src.buf + ((long long)h * R + row) * A;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int a = 4 * g + j;
-        if (a < A) {
-          const float x = __ldg(p + a);
-          v[j] = src.mode == MBRL_SAMPLE_INJECT_ACTIONS
-                     ? x
-                     : clipf(__fadd_rn(__ldg(src.mu + ms + a), __fmul_rn(__ldg(src.sd + ms + a), x)), src.lo, src.hi);
-        }
-      }
+      for (int j = 0; j < 4; ++j) z[j] = __ldg(p + min(4 * g + j, A - 1));
     } else {
       const uint4 r = philox4x32_10(make_uint4((uint32_t)(h * G + g), src.iteration,
                                                src.cand_offset + (uint32_t)cand_l,
                                                src.env_offset + (uint32_t)env_l), key);
-      float z[4];
       if (src.mode == MBRL_SAMPLE_GAUSSIAN) {
         const float4 q = box_muller4(r);
         z[0] = q.x; z[1] = q.y; z[2] = q.z; z[3] = q.w;
@@ -249,33 +255,36 @@ refit_kernel(ActionSource src, Shape sh, int A, const int* __restrict__ elite_id
         z[0] = u32_to_uniform(r.x); z[1] = u32_to_uniform(r.y);
         z[2] = u32_to_uniform(r.z); z[3] = u32_to_uniform(r.w);
       }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int a = 4 * g + j;
-        if (a < A) {
-          v[j] = src.mode == MBRL_SAMPLE_GAUSSIAN
-                     ? clipf(__fadd_rn(__ldg(src.mu + ms + a), __fmul_rn(__ldg(src.sd + ms + a), z[j])), src.lo, src.hi)
-                     : __fadd_rn(src.lo, __fmul_rn(__fsub_rn(src.hi, src.lo), z[j]));
-        }
-      }
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) moments_push(acc[j], v[j]);
+    for (int j = 0; j < 4; ++j) {
+      float v = z[j];  // same arithmetic as the rollout kernels' samplers: bit-identical actions
+      if (affine) v = clipf(__fadd_rn(mu_old[j], __fmul_rn(sd_old[j], v)), src.lo, src.hi);
+      else if (src.mode == MBRL_SAMPLE_UNIFORM) v = __fadd_rn(src.lo, __fmul_rn(__fsub_rn(src.hi, src.lo), v));
+      const float d = v - mu_old[j];
+      s1[j] += d;
+      s2[j] = fmaf(d, d, s2[j]);
+    }
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) acc[j] = moments_merge(acc[j], moments_shfl_xor(acc[j], d));
-    if (lane == 0) red[warp][j] = acc[j];
+    for (int d = 16; d > 0; d >>= 1) {
+      s1[j] += __shfl_xor_sync(0xFFFFFFFFu, s1[j], d);
+      s2[j] += __shfl_xor_sync(0xFFFFFFFFu, s2[j], d);
+    }
+    if (lane == 0) { red[warp][j] = s1[j]; red[warp][4 + j] = s2[j]; }
   }
   __syncthreads();
   if (t < 4) {
-    Moments m = red[0][t];
-    for (int w = 1; w < kRefitThreads / 32; ++w) m = moments_merge(m, red[w][t]);
+    float a1 = 0.f, a2 = 0.f;
+    for (int w = 0; w < kRefitThreads / 32; ++w) { a1 += red[w][t]; a2 += red[w][4 + t]; }
     const int a = 4 * g + t;
+    const float c = t == 0 ? mu_old[0] : t == 1 ? mu_old[1] : t == 2 ? mu_old[2] : mu_old[3];
     if (a < A) {
-      mu_new[ms + a] = m.mean;
-      sd_new[ms + a] = __fsqrt_rn(m.m2 / m.n);
+      const float inv = 1.0f / (float)k, m1 = a1 * inv;
+      mu_new[ms + a] = c + m1;
+      sd_new[ms + a] = __fsqrt_rn(fmaxf(fmaf(-m1, m1, a2 * inv), 0.f));
     }
   }
 }

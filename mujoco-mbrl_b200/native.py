@@ -266,10 +266,14 @@ class NativePlanner:
 
 
     def tc_debug(self, enable=True, fetch=False):
-        """Diagnostic: arm / fetch the raw accumulator dump of tile 0, step 0 ([3,128,256])."""
-        out = np.zeros((3, 128, 256), np.float32) if fetch else None
-        _check(self.lib.mbrl_tc_debug(self._h, int(enable), _hp(out)))
-        return out
+        """Diagnostic: arm / fetch the raw accumulator dump of tile 0, step 0 ([3,128,256]);
+        the clock64 timeline of tile 1 ([64,32] int64) is left in `self.tc_timeline`."""
+        buf = np.zeros(3 * 128 * 256 * 4 + 64 * 32 * 8, np.uint8) if fetch else None
+        _check(self.lib.mbrl_tc_debug(self._h, int(enable), _hp(buf)))
+        if buf is None:
+            return None
+        self.tc_timeline = buf[3 * 128 * 256 * 4:].view(np.int64).reshape(64, 32).copy()
+        return buf[:3 * 128 * 256 * 4].view(np.float32).reshape(3, 128, 256).copy()
 
     def emit(self, d_s0, d_best, d_mu_hist, d_sd_hist, iterations, mode, seed=0, d_injected=None, return_mean=False,
              cand_offset=0, env_offset=0):

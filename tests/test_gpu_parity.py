@@ -199,7 +199,9 @@ def test_refit_matches_oracle(native):
     mat = h.sample(native.SAMPLE_GAUSSIAN, 11, 2, mu0, sd0)
     m1, s1 = h.refit(elite.cuda(), k, native.SAMPLE_GAUSSIAN, 11, 2, d_mu=mu0, d_sd=sd0)
     m2, s2 = h.refit(elite.cuda(), k, native.SAMPLE_INJECT_ACTIONS, d_injected=mat)
-    assert torch.equal(m1, m2) and torch.equal(s1, s2)
+    # same actions bit for bit; the two paths centre their sums differently (old mean vs 0)
+    torch.testing.assert_close(m1, m2, rtol=0, atol=2e-6)
+    torch.testing.assert_close(s1, s2, rtol=1e-5, atol=2e-6)
 
 
 @pytest.mark.parametrize("name", ["cem_cheetah_small.npz", "cem_cartpole_small.npz"])

@@ -3,8 +3,10 @@
 Tolerances (stated here, per north_star): the reference is fp32; 16-bit operands are rounded
 once per layer input.  Against the fp32 oracle on the same injected actions:
   * per-step predicted states: relative error <= STATE_RTOL of the state scale per step
-    (fp16: 2e-3, bf16: 1.5e-2), checked on every step of the horizon;
-  * trajectory costs: relative error <= COST_RTOL (fp16: 2e-3, bf16: 1.5e-2).
+    (fp16: 5e-4 -- inside the north_star's 1e-3; bf16: 3e-3), checked on every step of the
+    horizon (measured on B200: fp16 1.6e-4, bf16 1.2e-3);
+  * trajectory costs: relative error <= COST_RTOL (fp16: 1e-4, bf16: 5e-4; measured 1.3e-5 /
+    1.3e-4).
 Elite indices are only required to be bit-exact on identical cost arrays (test_gpu_parity.py);
 here the elite SETS of the two precisions are compared by overlap.
 """
@@ -19,7 +21,7 @@ from oracle import planner_oracle as po
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp16": dict(state=2e-3, cost=2e-3), "bf16": dict(state=1.5e-2, cost=1.5e-2)}
+TOL = {"fp16": dict(state=5e-4, cost=1e-4), "bf16": dict(state=3e-3, cost=5e-4)}
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
 
 
@@ -45,12 +47,21 @@ def _round16(x, engine):
     return (t.half() if engine == "fp16" else t.bfloat16()).float()
 
 
+@pytest.fixture(params=["fused", "unfused"])
+def variant(request, monkeypatch):
+    """Both tensor-core kernels: the fused-recurrence engine (default) and the unfused fallback
+    (selected at handle creation through MBRL_TC_UNFUSED=1)."""
+    monkeypatch.setenv("MBRL_TC_UNFUSED", "1" if request.param == "unfused" else "0")
+    return request.param
+
+
 @pytest.mark.parametrize("engine", ["fp16", "bf16"])
-@pytest.mark.parametrize("dims", [(17, 6, 200), (5, 1, 50), (24, 6, 200), (33, 9, 100)])
-def test_layer_accumulators_match_16bit_emulation(native, engine, dims):
+@pytest.mark.parametrize("dims", [(17, 6, 200), (5, 1, 50), (24, 6, 200), (33, 9, 100), (12, 8, 64)])
+def test_layer_accumulators_match_16bit_emulation(native, engine, dims, variant):
     """Raw TMEM accumulators of tile 0 / step 0 against a numpy emulation that rounds the
     operands exactly where the kernel does -- pins the UMMA descriptors, the operand packing,
-    the in-place TMEM A operand and the bias-through-ones-column trick layer by layer."""
+    the TMEM A operand, the bias-through-ones-column trick and (fused engine) the host-side
+    W13 = W1s*W3 / b13 = b1 + W1s*b3 folding, layer by layer."""
     O, A, U = dims
     p = po.synthetic_params(O, A, U, seed=11)
     n, H = 128, 2
@@ -70,7 +81,14 @@ def test_layer_accumulators_match_16bit_emulation(native, engine, dims):
     W1, b1 = _round16(p.W1, engine), _round16(p.b1, engine)
     W2, b2 = _round16(p.W2, engine), _round16(p.b2, engine)
     W3 = _round16(p.W3, engine)
-    d1 = (torch.cat([xs, xa], 1).double() @ W1.double().t() + b1.double()).float()
+    if variant == "fused":
+        W1s, W1a = p.W1[:, :O].double(), p.W1[:, O:].double()
+        b13 = _round16((p.b1.double() + W1s @ p.b3.double()).float(), engine)
+        xs0 = _round16((((s0 - p.mu_s) / p.sd_s) - p.b3)[None].repeat(n, 1), engine)
+        d1 = (xa.double() @ _round16(W1a.float(), engine).double().t() + b13.double()
+              + xs0.double() @ _round16(W1s.float(), engine).double().t()).float()
+    else:
+        d1 = (torch.cat([xs, xa], 1).double() @ W1.double().t() + b1.double()).float()
     h1 = _round16(torch.relu(d1), engine)
     d2 = (h1.double() @ W2.double().t() + b2.double()).float()
     h2 = _round16(torch.relu(d2), engine)
@@ -80,7 +98,7 @@ def test_layer_accumulators_match_16bit_emulation(native, engine, dims):
     for name, got, want in (("D1", dump[0][:, :U], d1.numpy()), ("D2", dump[1][:, :U], d2.numpy()), ("D3", dump[2][:, :O], d3.numpy())):
         err = np.abs(got - want).max()
         scale = np.abs(want).max()
-        report.append(f"{engine} {dims} {name}: max|err|={err:.3e} scale={scale:.3e} got[0,:4]={got[0,:4]} want[0,:4]={want[0,:4]}")
+        report.append(f"{variant} {engine} {dims} {name}: max|err|={err:.3e} scale={scale:.3e} got[0,:4]={got[0,:4]} want[0,:4]={want[0,:4]}")
         ok &= bool(err <= 2e-3 * scale + 1e-4)
     report.append(f"ones column D1[:,U]={dump[0][:3, U]} (want 1) pad={dump[0][0, U + 1:Np]}")
     os.makedirs(OUT, exist_ok=True)
@@ -91,12 +109,12 @@ def test_layer_accumulators_match_16bit_emulation(native, engine, dims):
     np.testing.assert_allclose(dump[0][:, U], 1.0, atol=1e-6)
     # and the end-to-end predicted state of step 0
     want_s = (d3 + p.b3) * p.sd_s + p.mu_s
-    np.testing.assert_allclose(states.cpu().numpy()[:n], want_s.numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(states.cpu().numpy()[:n], want_s.numpy(), rtol=2e-4, atol=2e-4 if engine == "fp16" else 2e-3)
 
 
 @pytest.mark.parametrize("engine", ["fp16", "bf16"])
 @pytest.mark.parametrize("name", ["rs_cartpole.npz", "rs_cheetah_small.npz"])
-def test_tc_rollout_within_tolerance_of_reference(native, engine, name):
+def test_tc_rollout_within_tolerance_of_reference(native, engine, name, variant):
     g = load_golden(name)
     p = params_from_golden(g)
     n, H = int(g["n"]), int(g["horizon"])
@@ -110,7 +128,7 @@ def test_tc_rollout_within_tolerance_of_reference(native, engine, name):
     scale = np.abs(want).max(axis=(1, 2), keepdims=True)
     step_err = (np.abs(got - want) / scale).max(axis=(1, 2))
     cost_err = np.abs(costs.cpu().numpy() - g["costs"]) / np.abs(g["costs"])
-    msg = f"{engine} {name}: per-step state rel err max={step_err.max():.3e} (first {step_err[0]:.3e}, last {step_err[-1]:.3e}); cost rel err max={cost_err.max():.3e}"
+    msg = f"{variant} {engine} {name}: per-step state rel err max={step_err.max():.3e} (first {step_err[0]:.3e}, last {step_err[-1]:.3e}); cost rel err max={cost_err.max():.3e}"
     print(msg)
     with open(os.path.join(OUT, "tc_probe.txt"), "a") as f:
         f.write(msg + "\n")
@@ -119,7 +137,7 @@ def test_tc_rollout_within_tolerance_of_reference(native, engine, name):
 
 
 @pytest.mark.parametrize("engine", ["fp16", "bf16"])
-def test_tc_matches_fp32_engine_on_device_sampler(native, engine):
+def test_tc_matches_fp32_engine_on_device_sampler(native, engine, variant):
     """Same Philox stream on both engines: identical actions, costs within tolerance, large
     elite overlap; ragged tile (N not a multiple of 128) and 2 environments."""
     p = po.synthetic_params(17, 6, 200)
@@ -142,7 +160,7 @@ def test_tc_matches_fp32_engine_on_device_sampler(native, engine):
 
 
 @pytest.mark.parametrize("engine", ["fp16", "bf16"])
-def test_tc_cem_plan_consistent(native, engine):
+def test_tc_cem_plan_consistent(native, engine, variant):
     """Whole CEM plan on the tensor-core engine: the reported best cost is reproduced by the
     fp32 oracle on the emitted action sequence within the engine's cost tolerance, and the
     first action is inside the bounds."""
