@@ -332,7 +332,7 @@ static int launch_topk(const float* d_costs, int segments, int n, int k, int* d_
   MBRL_REQUIRE(segments >= 1 && n >= 1, "topk: empty input");
   MBRL_REQUIRE(k >= 1 && k <= n, "topk: k out of range [1,n]");
   if (n <= kSelectStageMax) {
-    const size_t smem = sizeof(uint32_t) * (size_t)n;
+    const size_t smem = sizeof(uint32_t) * (size_t)((n + 3) & ~3);
     MBRL_CUDA(cudaFuncSetAttribute(topk_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     topk_select_kernel<true><<<segments, kSelectThreads, smem, st>>>(d_costs, n, k, d_idx, d_cost, d_best, d_best_ever, iteration);
   } else {

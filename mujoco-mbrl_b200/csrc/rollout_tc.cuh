@@ -34,6 +34,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -137,6 +138,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "bra WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t"
       "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// One elected lane of a fully converged warp (what cute::elect_one_sync emits).  Code guarded by
+// this predicate is known to the compiler to run in exactly one thread, so warp-level
+// instructions (UTCHMMA, UTCBAR, UBLKCP) are emitted once with uniform-register operands instead
+// of inside a per-active-thread loop with R2UR moves.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

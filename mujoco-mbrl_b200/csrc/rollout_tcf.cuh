@@ -45,7 +45,8 @@ struct TcfGeom {
   int tab_off, xs_off, xa_off, bar_off, smem_bytes;
 };
 
-constexpr int kTcfBarriers = 5 + 2 * kTcMaxChunks;  // w, xa, dA, dB, y, hA[8], hB[8]
+constexpr int kTcfSlots = 3;  // action tiles in flight: the sampler runs up to 3 steps ahead
+constexpr int kTcfBarriers = 4 + kTcfSlots + 2 * kTcMaxChunks;  // w, dA, dB, y, xa[3], hA[8], hB[8]
 constexpr int kTcfCostWarp0 = 8;    // warps 8-11: cost epilogue (TMEM lane quarter = warp - 8)
 constexpr int kTcfSampWarp0 = 12;   // warps 12-15: action sampler
 constexpr int kTcfMmaWarp = 16;     // warp 16: TMEM alloc, weight TMA, MMA issue
@@ -67,7 +68,7 @@ inline bool tcf_geometry(int O, int A, int U, size_t max_smem, TcfGeom* g, std::
   g->tab_off = g->w_bytes;  // fp32: 6 tables of Oy, 2 of kMaxAct, 2 x 128 cost partials
   g->xs_off = round_up(g->tab_off + (6 * g->Oy + 2 * kMaxAct + 2 * kTcRows) * 4, 128);
   g->xa_off = g->xs_off + g->Ks * kTcRows * 2;
-  g->bar_off = g->xa_off + 2 * g->Ka * kTcRows * 2;
+  g->bar_off = g->xa_off + kTcfSlots * g->Ka * kTcRows * 2;
   g->smem_bytes = g->bar_off + 8 * kTcfBarriers + 16;
   if ((size_t)g->smem_bytes > max_smem) { *why = "fused operands do not fit shared memory"; return false; }
   return true;
@@ -130,12 +131,13 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.bar_off);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + g.bar_off + 8 * kTcfBarriers);
   const uint32_t bar0 = smem_u32(bars);
-  const uint32_t bar_w = bar0, bar_xa = bar0 + 8, bar_dA = bar0 + 16, bar_dB = bar0 + 24, bar_y = bar0 + 32;
-  const uint32_t bar_hA = bar0 + 40, bar_hB = bar0 + 40 + 8 * kTcMaxChunks;
+  const uint32_t bar_w = bar0, bar_dA = bar0 + 8, bar_dB = bar0 + 16, bar_y = bar0 + 24, bar_xa = bar0 + 32;
+  const uint32_t bar_hA = bar_xa + 8 * kTcfSlots, bar_hB = bar_hA + 8 * kTcMaxChunks;
 
   if (warp == kTcfMmaWarp) {
     if (lane == 0) {
-      mbar_init(bar_w, 1); mbar_init(bar_xa, 1); mbar_init(bar_dA, 1); mbar_init(bar_dB, 1); mbar_init(bar_y, 1);
+      mbar_init(bar_w, 1); mbar_init(bar_dA, 1); mbar_init(bar_dB, 1); mbar_init(bar_y, 1);
+      for (int i = 0; i < kTcfSlots; ++i) mbar_init(bar_xa + 8 * i, 1);
       for (int c = 0; c < kTcMaxChunks; ++c) { mbar_init(bar_hA + 8 * c, 4); mbar_init(bar_hB + 8 * c, 4); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -159,7 +161,7 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
     t_aoff[i] = i < A ? __ldg(m.mu_a + i) * inv : (i == A ? -1.f : 0.f);
   }
   // zero the action tiles once: chunks beyond the sampled ones stay zero for the whole rollout
-  for (int i = tid; i < 2 * xa_bytes / 16; i += kTcfThreads) reinterpret_cast<uint4*>(xa)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < kTcfSlots * xa_bytes / 16; i += kTcfThreads) reinterpret_cast<uint4*>(xa)[i] = make_uint4(0, 0, 0, 0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -167,86 +169,99 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
   const long long R = sh.rows();
 
   if (warp == kTcfMmaWarp) {
-    // ================= MMA issuer (one thread) =================
-    if (lane == 0) {
+    // ================= MMA issuer warp =================
+    // The whole warp stays converged and waits on the barriers; every tcgen05 instruction is
+    // issued by one elected lane (see elect_one()).
+    if (elect_one()) {
       mbar_arrive_expect_tx(bar_w, (uint32_t)g.w_bytes);
       bulk_g2s(smem_u32(smem), wimg, (uint32_t)g.w_bytes, bar_w);
-      const uint32_t idesc_a = umma_idesc(g.Na, FP16), idesc_h = umma_idesc(g.Np, FP16), idesc_y = umma_idesc(g.Oy, FP16);
-      const uint32_t lbo_a = (uint32_t)g.Na * 16, lbo_h = (uint32_t)g.Np * 16, lbo_x = kTcRows * 16;
-      const uint64_t d_wa = umma_desc(smem_u32(smem + g.wa_off), lbo_a, 128);
-      const uint64_t d_wy = umma_desc(smem_u32(smem + g.wa_off) + (uint32_t)g.Np * 16, lbo_a, 128);  // rows Np.. of [W13;W3]
-      const uint64_t d_waa = umma_desc(smem_u32(smem + g.waa_off), lbo_a, 128);
-      const uint64_t d_w1s = umma_desc(smem_u32(smem + g.w1s_off), lbo_h, 128);
-      const uint64_t d_w2 = umma_desc(smem_u32(smem + g.w2_off), lbo_h, 128);
-      const uint64_t d_xs = umma_desc(smem_u32(xs), lbo_x, 128);
-      const uint64_t d_xa0 = umma_desc(smem_u32(xa), lbo_x, 128), d_xa1 = umma_desc(smem_u32(xa + xa_bytes), lbo_x, 128);
-      const uint64_t step_a = (2 * lbo_a) >> 4, step_h = (2 * lbo_h) >> 4, step_x = (2 * lbo_x) >> 4;
-      const uint32_t tm_a = tmem, tm_b = tmem + kTcD2Col;
-      mbar_wait(bar_w, 0);
+    }
+    const uint32_t idesc_a = umma_idesc(g.Na, FP16), idesc_h = umma_idesc(g.Np, FP16), idesc_y = umma_idesc(g.Oy, FP16);
+    const uint32_t lbo_a = (uint32_t)g.Na * 16, lbo_h = (uint32_t)g.Np * 16, lbo_x = kTcRows * 16;
+    // Descriptors are loop invariant; a K-step advances the 14-bit start-address field by
+    // 2*LBO/16 (smem addresses stay below 256 KB, so the add never carries out of the field).
+    const uint64_t d_wa = umma_desc(smem_u32(smem + g.wa_off), lbo_a, 128);
+    const uint64_t d_wy = umma_desc(smem_u32(smem + g.wa_off) + (uint32_t)g.Np * 16, lbo_a, 128);  // rows Np.. of [W13;W3]
+    const uint64_t d_waa = umma_desc(smem_u32(smem + g.waa_off), lbo_a, 128);
+    const uint64_t d_w1s = umma_desc(smem_u32(smem + g.w1s_off), lbo_h, 128);
+    const uint64_t d_w2 = umma_desc(smem_u32(smem + g.w2_off), lbo_h, 128);
+    const uint64_t d_xs = umma_desc(smem_u32(xs), lbo_x, 128);
+    const uint64_t d_xa0 = umma_desc(smem_u32(xa), lbo_x, 128);
+    const uint64_t xa_step = (uint64_t)(xa_bytes >> 4);  // next action tile
+    const uint64_t step_a = (2 * lbo_a) >> 4, step_h = (2 * lbo_h) >> 4, step_x = (2 * lbo_x) >> 4;
+    const uint32_t tm_a = tmem, tm_b = tmem + kTcD2Col;
+    mbar_wait(bar_w, 0);
 
-      // ---- step 0: D_A = a(0).[W1a|b13]^T + (x0 - b3).W1s^T ----
-      mbar_wait(bar_xa, 0);
-      tc_fence_after();
-      {
-        uint64_t ad = d_xa0, bd = d_waa;
-        mma_ss(tm_a, ad, bd, idesc_a, 0);
-        for (int ks = 1; ks < KS_A; ++ks) { ad += step_x; bd += step_a; mma_ss(tm_a, ad, bd, idesc_a, 1); }
-        ad = d_xs; bd = d_w1s;
-        for (int ks = 0; ks < KS_S; ++ks) { mma_ss(tm_a, ad, bd, idesc_h, 1); ad += step_x; bd += step_h; }
-      }
+    // ---- step 0: D_A = a(0).[W1a|b13]^T + (x0 - b3).W1s^T ----
+    mbar_wait(bar_xa, 0);
+    tc_fence_after();
+    if (elect_one()) {
+      uint64_t ad = d_xa0, bd = d_waa;
+      mma_ss(tm_a, ad, bd, idesc_a, 0);
+      for (int ks = 1; ks < KS_A; ++ks) { ad += step_x; bd += step_a; mma_ss(tm_a, ad, bd, idesc_a, 1); }
+      ad = d_xs; bd = d_w1s;
+      for (int ks = 0; ks < KS_S; ++ks) { mma_ss(tm_a, ad, bd, idesc_h, 1); ad += step_x; bd += step_h; }
       tc_commit(bar_dA);
-
-      for (int h = 0; h < H; ++h) {
-        const uint32_t ph = h & 1;
-        tc_stamp(dbg, h, 0);
-        // ---- GEMM-B(h): D_B = h1(h) . W2p^T, K-steps released by epilogue A ----
-        {
-          // packed chunk c of h1 lives in the first half of its own 32 fp32 columns:
-          // K-step 2c at column 32c, K-step 2c+1 at column 32c+8
-          uint64_t bd = d_w2;
-          uint32_t a = tm_a, acc = 0;
-          int left = KS_H;
-          for (int c = 0; c < NC; ++c) {
-            mbar_wait(bar_hA + 8 * c, ph);
-            tc_fence_after();
-            mma_ts(tm_b, a, bd, idesc_h, acc);
-            acc = 1; bd += step_h;
-            if (left > 1) { mma_ts(tm_b, a + 8, bd, idesc_h, 1); bd += step_h; }
-            a += 32; left -= 2;
-          }
-        }
-        tc_commit(bar_dB);
-        tc_stamp(dbg, h, 1);
-        // ---- GEMM-A(h+1) (or, after the last step, only the y columns) ----
-        const bool last = h + 1 == H;
-        if (h >= 1) { mbar_wait(bar_y, (h - 1) & 1); }  // y(h-1) in D_A has been consumed
-        uint32_t acc = 0;
-        if (!last) {
-          mbar_wait(bar_xa, (h + 1) & 1);
-          tc_fence_after();
-          uint64_t ad = ((h + 1) & 1) ? d_xa1 : d_xa0, bd = d_waa;
-          for (int ks = 0; ks < KS_A; ++ks) { mma_ss(tm_a, ad, bd, idesc_a, acc); acc = 1; ad += step_x; bd += step_a; }
-        }
-        {
-          uint64_t bd = last ? d_wy : d_wa;
-          const uint32_t d = last ? tm_a + (uint32_t)g.Np : tm_a;
-          const uint32_t idesc = last ? idesc_y : idesc_a;
-          uint32_t a = tm_b;
-          int left = KS_H;
-          for (int c = 0; c < NC; ++c) {
-            mbar_wait(bar_hB + 8 * c, ph);
-            tc_fence_after();
-            mma_ts(d, a, bd, idesc, acc);
-            acc = 1; bd += step_a;
-            if (left > 1) { mma_ts(d, a + 8, bd, idesc, 1); bd += step_a; }
-            a += 32; left -= 2;
-          }
-        }
-        tc_commit(bar_dA);
-        tc_stamp(dbg, h, 2);
-      }
     }
     __syncwarp();
+
+    for (int h = 0; h < H; ++h) {
+      const uint32_t ph = h & 1;
+      // ---- GEMM-B(h): D_B = h1(h) . W2p^T, K-steps released by epilogue A ----
+      {
+        // packed chunk c of h1 lives in the first half of its own 32 fp32 columns:
+        // K-step 2c at column 32c, K-step 2c+1 at column 32c+8
+        uint64_t bd = d_w2;
+        uint32_t a = tm_a, acc = 0;
+        int left = KS_H;
+        for (int c = 0; c < NC; ++c) {
+          mbar_wait(bar_hA + 8 * c, ph);
+          tc_fence_after();
+          if (elect_one()) {
+            mma_ts(tm_b, a, bd, idesc_h, acc);
+            if (left > 1) mma_ts(tm_b, a + 8, bd + step_h, idesc_h, 1);
+            if (c + 1 == NC) tc_commit(bar_dB);
+          }
+          __syncwarp();
+          acc = 1; bd += 2 * step_h; a += 32; left -= 2;
+        }
+      }
+      // ---- GEMM-A(h+1) (or, after the last step, only the y columns) ----
+      const bool last = h + 1 == H;
+      if (h >= 1) { mbar_wait(bar_y, (h - 1) & 1); }  // y(h-1) in D_A has been consumed
+      uint32_t acc = 0;
+      if (!last) {
+        const int slot = (h + 1) % kTcfSlots;
+        mbar_wait(bar_xa + 8 * slot, ((h + 1) / kTcfSlots) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          uint64_t ad = d_xa0 + slot * xa_step, bd = d_waa;
+          mma_ss(tm_a, ad, bd, idesc_a, 0);
+          for (int ks = 1; ks < KS_A; ++ks) { ad += step_x; bd += step_a; mma_ss(tm_a, ad, bd, idesc_a, 1); }
+        }
+        __syncwarp();
+        acc = 1;
+      }
+      {
+        uint64_t bd = last ? d_wy : d_wa;
+        const uint32_t d = last ? tm_a + (uint32_t)g.Np : tm_a;
+        const uint32_t idesc = last ? idesc_y : idesc_a;
+        uint32_t a = tm_b;
+        int left = KS_H;
+        for (int c = 0; c < NC; ++c) {
+          mbar_wait(bar_hB + 8 * c, ph);
+          tc_fence_after();
+          if (elect_one()) {
+            mma_ts(d, a, bd, idesc, acc);
+            if (left > 1) mma_ts(d, a + 8, bd + step_a, idesc, 1);
+            if (c + 1 == NC) tc_commit(bar_dA);
+          }
+          __syncwarp();
+          acc = 1; bd += 2 * step_a; a += 32; left -= 2;
+        }
+      }
+      if (lane == 0) tc_stamp(dbg, h + 1, 0);
+    }
   } else if (warp >= kTcfSampWarp0) {
     // ================= sampler threads (one per row) =================
     const int srow = tid - kTcfSampWarp0 * 32;
@@ -261,7 +276,7 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
     auto stage_actions = [&](int hs) {
       float acc = 0.f;
       float* aout = (actions_out && valid) ? actions_out + ((long long)hs * R + row) * A : nullptr;
-      uint8_t* xt = xa + (hs & 1) * xa_bytes;
+      uint8_t* xt = xa + (hs % kTcfSlots) * xa_bytes;
       for (int q = 0; q < QA; ++q) {
         float v[8];
         {
@@ -305,19 +320,16 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
       pk.z = pack2<FP16>(xn[4], xn[5]); pk.w = pack2<FP16>(xn[6], xn[7]);
       *reinterpret_cast<uint4*>(xs + j * (kTcRows * 16) + srow * 16) = pk;
     }
-    stage_actions(0);
-    fence_proxy_async();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (srow == 0) mbar_arrive(bar_xa);
-    for (int hs = 1; hs < H; ++hs) {
-      // D_A(hs-1) complete: the MMA thread is past its wait on x-ready #(hs-1) (never two phases
-      // ahead) and GEMM-A(hs-2), the last reader of tile hs&1, has finished
-      mbar_wait(bar_dA, (hs - 1) & 1);
-      if (srow == 0) tc_stamp(dbg, hs - 1, 12);
+    for (int hs = 0; hs < H; ++hs) {
+      // Tile slot hs%3 was last read by GEMM-A(hs-3), and its barrier's previous phase was
+      // consumed before that GEMM: both are over once D_A(hs-3) is complete.  (The waits see
+      // phases #0, #1, ... in order.)
+      if (hs >= kTcfSlots) mbar_wait(bar_dA, (hs - kTcfSlots) & 1);
+      if (srow == 0) tc_stamp(dbg, hs, 12);
       stage_actions(hs);
       fence_proxy_async();   // generic-proxy tile writes -> visible to the MMA (async proxy)
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (srow == 0) { mbar_arrive(bar_xa); tc_stamp(dbg, hs - 1, 13); }
+      if (srow == 0) { mbar_arrive(bar_xa + 8 * (hs % kTcfSlots)); tc_stamp(dbg, hs, 13); }
     }
     costp[kTcRows + srow] = act_total;
   } else if (warp >= kTcfCostWarp0) {

@@ -20,6 +20,12 @@ __device__ __forceinline__ uint32_t cost_key(float c) {
 }
 
 constexpr int kSelectThreads = 1024;
+#ifdef MBRL_TOPK_PROFILE
+__device__ long long g_topk_stamps[32];
+#define TOPK_STAMP(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_topk_stamps[i] = clock64(); } while (0)
+#else
+#define TOPK_STAMP(i) do { } while (0)
+#endif
 
 struct BestEver {  // per environment, device resident
   float cost;
@@ -32,9 +38,9 @@ struct BestEver {  // per environment, device resident
 // staged once in shared memory (coalesced, loads in flight together) while the block min/max is
 // reduced.  The k-th smallest key T is then found by an ADAPTIVE radix select: every round
 // histograms the keys that are still in range into 1024 equal-width buckets of the CURRENT key
-// range [lo, hi] (so the candidates spread over the bins instead of piling onto the few leading
-// bit patterns that the costs of one population share), a block scan locates the bucket holding
-// the k-th key, and the range shrinks 1024x; it ends when the bucket width is 1 (<= 4 rounds).
+// range [lo, hi] (power-of-two width; the candidates spread over the bins instead of piling onto
+// the few leading bit patterns that the costs of one population share), a block scan locates the
+// bucket holding the k-th key, and the range shrinks >= 512x; it ends when the width is 1.
 // A final index-ordered compaction (ballot + warp-shuffle scans) emits every key < T plus the
 // first `take_eq` keys == T.
 //   best (nullable):      (min cost, ., argmin) of this launch per segment
@@ -44,142 +50,183 @@ struct BestEver {  // per environment, device resident
 constexpr int kSelectStageMax = 49152;  // keys staged in shared memory: 192 KB
 constexpr int kSelectBins = 1024;
 
+// inclusive warp scan
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+    if (lane >= d) v += o;
+  }
+  return v;
+}
+
 template <bool STAGED>
 __global__ void __launch_bounds__(kSelectThreads)
 topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restrict__ elite_idx,
                    float* __restrict__ elite_cost, MbrlPlanInfo* __restrict__ best,
                    BestEver* __restrict__ best_ever, int iteration) {
   extern __shared__ __align__(16) uint32_t sel_smem[];
-  uint32_t* keys = sel_smem;  // [n] when STAGED
+  uint32_t* keys = sel_smem;  // [round4(n)] when STAGED
   __shared__ uint32_t hist[kSelectBins];
-  __shared__ uint32_t s_lo, s_hi, s_remaining;
-  __shared__ uint32_t warp_less[32], warp_eq[32];
+  __shared__ uint32_t wtot[2][4][32];  // per-warp totals (double buffered; 4 trips per pass)
+  __shared__ uint32_t wtot2[2][4][32];
+  __shared__ uint32_t s_sel[2];        // winning bin, remaining rank
   __shared__ unsigned long long warp_min[32];
-  __shared__ uint32_t s_base_less, s_base_eq;
 
   const int seg = blockIdx.x;
   const float* c = costs + (long long)seg * n;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  auto key_at = [&](int i) -> uint32_t { return STAGED ? keys[i] : cost_key(__ldg(c + i)); };
+  const int n4 = (n + 3) & ~3;
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(c) & 15) == 0);
+  TOPK_STAMP(0);
 
-  // ---- stage + min/max ----
+  // four keys of indices i4..i4+3 (i4 multiple of 4); out-of-range -> 0xFFFFFFFF (masked by index)
+  auto load4 = [&](int i4, uint32_t (&kk)[4]) {
+    if (vec_ok && i4 + 3 < n) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(c + i4));
+      kk[0] = cost_key(q.x); kk[1] = cost_key(q.y); kk[2] = cost_key(q.z); kk[3] = cost_key(q.w);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) kk[j] = i4 + j < n ? cost_key(__ldg(c + i4 + j)) : 0xFFFFFFFFu;
+    }
+  };
+  auto key4_at = [&](int i4, uint32_t (&kk)[4]) {
+    if (STAGED) {
+      const uint4 q = *reinterpret_cast<const uint4*>(keys + i4);
+      kk[0] = q.x; kk[1] = q.y; kk[2] = q.z; kk[3] = q.w;
+    } else {
+      load4(i4, kk);
+    }
+  };
+
+  // ---- stage + min/max (16-byte loads, all in flight together) ----
   uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
-#pragma unroll 8
-  for (int i = t; i < n; i += kSelectThreads) {
-    const uint32_t key = cost_key(__ldg(c + i));
-    if (STAGED) keys[i] = key;
-    kmin = min(kmin, key);
-    kmax = max(kmax, key);
+#pragma unroll 4
+  for (int i4 = 4 * t; i4 < n4; i4 += 4 * kSelectThreads) {
+    uint32_t kk[4];
+    load4(i4, kk);
+    if (STAGED) *reinterpret_cast<uint4*>(keys + i4) = make_uint4(kk[0], kk[1], kk[2], kk[3]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (i4 + j < n) { kmin = min(kmin, kk[j]); kmax = max(kmax, kk[j]); }
   }
+  hist[t] = 0;
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
     kmin = min(kmin, __shfl_xor_sync(0xFFFFFFFFu, kmin, d));
     kmax = max(kmax, __shfl_xor_sync(0xFFFFFFFFu, kmax, d));
   }
-  if (lane == 0) { warp_less[warp] = kmin; warp_eq[warp] = kmax; }
+  if (lane == 0) { wtot[0][0][warp] = kmin; wtot[0][1][warp] = kmax; }
   __syncthreads();
-  if (warp == 0) {
-    kmin = warp_less[lane]; kmax = warp_eq[lane];
+  kmin = wtot[0][0][lane]; kmax = wtot[0][1][lane];  // every warp finishes the reduction itself
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      kmin = min(kmin, __shfl_xor_sync(0xFFFFFFFFu, kmin, d));
-      kmax = max(kmax, __shfl_xor_sync(0xFFFFFFFFu, kmax, d));
-    }
-    if (lane == 0) { s_lo = kmin; s_hi = kmax; s_remaining = (uint32_t)k; s_base_less = 0; s_base_eq = 0; }
+  for (int d = 16; d > 0; d >>= 1) {
+    kmin = min(kmin, __shfl_xor_sync(0xFFFFFFFFu, kmin, d));
+    kmax = max(kmax, __shfl_xor_sync(0xFFFFFFFFu, kmax, d));
   }
-  __syncthreads();
+  uint32_t lo = kmin, hi = kmax, rem = (uint32_t)k;
+  TOPK_STAMP(1);
 
-  // ---- adaptive radix select ----
-  for (int round = 0; round < 5; ++round) {
-    const uint32_t lo = s_lo, hi = s_hi, rem = s_remaining;
-    const uint32_t width = (uint32_t)(((unsigned long long)(hi - lo)) / kSelectBins) + 1u;  // bucket width
-    hist[t] = 0;
-    __syncthreads();
-#pragma unroll 4
-    for (int i = t; i < n; i += kSelectThreads) {
-      const uint32_t key = key_at(i);
-      if (key >= lo && key <= hi) atomicAdd(&hist[(key - lo) / width], 1u);
-    }
-    __syncthreads();
-    // block-wide inclusive scan of the 1024 bins (one bin per thread)
-    const uint32_t mine = hist[t];
-    uint32_t incl = mine;
+  // ---- adaptive radix select: power-of-two bucket width, <= 1024 buckets over [lo, hi] ----
+  for (int round = 0; round < 6; ++round) {
+    const uint32_t span = hi - lo;                              // in-range test: key - lo <= span
+    const int shift = span < (uint32_t)kSelectBins ? 0 : 32 - __clz(span) - 10;  // span >> shift < 1024
+    TOPK_STAMP(2 + 3 * round);
+    for (int i4 = 4 * t; i4 < n4; i4 += 4 * kSelectThreads) {
+      uint32_t kk[4];
+      key4_at(i4, kk);
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-      if (lane >= d) incl += v;
-    }
-    if (lane == 31) warp_less[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      const uint32_t tot = warp_less[lane];
-      uint32_t wi = tot;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, wi, d);
-        if (lane >= d) wi += v;
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t d = kk[j] - lo;
+        if (d <= span && i4 + j < n) atomicAdd(&hist[d >> shift], 1u);
       }
-      warp_eq[lane] = wi - tot;  // exclusive prefix of the warp totals
     }
     __syncthreads();
-    incl += warp_eq[warp];
-    const uint32_t excl = incl - mine;
-    if (rem > excl && rem <= incl) {  // exactly one bin holds the rem-th smallest in-range key
-      const uint32_t nlo = lo + (uint32_t)t * width;
-      const unsigned long long nhi = (unsigned long long)nlo + width - 1ull;
-      s_lo = nlo;
-      s_hi = nhi < (unsigned long long)hi ? (uint32_t)nhi : hi;
-      s_remaining = rem - excl;
-    }
+    TOPK_STAMP(3 + 3 * round);
+    // block-wide scan of the 1024 bins: one bin per thread, warp totals through shared memory,
+    // every warp scans the 32 totals itself (no single-warp phase)
+    const uint32_t mine = hist[t];
+    hist[t] = 0;  // ready for the next round
+    const uint32_t incl_w = warp_incl_scan(mine, lane);
+    const int buf = round & 1;
+    if (lane == 31) wtot[buf][0][warp] = incl_w;
     __syncthreads();
-    if (width == 1u) break;  // uniform: the bucket is a single key value
+    const uint32_t tot = wtot[buf][0][lane];
+    const uint32_t tot_incl = warp_incl_scan(tot, lane);
+    const uint32_t base = __shfl_sync(0xFFFFFFFFu, tot_incl - tot, warp);
+    const uint32_t incl = base + incl_w, excl = incl - mine;
+    if (rem > excl && rem <= incl) { s_sel[0] = (uint32_t)t; s_sel[1] = rem - excl; }  // exactly one bin
+    __syncthreads();
+    const uint32_t bin = s_sel[0];
+    rem = s_sel[1];
+    const uint32_t nspan = min(span - (bin << shift), (1u << shift) - 1u);
+    lo = lo + (bin << shift);
+    hi = lo + nspan;
+    TOPK_STAMP(4 + 3 * round);
+    if (shift == 0) break;  // uniform: buckets were single key values
   }
-  const uint32_t T = s_lo;               // k-th smallest key
-  const uint32_t take_eq = s_remaining;  // how many keys == T belong to the elite set
+  const uint32_t T = lo;          // k-th smallest key
+  const uint32_t take_eq = rem;   // how many keys == T belong to the elite set
+  TOPK_STAMP(20);
 
   // ---- index-ordered compaction + argmin ----
+  // A pass covers 4 trips of 4096 indices (thread t owns indices trip*4096 + 4t .. +3); the per-warp
+  // counts of all 4 trips meet in shared memory once, every warp scans them itself, and the
+  // running base lives in registers: one barrier per 16384 keys.
   unsigned long long my_min = ~0ull;
-  const int rounds = (n + kSelectThreads - 1) / kSelectThreads;
-  for (int r = 0; r < rounds; ++r) {
-    const int i = r * kSelectThreads + t;
-    uint32_t key = 0xFFFFFFFFu;
-    bool less = false, eq = false;
-    if (i < n) {
-      key = key_at(i);
-      less = key < T;
-      eq = key == T;
-      const unsigned long long packed = ((unsigned long long)key << 32) | (uint32_t)i;
-      my_min = packed < my_min ? packed : my_min;
-    }
-    const unsigned bl = __ballot_sync(0xFFFFFFFFu, less), be = __ballot_sync(0xFFFFFFFFu, eq);
-    const unsigned lt_mask = (1u << lane) - 1u;
-    if (lane == 0) { warp_less[warp] = __popc(bl); warp_eq[warp] = __popc(be); }
-    __syncthreads();
-    if (warp == 0) {
-      // exclusive scan of the 32 per-warp counts; carry the running base across rounds
-      const uint32_t cl = warp_less[lane], ce = warp_eq[lane];
-      uint32_t il = cl, ie = ce;
+  uint32_t base_less = 0, base_eq = 0;
+  int pass = 0;
+  for (int p0 = 0; p0 < n4; p0 += 16 * kSelectThreads, ++pass) {
+    uint32_t kk[4][4], il[4], ie[4], nl[4], ne[4];
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t vl = __shfl_up_sync(0xFFFFFFFFu, il, d), ve = __shfl_up_sync(0xFFFFFFFFu, ie, d);
-        if (lane >= d) { il += vl; ie += ve; }
+    for (int tr = 0; tr < 4; ++tr) {
+      const int i4 = p0 + tr * 4 * kSelectThreads + 4 * t;
+      nl[tr] = 0; ne[tr] = 0;
+      if (i4 < n4) {
+        key4_at(i4, kk[tr]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (i4 + j < n) {
+            nl[tr] += kk[tr][j] < T;
+            ne[tr] += kk[tr][j] == T;
+            const unsigned long long packed = ((unsigned long long)kk[tr][j] << 32) | (uint32_t)(i4 + j);
+            my_min = packed < my_min ? packed : my_min;
+          }
+        }
       }
-      const uint32_t bl0 = s_base_less, be0 = s_base_eq;
-      __syncwarp();
-      warp_less[lane] = bl0 + il - cl;
-      warp_eq[lane] = be0 + ie - ce;
-      if (lane == 31) { s_base_less = bl0 + il; s_base_eq = be0 + ie; }
+      il[tr] = warp_incl_scan(nl[tr], lane);
+      ie[tr] = warp_incl_scan(ne[tr], lane);
+      if (lane == 31) { wtot[pass & 1][tr][warp] = il[tr]; wtot2[pass & 1][tr][warp] = ie[tr]; }
     }
     __syncthreads();
-    const uint32_t less_before = warp_less[warp] + __popc(bl & lt_mask);
-    const uint32_t eq_before = warp_eq[warp] + __popc(be & lt_mask);
-    if (less || (eq && eq_before < take_eq)) {
-      const uint32_t pos = less_before + (eq_before < take_eq ? eq_before : take_eq);
-      elite_idx[(long long)seg * k + pos] = i;
-      if (elite_cost) elite_cost[(long long)seg * k + pos] = __ldg(c + i);
+#pragma unroll
+    for (int tr = 0; tr < 4; ++tr) {
+      const int i4 = p0 + tr * 4 * kSelectThreads + 4 * t;
+      const uint32_t tl = wtot[pass & 1][tr][lane], te = wtot2[pass & 1][tr][lane];
+      const uint32_t sl = warp_incl_scan(tl, lane), se = warp_incl_scan(te, lane);
+      uint32_t less_before = base_less + __shfl_sync(0xFFFFFFFFu, sl - tl, warp) + il[tr] - nl[tr];
+      uint32_t eq_before = base_eq + __shfl_sync(0xFFFFFFFFu, se - te, warp) + ie[tr] - ne[tr];
+      base_less += __shfl_sync(0xFFFFFFFFu, sl, 31);
+      base_eq += __shfl_sync(0xFFFFFFFFu, se, 31);
+      if (i4 < n4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = i4 + j;
+          if (i < n) {
+            const bool less = kk[tr][j] < T, eq = kk[tr][j] == T;
+            if (less || (eq && eq_before < take_eq)) {
+              const uint32_t pos = less_before + (eq_before < take_eq ? eq_before : take_eq);
+              elite_idx[(long long)seg * k + pos] = i;
+              if (elite_cost) elite_cost[(long long)seg * k + pos] = __ldg(c + i);
+            }
+            less_before += less;
+            eq_before += eq;
+          }
+        }
+      }
     }
-    __syncthreads();  // warp_less / warp_eq are rewritten next round
   }
+  TOPK_STAMP(21);
 
   // ---- block argmin (lowest index among equal minima) ----
 #pragma unroll
@@ -206,6 +253,7 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
       }
     }
   }
+  TOPK_STAMP(22);
 }
 
 // ---- refit ---------------------------------------------------------------------------
