@@ -129,15 +129,18 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  // try_wait with a suspend-time hint: the waiting thread sleeps in hardware until the phase
+  // completes (or the hint expires) instead of spinning -- with ~20 mostly-waiting warps per CTA,
+  // spinning waiters would take issue slots from the warp that issues the MMAs.
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra WAIT_DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t"
-      "}\n" ::"r"(bar), "r"(parity) : "memory");
+      "}\n" ::"r"(bar), "r"(parity), "r"(0x989680) : "memory");
 }
 // One elected lane of a fully converged warp (what cute::elect_one_sync emits).  Code guarded by
 // this predicate is known to the compiler to run in exactly one thread, so warp-level

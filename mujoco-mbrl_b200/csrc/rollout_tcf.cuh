@@ -14,17 +14,17 @@
 //                  columns [Np,Np+Oy)  -> y(h) = W3 h2(h): consumed OFF the critical path by the
 //                                         cost threads (fp32: + b3, un-normalise, SmoothAbs cost)
 //     GEMM-B(h):   D_B[128 x Np] = h1(h) . W2p^T                  (TS)
-// Both hidden epilogues (TMEM fp32 -> relu -> 16 bit -> TMEM, each 32-column chunk packed into the
+// Both hidden epilogues (TMEM fp32 -> relu -> 16 bit -> TMEM, each 16-column K-step packed into the
 // first half of its own columns, so no warp ever overwrites data another warp still has to read)
-// release the next GEMM's
-// K-steps chunk by chunk through mbarriers, so the tensor pipe only idles for the first-chunk
+// release the next GEMM's K-steps one by one through mbarriers, so the tensor pipe only idles for the first-chunk
 // latency of each epilogue.  Step 0 uses a state tile (x0 - b3, so that b13 gives exactly b1)
 // with W1s as extra SS K-steps.
 //
-// Warp roles (544 threads, 1 CTA/SM): warps 0-7 hidden epilogues (two warpgroups, even/odd
-// 32-column chunks); warps 8-11 cost epilogue, one thread per candidate row (fp32: y + b3,
-// un-normalise, SmoothAbs); warps 12-15 action sampler, one thread per row (Philox + Box-Muller
-// + clip, one step ahead, Cosh cost); warp 16 one thread: weight TMA + all tcgen05.mma issue.
+// Warp roles (800 threads, 1 CTA/SM): warps 0-15 hidden epilogues (four warpgroups; warpgroup g
+// owns the 16-column K-steps ks = g mod 4, each warp its TMEM lane quarter); then 4 warps cost
+// epilogue, one thread per candidate row (fp32: y + b3, un-normalise, SmoothAbs); 4 warps action
+// sampler, one thread per row (Philox + Box-Muller + clip, up to 3 steps ahead, Cosh cost); the
+// last warp: weight TMA + all tcgen05.mma issue (one elected lane).
 // The per-element epilogue math is written branch-free (zero-padded tables and masks): per-element
 // branches serialise the load -> fma -> sqrt chains and cost ~10x (measured).
 #pragma once
@@ -46,11 +46,13 @@ struct TcfGeom {
 };
 
 constexpr int kTcfSlots = 3;  // action tiles in flight: the sampler runs up to 3 steps ahead
-constexpr int kTcfBarriers = 4 + kTcfSlots + 2 * kTcMaxChunks;  // w, dA, dB, y, xa[3], hA[8], hB[8]
-constexpr int kTcfCostWarp0 = 8;    // warps 8-11: cost epilogue (TMEM lane quarter = warp - 8)
-constexpr int kTcfSampWarp0 = 12;   // warps 12-15: action sampler
-constexpr int kTcfMmaWarp = 16;     // warp 16: TMEM alloc, weight TMA, MMA issue
-constexpr int kTcfThreads = 17 * 32;
+constexpr int kTcfMaxKSteps = 16;  // hidden K-steps (Np <= 256)
+constexpr int kTcfBarriers = 4 + 2 * kTcfSlots + kTcfMaxKSteps;  // w, dA, dB, y, xa[3], xf[3], hA[8], hB[8]
+constexpr int kTcfEpiGroups = 4;                      // hidden-epilogue warpgroups (4 warps each)
+constexpr int kTcfCostWarp0 = 4 * kTcfEpiGroups;      // 4 warps: cost epilogue (TMEM lane quarter = warp & 3)
+constexpr int kTcfSampWarp0 = kTcfCostWarp0 + 4;      // 4 warps: action sampler
+constexpr int kTcfMmaWarp = kTcfSampWarp0 + 4;        // 1 warp: TMEM alloc, weight TMA, MMA issue
+constexpr int kTcfThreads = (kTcfMmaWarp + 1) * 32;
 
 inline bool tcf_geometry(int O, int A, int U, size_t max_smem, TcfGeom* g, std::string* why) {
   g->O = O; g->A = A; g->U = U;
@@ -117,7 +119,6 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
   uint8_t* const smem = tcf_smem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int O = g.O, A = g.A, H = sh.H;
-  const int NC = (g.Np + 31) >> 5;   // hidden epilogue chunks (32 columns, last may be 16)
   const int KS_H = g.Np >> 4;        // K-steps over a hidden operand
   const int KS_A = g.Ka >> 4, KS_S = g.Ks >> 4;
 
@@ -132,13 +133,17 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + g.bar_off + 8 * kTcfBarriers);
   const uint32_t bar0 = smem_u32(bars);
   const uint32_t bar_w = bar0, bar_dA = bar0 + 8, bar_dB = bar0 + 16, bar_y = bar0 + 24, bar_xa = bar0 + 32;
-  const uint32_t bar_hA = bar_xa + 8 * kTcfSlots, bar_hB = bar_hA + 8 * kTcMaxChunks;
+  const uint32_t bar_xf = bar_xa + 8 * kTcfSlots;  // action tile slot free again (its MMAs completed)
+  const uint32_t bar_hA = bar_xf + 8 * kTcfSlots, bar_hB = bar_hA + 4 * kTcfMaxKSteps;
 
   if (warp == kTcfMmaWarp) {
     if (lane == 0) {
       mbar_init(bar_w, 1); mbar_init(bar_dA, 1); mbar_init(bar_dB, 1); mbar_init(bar_y, 1);
-      for (int i = 0; i < kTcfSlots; ++i) mbar_init(bar_xa + 8 * i, 1);
-      for (int c = 0; c < kTcMaxChunks; ++c) { mbar_init(bar_hA + 8 * c, 4); mbar_init(bar_hB + 8 * c, 4); }
+      for (int i = 0; i < kTcfSlots; ++i) { mbar_init(bar_xa + 8 * i, 1); mbar_init(bar_xf + 8 * i, 1); }
+      for (int c = 0; c < kTcfMaxKSteps / 2; ++c) {  // one barrier per pair of K-steps: 4 warp arrivals per K-step
+        const uint32_t cnt = (2 * c + 1 < (g.Np >> 4)) ? 8u : 4u;
+        mbar_init(bar_hA + 8 * c, cnt); mbar_init(bar_hB + 8 * c, cnt);
+      }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -199,6 +204,7 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
       uint64_t ad = d_xa0, bd = d_waa;
       mma_ss(tm_a, ad, bd, idesc_a, 0);
       for (int ks = 1; ks < KS_A; ++ks) { ad += step_x; bd += step_a; mma_ss(tm_a, ad, bd, idesc_a, 1); }
+      tc_commit(bar_xf);  // slot 0 is free again once these MMAs have read it
       ad = d_xs; bd = d_w1s;
       for (int ks = 0; ks < KS_S; ++ks) { mma_ss(tm_a, ad, bd, idesc_h, 1); ad += step_x; bd += step_h; }
       tc_commit(bar_dA);
@@ -209,21 +215,21 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
       const uint32_t ph = h & 1;
       // ---- GEMM-B(h): D_B = h1(h) . W2p^T, K-steps released by epilogue A ----
       {
-        // packed chunk c of h1 lives in the first half of its own 32 fp32 columns:
-        // K-step 2c at column 32c, K-step 2c+1 at column 32c+8
+        // K-step ks of h1 (16 hidden units) is packed into the first 8 of its own 16 fp32 columns
+        // and released on its own barrier as soon as one warpgroup has converted it
         uint64_t bd = d_w2;
-        uint32_t a = tm_a, acc = 0;
-        int left = KS_H;
-        for (int c = 0; c < NC; ++c) {
-          mbar_wait(bar_hA + 8 * c, ph);
+        uint32_t a = tm_a;
+        for (int ks = 0; ks < KS_H; ks += 2) {
+          mbar_wait(bar_hA + 4 * ks, ph);  // barrier of the K-step pair ks/2
           tc_fence_after();
+          if (lane == 0 && (ks == 0 || ks + 2 >= KS_H)) tc_stamp(dbg, h, ks == 0 ? 1 : 2);
           if (elect_one()) {
-            mma_ts(tm_b, a, bd, idesc_h, acc);
-            if (left > 1) mma_ts(tm_b, a + 8, bd + step_h, idesc_h, 1);
-            if (c + 1 == NC) tc_commit(bar_dB);
+            mma_ts(tm_b, a, bd, idesc_h, ks > 0);
+            if (ks + 1 < KS_H) mma_ts(tm_b, a + 16, bd + step_h, idesc_h, 1);
+            if (ks + 2 >= KS_H) tc_commit(bar_dB);
           }
           __syncwarp();
-          acc = 1; bd += 2 * step_h; a += 32; left -= 2;
+          bd += 2 * step_h; a += 32;
         }
       }
       // ---- GEMM-A(h+1) (or, after the last step, only the y columns) ----
@@ -234,10 +240,12 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
         const int slot = (h + 1) % kTcfSlots;
         mbar_wait(bar_xa + 8 * slot, ((h + 1) / kTcfSlots) & 1);
         tc_fence_after();
+        if (lane == 0) tc_stamp(dbg, h, 3);
         if (elect_one()) {
           uint64_t ad = d_xa0 + slot * xa_step, bd = d_waa;
           mma_ss(tm_a, ad, bd, idesc_a, 0);
           for (int ks = 1; ks < KS_A; ++ks) { ad += step_x; bd += step_a; mma_ss(tm_a, ad, bd, idesc_a, 1); }
+          tc_commit(bar_xf + 8 * slot);
         }
         __syncwarp();
         acc = 1;
@@ -247,17 +255,17 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
         const uint32_t d = last ? tm_a + (uint32_t)g.Np : tm_a;
         const uint32_t idesc = last ? idesc_y : idesc_a;
         uint32_t a = tm_b;
-        int left = KS_H;
-        for (int c = 0; c < NC; ++c) {
-          mbar_wait(bar_hB + 8 * c, ph);
+        for (int ks = 0; ks < KS_H; ks += 2) {
+          mbar_wait(bar_hB + 4 * ks, ph);
           tc_fence_after();
+          if (lane == 0 && (ks == 0 || ks + 2 >= KS_H)) tc_stamp(dbg, h, ks == 0 ? 16 : 17);
           if (elect_one()) {
             mma_ts(d, a, bd, idesc, acc);
-            if (left > 1) mma_ts(d, a + 8, bd + step_a, idesc, 1);
-            if (c + 1 == NC) tc_commit(bar_dA);
+            if (ks + 1 < KS_H) mma_ts(d, a + 16, bd + step_a, idesc, 1);
+            if (ks + 2 >= KS_H) tc_commit(bar_dA);
           }
           __syncwarp();
-          acc = 1; bd += 2 * step_a; a += 32; left -= 2;
+          acc = 1; bd += 2 * step_a; a += 32;
         }
       }
       if (lane == 0) tc_stamp(dbg, h + 1, 0);
@@ -321,10 +329,10 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
       *reinterpret_cast<uint4*>(xs + j * (kTcRows * 16) + srow * 16) = pk;
     }
     for (int hs = 0; hs < H; ++hs) {
-      // Tile slot hs%3 was last read by GEMM-A(hs-3), and its barrier's previous phase was
-      // consumed before that GEMM: both are over once D_A(hs-3) is complete.  (The waits see
-      // phases #0, #1, ... in order.)
-      if (hs >= kTcfSlots) mbar_wait(bar_dA, (hs - kTcfSlots) & 1);
+      // Tile slot hs%3 was last read by the action MMAs of step hs-3; their commit on the slot's
+      // own "free" barrier is phase #(hs/3 - 1) -- the waiter is never more than one phase behind
+      // (a parity wait cannot tell phases that are 2 apart).
+      if (hs >= kTcfSlots) mbar_wait(bar_xf + 8 * (hs % kTcfSlots), (hs / kTcfSlots - 1) & 1);
       if (srow == 0) tc_stamp(dbg, hs, 12);
       stage_actions(hs);
       fence_proxy_async();   // generic-proxy tile writes -> visible to the MMA (async proxy)
@@ -337,7 +345,7 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
     const int crow = tid - kTcfCostWarp0 * 32;
     const long long row = (long long)blockIdx.x * kTcRows + crow;
     const bool valid = row < R;
-    const uint32_t lane_base = tmem + ((uint32_t)((warp - kTcfCostWarp0) * 32) << 16);
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     float st_total = 0.f;
     // Phases must be observed in order: a parity wait on phase #1 issued before phase #0 has
     // completed would fall through at once (it cannot tell "not yet" from "one phase ago").
@@ -396,47 +404,23 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
         tc_fence_after();
         if (tid == 0) tc_stamp(dbg, h, 4 + 2 * layer);
         const uint32_t bar_rel = layer == 0 ? bar_hA : bar_hB;
-        // first round: one chunk per warpgroup (fast first release), then two chunks in flight
-        bool first = true;
 #pragma unroll 1
-        for (int c = wg; c < NC;) {
-          const int c2 = c + 2;
-          const bool has2 = !first && c2 < NC;
-          const bool full = 32 * c + 32 <= g.Np, full2 = has2 && 32 * c2 + 32 <= g.Np;
-          uint32_t v[32], v2[32], pk[16];
-          if (full) tmem_ld32(lane_base + dcol + 32 * c, v);
-          else tmem_ld16(lane_base + dcol + 32 * c, v);
-          if (has2) {
-            if (full2) tmem_ld32(lane_base + dcol + 32 * c2, v2);
-            else tmem_ld16(lane_base + dcol + 32 * c2, v2);
-          }
+        for (int ks = wg; ks < KS_H; ks += kTcfEpiGroups) {
+          // one K-step: 16 fp32 columns -> 8 packed words in the first half of the same columns
+          uint32_t v[32], pk[16];
+          tmem_ld16(lane_base + dcol + 16 * ks, v);
           tmem_ld_wait();
           if (dbg && blockIdx.x == 0 && h == 0) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (full || i < 16) dbg[(layer * kTcRows + trow) * 256 + 32 * c + i] = __uint_as_float(v[i]);
-              if (has2 && (full2 || i < 16)) dbg[(layer * kTcRows + trow) * 256 + 32 * c2 + i] = __uint_as_float(v2[i]);
-            }
+            for (int i = 0; i < 16; ++i) dbg[(layer * kTcRows + trow) * 256 + 16 * ks + i] = __uint_as_float(v[i]);
           }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = pack_relu<FP16>(v[2 * i], v[2 * i + 1]);
-          if (full) tmem_st16(lane_base + dcol + 32 * c, pk);
-          else tmem_st8(lane_base + dcol + 32 * c, pk);
-          if (has2) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) pk[i] = pack_relu<FP16>(v2[2 * i], v2[2 * i + 1]);
-            if (full2) tmem_st16(lane_base + dcol + 32 * c2, pk);
-            else tmem_st8(lane_base + dcol + 32 * c2, pk);
-          }
+          for (int i = 0; i < 8; ++i) pk[i] = pack_relu<FP16>(v[2 * i], v[2 * i + 1]);
+          tmem_st8(lane_base + dcol + 16 * ks, pk);
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) {
-            mbar_arrive(bar_rel + 8 * c);
-            if (has2) mbar_arrive(bar_rel + 8 * c2);
-          }
-          c += first ? 2 : 4;
-          first = false;
+          if (lane == 0) mbar_arrive(bar_rel + 8 * (ks >> 1));
         }
         if (tid == 0) tc_stamp(dbg, h, 5 + 2 * layer);
       }

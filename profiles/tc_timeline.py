@@ -22,7 +22,8 @@ h.rollout(s0, native.SAMPLE_GAUSSIAN, 1, 0, d_mu=mu, d_sd=sd)
 torch.cuda.synchronize()
 h.tc_debug(True, fetch=True)
 t = h.tc_timeline[:H].astype(np.float64)
-names = {0: "mma:step start (dA committed)", 1: "mma:GEMM-B issued", 2: "mma:GEMM-A(h+1) issued", 4: "epi:dA ready", 5: "epi:epiA done",
+names = {0: "mma:step start (dA committed)", 1: "mma:GEMM-B chunk0 released", 2: "mma:GEMM-B last chunk released", 3: "mma:GEMM-A y+xa ready",
+         16: "mma:GEMM-A chunk0 released", 17: "mma:GEMM-A last chunk released", 4: "epi:dA ready", 5: "epi:epiA done",
          6: "epi:dB ready", 7: "epi:epiB done", 12: "smp:dA ready", 13: "smp:actions(h+1) arrived", 14: "cost:dA ready", 15: "cost:y consumed"}
 base = t[:, 0:1]
 rel = t - base
