@@ -10,8 +10,14 @@
 
 namespace mbrl {
 
-constexpr int kReplayThreads = 1024;
+constexpr int kReplayThreads = 256;  // measured: 256 beats 512 and 1024 (block barriers dominate; the layer is smem-bandwidth bound)
 constexpr int kReplayMaxSlices = 16;
+#ifdef MBRL_REPLAY_PROFILE
+__device__ long long g_replay_stamps[16];
+#define REPLAY_STAMP(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_replay_stamps[i] = clock64(); } while (0)
+#else
+#define REPLAY_STAMP(i) do { } while (0)
+#endif
 
 // Work split of one dense layer over the CTA: thread -> (output quad q, K-slice s).  Every
 // thread accumulates 4 adjacent outputs over its K-slice (one 16-byte weight load feeds 4 FMAs),
@@ -65,7 +71,7 @@ __device__ __forceinline__ void replay_layer(const float* __restrict__ W, const 
   }
   __syncthreads();
   for (int j = threadIdx.x; j < Nout; j += kReplayThreads) {
-    float acc = __ldg(bias + j);
+    float acc = bias[j];
     for (int sl = 0; sl < sp.slices; ++sl) acc += part[sl * sp.ld + j];
     out[j] = RELU ? fmaxf(acc, 0.f) : acc;
   }
@@ -73,7 +79,7 @@ __device__ __forceinline__ void replay_layer(const float* __restrict__ W, const 
 }
 
 struct ReplayLayout {  // shared-memory carve-up, in floats
-  int acts, x, h1, h2, y, part, w1, w2, w3, total;
+  int acts, x, h1, h2, y, part, vec, w1, w2, w3, total;  // vec: b1,b2 [ldu each], b3,mu_s,sd_s [ldo each], mu_a,sd_a [32 each]
 };
 __host__ __device__ inline ReplayLayout replay_layout(int O, int A, int U, int H, bool smem_w) {
   auto r4 = [](int v) { return (v + 3) & ~3; };
@@ -85,7 +91,8 @@ __host__ __device__ inline ReplayLayout replay_layout(int O, int A, int U, int H
   L.h2 = L.h1 + ldu;
   L.y = L.h2 + ldu;
   L.part = L.y + ldo;
-  L.w1 = L.part + kReplayMaxSlices * (ldu > ldo ? ldu : ldo);
+  L.vec = L.part + kReplayMaxSlices * (ldu > ldo ? ldu : ldo);
+  L.w1 = L.vec + 2 * ldu + 3 * ldo + 2 * kMaxAct;
   L.w2 = L.w1 + (smem_w ? D * ldu : 0);
   L.w3 = L.w2 + (smem_w ? U * ldu : 0);
   L.total = L.w3 + (smem_w ? U * ldo : 0);
@@ -108,24 +115,35 @@ replay_kernel(ModelDev m, ActionSource src, Shape sh, const float* __restrict__ 
               MbrlPlanInfo* __restrict__ info) {
   extern __shared__ __align__(16) float rs[];
   const int O = m.O, A = m.A, D = m.D, U = m.U, H = sh.H;
+  REPLAY_STAMP(0);
   const ReplayLayout L = replay_layout(O, A, U, H, SMEM_W);
   float *acts = rs + L.acts, *x = rs + L.x, *h1 = rs + L.h1, *h2 = rs + L.h2, *y = rs + L.y, *part = rs + L.part;
   const ReplaySplit sp1 = replay_split(D, U), sp2 = replay_split(U, U), sp3 = replay_split(U, O);
+  // small per-model vectors live in shared memory: every step of the recurrence re-reads them
+  float *vb1 = rs + L.vec, *vb2 = vb1 + sp1.ld, *vb3 = vb2 + sp2.ld, *vmu = vb3 + sp3.ld, *vsd = vmu + sp3.ld;
+  float *vmua = vsd + sp3.ld, *vsda = vmua + kMaxAct;
+  for (int i = threadIdx.x; i < U; i += kReplayThreads) { vb1[i] = __ldg(m.b1 + i); vb2[i] = __ldg(m.b2 + i); }
+  for (int i = threadIdx.x; i < O; i += kReplayThreads) { vb3[i] = __ldg(m.b3 + i); vmu[i] = __ldg(m.mu_s + i); vsd[i] = __ldg(m.sd_s + i); }
+  for (int i = threadIdx.x; i < A; i += kReplayThreads) { vmua[i] = __ldg(m.mu_a + i); vsda[i] = __ldg(m.sd_a + i); }
   const float *W1 = m.W1t, *W2 = m.W2t, *W3 = m.W3t;
   if (SMEM_W) {
     float *w1 = rs + L.w1, *w2 = rs + L.w2, *w3 = rs + L.w3;
-    for (int i = threadIdx.x; i < D * sp1.ld; i += kReplayThreads) {
-      const int k = i / sp1.ld, j = i - k * sp1.ld;
-      w1[i] = j < U ? __ldg(m.W1t + (long long)k * U + j) : 0.f;
-    }
-    for (int i = threadIdx.x; i < U * sp2.ld; i += kReplayThreads) {
-      const int k = i / sp2.ld, j = i - k * sp2.ld;
-      w2[i] = j < U ? __ldg(m.W2t + (long long)k * U + j) : 0.f;
-    }
-    for (int i = threadIdx.x; i < U * sp3.ld; i += kReplayThreads) {
-      const int k = i / sp3.ld, j = i - k * sp3.ld;
-      w3[i] = j < O ? __ldg(m.W3t + (long long)k * O + j) : 0.f;
-    }
+    auto copy_padded = [&](float* dst, const float* src, int rows, int cols, int ld) {
+      if (ld == cols && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {  // contiguous: 16-byte copies
+        const int n4 = rows * cols / 4;
+#pragma unroll 8
+        for (int i = threadIdx.x; i < n4; i += kReplayThreads)
+          reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+      } else {
+        for (int i = threadIdx.x; i < rows * ld; i += kReplayThreads) {
+          const int k = i / ld, j = i - k * ld;
+          dst[i] = j < cols ? __ldg(src + (long long)k * cols + j) : 0.f;
+        }
+      }
+    };
+    copy_padded(w1, m.W1t, D, U, sp1.ld);
+    copy_padded(w2, m.W2t, U, U, sp2.ld);
+    copy_padded(w3, m.W3t, U, O, sp3.ld);
     W1 = w1; W2 = w2; W3 = w3;
   }
   const int env_l = blockIdx.x;
@@ -148,23 +166,30 @@ replay_kernel(ModelDev m, ActionSource src, Shape sh, const float* __restrict__ 
   }
   for (int o = threadIdx.x; o < O; o += kReplayThreads) y[o] = __ldg(s0 + (long long)env_l * O + o);
   __syncthreads();
+  REPLAY_STAMP(1);
 
   for (int h = 0; h < H; ++h) {
     for (int i = threadIdx.x; i < D; i += kReplayThreads) {
-      x[i] = i < O ? __fdiv_rn(__fsub_rn(y[i], __ldg(m.mu_s + i)), __ldg(m.sd_s + i))
-                   : __fdiv_rn(__fsub_rn(acts[h * A + i - O], __ldg(m.mu_a + i - O)), __ldg(m.sd_a + i - O));
+      x[i] = i < O ? __fdiv_rn(__fsub_rn(y[i], vmu[i]), vsd[i])
+                   : __fdiv_rn(__fsub_rn(acts[h * A + i - O], vmua[i - O]), vsda[i - O]);
     }
     __syncthreads();
-    replay_layer<true, SMEM_W>(W1, m.b1, x, h1, part, D, U, sp1);
-    replay_layer<true, SMEM_W>(W2, m.b2, h1, h2, part, U, U, sp2);
-    replay_layer<false, SMEM_W>(W3, m.b3, h2, x, part, U, O, sp3);  // x[0..O) <- normalised prediction
+    if (h == 5) REPLAY_STAMP(2);
+    replay_layer<true, SMEM_W>(W1, vb1, x, h1, part, D, U, sp1);
+    if (h == 5) REPLAY_STAMP(3);
+    replay_layer<true, SMEM_W>(W2, vb2, h1, h2, part, U, U, sp2);
+    if (h == 5) REPLAY_STAMP(4);
+    replay_layer<false, SMEM_W>(W3, vb3, h2, x, part, U, O, sp3);  // x[0..O) <- normalised prediction
+    if (h == 5) REPLAY_STAMP(5);
     for (int o = threadIdx.x; o < O; o += kReplayThreads) {
-      const float s = __fadd_rn(__fmul_rn(x[o], __ldg(m.sd_s + o)), __ldg(m.mu_s + o));
+      const float s = __fadd_rn(__fmul_rn(x[o], vsd[o]), vmu[o]);
       y[o] = s;
       out_states[((long long)env_l * H + h) * O + o] = s;
     }
     __syncthreads();
+    if (h == 5) REPLAY_STAMP(6);
   }
+  REPLAY_STAMP(7);
   for (int i = threadIdx.x; i < H * A; i += kReplayThreads) out_actions[(long long)env_l * H * A + i] = acts[i];
   if (info && threadIdx.x == 0) {
     info[env_l].best_cost = b.cost;
