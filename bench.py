@@ -146,8 +146,9 @@ def run_reference(args, rank):
     reference is pure Python and cannot travel to the GPU box) on this box's host cores."""
     if rank != 0:
         return
-    w = WORKLOADS[args.workload]
-    iters = w["I"] if (args.steps + args.warmup) <= 40 else 1
+    w = dict(WORKLOADS[args.workload])
+    w["N"] = w["N"] * max(1, args.gpus)  # same whole-job population as the B200 arm at --gpus N
+    iters = w["I"] if (args.steps + args.warmup) <= 40 and args.gpus == 1 else 1
     sec, threads = cpu_reference_plan_time(w, iters, args.steps, args.warmup)
     value = w["N"] * w["H"] * iters / sec
     sample = (f"each step = one reference-composed CEM plan restricted to {iters} iteration(s) of "
@@ -155,7 +156,7 @@ def run_reference(args, rank):
     line = dict(
         impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
         ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-        config=dict(workload=w["name"], l2="n/a (CPU)"),
+        config=dict(workload=w["name"] + (f" x{args.gpus} (N_total={w['N']})" if args.gpus > 1 else ""), l2="n/a (CPU)"),
         cpu_baseline=dict(value=value, unit=UNIT, cores=threads, kind="port", sample=sample),
         e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
         gpu_launches=0,
@@ -268,7 +269,7 @@ def main():
     value = cand_steps_per_plan * args.steps / (total_ms * 1e-3)
 
     # ---- end to end through the host-buffer C-ABI call ----
-    e2e_lat = []
+    e2e_lat, e2e_lat_actions = [], []
     if sharded is None:
         for i in range(args.warmup + args.steps):
             s0 = states0[i].numpy()
@@ -277,6 +278,13 @@ def main():
             dt = time.perf_counter() - t0
             if i >= args.warmup:
                 e2e_lat.append(dt)
+        for i in range(args.warmup + args.steps):  # informational: first-action latency without the state replay
+            s0 = states0[i].numpy()
+            t0 = time.perf_counter()
+            out = h.plan(s0, iterations=I, elites=k, mode=native.SAMPLE_GAUSSIAN, seed=i, actions_only=True)
+            dt = time.perf_counter() - t0
+            if i >= args.warmup:
+                e2e_lat_actions.append(dt)
     else:
         pin = states0.pin_memory()
         for i in range(args.warmup + args.steps):
@@ -312,8 +320,13 @@ def main():
     peaks = measured_peaks()
     alg_flops = N * H * flops_per_cand_step(w)
     achieved = alg_flops / (k_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "rollout_traffic.json")  # dram bytes per launch from the ncu --set full capture
+    if os.path.exists(tpath) and args.workload == "cheetah":
+        with open(tpath) as f:
+            traffic = json.load(f).get(engine)
     roofline = dict(bound="tensor", kernel="rollout+cost (%s engine)" % engine, achieved=achieved,
-                    peak=peaks["bf16_tflops"], unit="TFLOP/s", frac=achieved / peaks["bf16_tflops"], traffic=None,
+                    peak=peaks["bf16_tflops"], unit="TFLOP/s", frac=achieved / peaks["bf16_tflops"], traffic=traffic,
                     peak_source=peaks["source"] + " cuBLAS bf16 burst", kernel_ms=k_ms,
                     algorithmic_flops_per_launch=alg_flops)
 
@@ -343,7 +356,9 @@ def main():
         plan_latency_ms_p50=statistics.median(step_ms),
         clocks=clocks,
         e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=4 * O, d2h_bytes_per_step=4 * H * (O + A) + 16,
-                 latency_ms_p50=statistics.median(e2e_lat) * 1e3, api="mbrl_plan (host buffers)" if world == 1 else "PopulationShardedCEM.plan (pinned s0 -> plan -> host)"),
+                 latency_ms_p50=statistics.median(e2e_lat) * 1e3,
+                 latency_ms_p50_actions_only=(statistics.median(e2e_lat_actions) * 1e3 if e2e_lat_actions else None),
+                 api="mbrl_plan (host buffers)" if world == 1 else "PopulationShardedCEM.plan (pinned s0 -> plan -> host)"),
         gpu_launches=launches_per_plan * args.steps,
         roofline=roofline,
         cpu_baseline=cpu,

@@ -84,6 +84,10 @@ typedef struct MbrlPlanArgs {
   const float* h_injected; /* [iterations, H*R, A] host (INJECT_* modes) or NULL               */
   const float* h_mu0;      /* [E, H, A] host initial mean, NULL -> (lo+hi)/2                    */
   const float* h_sd0;      /* [E, H, A] host initial std,  NULL -> (hi-lo)/2                    */
+  int32_t actions_only; /* 1: emit only the action sequence; the fp32 replay that produces the
+                           predicted states is skipped and out_states is zero-filled.  MPCPolicy
+                           only consumes plan[1][0] (src/mbrl/agents.py:56)                      */
+  int32_t reserved;
 } MbrlPlanArgs;
 
 typedef struct MbrlPlanInfo {

@@ -355,22 +355,23 @@ static int launch_refit(const MbrlPlanner* p, const ActionSource& src, const int
 
 static int launch_replay(MbrlPlanner* p, int mode, uint64_t seed, uint32_t cand_offset, uint32_t env_offset,
                          const float* d_s0, const float* d_injected, const float* d_mu_hist,
-                         const float* d_sd_hist, int iterations, int return_mean, const BestEver* d_best,
-                         float* d_out_states, float* d_out_actions, MbrlPlanInfo* d_info, cudaStream_t st) {
+                         const float* d_sd_hist, int iterations, int return_mean, int actions_only,
+                         const BestEver* d_best, float* d_out_states, float* d_out_actions, MbrlPlanInfo* d_info,
+                         cudaStream_t st) {
   if (!p->have_weights) return fail(MBRL_E_STATE, "mbrl_set_weights must be called before planning");
   ActionSource src = action_source(p, mode, seed, 0, cand_offset, env_offset, d_injected, d_mu_hist, d_sd_hist);
   Shape sh{p->H, p->N, p->E};
   const size_t smem_w = replay_smem_bytes(p->O, p->A, p->U, p->H, true);
-  if (smem_w <= p->max_smem) {
+  if (smem_w <= p->max_smem && !actions_only) {
     MBRL_CUDA(cudaFuncSetAttribute(replay_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
     replay_kernel<true><<<p->E, kReplayThreads, smem_w, st>>>(model_view(p), src, sh, d_s0, d_mu_hist, d_sd_hist, d_best,
-                                                             iterations, return_mean, d_out_states, d_out_actions, d_info);
+                                                             iterations, return_mean, actions_only, d_out_states, d_out_actions, d_info);
   } else {
     const size_t smem = replay_smem_bytes(p->O, p->A, p->U, p->H, false);
     MBRL_REQUIRE(smem <= p->max_smem, "horizon too long for the replay kernel's shared memory");
     MBRL_CUDA(cudaFuncSetAttribute(replay_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     replay_kernel<false><<<p->E, kReplayThreads, smem, st>>>(model_view(p), src, sh, d_s0, d_mu_hist, d_sd_hist, d_best,
-                                                            iterations, return_mean, d_out_states, d_out_actions, d_info);
+                                                            iterations, return_mean, actions_only, d_out_states, d_out_actions, d_info);
   }
   MBRL_CUDA(cudaGetLastError());
   return MBRL_OK;
@@ -453,7 +454,7 @@ extern "C" int mbrl_emit(MbrlPlanner* p, int32_t mode, uint64_t seed, uint32_t c
   MBRL_CUDA(cudaSetDevice(p->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;  // NULL = the CUDA default stream, as everywhere in CUDA
   return launch_replay(p, mode, seed, cand_offset, env_offset, d_s0, d_injected, d_mu_hist, d_sd_hist, iterations,
-                       return_mean, reinterpret_cast<const BestEver*>(d_best), d_out_states, d_out_actions, nullptr, st);
+                       return_mean, 0, reinterpret_cast<const BestEver*>(d_best), d_out_states, d_out_actions, nullptr, st);
 }
 
 extern "C" int mbrl_tc_debug(MbrlPlanner* p, int32_t enable, float* h_out) {
@@ -515,7 +516,8 @@ static int enqueue_plan(MbrlPlanner* p, const MbrlPlanArgs* a, const float* d_s0
     }
   }
   return launch_replay(p, a->sample_mode, a->seed, a->cand_offset, a->env_offset, d_s0, d_injected, p->d_mu_hist,
-                       p->d_sd_hist, I, a->return_mean, p->d_best_ever, d_out_states, d_out_actions, d_info, st);
+                       p->d_sd_hist, I, a->return_mean, a->actions_only, p->d_best_ever, d_out_states, d_out_actions,
+                       d_info, st);
 }
 
 extern "C" int mbrl_plan_device(MbrlPlanner* p, const MbrlPlanArgs* args, const float* d_s0,

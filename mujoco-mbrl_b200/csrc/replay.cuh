@@ -110,7 +110,7 @@ template <bool SMEM_W>
 __global__ void __launch_bounds__(kReplayThreads)
 replay_kernel(ModelDev m, ActionSource src, Shape sh, const float* __restrict__ s0,
               const float* __restrict__ mu_hist, const float* __restrict__ sd_hist,
-              const BestEver* __restrict__ best_ever, int iterations, int return_mean,
+              const BestEver* __restrict__ best_ever, int iterations, int return_mean, int actions_only,
               float* __restrict__ out_states, float* __restrict__ out_actions,
               MbrlPlanInfo* __restrict__ info) {
   extern __shared__ __align__(16) float rs[];
@@ -126,7 +126,7 @@ replay_kernel(ModelDev m, ActionSource src, Shape sh, const float* __restrict__ 
   for (int i = threadIdx.x; i < O; i += kReplayThreads) { vb3[i] = __ldg(m.b3 + i); vmu[i] = __ldg(m.mu_s + i); vsd[i] = __ldg(m.sd_s + i); }
   for (int i = threadIdx.x; i < A; i += kReplayThreads) { vmua[i] = __ldg(m.mu_a + i); vsda[i] = __ldg(m.sd_a + i); }
   const float *W1 = m.W1t, *W2 = m.W2t, *W3 = m.W3t;
-  if (SMEM_W) {
+  if (SMEM_W && !actions_only) {
     float *w1 = rs + L.w1, *w2 = rs + L.w2, *w3 = rs + L.w3;
     auto copy_padded = [&](float* dst, const float* src, int rows, int cols, int ld) {
       if (ld == cols && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {  // contiguous: 16-byte copies
@@ -168,7 +168,10 @@ replay_kernel(ModelDev m, ActionSource src, Shape sh, const float* __restrict__ 
   __syncthreads();
   REPLAY_STAMP(1);
 
-  for (int h = 0; h < H; ++h) {
+  if (actions_only) {
+    for (int i = threadIdx.x; i < H * O; i += kReplayThreads) out_states[(long long)env_l * H * O + i] = 0.f;
+  }
+  for (int h = 0; h < (actions_only ? 0 : H); ++h) {
     for (int i = threadIdx.x; i < D; i += kReplayThreads) {
       x[i] = i < O ? __fdiv_rn(__fsub_rn(y[i], vmu[i]), vsd[i])
                    : __fdiv_rn(__fsub_rn(acts[h * A + i - O], vmua[i - O]), vsda[i - O]);

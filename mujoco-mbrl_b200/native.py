@@ -40,6 +40,7 @@ class MbrlPlanArgs(C.Structure):
         ("iterations", C.c_int32), ("elites", C.c_int32), ("sample_mode", C.c_int32), ("return_mean", C.c_int32),
         ("seed", C.c_uint64), ("cand_offset", C.c_uint32), ("env_offset", C.c_uint32),
         ("h_injected", C.c_void_p), ("h_mu0", C.c_void_p), ("h_sd0", C.c_void_p),
+        ("actions_only", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -195,9 +196,11 @@ class NativePlanner:
         self.set_action_bounds(prob.act_lo, prob.act_hi)
 
     # ---- whole plans -----------------------------------------------------------------
-    def _args(self, iterations, elites, mode, seed, return_mean, cand_offset, env_offset, injected, mu0, sd0):
+    def _args(self, iterations, elites, mode, seed, return_mean, cand_offset, env_offset, injected, mu0, sd0,
+              actions_only=False):
         keep = []
         a = MbrlPlanArgs()
+        a.actions_only = int(actions_only)
         a.iterations, a.elites, a.sample_mode, a.return_mean = iterations, elites, mode, int(return_mean)
         a.seed, a.cand_offset, a.env_offset = int(seed) & (2 ** 64 - 1), cand_offset, env_offset
         for name, val, n in (("h_injected", injected, iterations * self.H * self.R * self.A),
@@ -211,11 +214,12 @@ class NativePlanner:
         return a, keep
 
     def plan(self, s0, iterations=1, elites=1, mode=SAMPLE_GAUSSIAN, seed=0, injected=None, mu0=None, sd0=None,
-             return_mean=False, want_dist=False, cand_offset=0, env_offset=0):
+             return_mean=False, want_dist=False, cand_offset=0, env_offset=0, actions_only=False):
         """mbrl_plan with host buffers.  s0: [O] or [E,O].  Returns a dict of numpy arrays:
         states [E,H,O], actions [E,H,A], info (structured [E]), optionally mu/sd [E,H,A]."""
         s0 = _f32(s0).reshape(self.E, self.O)
-        args, keep = self._args(iterations, elites, mode, seed, return_mean, cand_offset, env_offset, injected, mu0, sd0)
+        args, keep = self._args(iterations, elites, mode, seed, return_mean, cand_offset, env_offset, injected, mu0, sd0,
+                                actions_only)
         states = np.empty((self.E, self.H, self.O), np.float32)
         actions = np.empty((self.E, self.H, self.A), np.float32)
         info = np.zeros(self.E, PLAN_INFO_DTYPE)
@@ -227,9 +231,11 @@ class NativePlanner:
         return dict(states=states, actions=actions, info=info, mu=mu, sd=sd)
 
     def plan_device(self, d_s0, d_out_states, d_out_actions, d_info=None, iterations=1, elites=1,
-                    mode=SAMPLE_GAUSSIAN, seed=0, d_injected=None, return_mean=False, cand_offset=0, env_offset=0):
+                    mode=SAMPLE_GAUSSIAN, seed=0, d_injected=None, return_mean=False, cand_offset=0, env_offset=0,
+                    actions_only=False):
         """mbrl_plan_device: everything resident in HBM, enqueued on torch's current stream."""
-        args, keep = self._args(iterations, elites, mode, seed, return_mean, cand_offset, env_offset, None, None, None)
+        args, keep = self._args(iterations, elites, mode, seed, return_mean, cand_offset, env_offset, None, None, None,
+                                actions_only)
         _check(self.lib.mbrl_plan_device(self._h, C.byref(args), _dp(d_s0), _dp(d_injected), _dp(d_out_states),
                                          _dp(d_out_actions), _dp(d_info), _stream_ptr()))
 

@@ -72,12 +72,13 @@ class RandomShootingPlanner(ModelPlanner):
     """GPU random shooting: N candidate sequences rolled through the dynamics MLP for
     `horizon` steps, scored, argmin (first minimum) returned -- src/mbrl/planners.py:140-216.
 
-    kwargs: num_trajectories (default 1000, planners.py:141); sampler="device" (Philox uniform
+    kwargs: num_trajectories (default 1000, planners.py:141); return_states=False skips the fp32
+    replay that yields the predicted states (MPCPolicy only uses the first action); sampler="device" (Philox uniform
     on the GPU with the reference sampler's bounds) or "host" (call `sample_action` once on the
     host like the reference and inject the draws: bit-faithful to a given numpy stream);
     engine="fp32"|"bf16"|"fp16"; seed; device."""
 
-    defaults = dict(num_trajectories=1000, sampler="device", engine="fp32", seed=None, device=0)
+    defaults = dict(num_trajectories=1000, sampler="device", engine="fp32", seed=None, device=0, return_states=True)
 
     @staticmethod
     def plan(initial_state, model, cost, sample_action, horizon, initial_trajectory=None, **kwargs):
@@ -93,9 +94,11 @@ class RandomShootingPlanner(ModelPlanner):
         ent["calls"] += 1
         if sampler == "host":
             out = h.plan(initial_state, 1, 1, native.SAMPLE_INJECT_ACTIONS, seed,
-                         injected=_host_sample(sample_action, n, horizon, prob.act_dim))
+                         injected=_host_sample(sample_action, n, horizon, prob.act_dim),
+                         actions_only=not kwargs.get("return_states", d["return_states"]))
         elif sampler == "device":
-            out = h.plan(initial_state, 1, 1, native.SAMPLE_UNIFORM, seed)
+            out = h.plan(initial_state, 1, 1, native.SAMPLE_UNIFORM, seed,
+                         actions_only=not kwargs.get("return_states", d["return_states"]))
         else:
             raise ValueError("sampler must be 'device' or 'host'")
         return _as_torch(out["states"][0]), _as_torch(out["actions"][0])
@@ -110,8 +113,8 @@ class CEMPlanner(ModelPlanner):
     `initial_trajectory` (the warm start MPCPolicy passes, src/mbrl/agents.py:41-47) seeds the
     mean with its action sequence when given."""
 
-    defaults = dict(num_trajectories=16384, num_iterations=5, elite_frac=0.1, engine="fp32", seed=None, device=0,
-                    return_mean=False, init_std=None)
+    defaults = dict(num_trajectories=16384, num_iterations=5, elite_frac=0.1, engine="fp16", seed=None, device=0,
+                    return_mean=False, init_std=None, return_states=True)
 
     @staticmethod
     def plan(initial_state, model, cost, sample_action, horizon, initial_trajectory=None, **kwargs):
@@ -138,7 +141,8 @@ class CEMPlanner(ModelPlanner):
         noise = kwargs.get("noise")  # [I, H*N, A] recorded N(0,1) draws (parity runs)
         mode = native.SAMPLE_GAUSSIAN if noise is None else native.SAMPLE_INJECT_NOISE
         out = h.plan(initial_state, iters, k, mode, seed, injected=noise, mu0=mu0, sd0=sd0,
-                     return_mean=kwargs.get("return_mean", d["return_mean"]))
+                     return_mean=kwargs.get("return_mean", d["return_mean"]),
+                     actions_only=not kwargs.get("return_states", d["return_states"]))
         return _as_torch(out["states"][0]), _as_torch(out["actions"][0])
 
 

@@ -17,7 +17,7 @@ int main() {
   Shape sh{H, N, 1};
   const size_t smem = replay_smem_bytes(O, A, U, H, true);
   cudaFuncSetAttribute(replay_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  for (int r = 0; r < 3; ++r) replay_kernel<true><<<1, kReplayThreads, smem>>>(m, src, sh, s0, mu, sd, dbe, 1, 0, os, oa, nullptr);
+  for (int r = 0; r < 3; ++r) replay_kernel<true><<<1, kReplayThreads, smem>>>(m, src, sh, s0, mu, sd, dbe, 1, 0, 0, os, oa, nullptr);
   cudaError_t e = cudaDeviceSynchronize(); if (e != cudaSuccess) { printf("%s\n", cudaGetErrorString(e)); return 1; }
   long long st[16]; cudaMemcpyFromSymbol(st, g_replay_stamps, sizeof(st));
   printf("smem %zu B, threads %d\nsetup (weights->smem, actions) %lld\nstep 5: L1 %lld  L2 %lld  L3 %lld  state+sync %lld\ntotal %lld cycles (%.1f per step)\n", smem, kReplayThreads,

@@ -28,7 +28,7 @@ def test_struct_layouts_match_header():
     from mbrl_b200 import native
     assert ctypes.sizeof(native.MbrlConfig) == 40
     assert ctypes.sizeof(native.MbrlPlanInfo) == 16 == native.PLAN_INFO_DTYPE.itemsize
-    assert ctypes.sizeof(native.MbrlPlanArgs) == 56
+    assert ctypes.sizeof(native.MbrlPlanArgs) == 64
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

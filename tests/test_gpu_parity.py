@@ -121,6 +121,16 @@ def test_rs_plan_matches_reference_golden(native, name):
     np.testing.assert_allclose(out["states"][0], g["plan_states"], rtol=FP32_STATE_RTOL, atol=FP32_STATE_ATOL)
 
 
+def test_actions_only_plan_skips_replay(native):
+    g = load_golden("rs_cartpole.npz")
+    p = params_from_golden(g)
+    n, H = int(g["n"]), int(g["horizon"])
+    h = _planner(native, p, H, n)
+    out = h.plan(g["s0"], 1, 1, native.SAMPLE_INJECT_ACTIONS, injected=g["actions"], actions_only=True)
+    np.testing.assert_array_equal(out["actions"][0], g["plan_actions"])
+    assert int(out["info"]["best_index"][0]) == int(g["idx"]) and not out["states"].any()
+
+
 def test_rollout_ragged_rows_and_batched_envs(native):
     """N not a multiple of the row tile, several environments with distinct s0."""
     p = po.synthetic_params(9, 3, 40, seed=5)
