@@ -220,14 +220,16 @@ def main():
     # synthetic problem; the CPU arm's oracle generates the identical values
     from mbrl_b200.synthetic import synthetic_problem, synthetic_state
     prob = p = synthetic_problem(O, A, U)
-    h = native.NativePlanner(O, A, U, H, N, 1, I, min(k, N), engine, local_rank)
+    h = native.NativePlanner(O, A, U, H, N, 1, I, k, engine, local_rank)
     h.load_problem(prob)
+    if world > 1:
+        h.comm_init(rank, world)  # NCCL communicator inside the library: the sharded CEM loop runs on the stream
     states0 = torch.stack([synthetic_state(p, c) for c in range(args.warmup + args.steps)]).float()
     d_states0 = states0.to(dev)
     d_out_s = torch.empty(1, H, O, device=dev)
     d_out_a = torch.empty(1, H, A, device=dev)
     d_info = torch.zeros(1, 4, dtype=torch.int32, device=dev)
-    sharded = PopulationShardedCEM(NativeOps(h), N, H, A, rank, world, lo=p.act_lo, hi=p.act_hi) if world > 1 else None
+    sharded = None  # (the Python host loop mbrl_b200.sharding.PopulationShardedCEM remains as the tested reference of this logic)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
 
     def plan_resident(i):
@@ -344,7 +346,7 @@ def main():
                           f"oracle port of planners.py:189-216 incl. autograd + Python list build; {sec * 1e3:.0f} ms/plan",
                    ms_per_plan=sec * 1e3)
 
-    launches_per_plan = 1 + 2 * I + (I - 1) + 1
+    launches_per_plan = (1 + 2 * I + (I - 1) + 1) if world == 1 else (1 + 6 * I + (I - 1) + 1)
     line = dict(
         metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
@@ -352,13 +354,13 @@ def main():
         data="synthetic",
         config=dict(workload=w["name"] + (f" x{world} GPUs population-sharded, N_total={n_total}" if world > 1 else ""),
                     engine=engine, elites=k, l2="flushed between timed plans (256 MiB write)",
-                    parallelism=("population-sharded x%d, NCCL elite all-gather" % world) if world > 1 else "single GPU"),
+                    parallelism=("population-sharded x%d, one NCCL all-gather of (cost, index) elites per iteration" % world) if world > 1 else "single GPU"),
         plan_latency_ms_p50=statistics.median(step_ms),
         clocks=clocks,
         e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=4 * O, d2h_bytes_per_step=4 * H * (O + A) + 16,
                  latency_ms_p50=statistics.median(e2e_lat) * 1e3,
                  latency_ms_p50_actions_only=(statistics.median(e2e_lat_actions) * 1e3 if e2e_lat_actions else None),
-                 api="mbrl_plan (host buffers)" if world == 1 else "PopulationShardedCEM.plan (pinned s0 -> plan -> host)"),
+                 api="mbrl_plan (host buffers)" + ("" if world == 1 else ", population-sharded (in-library NCCL all-gather)")),
         gpu_launches=launches_per_plan * args.steps,
         roofline=roofline,
         cpu_baseline=cpu,

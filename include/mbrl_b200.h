@@ -187,6 +187,21 @@ int mbrl_emit(MbrlPlanner* p, int32_t sample_mode, uint64_t seed, uint32_t cand_
               int32_t return_mean, const MbrlPlanInfo* d_best, float* d_out_states,
               float* d_out_actions, void* stream);
 
+/* ---- population sharding over the GPUs of one node (one process per GPU, NCCL) ----------
+ * After mbrl_comm_init the handle is one shard of a population of world * num_candidates
+ * candidates (rank r owns global candidates [r*N, (r+1)*N)); mbrl_plan / mbrl_plan_device then
+ * run the sharded CEM loop entirely on the stream: per iteration one ncclAllGather of each
+ * rank's min(k, N) cheapest (cost, global index) pairs, the same global top-k selection on every
+ * rank (ties -> lower global index), and a redundant refit that regenerates the elites from
+ * their global indices (Philox counters carry the global index), so no second collective is
+ * needed and every rank holds bit-identical mean/std and emits the same plan.  args->elites is
+ * the GLOBAL k; info.best_index is a GLOBAL candidate index; num_envs must be 1; Philox sample
+ * modes only.  libnccl.so.2 is resolved at run time (dlopen), not at link time.
+ *   mbrl_nccl_unique_id: rank 0 fills 128 bytes, the host broadcasts them to all ranks.        */
+int mbrl_nccl_unique_id(uint8_t* h_id128);
+int mbrl_comm_init(MbrlPlanner* p, const uint8_t* h_id128, int32_t rank, int32_t world);
+int mbrl_comm_destroy(MbrlPlanner* p);
+
 /* Diagnostic for the tensor-core engines (tests only): enable != 0 arms a dump of the raw
  * fp32 accumulators of row tile 0 at step 0 ([3 layers][128 rows][256 cols] floats) followed
  * by a clock64() timeline of tile 1 ([64 steps][32 events] int64) by the next mbrl_rollout;

@@ -19,6 +19,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-shared",
     "-Xptxas", "-v",
     "--expt-relaxed-constexpr", "--expt-extended-lambda",
+    "-ldl",
 ]
 
 

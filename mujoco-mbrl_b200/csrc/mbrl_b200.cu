@@ -2,10 +2,12 @@
 // byte of planning arithmetic happens in the kernels included below.  There is no CPU
 // fallback: without a CUDA device every computing entry point returns MBRL_E_CUDA.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <new>
 #include <string>
 #include <vector>
@@ -42,6 +44,43 @@ static int fail(int code, const std::string& msg) {
   } while (0)
 
 // --------------------------------------------------------------------------------------
+// NCCL, resolved at run time (the library must load on machines without NCCL / without a GPU)
+// --------------------------------------------------------------------------------------
+struct NcclUniqueId { char internal[128]; };
+typedef void* NcclComm;
+struct NcclApi {
+  int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+  int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int) = nullptr;
+  int (*CommDestroy)(NcclComm) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+static NcclApi g_nccl;
+static int load_nccl() {
+  if (g_nccl.ok) return MBRL_OK;
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);  // torch has usually loaded it already
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) return fail(MBRL_E_UNSUPPORTED, std::string("cannot load libnccl.so.2: ") + dlerror());
+  g_nccl.GetUniqueId = (int (*)(NcclUniqueId*))dlsym(lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(NcclComm*, int, NcclUniqueId, int))dlsym(lib, "ncclCommInitRank");
+  g_nccl.CommDestroy = (int (*)(NcclComm))dlsym(lib, "ncclCommDestroy");
+  g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, NcclComm, cudaStream_t))dlsym(lib, "ncclAllGather");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllGather || !g_nccl.GetErrorString)
+    return fail(MBRL_E_UNSUPPORTED, "libnccl.so.2 lacks a required symbol");
+  g_nccl.ok = true;
+  return MBRL_OK;
+}
+#define MBRL_NCCL(expr)                                                                         \
+  do {                                                                                          \
+    int r__ = (expr);                                                                           \
+    if (r__ != 0) return fail(MBRL_E_CUDA, std::string(#expr) + ": " + g_nccl.GetErrorString(r__)); \
+  } while (0)
+constexpr int kNcclUint32 = 3;  // ncclUint32 (nccl.h ncclDataType_t)
+
+// --------------------------------------------------------------------------------------
 // handle
 // --------------------------------------------------------------------------------------
 struct MbrlPlanner {
@@ -74,6 +113,16 @@ struct MbrlPlanner {
   cudaStream_t stream = nullptr;
   int num_sms = 0;
   size_t max_smem = 0;
+  // population sharding (mbrl_comm_init)
+  NcclComm comm = nullptr;
+  int rank = 0, world = 1;
+  float* d_ecost = nullptr;     // [k_l] local elite costs
+  uint32_t* d_send = nullptr;   // [2*k_l]
+  uint32_t* d_recv = nullptr;   // [world*2*k_l]
+  float* d_gcost = nullptr;     // [world*k_l]
+  int* d_gidx = nullptr;        // [world*k_l]
+  int* d_pos = nullptr;         // [kmax]
+  MbrlPlanInfo* d_best_now = nullptr;
 };
 
 static ModelDev model_view(const MbrlPlanner* p) {
@@ -116,6 +165,9 @@ extern "C" int mbrl_destroy(MbrlPlanner* p) {
   if (p->d_elite) cudaFree(p->d_elite);
   if (p->d_best_ever) cudaFree(p->d_best_ever);
   if (p->d_info) cudaFree(p->d_info);
+  if (p->comm && g_nccl.ok) g_nccl.CommDestroy(p->comm);
+  void* shard[] = {p->d_ecost, p->d_send, p->d_recv, p->d_gcost, p->d_gidx, p->d_pos, p->d_best_now};
+  for (void* q : shard) if (q) cudaFree(q);
   tc_free(&p->tc);
   float* pinned[] = {p->h_s0, p->h_out_states, p->h_out_actions, p->h_mu, p->h_sd};
   for (float* q : pinned) if (q) cudaFreeHost(q);
@@ -136,7 +188,8 @@ extern "C" int mbrl_create(const MbrlConfig* cfg, MbrlPlanner** out) {
   MBRL_REQUIRE(cfg->num_envs >= 1, "num_envs must be >= 1");
   MBRL_REQUIRE((long long)cfg->num_envs * cfg->num_candidates < (1ll << 31), "E*N too large");
   MBRL_REQUIRE(cfg->max_iterations >= 1 && cfg->max_iterations <= 1024, "max_iterations out of range");
-  MBRL_REQUIRE(cfg->max_elites >= 1 && cfg->max_elites <= cfg->num_candidates, "max_elites out of range [1,N]");
+  MBRL_REQUIRE(cfg->max_elites >= 1 && (long long)cfg->max_elites <= 64ll * cfg->num_candidates,
+               "max_elites out of range [1, N] (or [1, world*N] for a population shard)");
   MBRL_REQUIRE(cfg->engine >= MBRL_ENGINE_SIMT_FP32 && cfg->engine <= MBRL_ENGINE_TC_FP16, "unknown engine");
   int ndev = 0;
   MBRL_CUDA(cudaGetDeviceCount(&ndev));
@@ -443,6 +496,52 @@ extern "C" int mbrl_refit(MbrlPlanner* p, int32_t mode, uint64_t seed, uint32_t 
 
 static_assert(sizeof(BestEver) == sizeof(MbrlPlanInfo), "BestEver and MbrlPlanInfo share one layout");
 
+extern "C" int mbrl_nccl_unique_id(uint8_t* h_id128) {
+  MBRL_REQUIRE(h_id128, "null id buffer");
+  int rc = load_nccl();
+  if (rc) return rc;
+  NcclUniqueId id;
+  MBRL_NCCL(g_nccl.GetUniqueId(&id));
+  std::memcpy(h_id128, id.internal, 128);
+  return MBRL_OK;
+}
+
+extern "C" int mbrl_comm_destroy(MbrlPlanner* p) {
+  if (!p) return fail(MBRL_E_INVALID, "null planner");
+  if (p->comm) {
+    MBRL_CUDA(cudaSetDevice(p->cfg.device));
+    MBRL_CUDA(cudaDeviceSynchronize());
+    g_nccl.CommDestroy(p->comm);
+    p->comm = nullptr;
+  }
+  p->rank = 0; p->world = 1;
+  return MBRL_OK;
+}
+
+extern "C" int mbrl_comm_init(MbrlPlanner* p, const uint8_t* h_id128, int32_t rank, int32_t world) {
+  if (!p) return fail(MBRL_E_INVALID, "null planner");
+  MBRL_REQUIRE(h_id128, "null id");
+  MBRL_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world, "bad rank/world");
+  MBRL_REQUIRE(p->E == 1, "population sharding needs num_envs == 1 (shard environments without a communicator)");
+  MBRL_REQUIRE(!p->comm, "communicator already initialised");
+  int rc = load_nccl();
+  if (rc) return rc;
+  MBRL_CUDA(cudaSetDevice(p->cfg.device));
+  NcclUniqueId id;
+  std::memcpy(id.internal, h_id128, 128);
+  MBRL_NCCL(g_nccl.CommInitRank(&p->comm, world, id, rank));
+  p->rank = rank; p->world = world;
+  const size_t kl = (size_t)std::min(p->cfg.max_elites, p->N);
+  MBRL_CUDA(dev_alloc(&p->d_ecost, kl));
+  MBRL_CUDA(dev_alloc(&p->d_send, 2 * kl));
+  MBRL_CUDA(dev_alloc(&p->d_recv, 2 * kl * world));
+  MBRL_CUDA(dev_alloc(&p->d_gcost, kl * world));
+  MBRL_CUDA(dev_alloc(&p->d_gidx, kl * world));
+  MBRL_CUDA(dev_alloc(&p->d_pos, (size_t)p->cfg.max_elites));
+  MBRL_CUDA(dev_alloc(&p->d_best_now, 1));
+  return MBRL_OK;
+}
+
 extern "C" int mbrl_emit(MbrlPlanner* p, int32_t mode, uint64_t seed, uint32_t cand_offset, uint32_t env_offset,
                          const float* d_s0, const float* d_injected, const float* d_mu_hist,
                          const float* d_sd_hist, int32_t iterations, int32_t return_mean,
@@ -502,12 +601,44 @@ static int enqueue_plan(MbrlPlanner* p, const MbrlPlanArgs* a, const float* d_s0
   }
   MBRL_CUDA(cudaGetLastError());
 
+  const bool sharded = p->comm != nullptr;
+  if (sharded) {
+    MBRL_REQUIRE(a->sample_mode == MBRL_SAMPLE_GAUSSIAN || a->sample_mode == MBRL_SAMPLE_UNIFORM,
+                 "population sharding supports the Philox sample modes only");
+    MBRL_REQUIRE((long long)k <= (long long)p->world * p->N, "elites exceed the global population");
+  } else {
+    MBRL_REQUIRE(k <= p->N, "elites exceed the population");
+  }
+  const uint32_t cand_offset = sharded ? (uint32_t)((long long)p->rank * p->N) : a->cand_offset;
   for (int it = 0; it < I; ++it) {
     const float* inj = d_injected ? d_injected + (long long)it * HRA : nullptr;
-    ActionSource src = action_source(p, a->sample_mode, a->seed, (uint32_t)it, a->cand_offset, a->env_offset, inj,
+    ActionSource src = action_source(p, a->sample_mode, a->seed, (uint32_t)it, cand_offset, a->env_offset, inj,
                                      p->d_mu_hist + it * EHA, p->d_sd_hist + it * EHA);
     int rc = launch_rollout(p, src, d_s0, p->d_costs, nullptr, nullptr, st);
     if (rc) return rc;
+    if (sharded) {
+      // local elites -> all-gather (cost, global index) -> same global top-k on every rank ->
+      // redundant refit from GLOBAL indices (cand_offset 0): no second collective
+      const int kl = std::min(k, p->N);
+      rc = launch_topk(p->d_costs, 1, p->N, kl, p->d_elite, p->d_ecost, nullptr, nullptr, it, st);
+      if (rc) return rc;
+      pack_elites_kernel<<<(kl + 255) / 256, 256, 0, st>>>(p->d_ecost, p->d_elite, kl, (int)cand_offset, p->d_send);
+      MBRL_NCCL(g_nccl.AllGather(p->d_send, p->d_recv, (size_t)2 * kl, kNcclUint32, p->comm, st));
+      const int ng = kl * p->world;
+      unpack_gathered_kernel<<<(ng + 255) / 256, 256, 0, st>>>(p->d_recv, p->world, kl, p->d_gcost, p->d_gidx);
+      rc = launch_topk(p->d_gcost, 1, ng, k, p->d_pos, nullptr, p->d_best_now, nullptr, it, st);
+      if (rc) return rc;
+      remap_elites_kernel<<<(k + 255) / 256, 256, 0, st>>>(p->d_pos, p->d_gidx, k, p->d_elite, p->d_best_now,
+                                                          p->d_best_ever, it);
+      MBRL_CUDA(cudaGetLastError());
+      if (it + 1 < I || need_final_dist) {
+        ActionSource gsrc = src;
+        gsrc.cand_offset = 0;
+        rc = launch_refit(p, gsrc, p->d_elite, k, p->d_mu_hist + (it + 1) * EHA, p->d_sd_hist + (it + 1) * EHA, st);
+        if (rc) return rc;
+      }
+      continue;
+    }
     rc = launch_topk(p->d_costs, p->E, p->N, k, p->d_elite, nullptr, nullptr, p->d_best_ever, it, st);
     if (rc) return rc;
     if (it + 1 < I || need_final_dist) {
@@ -515,9 +646,9 @@ static int enqueue_plan(MbrlPlanner* p, const MbrlPlanArgs* a, const float* d_s0
       if (rc) return rc;
     }
   }
-  return launch_replay(p, a->sample_mode, a->seed, a->cand_offset, a->env_offset, d_s0, d_injected, p->d_mu_hist,
-                       p->d_sd_hist, I, a->return_mean, a->actions_only, p->d_best_ever, d_out_states, d_out_actions,
-                       d_info, st);
+  return launch_replay(p, a->sample_mode, a->seed, sharded ? 0u : a->cand_offset, a->env_offset, d_s0, d_injected,
+                       p->d_mu_hist, p->d_sd_hist, I, a->return_mean, a->actions_only, p->d_best_ever, d_out_states,
+                       d_out_actions, d_info, st);
 }
 
 extern "C" int mbrl_plan_device(MbrlPlanner* p, const MbrlPlanArgs* args, const float* d_s0,

@@ -337,6 +337,43 @@ refit_kernel(ActionSource src, Shape sh, int A, const int* __restrict__ elite_id
   }
 }
 
+// ---- population-sharded elite merge (see mbrl_comm_init) ---------------------------------------
+// send buffer of one rank: [k_l costs (bits) | k_l global indices]
+__global__ void pack_elites_kernel(const float* __restrict__ elite_cost, const int* __restrict__ elite_idx,
+                                   int k_l, int idx_offset, uint32_t* __restrict__ send) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < k_l) {
+    send[i] = __float_as_uint(elite_cost[i]);
+    send[k_l + i] = (uint32_t)(elite_idx[i] + idx_offset);
+  }
+}
+// gathered [world][2*k_l] -> contiguous costs / global indices in rank order (== ascending global
+// index, so "ties -> lower position" in the merge is "ties -> lower global index")
+__global__ void unpack_gathered_kernel(const uint32_t* __restrict__ recv, int world, int k_l,
+                                       float* __restrict__ gcost, int* __restrict__ gidx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < world * k_l) {
+    const int r = i / k_l, j = i - r * k_l;
+    gcost[i] = __uint_as_float(recv[(long long)r * 2 * k_l + j]);
+    gidx[i] = (int)recv[(long long)r * 2 * k_l + k_l + j];
+  }
+}
+// positions in the gathered list -> global candidate indices; best-ever bookkeeping in global indices
+__global__ void remap_elites_kernel(const int* __restrict__ pos, const int* __restrict__ gidx, int k,
+                                    int* __restrict__ elite_global, const MbrlPlanInfo* __restrict__ best_now,
+                                    BestEver* __restrict__ best_ever, int iteration) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < k) elite_global[i] = gidx[pos[i]];
+  if (i == 0) {
+    const float cmin = best_now->best_cost;
+    BestEver b = *best_ever;
+    if (b.iteration < 0 || cmin < b.cost) {
+      b.cost = cmin; b.iteration = iteration; b.index = gidx[best_now->best_index];
+      *best_ever = b;
+    }
+  }
+}
+
 // mu/sd initialisation: (lo+hi)/2 and (hi-lo)/2 per (env, h, a); best-ever reset.
 __global__ void init_plan_kernel(float* __restrict__ mu, float* __restrict__ sd, long long n,
                                  float lo, float hi, BestEver* __restrict__ best_ever, int E) {

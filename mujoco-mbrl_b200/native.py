@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "mbrl_abi_version", "mbrl_last_error", "mbrl_create", "mbrl_destroy", "mbrl_set_weights",
     "mbrl_set_norm", "mbrl_set_cost", "mbrl_set_action_bounds", "mbrl_plan", "mbrl_plan_device",
     "mbrl_rollout", "mbrl_sample", "mbrl_philox_raw", "mbrl_topk", "mbrl_refit", "mbrl_emit",
-    "mbrl_tc_debug",
+    "mbrl_tc_debug", "mbrl_nccl_unique_id", "mbrl_comm_init", "mbrl_comm_destroy",
 ]
 
 
@@ -95,6 +95,9 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         "mbrl_refit": [p, i32, u64, u32, u32, u32, vp, vp, vp, vp, i32, vp, vp, vp],
         "mbrl_emit": [p, i32, u64, u32, u32, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp],
         "mbrl_tc_debug": [p, i32, vp],
+        "mbrl_nccl_unique_id": [vp],
+        "mbrl_comm_init": [p, vp, i32, i32],
+        "mbrl_comm_destroy": [p],
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)
@@ -270,6 +273,26 @@ class NativePlanner:
                                    _dp(d_mu), _dp(d_sd), _dp(d_elite_idx), k, _dp(mu), _dp(sd), _stream_ptr()))
         return mu, sd
 
+
+    def comm_init(self, rank=None, world=None, group=None):
+        """Make this handle one shard of a population split over the ranks of a torch.distributed
+        group (NCCL inside the library; rank 0's unique id is broadcast through torch)."""
+        import torch
+        import torch.distributed as dist
+        if world is None:
+            world = dist.get_world_size(group) if dist.is_initialized() else 1
+            rank = dist.get_rank(group) if dist.is_initialized() else 0
+        buf = np.zeros(128, np.uint8)
+        if rank == 0:
+            _check(self.lib.mbrl_nccl_unique_id(_hp(buf)))
+        if world > 1:
+            t = torch.from_numpy(buf)
+            if dist.get_backend(group) == "nccl":
+                t = t.cuda(self.device)
+            dist.broadcast(t, src=0, group=group)
+            buf = t.cpu().numpy().copy()
+        _check(self.lib.mbrl_comm_init(self._h, _hp(buf), rank, world))
+        self.rank, self.world = rank, world
 
     def tc_debug(self, enable=True, fetch=False):
         """Diagnostic: arm / fetch the raw accumulator dump of tile 0, step 0 ([3,128,256]);

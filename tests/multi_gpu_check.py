@@ -1,0 +1,58 @@
+"""Multi-GPU check of the in-library NCCL population sharding (run under torchrun on >= 2 GPUs):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/multi_gpu_check.py
+
+Every rank plans on its shard; all ranks must return the same plan, and it must equal the
+UNSHARDED plan over the whole population (bit for bit: Philox counters carry global indices,
+the merge keeps the lower-global-index tie rule, the refit regenerates elites from global indices)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from mbrl_b200 import native  # noqa: E402
+from mbrl_b200.synthetic import synthetic_problem, synthetic_state  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    O, A, U, H, I = 24, 6, 200, 30, 4  # walker-walk shape (BASELINE config 4)
+    n_local = 2048
+    n_total, k = n_local * world, int(0.1 * n_local * world)
+    prob = synthetic_problem(O, A, U)
+    s0 = synthetic_state(prob, 4).numpy()
+    for engine in ("fp32", "fp16"):
+        h = native.NativePlanner(O, A, U, H, n_local, 1, I, k, engine, local)
+        h.load_problem(prob)
+        h.comm_init(rank, world)
+        out = h.plan(s0, I, k, native.SAMPLE_GAUSSIAN, seed=21, want_dist=True)
+        mine = torch.from_numpy(np.concatenate([out["actions"].ravel(), out["states"].ravel(), out["mu"].ravel(),
+                                                out["sd"].ravel(), out["info"]["best_cost"],
+                                                out["info"]["best_index"].astype(np.float32),
+                                                out["info"]["best_iteration"].astype(np.float32)])).cuda()
+        ref = mine.clone()
+        dist.broadcast(ref, src=0)
+        assert torch.equal(mine, ref), f"rank {rank}: plan differs from rank 0 ({engine})"
+        if rank == 0:
+            full = native.NativePlanner(O, A, U, H, n_total, 1, I, k, engine, local)
+            full.load_problem(prob)
+            want = full.plan(s0, I, k, native.SAMPLE_GAUSSIAN, seed=21, want_dist=True)
+            for key in ("actions", "states", "mu", "sd"):
+                np.testing.assert_array_equal(out[key], want[key], err_msg=f"{engine} {key}")
+            for key in ("best_cost", "best_index", "best_iteration"):
+                np.testing.assert_array_equal(out["info"][key], want["info"][key], err_msg=f"{engine} {key}")
+            print(f"multi_gpu_check[{engine}]: {world} ranks == unsharded N={n_total}: best cost "
+                  f"{out['info']['best_cost'][0]:.4f} idx {out['info']['best_index'][0]} it {out['info']['best_iteration'][0]}")
+        dist.barrier()
+        h.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

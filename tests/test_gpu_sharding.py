@@ -86,3 +86,20 @@ def test_environment_shards_draw_the_same_streams(native):
     c_hi, _, _ = two.rollout(s0[2:].contiguous(), native.SAMPLE_GAUSSIAN, 5, 1, d_mu=mu[2:].contiguous(),
                              d_sd=sd[2:].contiguous(), env_offset=2)
     assert torch.equal(c_all[2 * N:], c_hi)
+
+
+def test_in_library_nccl_world1_equals_plain_plan(native):
+    """mbrl_comm_init with a 1-rank communicator: the sharded code path (pack, ncclAllGather,
+    merge, remap, global-index refit) must reproduce the plain plan bit for bit."""
+    p = po.synthetic_params(17, 6, 200)
+    H, N, I, k = 30, 4096, 4, 409
+    s0 = po.synthetic_state(p, 7).numpy()
+    plain = _planner(native, p, H, N, 1, I, engine="fp16")
+    want = plain.plan(s0, I, k, native.SAMPLE_GAUSSIAN, seed=3, want_dist=True)
+    sh = _planner(native, p, H, N, 1, I, engine="fp16")
+    sh.comm_init(0, 1)
+    got = sh.plan(s0, I, k, native.SAMPLE_GAUSSIAN, seed=3, want_dist=True)
+    for key in ("actions", "states", "mu", "sd"):
+        np.testing.assert_array_equal(got[key], want[key])
+    for key in ("best_cost", "best_index", "best_iteration"):
+        np.testing.assert_array_equal(got["info"][key], want["info"][key])
