@@ -196,7 +196,10 @@ int mbrl_emit(MbrlPlanner* p, int32_t sample_mode, uint64_t seed, uint32_t cand_
  * their global indices (Philox counters carry the global index), so no second collective is
  * needed and every rank holds bit-identical mean/std and emits the same plan.  args->elites is
  * the GLOBAL k; info.best_index is a GLOBAL candidate index; num_envs must be 1; Philox sample
- * modes only.  libnccl.so.2 is resolved at run time (dlopen), not at link time.
+ * modes only.  Ranks send 2x their expected share of the elites (the shards are i.i.d.) and the
+ * merge verifies on the device that this was exact; otherwise info.reserved = 1 and mbrl_plan
+ * transparently redoes the plan with worst-case-size gathers (mbrl_plan_device leaves the flag
+ * to the caller).  libnccl.so.2 is resolved at run time (dlopen), not at link time.
  *   mbrl_nccl_unique_id: rank 0 fills 128 bytes, the host broadcasts them to all ranks.        */
 int mbrl_nccl_unique_id(uint8_t* h_id128);
 int mbrl_comm_init(MbrlPlanner* p, const uint8_t* h_id128, int32_t rank, int32_t world);

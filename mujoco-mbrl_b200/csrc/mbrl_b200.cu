@@ -6,6 +6,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
 #include <new>
@@ -123,6 +124,8 @@ struct MbrlPlanner {
   int* d_gidx = nullptr;        // [world*k_l]
   int* d_pos = nullptr;         // [kmax]
   MbrlPlanInfo* d_best_now = nullptr;
+  int* d_trunc = nullptr;       // truncation flag of the reduced-size elite gather
+  bool full_gather = false;     // force worst-case-size gathers (set after a flagged plan)
 };
 
 static ModelDev model_view(const MbrlPlanner* p) {
@@ -166,7 +169,7 @@ extern "C" int mbrl_destroy(MbrlPlanner* p) {
   if (p->d_best_ever) cudaFree(p->d_best_ever);
   if (p->d_info) cudaFree(p->d_info);
   if (p->comm && g_nccl.ok) g_nccl.CommDestroy(p->comm);
-  void* shard[] = {p->d_ecost, p->d_send, p->d_recv, p->d_gcost, p->d_gidx, p->d_pos, p->d_best_now};
+  void* shard[] = {p->d_ecost, p->d_send, p->d_recv, p->d_gcost, p->d_gidx, p->d_pos, p->d_best_now, p->d_trunc};
   for (void* q : shard) if (q) cudaFree(q);
   tc_free(&p->tc);
   float* pinned[] = {p->h_s0, p->h_out_states, p->h_out_actions, p->h_mu, p->h_sd};
@@ -539,6 +542,8 @@ extern "C" int mbrl_comm_init(MbrlPlanner* p, const uint8_t* h_id128, int32_t ra
   MBRL_CUDA(dev_alloc(&p->d_gidx, kl * world));
   MBRL_CUDA(dev_alloc(&p->d_pos, (size_t)p->cfg.max_elites));
   MBRL_CUDA(dev_alloc(&p->d_best_now, 1));
+  MBRL_CUDA(dev_alloc(&p->d_trunc, 1));
+  MBRL_CUDA(cudaMemset(p->d_trunc, 0, sizeof(int)));
   return MBRL_OK;
 }
 
@@ -619,7 +624,15 @@ static int enqueue_plan(MbrlPlanner* p, const MbrlPlanArgs* a, const float* d_s0
     if (sharded) {
       // local elites -> all-gather (cost, global index) -> same global top-k on every rank ->
       // redundant refit from GLOBAL indices (cand_offset 0): no second collective
-      const int kl = std::min(k, p->N);
+      // Worst case a single shard holds all k global elites (k_full = min(k, N) per rank); the
+      // shards are i.i.d., so the expected share is k/world.  Send 2x the expected share (+64) and
+      // verify exactness on the device (remap_elites_kernel); a flagged plan is redone in full.
+      const int k_full = std::min(k, p->N);
+      int kl = (p->full_gather || p->world == 1) ? k_full : std::min(k_full, 2 * ((k + p->world - 1) / p->world) + 64);
+      if (const char* force = getenv("MBRL_SHARD_KL")) {  // tests: "min" = the smallest legal gather (exactly the
+        // expected share), which the exactness check must flag so that the redo path is exercised
+        if (!p->full_gather && p->world > 1 && force[0] == 'm') kl = std::min(k_full, (k + p->world - 1) / p->world);
+      }
       rc = launch_topk(p->d_costs, 1, p->N, kl, p->d_elite, p->d_ecost, nullptr, nullptr, it, st);
       if (rc) return rc;
       pack_elites_kernel<<<(kl + 255) / 256, 256, 0, st>>>(p->d_ecost, p->d_elite, kl, (int)cand_offset, p->d_send);
@@ -628,8 +641,8 @@ static int enqueue_plan(MbrlPlanner* p, const MbrlPlanArgs* a, const float* d_s0
       unpack_gathered_kernel<<<(ng + 255) / 256, 256, 0, st>>>(p->d_recv, p->world, kl, p->d_gcost, p->d_gidx);
       rc = launch_topk(p->d_gcost, 1, ng, k, p->d_pos, nullptr, p->d_best_now, nullptr, it, st);
       if (rc) return rc;
-      remap_elites_kernel<<<(k + 255) / 256, 256, 0, st>>>(p->d_pos, p->d_gidx, k, p->d_elite, p->d_best_now,
-                                                          p->d_best_ever, it);
+      remap_elites_kernel<<<(std::max(k, p->world) + 255) / 256, 256, 0, st>>>(
+          p->d_pos, p->d_gidx, k, p->d_elite, p->d_best_now, p->d_best_ever, it, p->world, kl, k_full, p->d_trunc);
       MBRL_CUDA(cudaGetLastError());
       if (it + 1 < I || need_final_dist) {
         ActionSource gsrc = src;
@@ -646,9 +659,15 @@ static int enqueue_plan(MbrlPlanner* p, const MbrlPlanArgs* a, const float* d_s0
       if (rc) return rc;
     }
   }
-  return launch_replay(p, a->sample_mode, a->seed, sharded ? 0u : a->cand_offset, a->env_offset, d_s0, d_injected,
-                       p->d_mu_hist, p->d_sd_hist, I, a->return_mean, a->actions_only, p->d_best_ever, d_out_states,
-                       d_out_actions, d_info, st);
+  int rc = launch_replay(p, a->sample_mode, a->seed, sharded ? 0u : a->cand_offset, a->env_offset, d_s0, d_injected,
+                         p->d_mu_hist, p->d_sd_hist, I, a->return_mean, a->actions_only, p->d_best_ever, d_out_states,
+                         d_out_actions, d_info, st);
+  if (rc) return rc;
+  if (sharded && d_info) {  // info.reserved = 1: the reduced-size elite gather was not provably exact
+    MBRL_CUDA(cudaMemcpyAsync(&d_info[0].reserved, p->d_trunc, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    MBRL_CUDA(cudaMemsetAsync(p->d_trunc, 0, sizeof(int), st));
+  }
+  return MBRL_OK;
 }
 
 extern "C" int mbrl_plan_device(MbrlPlanner* p, const MbrlPlanArgs* args, const float* d_s0,
@@ -699,6 +718,12 @@ extern "C" int mbrl_plan(MbrlPlanner* p, const MbrlPlanArgs* args, const float* 
     MBRL_CUDA(cudaMemcpyAsync(p->h_sd, p->d_sd_hist + (size_t)args->iterations * EHA, sizeof(float) * EHA, cudaMemcpyDeviceToHost, st));
   }
   MBRL_CUDA(cudaStreamSynchronize(st));
+  if (p->comm && p->h_info[0].reserved != 0 && !p->full_gather) {
+    // Practically unreachable (the shards are i.i.d.): some rank's reduced elite list was used up.
+    // The flag derives from the gathered data, so every rank sees it and redoes the plan in lockstep.
+    p->full_gather = true;
+    return mbrl_plan(p, args, h_s0, h_out_states, h_out_actions, h_info, h_out_mu, h_out_sd);
+  }
   std::memcpy(h_out_actions, p->h_out_actions, sizeof(float) * EHA);
   std::memcpy(h_out_states, p->h_out_states, sizeof(float) * E * H * O);
   if (h_info) std::memcpy(h_info, p->h_info, sizeof(MbrlPlanInfo) * E);

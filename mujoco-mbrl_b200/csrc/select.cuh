@@ -359,11 +359,24 @@ __global__ void unpack_gathered_kernel(const uint32_t* __restrict__ recv, int wo
   }
 }
 // positions in the gathered list -> global candidate indices; best-ever bookkeeping in global indices
+// Truncation check: each rank sent only its k_s cheapest (k_s < the worst-case min(k, N)); the merge
+// is exact unless ALL k_s candidates of some rank were selected (then cheaper-than-threshold
+// candidates of that rank may have been left out) -> *trunc_flag = 1, the caller redoes the plan
+// with full-size gathers.  pos is ascending, so per-rank counts are two binary searches.
 __global__ void remap_elites_kernel(const int* __restrict__ pos, const int* __restrict__ gidx, int k,
                                     int* __restrict__ elite_global, const MbrlPlanInfo* __restrict__ best_now,
-                                    BestEver* __restrict__ best_ever, int iteration) {
+                                    BestEver* __restrict__ best_ever, int iteration, int world, int k_s,
+                                    int k_full, int* __restrict__ trunc_flag) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < k) elite_global[i] = gidx[pos[i]];
+  if (i < world && k_s < k_full) {
+    auto lower_bound = [&](int v) {
+      int lo = 0, hi = k;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (pos[mid] < v) lo = mid + 1; else hi = mid; }
+      return lo;
+    };
+    if (lower_bound((i + 1) * k_s) - lower_bound(i * k_s) == k_s) atomicOr(trunc_flag, 1);
+  }
   if (i == 0) {
     const float cmin = best_now->best_cost;
     BestEver b = *best_ever;

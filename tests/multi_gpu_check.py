@@ -27,7 +27,11 @@ def main():
     n_total, k = n_local * world, int(0.1 * n_local * world)
     prob = synthetic_problem(O, A, U)
     s0 = synthetic_state(prob, 4).numpy()
-    for engine in ("fp32", "fp16"):
+    for engine, force_kl in (("fp32", None), ("fp16", None), ("fp16", "min")):
+        if force_kl is None:
+            os.environ.pop("MBRL_SHARD_KL", None)
+        else:  # a gather that is far too small: the on-device check must flag it and the plan is redone in full
+            os.environ["MBRL_SHARD_KL"] = force_kl
         h = native.NativePlanner(O, A, U, H, n_local, 1, I, k, engine, local)
         h.load_problem(prob)
         h.comm_init(rank, world)
@@ -47,7 +51,7 @@ def main():
                 np.testing.assert_array_equal(out[key], want[key], err_msg=f"{engine} {key}")
             for key in ("best_cost", "best_index", "best_iteration"):
                 np.testing.assert_array_equal(out["info"][key], want["info"][key], err_msg=f"{engine} {key}")
-            print(f"multi_gpu_check[{engine}]: {world} ranks == unsharded N={n_total}: best cost "
+            print(f"multi_gpu_check[{engine}{', forced tiny gather' if force_kl else ''}]: {world} ranks == unsharded N={n_total}: best cost "
                   f"{out['info']['best_cost'][0]:.4f} idx {out['info']['best_index'][0]} it {out['info']['best_iteration'][0]}")
         dist.barrier()
         h.close()
