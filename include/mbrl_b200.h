@@ -57,6 +57,11 @@ extern "C" {
 /* cost kinds (epilogue of the rollout kernel) */
 #define MBRL_COST_SMOOTHABS_COSH 0 /* state_action_cost = SmoothAbsLoss + CoshLoss
                                       (src/mbrl/agents.py:182-183, models.py:244-272)          */
+#define MBRL_COST_DMC_CARTPOLE_SWINGUP 1 /* 1 - smooth cartpole reward restated on the observation
+                                      [x, cos, sin, x_dot, theta_dot] and the control
+                                      (dm_control/suite/cartpole.py:216-226, utils/rewards.py:88-130);
+                                      not used by the reference planner;
+                                      fp32 engine only this round; weights/goal are ignored   */
 
 typedef struct MbrlPlanner MbrlPlanner;
 

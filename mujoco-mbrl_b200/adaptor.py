@@ -42,6 +42,7 @@ class PlanningProblem:
     beta: float = 0.25
     act_lo: float = -1.0
     act_hi: float = 1.0
+    cost_kind: int = 0  # native.COST_*: 0 = SmoothAbs + Cosh (the reference's), 1 = dm_control cartpole swing-up
 
     @property
     def obs_dim(self) -> int:

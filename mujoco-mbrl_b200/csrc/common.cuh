@@ -68,4 +68,18 @@ __device__ __forceinline__ float cosh_term(float a, float beta) {
   return __fsub_rn(coshf(__fdiv_rn(a, beta)), 1.0f);
 }
 
+// 1 - cartpole swing-up reward (dm_control/suite/cartpole.py:216-226) from x, cos(theta),
+// theta_dot and the control; rewards.tolerance with the default gaussian sigmoid is
+// exp(ln(0.1) * (d/margin)^2), the quadratic one with value_at_margin 0 is 1 - d^2 inside |d| < 1.
+__device__ __forceinline__ float dmc_cartpole_cost(float x, float cosang, float thdot, float a0) {
+  const float ln01 = -2.302585092994046f;
+  const float upright = 0.5f * (cosang + 1.0f);
+  const float xc = 0.5f * x, vc = 0.2f * thdot;
+  const float centered = 0.5f * (1.0f + expf(ln01 * xc * xc));
+  const float small_velocity = 0.5f * (1.0f + expf(ln01 * vc * vc));
+  const float ctl = fabsf(a0) < 1.0f ? 1.0f - a0 * a0 : 0.0f;
+  const float small_control = 0.2f * (4.0f + ctl);
+  return 1.0f - upright * small_control * small_velocity * centered;
+}
+
 }  // namespace mbrl

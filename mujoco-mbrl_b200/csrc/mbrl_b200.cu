@@ -308,13 +308,19 @@ extern "C" int mbrl_set_norm(MbrlPlanner* p, const float* mu_s, const float* sd_
 extern "C" int mbrl_set_cost(MbrlPlanner* p, int32_t kind, const float* w, const float* goal, double alpha,
                              double beta) {
   if (!p) return fail(MBRL_E_INVALID, "null planner");
-  MBRL_REQUIRE(kind == MBRL_COST_SMOOTHABS_COSH, "unknown cost kind");
-  MBRL_REQUIRE(w && goal, "null cost pointer");
-  MBRL_REQUIRE(beta != 0.0, "beta must be non-zero");
+  MBRL_REQUIRE(kind == MBRL_COST_SMOOTHABS_COSH || kind == MBRL_COST_DMC_CARTPOLE_SWINGUP, "unknown cost kind");
   MBRL_CUDA(cudaSetDevice(p->cfg.device));
   MBRL_CUDA(cudaStreamSynchronize(p->stream));
-  MBRL_CUDA(cudaMemcpy(p->cost_w, w, sizeof(float) * p->O, cudaMemcpyHostToDevice));
-  MBRL_CUDA(cudaMemcpy(p->goal, goal, sizeof(float) * p->O, cudaMemcpyHostToDevice));
+  if (kind == MBRL_COST_DMC_CARTPOLE_SWINGUP) {
+    MBRL_REQUIRE(p->O >= 5 && p->A >= 1, "cartpole cost needs the 5-d cartpole observation");
+    if (p->cfg.engine != MBRL_ENGINE_SIMT_FP32)
+      return fail(MBRL_E_UNSUPPORTED, "the dm_control task-cost epilogue is implemented for the fp32 engine only");
+  } else {
+    MBRL_REQUIRE(w && goal, "null cost pointer");
+    MBRL_REQUIRE(beta != 0.0, "beta must be non-zero");
+    MBRL_CUDA(cudaMemcpy(p->cost_w, w, sizeof(float) * p->O, cudaMemcpyHostToDevice));
+    MBRL_CUDA(cudaMemcpy(p->goal, goal, sizeof(float) * p->O, cudaMemcpyHostToDevice));
+  }
   p->cost_kind = kind;
   p->alpha = (float)alpha; p->alpha2 = (float)(alpha * alpha);
   p->beta = (float)beta; p->beta2 = (float)(beta * beta);

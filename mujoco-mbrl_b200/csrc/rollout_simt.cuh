@@ -111,7 +111,7 @@ rollout_simt_kernel(ModelDev m, ActionSource src, Shape sh, const float* __restr
   }
 
   for (int h = 0; h < sh.H; ++h) {
-    float act_cost = 0.0f;
+    float act_cost = 0.0f, a0 = 0.0f;
     if (row_thread) {
       // normalize_state: (s - mean) / std   (data.py:258-260)
       for (int o = 0; o < O; ++o)
@@ -121,6 +121,7 @@ rollout_simt_kernel(ModelDev m, ActionSource src, Shape sh, const float* __restr
         for_each_action(src, A, sh.H, h, env_l, cand_l, row, R, [&](int a, float v) {
           bufA[(O + a) * TM + t] = __fdiv_rn(__fsub_rn(v, __ldg(m.mu_a + a)), __ldg(m.sd_a + a));
           act_cost = __fadd_rn(act_cost, cosh_term(v, m.beta));
+          if (a == 0) a0 = v;
           if (aout) aout[a] = v;
         });
       } else {
@@ -137,16 +138,21 @@ rollout_simt_kernel(ModelDev m, ActionSource src, Shape sh, const float* __restr
     if (row_thread) {
       float st_cost = 0.0f;
       float* sout = (states_out && valid) ? states_out + ((long long)h * R + row) * O : nullptr;
+      const bool smooth = m.cost_kind == MBRL_COST_SMOOTHABS_COSH;
       for (int o = 0; o < O; ++o) {
         // unnormalize_state: y * std + mean   (data.py:255-257)
         const float s = __fadd_rn(__fmul_rn(bufB[o * TM + t], __ldg(m.sd_s + o)), __ldg(m.mu_s + o));
         bufS[o * TM + t] = s;
-        st_cost = __fadd_rn(st_cost, smooth_abs_term(s, __ldg(m.goal + o), __ldg(m.cost_w + o), m.alpha, m.alpha2));
+        if (smooth) st_cost = __fadd_rn(st_cost, smooth_abs_term(s, __ldg(m.goal + o), __ldg(m.cost_w + o), m.alpha, m.alpha2));
         if (sout) sout[o] = s;
       }
-      // CoshLoss: beta^2 * mean_a(cosh(a/beta) - 1); row cost pairs s_{h+1} with a_h
-      const float ac = __fmul_rn(m.beta2, __fdiv_rn(act_cost, (float)A));
-      cost = __fadd_rn(cost, __fadd_rn(st_cost, ac));
+      if (smooth) {
+        // CoshLoss: beta^2 * mean_a(cosh(a/beta) - 1); row cost pairs s_{h+1} with a_h
+        const float ac = __fmul_rn(m.beta2, __fdiv_rn(act_cost, (float)A));
+        cost = __fadd_rn(cost, __fadd_rn(st_cost, ac));
+      } else {  // MBRL_COST_DMC_CARTPOLE_SWINGUP (O >= 5 checked by the host)
+        cost += dmc_cartpole_cost(bufS[0 * TM + t], bufS[1 * TM + t], bufS[4 * TM + t], a0);
+      }
     }
     // bufA is rewritten by row threads next step: every warp has passed the barrier after
     // layer 3, which was the last reader of bufA.

@@ -110,7 +110,9 @@ inline void tcf_pack(const TcfGeom& g, bool fp16, const float* W1, const float* 
   }
 }
 
-template <bool FP16>
+// DBG: accumulator dump + clock64 timeline instrumentation (tests / profiling only); the
+// production instantiation carries none of it.
+template <bool FP16, bool DBG>
 __global__ void __launch_bounds__(kTcfThreads, 1)
 rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, ActionSource src, Shape sh,
                    const float* __restrict__ s0, float* __restrict__ costs, float* __restrict__ states_out,
@@ -222,7 +224,7 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
         for (int ks = 0; ks < KS_H; ks += 2) {
           mbar_wait(bar_hA + 4 * ks, ph);  // barrier of the K-step pair ks/2
           tc_fence_after();
-          if (lane == 0 && (ks == 0 || ks + 2 >= KS_H)) tc_stamp(dbg, h, ks == 0 ? 1 : 2);
+          if (lane == 0 && (ks == 0 || ks + 2 >= KS_H)) if (DBG) tc_stamp(dbg, h, ks == 0 ? 1 : 2);
           if (elect_one()) {
             mma_ts(tm_b, a, bd, idesc_h, ks > 0);
             if (ks + 1 < KS_H) mma_ts(tm_b, a + 16, bd + step_h, idesc_h, 1);
@@ -240,7 +242,7 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
         const int slot = (h + 1) % kTcfSlots;
         mbar_wait(bar_xa + 8 * slot, ((h + 1) / kTcfSlots) & 1);
         tc_fence_after();
-        if (lane == 0) tc_stamp(dbg, h, 3);
+        if (lane == 0) if (DBG) tc_stamp(dbg, h, 3);
         if (elect_one()) {
           uint64_t ad = d_xa0 + slot * xa_step, bd = d_waa;
           mma_ss(tm_a, ad, bd, idesc_a, 0);
@@ -258,7 +260,7 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
         for (int ks = 0; ks < KS_H; ks += 2) {
           mbar_wait(bar_hB + 4 * ks, ph);
           tc_fence_after();
-          if (lane == 0 && (ks == 0 || ks + 2 >= KS_H)) tc_stamp(dbg, h, ks == 0 ? 16 : 17);
+          if (lane == 0 && (ks == 0 || ks + 2 >= KS_H)) if (DBG) tc_stamp(dbg, h, ks == 0 ? 16 : 17);
           if (elect_one()) {
             mma_ts(d, a, bd, idesc, acc);
             if (ks + 1 < KS_H) mma_ts(d, a + 16, bd + step_a, idesc, 1);
@@ -268,7 +270,7 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
           acc = 1; bd += 2 * step_a; a += 32;
         }
       }
-      if (lane == 0) tc_stamp(dbg, h + 1, 0);
+      if (lane == 0) if (DBG) tc_stamp(dbg, h + 1, 0);
     }
   } else if (warp >= kTcfSampWarp0) {
     // ================= sampler threads (one per row) =================
@@ -333,11 +335,11 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
       // own "free" barrier is phase #(hs/3 - 1) -- the waiter is never more than one phase behind
       // (a parity wait cannot tell phases that are 2 apart).
       if (hs >= kTcfSlots) mbar_wait(bar_xf + 8 * (hs % kTcfSlots), (hs / kTcfSlots - 1) & 1);
-      if (srow == 0) tc_stamp(dbg, hs, 12);
+      if (srow == 0) if (DBG) tc_stamp(dbg, hs, 12);
       stage_actions(hs);
       fence_proxy_async();   // generic-proxy tile writes -> visible to the MMA (async proxy)
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (srow == 0) { mbar_arrive(bar_xa + 8 * (hs % kTcfSlots)); tc_stamp(dbg, hs, 13); }
+      if (srow == 0) { mbar_arrive(bar_xa + 8 * (hs % kTcfSlots)); if (DBG) tc_stamp(dbg, hs, 13); }
     }
     costp[kTcRows + srow] = act_total;
   } else if (warp >= kTcfCostWarp0) {
@@ -354,14 +356,14 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
       // D_A(j) carries y(j-1) = W3 h2(j-1) in columns [Np, Np+Oy)  (j == H: the y-only GEMM)
       mbar_wait(bar_dA, j & 1);
       tc_fence_after();
-      if (crow == 0) tc_stamp(dbg, j - 1, 14);
+      if (crow == 0) if (DBG) tc_stamp(dbg, j - 1, 14);
       float* sout = (states_out && valid) ? states_out + ((long long)(j - 1) * R + row) * O : nullptr;
 #pragma unroll 1
       for (int cc = 0; cc < (g.Oy >> 4); ++cc) {
         uint32_t v[32];
         tmem_ld16(lane_base + (uint32_t)(g.Np + 16 * cc), v);
         tmem_ld_wait();
-        if (dbg && blockIdx.x == 0 && j == 1) {
+        if (DBG && dbg && blockIdx.x == 0 && j == 1) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) dbg[(2 * kTcRows + crow) * 256 + 16 * cc + i] = __uint_as_float(v[i]);
         }
@@ -386,7 +388,7 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
       if (j < H) {
         tc_fence_before();  // our tcgen05.ld of y is ordered before GEMM-A(j+1) overwrites it
         asm volatile("bar.sync 2, 128;" ::: "memory");
-        if (crow == 0) { mbar_arrive(bar_y); tc_stamp(dbg, j - 1, 15); }  // completion #(j-1)
+        if (crow == 0) { mbar_arrive(bar_y); if (DBG) tc_stamp(dbg, j - 1, 15); }  // completion #(j-1)
       }
     }
     costp[crow] = valid ? st_total : 0.f;
@@ -402,7 +404,7 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
         const uint32_t dcol = layer == 0 ? 0u : (uint32_t)kTcD2Col;
         mbar_wait(layer == 0 ? bar_dA : bar_dB, ph);
         tc_fence_after();
-        if (tid == 0) tc_stamp(dbg, h, 4 + 2 * layer);
+        if (tid == 0) if (DBG) tc_stamp(dbg, h, 4 + 2 * layer);
         const uint32_t bar_rel = layer == 0 ? bar_hA : bar_hB;
 #pragma unroll 1
         for (int ks = wg; ks < KS_H; ks += kTcfEpiGroups) {
@@ -410,7 +412,7 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
           uint32_t v[32], pk[16];
           tmem_ld16(lane_base + dcol + 16 * ks, v);
           tmem_ld_wait();
-          if (dbg && blockIdx.x == 0 && h == 0) {
+          if (DBG && dbg && blockIdx.x == 0 && h == 0) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) dbg[(layer * kTcRows + trow) * 256 + 16 * ks + i] = __uint_as_float(v[i]);
           }
@@ -422,7 +424,7 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_rel + 8 * (ks >> 1));
         }
-        if (tid == 0) tc_stamp(dbg, h, 5 + 2 * layer);
+        if (tid == 0) if (DBG) tc_stamp(dbg, h, 5 + 2 * layer);
       }
     }
   }
@@ -501,8 +503,11 @@ inline cudaError_t tc_launch_rollout(TcModel* t, const ModelDev& m, const Action
   (void)num_sms;
   if (!t->ready) return cudaErrorNotReady;
   if (t->fused) {
-    if (t->fp16) return tc_launch_one(rollout_tcf_kernel<true>, t->fg, t->fg.smem_bytes, kTcfThreads, t, m, src, sh, d_s0, d_costs, d_states, d_actions, st);
-    return tc_launch_one(rollout_tcf_kernel<false>, t->fg, t->fg.smem_bytes, kTcfThreads, t, m, src, sh, d_s0, d_costs, d_states, d_actions, st);
+    const bool dbg = t->d_dbg != nullptr;
+    if (t->fp16 && !dbg) return tc_launch_one(rollout_tcf_kernel<true, false>, t->fg, t->fg.smem_bytes, kTcfThreads, t, m, src, sh, d_s0, d_costs, d_states, d_actions, st);
+    if (t->fp16) return tc_launch_one(rollout_tcf_kernel<true, true>, t->fg, t->fg.smem_bytes, kTcfThreads, t, m, src, sh, d_s0, d_costs, d_states, d_actions, st);
+    if (!dbg) return tc_launch_one(rollout_tcf_kernel<false, false>, t->fg, t->fg.smem_bytes, kTcfThreads, t, m, src, sh, d_s0, d_costs, d_states, d_actions, st);
+    return tc_launch_one(rollout_tcf_kernel<false, true>, t->fg, t->fg.smem_bytes, kTcfThreads, t, m, src, sh, d_s0, d_costs, d_states, d_actions, st);
   }
   if (t->fp16) return tc_launch_one(rollout_tc_kernel<true>, t->g, t->g.smem_bytes, kTcThreads, t, m, src, sh, d_s0, d_costs, d_states, d_actions, st);
   return tc_launch_one(rollout_tc_kernel<false>, t->g, t->g.smem_bytes, kTcThreads, t, m, src, sh, d_s0, d_costs, d_states, d_actions, st);

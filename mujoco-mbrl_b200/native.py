@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libmbrl_b200.so")
 ENGINE_SIMT_FP32, ENGINE_TC_BF16, ENGINE_TC_FP16 = 0, 1, 2
 ENGINES = {"fp32": ENGINE_SIMT_FP32, "simt": ENGINE_SIMT_FP32, "bf16": ENGINE_TC_BF16, "fp16": ENGINE_TC_FP16}
 SAMPLE_INJECT_ACTIONS, SAMPLE_INJECT_NOISE, SAMPLE_GAUSSIAN, SAMPLE_UNIFORM = 0, 1, 2, 3
-COST_SMOOTHABS_COSH = 0
+COST_SMOOTHABS_COSH, COST_DMC_CARTPOLE_SWINGUP = 0, 1
 
 # every symbol include/mbrl_b200.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
@@ -182,7 +182,10 @@ class NativePlanner:
                 raise ValueError(f"stat shape {a.shape} != ({n},)")
         _check(self.lib.mbrl_set_norm(self._h, *[_hp(a) for a in arrs]))
 
-    def set_cost(self, weights, goal, alpha=0.4, beta=0.25, kind=COST_SMOOTHABS_COSH):
+    def set_cost(self, weights=None, goal=None, alpha=0.4, beta=0.25, kind=COST_SMOOTHABS_COSH):
+        if kind != COST_SMOOTHABS_COSH:
+            _check(self.lib.mbrl_set_cost(self._h, kind, None, None, float(alpha), float(beta)))
+            return
         w, g = _f32(weights).reshape(-1), _f32(goal).reshape(-1)
         if w.shape != (self.O,) or g.shape != (self.O,):
             raise ValueError("cost weights/goal must have obs_dim entries")
@@ -195,7 +198,7 @@ class NativePlanner:
         """Upload a PlanningProblem (adaptor.py)."""
         self.set_weights(prob.W1, prob.b1, prob.W2, prob.b2, prob.W3, prob.b3)
         self.set_norm(prob.mu_s, prob.sd_s, prob.mu_a, prob.sd_a)
-        self.set_cost(prob.cost_w, prob.goal, prob.alpha, prob.beta)
+        self.set_cost(prob.cost_w, prob.goal, prob.alpha, prob.beta, getattr(prob, "cost_kind", COST_SMOOTHABS_COSH))
         self.set_action_bounds(prob.act_lo, prob.act_hi)
 
     # ---- whole plans -----------------------------------------------------------------

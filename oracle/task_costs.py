@@ -1,0 +1,61 @@
+"""dm_control task costs restated on observations (TEST INFRASTRUCTURE).
+
+The reference planner never calls these (the environment computes rewards from MuJoCo physics,
+dm_control/dm_control/rl/control.py:111); they are the north_star's optional "task cost"
+epilogue.  ``tolerance`` restates dm_control/dm_control/utils/rewards.py:28-130 and is pinned
+against values produced by the reference module itself (tests/golden/tolerance.npz)."""
+import numpy as np
+
+_DEFAULT_VALUE_AT_MARGIN = 0.1  # rewards.py:25
+
+
+def _sigmoid(x, value_at_1, kind):
+    """rewards.py:28-85: 1 at x == 0, value_at_1 at x == 1."""
+    if kind == "gaussian":
+        scale = np.sqrt(-2 * np.log(value_at_1))
+        return np.exp(-0.5 * (x * scale) ** 2)
+    if kind == "hyperbolic":
+        scale = np.arccosh(1 / value_at_1)
+        return 1 / np.cosh(x * scale)
+    if kind == "long_tail":
+        scale = np.sqrt(1 / value_at_1 - 1)
+        return 1 / ((x * scale) ** 2 + 1)
+    if kind == "cosine":
+        scale = np.arccos(2 * value_at_1 - 1) / np.pi
+        sx = x * scale
+        with np.errstate(invalid="ignore"):
+            return np.where(np.abs(sx) < 1, (1 + np.cos(np.pi * sx)) / 2, 0.0)
+    if kind == "linear":
+        sx = x * (1 - value_at_1)
+        return np.where(np.abs(sx) < 1, 1 - sx, 0.0)
+    if kind == "quadratic":
+        sx = x * np.sqrt(1 - value_at_1)
+        return np.where(np.abs(sx) < 1, 1 - sx ** 2, 0.0)
+    if kind == "tanh_squared":
+        scale = np.arctanh(np.sqrt(1 - value_at_1))
+        return 1 - np.tanh(x * scale) ** 2
+    raise ValueError(f"unknown sigmoid {kind!r}")
+
+
+def tolerance(x, bounds=(0.0, 0.0), margin=0.0, sigmoid="gaussian", value_at_margin=_DEFAULT_VALUE_AT_MARGIN):
+    """rewards.py:88-130: 1 inside [lower, upper], sigmoidal decay over `margin` outside."""
+    x = np.asarray(x, dtype=np.float64)
+    lower, upper = bounds
+    in_bounds = np.logical_and(lower <= x, x <= upper)
+    if margin == 0:
+        return np.where(in_bounds, 1.0, 0.0)
+    d = np.where(x < lower, lower - x, x - upper) / margin
+    return np.where(in_bounds, 1.0, _sigmoid(d, value_at_margin, sigmoid))
+
+
+def cartpole_swingup_cost(obs, act):
+    """1 - smooth cartpole reward (dm_control/dm_control/suite/cartpole.py:216-226) from the
+    observation [x, cos(theta), sin(theta), x_dot, theta_dot] (cartpole.py:150-153, 202-207) and
+    the control.  obs [..., 5], act [..., 1] -> cost [...]."""
+    obs = np.asarray(obs, dtype=np.float64)
+    act = np.asarray(act, dtype=np.float64)
+    upright = (obs[..., 1] + 1) / 2
+    centered = (1 + tolerance(obs[..., 0], margin=2)) / 2
+    small_control = (4 + tolerance(act[..., 0], margin=1, value_at_margin=0, sigmoid="quadratic")) / 5
+    small_velocity = (1 + tolerance(obs[..., 4], margin=5)) / 2
+    return 1.0 - upright * small_control * small_velocity * centered

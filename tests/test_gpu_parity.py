@@ -131,6 +131,24 @@ def test_actions_only_plan_skips_replay(native):
     assert int(out["info"]["best_index"][0]) == int(g["idx"]) and not out["states"].any()
 
 
+def test_dmc_cartpole_task_cost_epilogue(native):
+    """Cost option C: 1 - cartpole swing-up reward restated on observations,
+    against the oracle built on the reference's rewards.tolerance (fp32 engine)."""
+    from oracle import task_costs
+    g = load_golden("rs_cartpole.npz")
+    p = params_from_golden(g)
+    n, H = int(g["n"]), int(g["horizon"])
+    h = _planner(native, p, H, n)
+    h.set_cost(kind=native.COST_DMC_CARTPOLE_SWINGUP)
+    acts = torch.from_numpy(g["actions"])
+    costs, states, _ = h.rollout(_cuda(g["s0"][None]), native.SAMPLE_INJECT_ACTIONS, d_injected=acts.cuda(), want_states=True)
+    st, _ = po.rollout_costs(p, torch.from_numpy(g["s0"]), acts, H, n)
+    want = task_costs.cartpole_swingup_cost(st.numpy(), g["actions"]).reshape(H, n).sum(0)
+    np.testing.assert_allclose(costs.cpu().numpy(), want, rtol=2e-5, atol=2e-5)
+    with pytest.raises(native.MbrlError):
+        _planner(native, p, H, n, engine="fp16").set_cost(kind=native.COST_DMC_CARTPOLE_SWINGUP)
+
+
 def test_rollout_ragged_rows_and_batched_envs(native):
     """N not a multiple of the row tile, several environments with distinct s0."""
     p = po.synthetic_params(9, 3, 40, seed=5)
@@ -146,6 +164,30 @@ def test_rollout_ragged_rows_and_batched_envs(native):
         np.testing.assert_allclose(costs.cpu().numpy()[e * n:(e + 1) * n], c, rtol=FP32_COST_RTOL)
         np.testing.assert_allclose(states.cpu().view(H, E, n, 9)[:, e].numpy(), st.view(H, n, 9).numpy(),
                                    rtol=FP32_STATE_RTOL, atol=FP32_STATE_ATOL)
+
+
+def test_humanoid_shape_batched_envs_fp32_engine(native):
+    """BASELINE config 5 shape (obs 67, act 21, hidden 512, batched independent environments) on
+    the fp32 engine -- the tensor-core engines do not cover hidden > 255 yet and must say so."""
+    p = po.synthetic_params(67, 21, 512, seed=9)
+    H, n, E = 6, 96, 3
+    h = _planner(native, p, H, n, E, iters=2)
+    g = torch.Generator().manual_seed(4)
+    s0 = p.mu_s + p.sd_s * torch.randn(E, 67, generator=g)
+    acts = torch.rand(H * E * n, 21, generator=g) * 2 - 1
+    costs, states, _ = h.rollout(s0.cuda(), native.SAMPLE_INJECT_ACTIONS, d_injected=acts.cuda(), want_states=True)
+    a4 = acts.view(H, E, n, 21)
+    for e in range(E):
+        st, c = po.rollout_costs(p, s0[e], a4[:, e].reshape(H * n, 21), H, n)
+        np.testing.assert_allclose(costs.cpu().numpy()[e * n:(e + 1) * n], c, rtol=5e-5)
+        np.testing.assert_allclose(states.cpu().view(H, E, n, 67)[:, e].numpy(), st.view(H, n, 67).numpy(), rtol=1e-4, atol=1e-4)
+    out = h.plan(s0.numpy(), 2, 9, native.SAMPLE_GAUSSIAN, seed=1)  # batched CEM: per-environment elites and plans
+    assert out["actions"].shape == (E, H, 21) and np.isfinite(out["states"]).all()
+    for e in range(E):
+        _, c = po.rollout_costs(p, s0[e], torch.from_numpy(out["actions"][e]), H, 1)
+        np.testing.assert_allclose(out["info"]["best_cost"][e], c[0], rtol=5e-5)
+    with pytest.raises(native.MbrlError, match="hidden"):
+        native.NativePlanner(67, 21, 512, H, n, E, engine="fp16")
 
 
 # ---------------------------------------------------------------------------------------
