@@ -136,15 +136,18 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
   const uint32_t bar0 = smem_u32(bars);
   const uint32_t bar_w = bar0, bar_dA = bar0 + 8, bar_dB = bar0 + 16, bar_y = bar0 + 24, bar_xa = bar0 + 32;
   const uint32_t bar_xf = bar_xa + 8 * kTcfSlots;  // action tile slot free again (its MMAs completed)
-  const uint32_t bar_hA = bar_xf + 8 * kTcfSlots, bar_hB = bar_hA + 4 * kTcfMaxKSteps;
+  const uint32_t bar_hA = bar_xf + 8 * kTcfSlots, bar_hB = bar_hA + 2 * kTcfMaxKSteps;
 
   if (warp == kTcfMmaWarp) {
     if (lane == 0) {
       mbar_init(bar_w, 1); mbar_init(bar_dA, 1); mbar_init(bar_dB, 1); mbar_init(bar_y, 1);
       for (int i = 0; i < kTcfSlots; ++i) { mbar_init(bar_xa + 8 * i, 1); mbar_init(bar_xf + 8 * i, 1); }
-      for (int c = 0; c < kTcfMaxKSteps / 2; ++c) {  // one barrier per pair of K-steps: 4 warp arrivals per K-step
-        const uint32_t cnt = (2 * c + 1 < (g.Np >> 4)) ? 8u : 4u;
-        mbar_init(bar_hA + 8 * c, cnt); mbar_init(bar_hB + 8 * c, cnt);
+      for (int c = 0; c < kTcfMaxKSteps / 4; ++c) {
+        // one barrier per group of 4 K-steps (the 4 warpgroups convert one K-step each, in
+        // parallel): 4 warp arrivals per K-step.  Coarser than a pair so that the issue loop's
+        // fixed cost (~290 cycles per barrier wait + fence + elect) is paid once per 4 MMAs.
+        const int ksteps = min(4, max(0, (g.Np >> 4) - 4 * c));
+        if (ksteps > 0) { mbar_init(bar_hA + 8 * c, 4 * ksteps); mbar_init(bar_hB + 8 * c, 4 * ksteps); }
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -221,17 +224,18 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
         // and released on its own barrier as soon as one warpgroup has converted it
         uint64_t bd = d_w2;
         uint32_t a = tm_a;
-        for (int ks = 0; ks < KS_H; ks += 2) {
-          mbar_wait(bar_hA + 4 * ks, ph);  // barrier of the K-step pair ks/2
+        for (int ks = 0; ks < KS_H; ks += 4) {
+          mbar_wait(bar_hA + 2 * ks, ph);  // barrier of the K-step group ks/4
           tc_fence_after();
-          if (lane == 0 && (ks == 0 || ks + 2 >= KS_H)) if (DBG) tc_stamp(dbg, h, ks == 0 ? 1 : 2);
+          if (lane == 0 && (ks == 0 || ks + 4 >= KS_H)) if (DBG) tc_stamp(dbg, h, ks == 0 ? 1 : 2);
           if (elect_one()) {
-            mma_ts(tm_b, a, bd, idesc_h, ks > 0);
-            if (ks + 1 < KS_H) mma_ts(tm_b, a + 16, bd + step_h, idesc_h, 1);
-            if (ks + 2 >= KS_H) tc_commit(bar_dB);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (ks + i < KS_H) mma_ts(tm_b, a + 16 * i, bd + i * step_h, idesc_h, (ks + i) > 0);
+            if (ks + 4 >= KS_H) tc_commit(bar_dB);
           }
           __syncwarp();
-          bd += 2 * step_h; a += 32;
+          bd += 4 * step_h; a += 64;
         }
       }
       // ---- GEMM-A(h+1) (or, after the last step, only the y columns) ----
@@ -257,17 +261,18 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
         const uint32_t d = last ? tm_a + (uint32_t)g.Np : tm_a;
         const uint32_t idesc = last ? idesc_y : idesc_a;
         uint32_t a = tm_b;
-        for (int ks = 0; ks < KS_H; ks += 2) {
-          mbar_wait(bar_hB + 4 * ks, ph);
+        for (int ks = 0; ks < KS_H; ks += 4) {
+          mbar_wait(bar_hB + 2 * ks, ph);
           tc_fence_after();
-          if (lane == 0 && (ks == 0 || ks + 2 >= KS_H)) if (DBG) tc_stamp(dbg, h, ks == 0 ? 16 : 17);
+          if (lane == 0 && (ks == 0 || ks + 4 >= KS_H)) if (DBG) tc_stamp(dbg, h, ks == 0 ? 16 : 17);
           if (elect_one()) {
-            mma_ts(d, a, bd, idesc, acc);
-            if (ks + 1 < KS_H) mma_ts(d, a + 16, bd + step_a, idesc, 1);
-            if (ks + 2 >= KS_H) tc_commit(bar_dA);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (ks + i < KS_H) mma_ts(d, a + 16 * i, bd + i * step_a, idesc, (ks + i) > 0 ? 1u : acc);
+            if (ks + 4 >= KS_H) tc_commit(bar_dA);
           }
           __syncwarp();
-          acc = 1; bd += 2 * step_a; a += 32;
+          bd += 4 * step_a; a += 64;
         }
       }
       if (lane == 0) if (DBG) tc_stamp(dbg, h + 1, 0);
@@ -422,7 +427,7 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_rel + 8 * (ks >> 1));
+          if (lane == 0) mbar_arrive(bar_rel + 8 * (ks >> 2));
         }
         if (tid == 0) if (DBG) tc_stamp(dbg, h, 5 + 2 * layer);
       }

@@ -44,6 +44,17 @@ __global__ void __launch_bounds__(160, 1) ubench(long long* out, int n_mma, int 
       long long t2 = clock64();
       if (lane == 0) { out[rep * 2] = t1 - t0; out[rep * 2 + 1] = t2 - t0; }
     }
+  } else if (swz_unused) {
+    // contention mode: hammer TMEM with load/convert/store round trips while warp 4 times its MMAs
+    uint32_t v[32], pk[16];
+    const uint32_t base = tmem + ((uint32_t)(warp * 32) << 16);
+    for (int it = 0; it < swz_unused; ++it) {
+      tmem_ld32(base + 300 + 32 * (it & 3), v); tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) pk[i] = pack_relu<true>(v[2 * i], v[2 * i + 1]);
+      tmem_st16(base + 300 + 32 * (it & 3), pk); tmem_st_wait();
+    }
+    if (pk[3] == 0x12345u) out[63] = v[5];
   } else {
     // TMEM round trips by one warp (others idle) and by four warps
     uint32_t v[32], pk[16];
@@ -83,6 +94,17 @@ int main() {
         cudaMemcpy(h.data(), d, 64 * 8, cudaMemcpyDeviceToHost);
         printf("%s %4d %3d : %6lld %6lld  (%.1f)\n", ts ? "TS" : "SS", N, n, h[4], h[5], (double)h[5] / n);
       }
+  printf("-- MMA cost with 4 warps doing TMEM ld32/pack/st16 round trips concurrently --\n");
+  for (int ts = 0; ts < 2; ++ts)
+    for (int N : {208, 240})
+      for (int traffic : {0, 40, 400}) {
+        cudaMemset(d, 0, 64 * 8);
+        ubench<<<1, 160, 200 * 1024>>>(d, 26, N, ts, traffic);
+        cudaDeviceSynchronize();
+        cudaMemcpy(h.data(), d, 64 * 8, cudaMemcpyDeviceToHost);
+        printf("%s N=%d 26 MMAs, %3d concurrent round trips/warp: done %lld (%.1f per MMA)\n", ts ? "TS" : "SS", N, traffic, h[5], (double)h[5] / 26);
+      }
+  ubench<<<1, 160, 200 * 1024>>>(d, 1, 64, 1, 0); cudaDeviceSynchronize(); cudaMemcpy(h.data(), d, 64 * 8, cudaMemcpyDeviceToHost);
   printf("TMEM per warp (ld32+wait, 16x relu-pack, st16+wait, fence): ");
   for (int w = 0; w < 4; ++w) printf("[%lld %lld %lld %lld] ", h[8 + w * 4], h[9 + w * 4], h[10 + w * 4], h[11 + w * 4]);
   printf("\n");
