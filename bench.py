@@ -188,6 +188,8 @@ def main():
     ap.add_argument("--engine", default="auto", choices=["auto", "fp32", "fp16", "bf16"])
     ap.add_argument("--workload", default="cheetah", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],
+                    help="elite exchange of the population-sharded loop: NVLink peer stores (CUDA IPC) or ncclAllGather")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -223,7 +225,12 @@ def main():
     h = native.NativePlanner(O, A, U, H, N, 1, I, k, engine, local_rank)
     h.load_problem(prob)
     if world > 1:
-        h.comm_init(rank, world)  # NCCL communicator inside the library: the sharded CEM loop runs on the stream
+        # the sharded CEM loop runs on the stream inside the library; elite exchange over NVLink peer
+        # memory (default) or an in-library ncclAllGather
+        if args.transport == "p2p":
+            h.p2p_init(rank, world)
+        else:
+            h.comm_init(rank, world)
     states0 = torch.stack([synthetic_state(p, c) for c in range(args.warmup + args.steps)]).float()
     d_states0 = states0.to(dev)
     d_out_s = torch.empty(1, H, O, device=dev)
@@ -365,13 +372,13 @@ def main():
         data="synthetic",
         config=dict(workload=w["name"] + (f" x{world} GPUs population-sharded, N_total={n_total}" if world > 1 else ""),
                     engine=engine, elites=k, l2="flushed between timed plans (256 MiB write)",
-                    parallelism=("population-sharded x%d, one NCCL all-gather of (cost, index) elites per iteration" % world) if world > 1 else "single GPU"),
+                    parallelism=("population-sharded x%d, one (cost, index) elite exchange per iteration over %s" % (world, "NVLink peer memory" if args.transport == "p2p" else "ncclAllGather")) if world > 1 else "single GPU"),
         plan_latency_ms_p50=statistics.median(step_ms),
         clocks=clocks,
         e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=4 * O, d2h_bytes_per_step=4 * H * (O + A) + 16,
                  latency_ms_p50=statistics.median(e2e_lat) * 1e3,
                  latency_ms_p50_actions_only=(statistics.median(e2e_lat_actions) * 1e3 if e2e_lat_actions else None),
-                 api="mbrl_plan (host buffers)" + ("" if world == 1 else ", population-sharded (in-library NCCL all-gather)")),
+                 api="mbrl_plan (host buffers)" + ("" if world == 1 else ", population-sharded (in-library elite exchange: %s)" % args.transport)),
         gpu_launches=launches_per_plan * args.steps,
         roofline=roofline,
         cpu_baseline=cpu,

@@ -206,6 +206,16 @@ int mbrl_emit(MbrlPlanner* p, int32_t sample_mode, uint64_t seed, uint32_t cand_
  * transparently redoes the plan with worst-case-size gathers (mbrl_plan_device leaves the flag
  * to the caller).  libnccl.so.2 is resolved at run time (dlopen), not at link time.
  *   mbrl_nccl_unique_id: rank 0 fills 128 bytes, the host broadcasts them to all ranks.        */
+/* Peer-memory transport for the same sharded loop (NVLink P2P through CUDA IPC instead of the
+ * ncclAllGather): every rank exports one gather buffer (mbrl_p2p_export: 64-byte IPC handle),
+ * the host all-gathers the handles, mbrl_p2p_attach opens the peers' buffers.  Per iteration a
+ * single kernel then stores this rank's (cost, global index) elites straight into every peer's
+ * buffer and publishes a sequence flag (st.release.sys); the consumer kernel acquires the flags
+ * of all ranks before it reads.  Buffers are double-buffered by iteration parity; a writer can
+ * never be two iterations ahead of a reader because its own merge needs every rank's flag.
+ * Falls back to NCCL when no peer buffers are attached.                                        */
+int mbrl_p2p_export(MbrlPlanner* p, int32_t world, uint8_t* h_handle64);
+int mbrl_p2p_attach(MbrlPlanner* p, const uint8_t* h_handles, int32_t rank, int32_t world);
 int mbrl_nccl_unique_id(uint8_t* h_id128);
 int mbrl_comm_init(MbrlPlanner* p, const uint8_t* h_id128, int32_t rank, int32_t world);
 int mbrl_comm_destroy(MbrlPlanner* p);

@@ -126,6 +126,14 @@ struct MbrlPlanner {
   MbrlPlanInfo* d_best_now = nullptr;
   int* d_trunc = nullptr;       // truncation flag of the reduced-size elite gather
   bool full_gather = false;     // force worst-case-size gathers (set after a flagged plan)
+  // peer-memory transport (mbrl_p2p_export / mbrl_p2p_attach)
+  uint32_t* d_p2p_local = nullptr;  // exported: [2][world][2*slot] data + [world] flags
+  int p2p_slot = 0, p2p_world = 0;
+  bool p2p_attached = false;
+  P2pPeers p2p_peers{};
+  unsigned int* d_p2p_counter = nullptr;
+  int* d_p2p_error = nullptr;
+  uint32_t p2p_seq = 0;
 };
 
 static ModelDev model_view(const MbrlPlanner* p) {
@@ -169,6 +177,12 @@ extern "C" int mbrl_destroy(MbrlPlanner* p) {
   if (p->d_best_ever) cudaFree(p->d_best_ever);
   if (p->d_info) cudaFree(p->d_info);
   if (p->comm && g_nccl.ok) g_nccl.CommDestroy(p->comm);
+  if (p->p2p_attached)
+    for (int r = 0; r < p->world; ++r)
+      if (r != p->rank && p->p2p_peers.base[r]) cudaIpcCloseMemHandle(p->p2p_peers.base[r]);
+  if (p->d_p2p_local) cudaFree(p->d_p2p_local);
+  if (p->d_p2p_counter) cudaFree(p->d_p2p_counter);
+  if (p->d_p2p_error) cudaFree(p->d_p2p_error);
   void* shard[] = {p->d_ecost, p->d_send, p->d_recv, p->d_gcost, p->d_gidx, p->d_pos, p->d_best_now, p->d_trunc};
   for (void* q : shard) if (q) cudaFree(q);
   tc_free(&p->tc);
@@ -527,6 +541,62 @@ extern "C" int mbrl_comm_destroy(MbrlPlanner* p) {
   return MBRL_OK;
 }
 
+static int alloc_shard_scratch(MbrlPlanner* p, int world) {
+  if (p->d_ecost) return MBRL_OK;
+  const size_t kl = (size_t)std::min(p->cfg.max_elites, p->N);
+  MBRL_CUDA(dev_alloc(&p->d_ecost, kl));
+  MBRL_CUDA(dev_alloc(&p->d_send, 2 * kl));
+  MBRL_CUDA(dev_alloc(&p->d_recv, 2 * kl * world));
+  MBRL_CUDA(dev_alloc(&p->d_gcost, kl * world));
+  MBRL_CUDA(dev_alloc(&p->d_gidx, kl * world));
+  MBRL_CUDA(dev_alloc(&p->d_pos, (size_t)p->cfg.max_elites));
+  MBRL_CUDA(dev_alloc(&p->d_best_now, 1));
+  MBRL_CUDA(dev_alloc(&p->d_trunc, 1));
+  MBRL_CUDA(cudaMemset(p->d_trunc, 0, sizeof(int)));
+  return MBRL_OK;
+}
+
+extern "C" int mbrl_p2p_export(MbrlPlanner* p, int32_t world, uint8_t* h_handle64) {
+  if (!p) return fail(MBRL_E_INVALID, "null planner");
+  MBRL_REQUIRE(h_handle64 && world >= 1 && world <= 64, "p2p_export: bad argument");
+  MBRL_REQUIRE(p->E == 1, "population sharding needs num_envs == 1");
+  MBRL_REQUIRE(!p->d_p2p_local, "p2p buffer already exported");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  MBRL_CUDA(cudaSetDevice(p->cfg.device));
+  p->p2p_slot = std::min(p->cfg.max_elites, p->N);
+  p->p2p_world = world;
+  const size_t words = (size_t)2 * world * 2 * p->p2p_slot + world;
+  MBRL_CUDA(dev_alloc(&p->d_p2p_local, words));
+  MBRL_CUDA(cudaMemset(p->d_p2p_local, 0, sizeof(uint32_t) * words));
+  MBRL_CUDA(dev_alloc(&p->d_p2p_counter, 1));
+  MBRL_CUDA(cudaMemset(p->d_p2p_counter, 0, sizeof(unsigned int)));
+  MBRL_CUDA(dev_alloc(&p->d_p2p_error, 1));
+  MBRL_CUDA(cudaMemset(p->d_p2p_error, 0, sizeof(int)));
+  cudaIpcMemHandle_t hdl;
+  MBRL_CUDA(cudaIpcGetMemHandle(&hdl, p->d_p2p_local));
+  std::memcpy(h_handle64, &hdl, 64);
+  return MBRL_OK;
+}
+
+extern "C" int mbrl_p2p_attach(MbrlPlanner* p, const uint8_t* h_handles, int32_t rank, int32_t world) {
+  if (!p) return fail(MBRL_E_INVALID, "null planner");
+  MBRL_REQUIRE(h_handles && p->d_p2p_local && world == p->p2p_world && rank >= 0 && rank < world,
+               "p2p_attach: export first, with the same world size");
+  MBRL_REQUIRE(!p->p2p_attached, "p2p already attached");
+  MBRL_CUDA(cudaSetDevice(p->cfg.device));
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { p->p2p_peers.base[r] = p->d_p2p_local; continue; }
+    cudaIpcMemHandle_t hdl;
+    std::memcpy(&hdl, h_handles + 64 * r, 64);
+    void* ptr = nullptr;
+    MBRL_CUDA(cudaIpcOpenMemHandle(&ptr, hdl, cudaIpcMemLazyEnablePeerAccess));
+    p->p2p_peers.base[r] = (uint32_t*)ptr;
+  }
+  p->rank = rank; p->world = world;
+  p->p2p_attached = true;
+  return alloc_shard_scratch(p, world);
+}
+
 extern "C" int mbrl_comm_init(MbrlPlanner* p, const uint8_t* h_id128, int32_t rank, int32_t world) {
   if (!p) return fail(MBRL_E_INVALID, "null planner");
   MBRL_REQUIRE(h_id128, "null id");
@@ -539,18 +609,9 @@ extern "C" int mbrl_comm_init(MbrlPlanner* p, const uint8_t* h_id128, int32_t ra
   NcclUniqueId id;
   std::memcpy(id.internal, h_id128, 128);
   MBRL_NCCL(g_nccl.CommInitRank(&p->comm, world, id, rank));
+  MBRL_REQUIRE(!p->p2p_attached || (p->rank == rank && p->world == world), "rank/world differ from the p2p attachment");
   p->rank = rank; p->world = world;
-  const size_t kl = (size_t)std::min(p->cfg.max_elites, p->N);
-  MBRL_CUDA(dev_alloc(&p->d_ecost, kl));
-  MBRL_CUDA(dev_alloc(&p->d_send, 2 * kl));
-  MBRL_CUDA(dev_alloc(&p->d_recv, 2 * kl * world));
-  MBRL_CUDA(dev_alloc(&p->d_gcost, kl * world));
-  MBRL_CUDA(dev_alloc(&p->d_gidx, kl * world));
-  MBRL_CUDA(dev_alloc(&p->d_pos, (size_t)p->cfg.max_elites));
-  MBRL_CUDA(dev_alloc(&p->d_best_now, 1));
-  MBRL_CUDA(dev_alloc(&p->d_trunc, 1));
-  MBRL_CUDA(cudaMemset(p->d_trunc, 0, sizeof(int)));
-  return MBRL_OK;
+  return alloc_shard_scratch(p, world);
 }
 
 extern "C" int mbrl_emit(MbrlPlanner* p, int32_t mode, uint64_t seed, uint32_t cand_offset, uint32_t env_offset,
@@ -612,7 +673,7 @@ static int enqueue_plan(MbrlPlanner* p, const MbrlPlanArgs* a, const float* d_s0
   }
   MBRL_CUDA(cudaGetLastError());
 
-  const bool sharded = p->comm != nullptr;
+  const bool sharded = p->comm != nullptr || p->p2p_attached;
   if (sharded) {
     MBRL_REQUIRE(a->sample_mode == MBRL_SAMPLE_GAUSSIAN || a->sample_mode == MBRL_SAMPLE_UNIFORM,
                  "population sharding supports the Philox sample modes only");
@@ -641,10 +702,21 @@ static int enqueue_plan(MbrlPlanner* p, const MbrlPlanArgs* a, const float* d_s0
       }
       rc = launch_topk(p->d_costs, 1, p->N, kl, p->d_elite, p->d_ecost, nullptr, nullptr, it, st);
       if (rc) return rc;
-      pack_elites_kernel<<<(kl + 255) / 256, 256, 0, st>>>(p->d_ecost, p->d_elite, kl, (int)cand_offset, p->d_send);
-      MBRL_NCCL(g_nccl.AllGather(p->d_send, p->d_recv, (size_t)2 * kl, kNcclUint32, p->comm, st));
       const int ng = kl * p->world;
-      unpack_gathered_kernel<<<(ng + 255) / 256, 256, 0, st>>>(p->d_recv, p->world, kl, p->d_gcost, p->d_gidx);
+      if (p->p2p_attached) {
+        // peer-memory exchange: one kernel stores our elites into every rank's buffer and publishes
+        // the sequence flag; the consumer acquires all ranks' flags, then unpacks
+        const uint32_t seq = ++p->p2p_seq;
+        p2p_scatter_kernel<<<(kl + 255) / 256, 256, 0, st>>>(p->d_ecost, p->d_elite, kl, (int)cand_offset, p->p2p_peers,
+                                                            p->rank, p->world, p->p2p_slot, (int)(seq & 1), seq,
+                                                            p->d_p2p_counter);
+        p2p_wait_unpack_kernel<<<(ng + 255) / 256, 256, 0, st>>>(p->d_p2p_local, p->world, p->p2p_slot, kl, (int)(seq & 1),
+                                                                seq, p->d_gcost, p->d_gidx, p->d_p2p_error);
+      } else {
+        pack_elites_kernel<<<(kl + 255) / 256, 256, 0, st>>>(p->d_ecost, p->d_elite, kl, (int)cand_offset, p->d_send);
+        MBRL_NCCL(g_nccl.AllGather(p->d_send, p->d_recv, (size_t)2 * kl, kNcclUint32, p->comm, st));
+        unpack_gathered_kernel<<<(ng + 255) / 256, 256, 0, st>>>(p->d_recv, p->world, kl, p->d_gcost, p->d_gidx);
+      }
       rc = launch_topk(p->d_gcost, 1, ng, k, p->d_pos, nullptr, p->d_best_now, nullptr, it, st);
       if (rc) return rc;
       remap_elites_kernel<<<(std::max(k, p->world) + 255) / 256, 256, 0, st>>>(
@@ -724,7 +796,12 @@ extern "C" int mbrl_plan(MbrlPlanner* p, const MbrlPlanArgs* args, const float* 
     MBRL_CUDA(cudaMemcpyAsync(p->h_sd, p->d_sd_hist + (size_t)args->iterations * EHA, sizeof(float) * EHA, cudaMemcpyDeviceToHost, st));
   }
   MBRL_CUDA(cudaStreamSynchronize(st));
-  if (p->comm && p->h_info[0].reserved != 0 && !p->full_gather) {
+  if (p->p2p_attached) {
+    int perr = 0;
+    MBRL_CUDA(cudaMemcpy(&perr, p->d_p2p_error, sizeof(int), cudaMemcpyDeviceToHost));
+    if (perr) return fail(MBRL_E_CUDA, "peer-memory elite exchange timed out waiting for another rank");
+  }
+  if ((p->comm || p->p2p_attached) && p->h_info[0].reserved != 0 && !p->full_gather) {
     // Practically unreachable (the shards are i.i.d.): some rank's reduced elite list was used up.
     // The flag derives from the gathered data, so every rank sees it and redoes the plan in lockstep.
     p->full_gather = true;

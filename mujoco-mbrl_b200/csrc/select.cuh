@@ -347,6 +347,75 @@ __global__ void pack_elites_kernel(const float* __restrict__ elite_cost, const i
     send[k_l + i] = (uint32_t)(elite_idx[i] + idx_offset);
   }
 }
+// ---- peer-memory (NVLink P2P) elite exchange ---------------------------------------------------
+// Layout of every rank's exported buffer: [2 parities][world][2*slot] uint32 data, then
+// [world] uint32 sequence flags (one per source rank).  slot = k_l capacity.
+struct P2pPeers {
+  uint32_t* base[64];  // peer r's exported buffer (own rank: the local pointer)
+};
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// One launch per iteration: writes this rank's k_l (cost bits | global index) pairs into slot
+// [parity][rank] of EVERY rank's buffer (peer stores over NVLink), then -- after a system-scope
+// fence and a grid-wide arrival count -- the last block publishes `seq` in flag[rank] of every peer.
+__global__ void p2p_scatter_kernel(const float* __restrict__ elite_cost, const int* __restrict__ elite_idx,
+                                   int k_l, int idx_offset, P2pPeers peers, int rank, int world, int slot,
+                                   int parity, uint32_t seq, unsigned int* __restrict__ arrive_counter) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < k_l) {
+    const uint32_t c = __float_as_uint(elite_cost[i]);
+    const uint32_t g = (uint32_t)(elite_idx[i] + idx_offset);
+    const size_t off = ((size_t)parity * world + rank) * 2 * slot;
+    for (int r = 0; r < world; ++r) {
+      uint32_t* dst = peers.base[r] + off;
+      dst[i] = c;
+      dst[k_l + i] = g;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(arrive_counter, 1u) + 1u;
+    if (done == gridDim.x) {
+      *arrive_counter = 0;  // ready for the next launch (stream order)
+      __threadfence_system();
+      const size_t flags = (size_t)2 * world * 2 * slot;
+      for (int r = 0; r < world; ++r) st_release_sys(peers.base[r] + flags + rank, seq);
+    }
+  }
+}
+// Consumer: acquire every rank's flag (>= seq), then unpack [parity][r][..] into contiguous costs /
+// global indices in rank order.  A rank that never shows up trips the timeout: *error = 1.
+__global__ void p2p_wait_unpack_kernel(const uint32_t* __restrict__ local, int world, int slot, int k_l, int parity,
+                                       uint32_t seq, float* __restrict__ gcost, int* __restrict__ gidx,
+                                       int* __restrict__ error) {
+  __shared__ int s_ok;
+  if (threadIdx.x == 0) s_ok = 1;
+  __syncthreads();
+  if (threadIdx.x < world) {
+    const uint32_t* flag = local + (size_t)2 * world * 2 * slot + threadIdx.x;
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(flag) - seq) < 0) {
+      if (clock64() - t0 > 20000000000ll) { s_ok = 0; break; }  // ~10 s
+    }
+  }
+  __syncthreads();
+  if (!s_ok) { if (threadIdx.x == 0 && blockIdx.x == 0) *error = 1; return; }
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < world * k_l) {
+    const int r = i / k_l, j = i - r * k_l;
+    const uint32_t* src = local + ((size_t)parity * world + r) * 2 * slot;
+    gcost[i] = __uint_as_float(__ldcg(src + j));
+    gidx[i] = (int)__ldcg(src + k_l + j);
+  }
+}
+
 // gathered [world][2*k_l] -> contiguous costs / global indices in rank order (== ascending global
 // index, so "ties -> lower position" in the merge is "ties -> lower global index")
 __global__ void unpack_gathered_kernel(const uint32_t* __restrict__ recv, int world, int k_l,

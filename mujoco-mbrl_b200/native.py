@@ -26,6 +26,7 @@ ABI_SYMBOLS = [
     "mbrl_set_norm", "mbrl_set_cost", "mbrl_set_action_bounds", "mbrl_plan", "mbrl_plan_device",
     "mbrl_rollout", "mbrl_sample", "mbrl_philox_raw", "mbrl_topk", "mbrl_refit", "mbrl_emit",
     "mbrl_tc_debug", "mbrl_nccl_unique_id", "mbrl_comm_init", "mbrl_comm_destroy",
+    "mbrl_p2p_export", "mbrl_p2p_attach",
 ]
 
 
@@ -98,6 +99,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         "mbrl_nccl_unique_id": [vp],
         "mbrl_comm_init": [p, vp, i32, i32],
         "mbrl_comm_destroy": [p],
+        "mbrl_p2p_export": [p, i32, vp],
+        "mbrl_p2p_attach": [p, vp, i32, i32],
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)
@@ -295,6 +298,25 @@ class NativePlanner:
             dist.broadcast(t, src=0, group=group)
             buf = t.cpu().numpy().copy()
         _check(self.lib.mbrl_comm_init(self._h, _hp(buf), rank, world))
+        self.rank, self.world = rank, world
+
+    def p2p_init(self, rank=None, world=None, group=None):
+        """Peer-memory (NVLink P2P, CUDA IPC) transport for the sharded loop: export this rank's gather
+        buffer, all-gather the 64-byte IPC handles through torch.distributed, open the peers' buffers."""
+        import torch
+        import torch.distributed as dist
+        if world is None:
+            world, rank = dist.get_world_size(group), dist.get_rank(group)
+        mine = np.zeros(64, np.uint8)
+        _check(self.lib.mbrl_p2p_export(self._h, world, _hp(mine)))
+        t = torch.from_numpy(mine)
+        on_gpu = dist.get_backend(group) == "nccl"
+        if on_gpu:
+            t = t.cuda(self.device)
+        allh = torch.empty(world * 64, dtype=torch.uint8, device=t.device)
+        dist.all_gather_into_tensor(allh, t, group=group)
+        handles = np.ascontiguousarray(allh.cpu().numpy())
+        _check(self.lib.mbrl_p2p_attach(self._h, _hp(handles), rank, world))
         self.rank, self.world = rank, world
 
     def tc_debug(self, enable=True, fetch=False):

@@ -27,14 +27,20 @@ def main():
     n_total, k = n_local * world, int(0.1 * n_local * world)
     prob = synthetic_problem(O, A, U)
     s0 = synthetic_state(prob, 4).numpy()
-    for engine, force_kl in (("fp32", None), ("fp16", None), ("fp16", "min")):
+    for engine, force_kl, transport in (("fp32", None, "nccl"), ("fp16", None, "nccl"), ("fp16", "min", "nccl"),
+                                        ("fp16", None, "p2p"), ("fp16", "min", "p2p")):
         if force_kl is None:
             os.environ.pop("MBRL_SHARD_KL", None)
         else:  # a gather that is far too small: the on-device check must flag it and the plan is redone in full
             os.environ["MBRL_SHARD_KL"] = force_kl
         h = native.NativePlanner(O, A, U, H, n_local, 1, I, k, engine, local)
         h.load_problem(prob)
-        h.comm_init(rank, world)
+        if transport == "p2p":
+            h.p2p_init(rank, world)   # NVLink peer stores + sequence flags instead of ncclAllGather
+        else:
+            h.comm_init(rank, world)
+        for rep in range(3):          # repeated plans: sequence numbers / double buffering keep working
+            out = h.plan(s0, I, k, native.SAMPLE_GAUSSIAN, seed=20 + rep, want_dist=True)
         out = h.plan(s0, I, k, native.SAMPLE_GAUSSIAN, seed=21, want_dist=True)
         mine = torch.from_numpy(np.concatenate([out["actions"].ravel(), out["states"].ravel(), out["mu"].ravel(),
                                                 out["sd"].ravel(), out["info"]["best_cost"],
@@ -51,7 +57,7 @@ def main():
                 np.testing.assert_array_equal(out[key], want[key], err_msg=f"{engine} {key}")
             for key in ("best_cost", "best_index", "best_iteration"):
                 np.testing.assert_array_equal(out["info"][key], want["info"][key], err_msg=f"{engine} {key}")
-            print(f"multi_gpu_check[{engine}{', forced tiny gather' if force_kl else ''}]: {world} ranks == unsharded N={n_total}: best cost "
+            print(f"multi_gpu_check[{engine}, {transport}{', forced tiny gather' if force_kl else ''}]: {world} ranks == unsharded N={n_total}: best cost "
                   f"{out['info']['best_cost'][0]:.4f} idx {out['info']['best_index'][0]} it {out['info']['best_iteration'][0]}")
         dist.barrier()
         h.close()
