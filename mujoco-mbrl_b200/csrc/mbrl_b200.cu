@@ -352,6 +352,20 @@ extern "C" int mbrl_set_action_bounds(MbrlPlanner* p, float lo, float hi) {
 // --------------------------------------------------------------------------------------
 // kernel launchers
 // --------------------------------------------------------------------------------------
+// Launch with programmatic stream serialization (PDL): the kernel may begin while its stream
+// predecessor is still running; every kernel of this library calls pdl_wait() before it touches
+// data a predecessor produces (see common.cuh).
+static bool g_use_pdl = getenv("MBRL_NO_PDL") == nullptr;
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = g_use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 template <int TM, int CPT>
 static cudaError_t launch_simt_t(const MbrlPlanner* p, const ActionSource& src, const float* d_s0,
                                  float* d_costs, float* d_states, float* d_actions, cudaStream_t st) {
@@ -410,9 +424,11 @@ static int launch_topk(const float* d_costs, int segments, int n, int k, int* d_
   if (n <= kSelectStageMax) {
     const size_t smem = sizeof(uint32_t) * (size_t)((n + 3) & ~3);
     MBRL_CUDA(cudaFuncSetAttribute(topk_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    topk_select_kernel<true><<<segments, kSelectThreads, smem, st>>>(d_costs, n, k, d_idx, d_cost, d_best, d_best_ever, iteration);
+    MBRL_CUDA(launch_pdl(topk_select_kernel<true>, dim3(segments), dim3(kSelectThreads), smem, st, d_costs, n, k, d_idx, d_cost,
+                         d_best, d_best_ever, iteration));
   } else {
-    topk_select_kernel<false><<<segments, kSelectThreads, 0, st>>>(d_costs, n, k, d_idx, d_cost, d_best, d_best_ever, iteration);
+    MBRL_CUDA(launch_pdl(topk_select_kernel<false>, dim3(segments), dim3(kSelectThreads), 0, st, d_costs, n, k, d_idx, d_cost,
+                         d_best, d_best_ever, iteration));
   }
   MBRL_CUDA(cudaGetLastError());
   return MBRL_OK;
@@ -424,7 +440,7 @@ static int launch_refit(const MbrlPlanner* p, const ActionSource& src, const int
   const int G = (p->A + 3) / 4;
   Shape sh{p->H, p->N, p->E};
   dim3 grid(p->H * G, p->E);
-  refit_kernel<<<grid, kRefitThreads, 0, st>>>(src, sh, p->A, d_elite, k, d_mu_new, d_sd_new);
+  MBRL_CUDA(launch_pdl(refit_kernel, grid, dim3(kRefitThreads), 0, st, src, sh, p->A, d_elite, k, d_mu_new, d_sd_new));
   MBRL_CUDA(cudaGetLastError());
   return MBRL_OK;
 }
@@ -440,8 +456,8 @@ static int launch_replay(MbrlPlanner* p, int mode, uint64_t seed, uint32_t cand_
   const size_t smem_w = replay_smem_bytes(p->O, p->A, p->U, p->H, true);
   if (smem_w <= p->max_smem && !actions_only) {
     MBRL_CUDA(cudaFuncSetAttribute(replay_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
-    replay_kernel<true><<<p->E, kReplayThreads, smem_w, st>>>(model_view(p), src, sh, d_s0, d_mu_hist, d_sd_hist, d_best,
-                                                             iterations, return_mean, actions_only, d_out_states, d_out_actions, d_info);
+    MBRL_CUDA(launch_pdl(replay_kernel<true>, dim3(p->E), dim3(kReplayThreads), smem_w, st, model_view(p), src, sh, d_s0,
+                         d_mu_hist, d_sd_hist, d_best, iterations, return_mean, actions_only, d_out_states, d_out_actions, d_info));
   } else {
     const size_t smem = replay_smem_bytes(p->O, p->A, p->U, p->H, false);
     MBRL_REQUIRE(smem <= p->max_smem, "horizon too long for the replay kernel's shared memory");

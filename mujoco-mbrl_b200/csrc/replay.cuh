@@ -150,6 +150,9 @@ replay_kernel(ModelDev m, ActionSource src, Shape sh, const float* __restrict__ 
   const long long R = sh.rows();
   const long long EHA = (long long)sh.E * H * A;
 
+  // everything above only touched the (static) model: under PDL it overlaps the last top-k
+  pdl_trigger();
+  pdl_wait();
   const BestEver b = best_ever[env_l];
   if (return_mean) {
     const float* mu = mu_hist + (long long)iterations * EHA + (long long)env_l * H * A;

@@ -90,6 +90,8 @@ rollout_simt_kernel(ModelDev m, ActionSource src, Shape sh, const float* __restr
                     float* __restrict__ actions_out) {
   extern __shared__ __align__(16) float simt_smem[];
   float* const smem = simt_smem;
+  pdl_trigger();
+  pdl_wait();
   const int O = m.O, A = m.A, D = m.D, U = m.U;
   const int KA = D > U ? D : U;
   const int KB = U > O ? U : O;

@@ -309,6 +309,8 @@ rollout_tc_kernel(TcGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Action
                   float* __restrict__ actions_out, float* __restrict__ dbg) {
   extern __shared__ __align__(128) uint8_t tc_smem[];
   uint8_t* const smem = tc_smem;
+  pdl_trigger();
+  pdl_wait();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int O = g.O, A = g.A, H = sh.H;
   const int NC = (g.Np + 31) >> 5;       // hidden epilogue chunks (32 columns, last may be 16)

@@ -119,6 +119,11 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
                    float* __restrict__ actions_out, float* __restrict__ dbg) {
   extern __shared__ __align__(128) uint8_t tcf_smem[];
   uint8_t* const smem = tcf_smem;
+  // PDL: barrier init, TMEM allocation, the 207 KB weight TMA and the table fill only touch static
+  // model data, so they overlap the tail of the preceding refit / top-k.  The sampler and cost
+  // threads are the only consumers of upstream results (mean/std, s0) and wait below; the final
+  // cost write follows a block barrier that those threads have passed.
+  pdl_trigger();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int O = g.O, A = g.A, H = sh.H;
   const int KS_H = g.Np >> 4;        // K-steps over a hidden operand
@@ -287,6 +292,7 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
     const float inv_beta = 1.0f / m.beta, cscale = valid ? m.beta2 / (float)A : 0.f;
     const int QA = (A + 8) >> 3;  // 8-wide chunks holding the actions and the constant 1
     float act_total = 0.f;
+    pdl_wait();
 
     auto stage_actions = [&](int hs) {
       float acc = 0.f;
@@ -354,6 +360,7 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
     const bool valid = row < R;
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     float st_total = 0.f;
+    pdl_wait();
     // Phases must be observed in order: a parity wait on phase #1 issued before phase #0 has
     // completed would fall through at once (it cannot tell "not yet" from "one phase ago").
     mbar_wait(bar_dA, 0);
@@ -498,8 +505,16 @@ inline cudaError_t tc_launch_one(Kern kern, const Geom& g, int smem_bytes, int t
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return e;
   const unsigned grid = (unsigned)((sh.rows() + kTcRows - 1) / kTcRows);
-  kern<<<grid, threads, smem_bytes, st>>>(g, t->d_wimg, m, src, sh, d_s0, d_costs, d_states, d_actions, t->d_dbg);
-  return cudaGetLastError();
+  // programmatic dependent launch: the prologue (barriers, TMEM, weight TMA) overlaps the predecessor
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = (size_t)smem_bytes; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = getenv("MBRL_NO_PDL") ? 0 : 1;
+  const uint8_t* wimg = t->d_wimg;
+  float* dbg = t->d_dbg;
+  return cudaLaunchKernelEx(&cfg, kern, g, wimg, m, src, sh, d_s0, d_costs, d_states, d_actions, dbg);
 }
 
 inline cudaError_t tc_launch_rollout(TcModel* t, const ModelDev& m, const ActionSource& src, const Shape& sh,

@@ -78,6 +78,8 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int n4 = (n + 3) & ~3;
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(c) & 15) == 0);
+  pdl_trigger();
+  pdl_wait();  // the costs come from the preceding rollout / unpack kernel
   TOPK_STAMP(0);
 
   // four keys of indices i4..i4+3 (i4 multiple of 4); out-of-range -> 0xFFFFFFFF (masked by index)
@@ -277,6 +279,8 @@ refit_kernel(ActionSource src, Shape sh, int A, const int* __restrict__ elite_id
   const bool inject = src.mode == MBRL_SAMPLE_INJECT_ACTIONS || src.mode == MBRL_SAMPLE_INJECT_NOISE;
   const bool affine = src.mode == MBRL_SAMPLE_INJECT_NOISE || src.mode == MBRL_SAMPLE_GAUSSIAN;
   float mu_old[4], sd_old[4], s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  pdl_trigger();
+  pdl_wait();  // elite indices (top-k / remap) and the old mean/std (previous refit)
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int ac = min(4 * g + j, A - 1);
@@ -342,6 +346,8 @@ refit_kernel(ActionSource src, Shape sh, int A, const int* __restrict__ elite_id
 __global__ void pack_elites_kernel(const float* __restrict__ elite_cost, const int* __restrict__ elite_idx,
                                    int k_l, int idx_offset, uint32_t* __restrict__ send) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_trigger();
+  pdl_wait();
   if (i < k_l) {
     send[i] = __float_as_uint(elite_cost[i]);
     send[k_l + i] = (uint32_t)(elite_idx[i] + idx_offset);
@@ -368,6 +374,8 @@ __global__ void p2p_scatter_kernel(const float* __restrict__ elite_cost, const i
                                    int k_l, int idx_offset, P2pPeers peers, int rank, int world, int slot,
                                    int parity, uint32_t seq, unsigned int* __restrict__ arrive_counter) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_trigger();
+  pdl_wait();
   if (i < k_l) {
     const uint32_t c = __float_as_uint(elite_cost[i]);
     const uint32_t g = (uint32_t)(elite_idx[i] + idx_offset);
@@ -396,6 +404,8 @@ __global__ void p2p_wait_unpack_kernel(const uint32_t* __restrict__ local, int w
                                        uint32_t seq, float* __restrict__ gcost, int* __restrict__ gidx,
                                        int* __restrict__ error) {
   __shared__ int s_ok;
+  pdl_trigger();
+  pdl_wait();
   if (threadIdx.x == 0) s_ok = 1;
   __syncthreads();
   if (threadIdx.x < world) {
@@ -421,6 +431,8 @@ __global__ void p2p_wait_unpack_kernel(const uint32_t* __restrict__ local, int w
 __global__ void unpack_gathered_kernel(const uint32_t* __restrict__ recv, int world, int k_l,
                                        float* __restrict__ gcost, int* __restrict__ gidx) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_trigger();
+  pdl_wait();
   if (i < world * k_l) {
     const int r = i / k_l, j = i - r * k_l;
     gcost[i] = __uint_as_float(recv[(long long)r * 2 * k_l + j]);
@@ -437,6 +449,8 @@ __global__ void remap_elites_kernel(const int* __restrict__ pos, const int* __re
                                     BestEver* __restrict__ best_ever, int iteration, int world, int k_s,
                                     int k_full, int* __restrict__ trunc_flag) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_trigger();
+  pdl_wait();
   if (i < k) elite_global[i] = gidx[pos[i]];
   if (i < world && k_s < k_full) {
     auto lower_bound = [&](int v) {
@@ -460,6 +474,8 @@ __global__ void remap_elites_kernel(const int* __restrict__ pos, const int* __re
 __global__ void init_plan_kernel(float* __restrict__ mu, float* __restrict__ sd, long long n,
                                  float lo, float hi, BestEver* __restrict__ best_ever, int E) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  pdl_trigger();
+  pdl_wait();
   if (mu && i < n) { mu[i] = 0.5f * (lo + hi); sd[i] = 0.5f * (hi - lo); }
   if (best_ever && i < E) best_ever[i] = BestEver{0.f, -1, -1, 0};
 }
