@@ -201,7 +201,7 @@ int mbrl_emit(MbrlPlanner* p, int32_t sample_mode, uint64_t seed, uint32_t cand_
  * their global indices (Philox counters carry the global index), so no second collective is
  * needed and every rank holds bit-identical mean/std and emits the same plan.  args->elites is
  * the GLOBAL k; info.best_index is a GLOBAL candidate index; num_envs must be 1; Philox sample
- * modes only.  Ranks send 2x their expected share of the elites (the shards are i.i.d.) and the
+ * modes only.  Ranks send their expected share of the elites plus 8 sigma (the shards are i.i.d.) and the
  * merge verifies on the device that this was exact; otherwise info.reserved = 1 and mbrl_plan
  * transparently redoes the plan with worst-case-size gathers (mbrl_plan_device leaves the flag
  * to the caller).  libnccl.so.2 is resolved at run time (dlopen), not at link time.

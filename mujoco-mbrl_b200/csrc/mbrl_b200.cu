@@ -708,10 +708,12 @@ static int enqueue_plan(MbrlPlanner* p, const MbrlPlanArgs* a, const float* d_s0
       // local elites -> all-gather (cost, global index) -> same global top-k on every rank ->
       // redundant refit from GLOBAL indices (cand_offset 0): no second collective
       // Worst case a single shard holds all k global elites (k_full = min(k, N) per rank); the
-      // shards are i.i.d., so the expected share is k/world.  Send 2x the expected share (+64) and
-      // verify exactness on the device (remap_elites_kernel); a flagged plan is redone in full.
+      // shards are i.i.d., so a rank's share is Binomial(k, 1/world): send the expected share plus
+      // 8 standard deviations (+64) and verify exactness on the device (remap_elites_kernel); a
+      // flagged plan -- probability ~1e-15 per iteration -- is redone with full-size gathers.
       const int k_full = std::min(k, p->N);
-      int kl = (p->full_gather || p->world == 1) ? k_full : std::min(k_full, 2 * ((k + p->world - 1) / p->world) + 64);
+      const int share = (k + p->world - 1) / p->world;
+      int kl = (p->full_gather || p->world == 1) ? k_full : std::min(k_full, share + 8 * (int)std::ceil(std::sqrt((double)share)) + 64);
       if (const char* force = getenv("MBRL_SHARD_KL")) {  // tests: "min" = the smallest legal gather (exactly the
         // expected share), which the exactness check must flag so that the redo path is exercised
         if (!p->full_gather && p->world > 1 && force[0] == 'm') kl = std::min(k_full, (k + p->world - 1) / p->world);
@@ -723,11 +725,11 @@ static int enqueue_plan(MbrlPlanner* p, const MbrlPlanArgs* a, const float* d_s0
         // peer-memory exchange: one kernel stores our elites into every rank's buffer and publishes
         // the sequence flag; the consumer acquires all ranks' flags, then unpacks
         const uint32_t seq = ++p->p2p_seq;
-        p2p_scatter_kernel<<<(kl + 255) / 256, 256, 0, st>>>(p->d_ecost, p->d_elite, kl, (int)cand_offset, p->p2p_peers,
-                                                            p->rank, p->world, p->p2p_slot, (int)(seq & 1), seq,
-                                                            p->d_p2p_counter);
-        p2p_wait_unpack_kernel<<<(ng + 255) / 256, 256, 0, st>>>(p->d_p2p_local, p->world, p->p2p_slot, kl, (int)(seq & 1),
-                                                                seq, p->d_gcost, p->d_gidx, p->d_p2p_error);
+        MBRL_CUDA(launch_pdl(p2p_scatter_kernel, dim3((kl + 255) / 256), dim3(256), 0, st, p->d_ecost, p->d_elite, kl,
+                             (int)cand_offset, p->p2p_peers, p->rank, p->world, p->p2p_slot, (int)(seq & 1), seq,
+                             p->d_p2p_counter));
+        MBRL_CUDA(launch_pdl(p2p_wait_unpack_kernel, dim3((ng + 255) / 256), dim3(256), 0, st, p->d_p2p_local, p->world,
+                             p->p2p_slot, kl, (int)(seq & 1), seq, p->d_gcost, p->d_gidx, p->d_p2p_error));
       } else {
         pack_elites_kernel<<<(kl + 255) / 256, 256, 0, st>>>(p->d_ecost, p->d_elite, kl, (int)cand_offset, p->d_send);
         MBRL_NCCL(g_nccl.AllGather(p->d_send, p->d_recv, (size_t)2 * kl, kNcclUint32, p->comm, st));
@@ -735,8 +737,8 @@ static int enqueue_plan(MbrlPlanner* p, const MbrlPlanArgs* a, const float* d_s0
       }
       rc = launch_topk(p->d_gcost, 1, ng, k, p->d_pos, nullptr, p->d_best_now, nullptr, it, st);
       if (rc) return rc;
-      remap_elites_kernel<<<(std::max(k, p->world) + 255) / 256, 256, 0, st>>>(
-          p->d_pos, p->d_gidx, k, p->d_elite, p->d_best_now, p->d_best_ever, it, p->world, kl, k_full, p->d_trunc);
+      MBRL_CUDA(launch_pdl(remap_elites_kernel, dim3((std::max(k, p->world) + 255) / 256), dim3(256), 0, st, p->d_pos,
+                           p->d_gidx, k, p->d_elite, p->d_best_now, p->d_best_ever, it, p->world, kl, k_full, p->d_trunc));
       MBRL_CUDA(cudaGetLastError());
       if (it + 1 < I || need_final_dist) {
         ActionSource gsrc = src;
