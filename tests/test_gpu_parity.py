@@ -396,3 +396,33 @@ def test_full_size_cem_properties(native):
     # replayed plan reproduces its own cost under the oracle
     _, c_plan = po.rollout_costs(p, s0, torch.from_numpy(out["actions"][0]), H, 1)
     np.testing.assert_allclose(c_plan[0], out["info"]["best_cost"][0], rtol=FP32_COST_RTOL)
+
+
+def test_warm_start_and_return_mean(native):
+    """Warm start (mu0/sd0, what CEMPlanner builds from MPCPolicy's initial_trajectory,
+    src/mbrl/agents.py:41-47) and return_mean: checked against the oracle CEM with the device's own
+    draws injected."""
+    p = po.synthetic_params(9, 3, 40, seed=6)
+    H, n, I, k = 8, 1024, 3, 100
+    s0 = po.synthetic_state(p, 1)
+    g = torch.Generator().manual_seed(8)
+    mu0 = torch.rand(H, 3, generator=g) * 0.6 - 0.3
+    sd0 = torch.rand(H, 3, generator=g) * 0.3 + 0.1
+    h = _planner(native, p, H, n, 1, I)
+    out = h.plan(s0.numpy(), I, k, native.SAMPLE_GAUSSIAN, seed=4, mu0=mu0[None].numpy(), sd0=sd0[None].numpy(), want_dist=True)
+    # recover the N(0,1) draws of every iteration from the materialising sampler (mu=0, sd=1, wide bounds)
+    h.set_action_bounds(-1e6, 1e6)
+    z = torch.stack([h.sample(native.SAMPLE_GAUSSIAN, 4, it, torch.zeros(1, H, 3, device="cuda"),
+                              torch.ones(1, H, 3, device="cuda")).cpu() for it in range(I)])
+    h.set_action_bounds(p.act_lo, p.act_hi)
+    ref = po.cem_plan(p, s0, z, H, n, k, mu0=mu0, sd0=sd0)
+    assert (int(out["info"]["best_iteration"][0]), int(out["info"]["best_index"][0])) == (ref["best"]["it"], ref["best"]["idx"])
+    np.testing.assert_allclose(out["actions"][0], ref["best"]["actions"].numpy(), atol=2e-6)
+    np.testing.assert_allclose(out["mu"][0], ref["mu"].numpy(), rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(out["sd"][0], ref["sd"].numpy(), rtol=1e-3, atol=2e-5)
+    # return_mean: the emitted sequence is the final mean, replayed through the model
+    outm = h.plan(s0.numpy(), I, k, native.SAMPLE_GAUSSIAN, seed=4, mu0=mu0[None].numpy(), sd0=sd0[None].numpy(),
+                  return_mean=True, want_dist=True)
+    np.testing.assert_allclose(outm["actions"][0], outm["mu"][0], atol=1e-7)
+    st, _ = po.rollout_costs(p, s0, torch.from_numpy(outm["actions"][0]), H, 1)
+    np.testing.assert_allclose(outm["states"][0], st.numpy(), rtol=1e-4, atol=1e-4)
