@@ -454,7 +454,19 @@ static int launch_replay(MbrlPlanner* p, int mode, uint64_t seed, uint32_t cand_
   ActionSource src = action_source(p, mode, seed, 0, cand_offset, env_offset, d_injected, d_mu_hist, d_sd_hist);
   Shape sh{p->H, p->N, p->E};
   const size_t smem_w = replay_smem_bytes(p->O, p->A, p->U, p->H, true);
-  if (smem_w <= p->max_smem && !actions_only) {
+  const RegGeom rg = replay_reg_geometry(p->O, p->A, p->U, p->H);
+  static const bool no_reg = std::getenv("MBRL_REPLAY_NO_REG") != nullptr;  // A/B switch for profiling
+  if (rg.ok && sizeof(float) * (size_t)rg.total <= p->max_smem && !actions_only && !no_reg) {
+    const size_t smem = sizeof(float) * (size_t)rg.total;
+    auto launch = [&](auto kernel) -> cudaError_t {
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      return launch_pdl(kernel, dim3(p->E), dim3(kRegThreads), smem, st, model_view(p), src, sh, rg, d_s0, d_mu_hist,
+                        d_sd_hist, d_best, iterations, return_mean, d_out_states, d_out_actions, d_info);
+    };
+    if (rg.kpt2 == 16) MBRL_CUDA(launch(replay_reg_kernel<8, 16>));
+    else MBRL_CUDA(launch(replay_reg_kernel<5, 40>));
+  } else if (smem_w <= p->max_smem && !actions_only) {
     MBRL_CUDA(cudaFuncSetAttribute(replay_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
     MBRL_CUDA(launch_pdl(replay_kernel<true>, dim3(p->E), dim3(kReplayThreads), smem_w, st, model_view(p), src, sh, d_s0,
                          d_mu_hist, d_sd_hist, d_best, iterations, return_mean, actions_only, d_out_states, d_out_actions, d_info));

@@ -205,4 +205,214 @@ replay_kernel(ModelDev m, ActionSource src, Shape sh, const float* __restrict__ 
   }
 }
 
+// --------------------------------------------------------------------------------------
+// Register-resident variant.  The recurrence is one environment, batch 1: per step the only
+// real work is streaming W2 (U*U floats) past the hidden vector; everything else is a chain of
+// dependent shared-memory latencies and block barriers, and barriers get dearer with the thread
+// count.  So: 256 threads, and W2 lives in their REGISTERS -- thread (s, q) holds the 4 output
+// columns 4q..4q+3 of the K slice [s*KPT2, s*KPT2+KPT2) (160 floats for U = 200).  W1 and W3
+// (small) sit in shared memory, W3 transposed and row-skewed so that 8 lanes reduce one output
+// with conflict-free loads + 3 shuffles.  Trip counts are template constants and every buffer is
+// zero-padded to them: straight-line code, independent loads, no per-element predicates.
+// Layer 1 (K = D, short) is one thread per output.  4 block barriers per step.  Shapes that fit
+// no instantiation use replay_kernel.
+// --------------------------------------------------------------------------------------
+constexpr int kRegThreads = 256;
+
+struct RegGeom {
+  int S, kpt2, Q, ldu, ldo, kp1, kp2, k3, ld3, o3;
+  int acts, x, y, h1, h2, part, vec, w1, w3, total;  // shared-memory offsets, in floats
+  bool ok;
+};
+__host__ __device__ inline RegGeom replay_reg_geometry(int O, int A, int U, int H) {
+  auto r4 = [](int v) { return (v + 3) & ~3; };
+  RegGeom g;
+  const int D = O + A;
+  if (U <= 128) { g.S = 8; g.kpt2 = 16; } else { g.S = 5; g.kpt2 = 40; }
+  g.Q = (U + 3) / 4;
+  g.ok = U >= 1 && U <= g.S * g.kpt2 && g.Q * g.S <= kRegThreads && O <= 128 && A <= kMaxAct;
+  g.ldu = 4 * g.Q;
+  g.ldo = r4(O);
+  g.kp1 = (D + 7) & ~7;
+  g.kp2 = g.S * g.kpt2;
+  g.k3 = (g.kp2 + 7) / 8;  // layer-3 K elements per lane (8 lanes per output)
+  g.ld3 = 8 * g.k3 + 8;    // +8 words: the 4 outputs of a warp land in 4 distinct bank octets
+  g.o3 = r4(O);            // outputs padded to whole warps of 4
+  g.acts = 0;
+  g.x = r4(H * A);
+  g.y = g.x + g.kp1;
+  g.h1 = g.y + g.ldo;
+  g.h2 = g.h1 + g.kp2;
+  g.part = g.h2 + 8 * g.k3;
+  g.vec = g.part + g.S * g.ldu;
+  g.w1 = g.vec + 2 * g.ldu + 3 * g.ldo + 2 * kMaxAct;
+  g.w3 = g.w1 + g.kp1 * g.ldu;
+  g.total = g.w3 + g.o3 * g.ld3;
+  return g;
+}
+
+template <int S, int KPT2>
+__global__ void __launch_bounds__(kRegThreads, 1)
+replay_reg_kernel(ModelDev m, ActionSource src, Shape sh, RegGeom g, const float* __restrict__ s0,
+                  const float* __restrict__ mu_hist, const float* __restrict__ sd_hist,
+                  const BestEver* __restrict__ best_ever, int iterations, int return_mean,
+                  float* __restrict__ out_states, float* __restrict__ out_actions,
+                  MbrlPlanInfo* __restrict__ info) {
+  extern __shared__ __align__(16) float rr[];
+  constexpr int K3 = (S * KPT2 + 7) / 8;
+  const int O = m.O, A = m.A, D = m.D, U = m.U, H = sh.H;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  REPLAY_STAMP(0);
+  float *acts = rr + g.acts, *x = rr + g.x, *y = rr + g.y, *h1 = rr + g.h1, *h2 = rr + g.h2, *part = rr + g.part;
+  float *vb1 = rr + g.vec, *vb2 = vb1 + g.ldu, *vb3 = vb2 + g.ldu, *vmu = vb3 + g.ldo, *vsd = vmu + g.ldo;
+  float *vmua = vsd + g.ldo, *vsda = vmua + kMaxAct;
+  float *w1 = rr + g.w1, *w3 = rr + g.w3;
+  const bool active = t < S * g.Q;
+  const int q = active ? t % g.Q : 0, s = active ? t / g.Q : 0;
+
+  // ---- static model: overlaps the previous kernel under PDL ----
+  float w2[KPT2][4];
+#pragma unroll
+  for (int i = 0; i < KPT2; ++i) {
+    const int k = s * KPT2 + i;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      w2[i][c] = (active && k < U && 4 * q + c < U) ? __ldg(m.W2t + (long long)k * U + 4 * q + c) : 0.f;
+  }
+  for (int i = t; i < U; i += kRegThreads) { vb1[i] = __ldg(m.b1 + i); vb2[i] = __ldg(m.b2 + i); }
+  for (int i = t; i < O; i += kRegThreads) { vb3[i] = __ldg(m.b3 + i); vmu[i] = __ldg(m.mu_s + i); vsd[i] = __ldg(m.sd_s + i); }
+  for (int i = t; i < A; i += kRegThreads) { vmua[i] = __ldg(m.mu_a + i); vsda[i] = __ldg(m.sd_a + i); }
+  for (int i = t; i < g.kp1 * g.ldu; i += kRegThreads) {
+    const int k = i / g.ldu, c = i - k * g.ldu;
+    w1[i] = (k < D && c < U) ? __ldg(m.W1t + (long long)k * U + c) : 0.f;
+  }
+  for (int i = t; i < g.o3 * g.ld3; i += kRegThreads) {  // transposed: w3[o][k]
+    const int o = i / g.ld3, k = i - o * g.ld3;
+    w3[i] = (o < O && k < U) ? __ldg(m.W3t + (long long)k * O + o) : 0.f;
+  }
+  for (int i = t; i < g.kp1; i += kRegThreads) x[i] = 0.f;
+  for (int i = t; i < g.kp2; i += kRegThreads) h1[i] = 0.f;
+  for (int i = t; i < 8 * g.k3; i += kRegThreads) h2[i] = 0.f;
+
+  const int env_l = blockIdx.x;
+  pdl_trigger();
+  pdl_wait();
+  const BestEver b = best_ever[env_l];
+  {
+    const long long R = sh.rows();
+    const long long EHA = (long long)sh.E * H * A;
+    if (return_mean) {
+      const float* mu = mu_hist + (long long)iterations * EHA + (long long)env_l * H * A;
+      for (int i = t; i < H * A; i += kRegThreads) acts[i] = clipf(mu[i], src.lo, src.hi);
+    } else {
+      ActionSource as = src;
+      as.iteration = (uint32_t)b.iteration;
+      as.mu = mu_hist + (long long)b.iteration * EHA;
+      as.sd = sd_hist + (long long)b.iteration * EHA;
+      if (as.buf) as.buf += (long long)b.iteration * H * R * A;
+      const long long row = (long long)env_l * sh.N + b.index;
+      for (int h = t; h < H; h += kRegThreads)
+        for_each_action(as, A, H, h, env_l, b.index, row, R, [&](int a, float v) { acts[h * A + a] = v; });
+    }
+  }
+  __syncthreads();
+  for (int i = t; i < D; i += kRegThreads) {
+    x[i] = i < O ? __fdiv_rn(__fsub_rn(__ldg(s0 + (long long)env_l * O + i), vmu[i]), vsd[i])
+                 : __fdiv_rn(__fsub_rn(acts[i - O], vmua[i - O]), vsda[i - O]);
+  }
+  __syncthreads();
+  REPLAY_STAMP(1);
+
+  const float* w1_t = w1 + t;
+  const float4* h1_sl = reinterpret_cast<const float4*>(h1 + s * KPT2);
+  float4* part_w = reinterpret_cast<float4*>(part + s * g.ldu + 4 * q);
+  const float* part_r = part + t;
+  const int o3 = warp * 4 + (lane >> 3), kl = lane & 7;  // layer 3: 4 outputs per warp, 8 lanes each
+  const float* w3_l = w3 + o3 * g.ld3 + kl;
+  const float* h2_l = h2 + kl;
+  const bool l3 = o3 < g.o3;
+  float* out_env = out_states + (long long)env_l * H * O;
+
+  for (int h = 0; h < H; ++h) {
+    if (h == 5) REPLAY_STAMP(2);
+    if (t < U) {
+      float a0 = vb1[t], a1 = 0.f;
+      for (int k = 0; k < g.kp1; k += 8) {
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          a0 = fmaf(x[k + i], w1_t[(k + i) * g.ldu], a0);
+          a1 = fmaf(x[k + i + 1], w1_t[(k + i + 1) * g.ldu], a1);
+        }
+      }
+      h1[t] = fmaxf(a0 + a1, 0.f);
+    }
+    __syncthreads();
+    if (h == 5) REPLAY_STAMP(3);
+    // layer 2: W2 from registers
+    if (active) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i4 = 0; i4 < KPT2 / 4; ++i4) {
+        const float4 a = h1_sl[i4];
+        const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc.x = fmaf(av[e], w2[i4 * 4 + e][0], acc.x);
+          acc.y = fmaf(av[e], w2[i4 * 4 + e][1], acc.y);
+          acc.z = fmaf(av[e], w2[i4 * 4 + e][2], acc.z);
+          acc.w = fmaf(av[e], w2[i4 * 4 + e][3], acc.w);
+        }
+      }
+      *part_w = acc;
+    }
+    if (h == 5) REPLAY_STAMP(8);
+    __syncthreads();
+    if (h == 5) REPLAY_STAMP(9);
+    if (t < U) {
+      float p[S];
+#pragma unroll
+      for (int sl = 0; sl < S; ++sl) p[sl] = part_r[sl * g.ldu];
+      float acc = vb2[t];
+#pragma unroll
+      for (int sl = 0; sl < S; ++sl) acc += p[sl];
+      h2[t] = fmaxf(acc, 0.f);
+    }
+    __syncthreads();
+    if (h == 5) REPLAY_STAMP(4);
+    // layer 3: 8 lanes per output
+    if (l3) {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < K3; i += 2) {
+        a0 = fmaf(h2_l[8 * i], w3_l[8 * i], a0);
+        if (i + 1 < K3) a1 = fmaf(h2_l[8 * (i + 1)], w3_l[8 * (i + 1)], a1);
+      }
+      float acc = a0 + a1;
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (kl == 0 && o3 < O) {
+        const float sv = __fadd_rn(__fmul_rn(acc + vb3[o3], vsd[o3]), vmu[o3]);  // unnormalize_state (data.py:255-257)
+        y[o3] = sv;
+        out_env[h * O + o3] = sv;
+        x[o3] = __fdiv_rn(__fsub_rn(sv, vmu[o3]), vsd[o3]);                      // next step's normalize_state
+      }
+    }
+    if (t >= kRegThreads - A && h + 1 < H) {
+      const int a = t - (kRegThreads - A);
+      x[O + a] = __fdiv_rn(__fsub_rn(acts[(h + 1) * A + a], vmua[a]), vsda[a]);
+    }
+    __syncthreads();
+    if (h == 5) REPLAY_STAMP(5);
+  }
+  REPLAY_STAMP(7);
+  for (int i = t; i < H * A; i += kRegThreads) out_actions[(long long)env_l * H * A + i] = acts[i];
+  if (info && t == 0) {
+    info[env_l].best_cost = b.cost;
+    info[env_l].best_iteration = b.iteration;
+    info[env_l].best_index = b.index;
+    info[env_l].reserved = 0;
+  }
+}
+
 }  // namespace mbrl

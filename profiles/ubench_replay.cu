@@ -22,5 +22,15 @@ int main() {
   long long st[16]; cudaMemcpyFromSymbol(st, g_replay_stamps, sizeof(st));
   printf("smem %zu B, threads %d\nsetup (weights->smem, actions) %lld\nstep 5: L1 %lld  L2 %lld  L3 %lld  state+sync %lld\ntotal %lld cycles (%.1f per step)\n", smem, kReplayThreads,
          st[1] - st[0], st[3] - st[2], st[4] - st[3], st[5] - st[4], st[6] - st[5], st[7] - st[0], (double)(st[7] - st[1]) / H);
+  {
+    const RegGeom g = replay_reg_geometry(O, A, U, H);
+    const size_t sm = sizeof(float) * (size_t)g.total;
+    cudaFuncSetAttribute(replay_reg_kernel<5, 40>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    for (int r = 0; r < 3; ++r) replay_reg_kernel<5, 40><<<1, kRegThreads, sm>>>(m, src, sh, g, s0, mu, sd, dbe, 1, 0, os, oa, nullptr);
+    e = cudaDeviceSynchronize(); if (e != cudaSuccess) { printf("%s\n", cudaGetErrorString(e)); return 1; }
+    cudaMemcpyFromSymbol(st, g_replay_stamps, sizeof(st));
+    printf("register variant: smem %zu B, S=%d kpt2=%d\nsetup %lld\nstep 5: L1 %lld  L2 %lld (fma %lld, barrier %lld, reduce %lld)  L3 %lld\ntotal %lld cycles (%.1f per step)\n", sm, g.S, g.kpt2,
+           st[1] - st[0], st[3] - st[2], st[4] - st[3], st[8] - st[3], st[9] - st[8], st[4] - st[9], st[5] - st[4], st[7] - st[0], (double)(st[7] - st[1]) / H);
+  }
   return 0;
 }
