@@ -266,6 +266,7 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
         const uint32_t d = last ? tm_a + (uint32_t)g.Np : tm_a;
         const uint32_t idesc = last ? idesc_y : idesc_a;
         uint32_t a = tm_b;
+        if (lane == 0) if (DBG) tc_stamp(dbg, h, 18);
         for (int ks = 0; ks < KS_H; ks += 4) {
           mbar_wait(bar_hB + 2 * ks, ph);
           tc_fence_after();
@@ -435,6 +436,11 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_rel + 8 * (ks >> 2));
+          if (DBG && lane == 0 && ks == wg) {  // first unit of this warp: own stamp for warps 0/15, latest over all 16
+            if (warp == 0 || warp == 15) tc_stamp(dbg, h, (warp == 0 ? 19 : 21) + layer);
+            if (dbg && blockIdx.x == 1 && h < kTcTimelineSteps)
+              atomicMax(reinterpret_cast<long long*>(dbg + kTcDbgFloats) + h * kTcTimelineEvents + 23 + layer, clock64());
+          }
         }
         if (tid == 0) if (DBG) tc_stamp(dbg, h, 5 + 2 * layer);
       }

@@ -24,7 +24,7 @@ h.tc_debug(True, fetch=True)
 t = h.tc_timeline[:H].astype(np.float64)
 names = {0: "mma:step start (dA committed)", 1: "mma:GEMM-B chunk0 released", 2: "mma:GEMM-B last chunk released", 3: "mma:GEMM-A y+xa ready",
          16: "mma:GEMM-A chunk0 released", 17: "mma:GEMM-A last chunk released", 4: "epi:dA ready", 5: "epi:epiA done",
-         6: "epi:dB ready", 7: "epi:epiB done", 12: "smp:dA ready", 13: "smp:actions(h+1) arrived", 14: "cost:dA ready", 15: "cost:y consumed"}
+         6: "epi:dB ready", 7: "epi:epiB done", 18: "mma:before wait GEMM-A chunk0", 19: "epi:warp0 first unit A", 20: "epi:warp0 first unit B", 21: "epi:warp15 first unit A", 22: "epi:warp15 first unit B", 23: "epi:slowest warp first unit A", 24: "epi:slowest warp first unit B", 12: "smp:dA ready", 13: "smp:actions(h+1) arrived", 14: "cost:dA ready", 15: "cost:y consumed"}
 base = t[:, 0:1]
 rel = t - base
 print("median cycles since mma step start, steps 2..H-2 (step period = %d)" % np.median(np.diff(t[2:-1, 0])))
