@@ -311,12 +311,13 @@ def main():
 
     # A timed region of K sub-millisecond plans is shorter than nvidia-smi's sampling period: keep the
     # same load running (untimed) until the sampler has a few readings under load.
-    t_end = time.perf_counter() + 1.5
-    j = 0
-    while time.perf_counter() < t_end:
+    # The number of tail plans is derived from the all-reduced step time, so every rank runs the SAME
+    # count: a sharded plan contains an elite exchange, and a rank that planned more often than its
+    # peers would wait for exchanges that never come.
+    n_tail = min(20000, int(1500.0 / max(total_ms / args.steps, 1e-3)) + 1)
+    for j in range(n_tail):
         plan_resident(args.warmup + (j % args.steps))
-        j += 1
-        if j % 50 == 0:
+        if (j + 1) % 50 == 0:
             torch.cuda.synchronize()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
