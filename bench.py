@@ -146,6 +146,11 @@ def run_reference(args, rank):
     reference is pure Python and cannot travel to the GPU box) on this box's host cores."""
     if rank != 0:
         return
+    import torch
+    try:  # torchrun exports OMP_NUM_THREADS=1; the CPU arm is entitled to every host thread it can use
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, RuntimeError):
+        pass
     w = dict(WORKLOADS[args.workload])
     w["N"] = w["N"] * max(1, args.gpus)  # same whole-job population as the B200 arm at --gpus N
     iters = w["I"] if (args.steps + args.warmup) <= 40 and args.gpus == 1 else 1
