@@ -55,7 +55,13 @@ struct ActionSource {
 // attribute may start while its predecessor is still running; pdl_wait() blocks until every
 // prerequisite grid has completed and its writes are visible, pdl_trigger() lets the successor
 // start its own prologue.  Both are no-ops for ordinary launches.
+// IMPORTANT: data produced by a predecessor kernel must be read with dep_load() (ld.global.cg), never
+// with __ldg / through a const __restrict__ pointer: ptxas treats non-coherent loads (LDG.CONSTANT)
+// as freely movable and hoists them ABOVE griddepcontrol.wait (seen in SASS: the refit kernel read
+// the old mean before its producer had written it), and the L1 line may be stale besides.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename T>
+__device__ __forceinline__ T dep_load(const T* p) { return __ldcg(p); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ float clipf(float x, float lo, float hi) {

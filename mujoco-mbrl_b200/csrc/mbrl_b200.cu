@@ -125,6 +125,8 @@ struct MbrlPlanner {
   int* d_pos = nullptr;         // [kmax]
   MbrlPlanInfo* d_best_now = nullptr;
   int* d_trunc = nullptr;       // truncation flag of the reduced-size elite gather
+  float* d_refit_part = nullptr;           // [E][H*G][chunks][8] partial sums of the chunked refit
+  unsigned int* d_refit_arrive = nullptr;  // [E][H*G] arrival counters (self-resetting)
   bool full_gather = false;     // force worst-case-size gathers (set after a flagged plan)
   // peer-memory transport (mbrl_p2p_export / mbrl_p2p_attach)
   uint32_t* d_p2p_local = nullptr;  // exported: [2][world][2*slot] data + [world] flags
@@ -174,6 +176,8 @@ extern "C" int mbrl_destroy(MbrlPlanner* p) {
                   p->d_out_states, p->d_out_actions, p->d_injected};
   for (float* q : dev) if (q) cudaFree(q);
   if (p->d_elite) cudaFree(p->d_elite);
+  if (p->d_refit_part) cudaFree(p->d_refit_part);
+  if (p->d_refit_arrive) cudaFree(p->d_refit_arrive);
   if (p->d_best_ever) cudaFree(p->d_best_ever);
   if (p->d_info) cudaFree(p->d_info);
   if (p->comm && g_nccl.ok) g_nccl.CommDestroy(p->comm);
@@ -242,6 +246,12 @@ extern "C" int mbrl_create(const MbrlConfig* cfg, MbrlPlanner** out) {
   A_(dev_alloc(&p->d_mu_hist, EHA * (cfg->max_iterations + 1)));
   A_(dev_alloc(&p->d_sd_hist, EHA * (cfg->max_iterations + 1)));
   A_(dev_alloc(&p->d_elite, (size_t)E * cfg->max_elites));
+  {
+    const size_t slots = (size_t)E * H * ((A + 3) / 4), chunks = (size_t)(cfg->max_elites + kRefitChunk - 1) / kRefitChunk;
+    A_(dev_alloc(&p->d_refit_part, slots * chunks * 8));
+    A_(dev_alloc(&p->d_refit_arrive, slots));
+    if (ok) A_(cudaMemset(p->d_refit_arrive, 0, sizeof(unsigned int) * slots));
+  }
   A_(dev_alloc(&p->d_best_ever, E)); A_(dev_alloc(&p->d_info, E));
   A_(dev_alloc(&p->d_out_states, (size_t)E * H * O)); A_(dev_alloc(&p->d_out_actions, EHA));
   A_(cudaMallocHost((void**)&p->h_s0, sizeof(float) * E * O));
@@ -436,11 +446,12 @@ static int launch_topk(const float* d_costs, int segments, int n, int k, int* d_
 
 static int launch_refit(const MbrlPlanner* p, const ActionSource& src, const int* d_elite, int k,
                         float* d_mu_new, float* d_sd_new, cudaStream_t st) {
-  MBRL_REQUIRE(k >= 1, "refit: k must be >= 1");
+  MBRL_REQUIRE(k >= 1 && k <= p->cfg.max_elites, "refit: k out of range [1, max_elites]");
   const int G = (p->A + 3) / 4;
   Shape sh{p->H, p->N, p->E};
-  dim3 grid(p->H * G, p->E);
-  MBRL_CUDA(launch_pdl(refit_kernel, grid, dim3(kRefitThreads), 0, st, src, sh, p->A, d_elite, k, d_mu_new, d_sd_new));
+  dim3 grid(p->H * G, p->E, (k + kRefitChunk - 1) / kRefitChunk);
+  MBRL_CUDA(launch_pdl(refit_kernel, grid, dim3(kRefitThreads), 0, st, src, sh, p->A, d_elite, k, d_mu_new, d_sd_new,
+                       p->d_refit_part, p->d_refit_arrive));
   MBRL_CUDA(cudaGetLastError());
   return MBRL_OK;
 }

@@ -59,7 +59,7 @@ __device__ __forceinline__ void for_each_action(const ActionSource& s, int A, in
     const float* p = s.buf + ((long long)h * R + row) * A;
     for (int a = 0; a < A; ++a) {
       // clamp(mu + sd*z): separate mul and add, as the torch op chain rounds
-      const float v = __fadd_rn(__ldg(s.mu + ms + a), __fmul_rn(__ldg(s.sd + ms + a), __ldg(p + a)));
+      const float v = __fadd_rn(dep_load(s.mu + ms + a), __fmul_rn(dep_load(s.sd + ms + a), __ldg(p + a)));
       emit(a, clipf(v, s.lo, s.hi));
     }
   } else {
@@ -84,7 +84,7 @@ __device__ __forceinline__ void for_each_action(const ActionSource& s, int A, in
         if (a < A) {
           float out;
           if (s.mode == MBRL_SAMPLE_GAUSSIAN)
-            out = clipf(__fadd_rn(__ldg(s.mu + ms + a), __fmul_rn(__ldg(s.sd + ms + a), v[j])), s.lo, s.hi);
+            out = clipf(__fadd_rn(dep_load(s.mu + ms + a), __fmul_rn(dep_load(s.sd + ms + a), v[j])), s.lo, s.hi);
           else
             out = __fadd_rn(s.lo, __fmul_rn(__fsub_rn(s.hi, s.lo), v[j]));
           emit(a, out);

@@ -153,10 +153,14 @@ replay_kernel(ModelDev m, ActionSource src, Shape sh, const float* __restrict__ 
   // everything above only touched the (static) model: under PDL it overlaps the last top-k
   pdl_trigger();
   pdl_wait();
-  const BestEver b = best_ever[env_l];
+  BestEver b;
+  {
+    const int4 raw = dep_load(reinterpret_cast<const int4*>(best_ever + env_l));  // written by the last top-k
+    b.cost = __int_as_float(raw.x); b.iteration = raw.y; b.index = raw.z; b.pad = raw.w;
+  }
   if (return_mean) {
     const float* mu = mu_hist + (long long)iterations * EHA + (long long)env_l * H * A;
-    for (int i = threadIdx.x; i < H * A; i += kReplayThreads) acts[i] = clipf(mu[i], src.lo, src.hi);
+    for (int i = threadIdx.x; i < H * A; i += kReplayThreads) acts[i] = clipf(dep_load(mu + i), src.lo, src.hi);
   } else {
     ActionSource s = src;
     s.iteration = (uint32_t)b.iteration;
@@ -167,7 +171,7 @@ replay_kernel(ModelDev m, ActionSource src, Shape sh, const float* __restrict__ 
     for (int h = threadIdx.x; h < H; h += kReplayThreads)
       for_each_action(s, A, H, h, env_l, b.index, row, R, [&](int a, float v) { acts[h * A + a] = v; });
   }
-  for (int o = threadIdx.x; o < O; o += kReplayThreads) y[o] = __ldg(s0 + (long long)env_l * O + o);
+  for (int o = threadIdx.x; o < O; o += kReplayThreads) y[o] = dep_load(s0 + (long long)env_l * O + o);
   __syncthreads();
   REPLAY_STAMP(1);
 
@@ -297,13 +301,17 @@ replay_reg_kernel(ModelDev m, ActionSource src, Shape sh, RegGeom g, const float
   const int env_l = blockIdx.x;
   pdl_trigger();
   pdl_wait();
-  const BestEver b = best_ever[env_l];
+  BestEver b;
+  {
+    const int4 raw = dep_load(reinterpret_cast<const int4*>(best_ever + env_l));  // written by the last top-k
+    b.cost = __int_as_float(raw.x); b.iteration = raw.y; b.index = raw.z; b.pad = raw.w;
+  }
   {
     const long long R = sh.rows();
     const long long EHA = (long long)sh.E * H * A;
     if (return_mean) {
       const float* mu = mu_hist + (long long)iterations * EHA + (long long)env_l * H * A;
-      for (int i = t; i < H * A; i += kRegThreads) acts[i] = clipf(mu[i], src.lo, src.hi);
+      for (int i = t; i < H * A; i += kRegThreads) acts[i] = clipf(dep_load(mu + i), src.lo, src.hi);
     } else {
       ActionSource as = src;
       as.iteration = (uint32_t)b.iteration;
@@ -317,7 +325,7 @@ replay_reg_kernel(ModelDev m, ActionSource src, Shape sh, RegGeom g, const float
   }
   __syncthreads();
   for (int i = t; i < D; i += kRegThreads) {
-    x[i] = i < O ? __fdiv_rn(__fsub_rn(__ldg(s0 + (long long)env_l * O + i), vmu[i]), vsd[i])
+    x[i] = i < O ? __fdiv_rn(__fsub_rn(dep_load(s0 + (long long)env_l * O + i), vmu[i]), vsd[i])
                  : __fdiv_rn(__fsub_rn(acts[i - O], vmua[i - O]), vsda[i - O]);
   }
   __syncthreads();

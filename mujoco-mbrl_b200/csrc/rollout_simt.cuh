@@ -109,7 +109,7 @@ rollout_simt_kernel(ModelDev m, ActionSource src, Shape sh, const float* __restr
   float cost = 0.0f;
 
   if (row_thread) {
-    for (int o = 0; o < O; ++o) bufS[o * TM + t] = valid ? __ldg(s0 + (long long)env_l * O + o) : 0.0f;
+    for (int o = 0; o < O; ++o) bufS[o * TM + t] = valid ? dep_load(s0 + (long long)env_l * O + o) : 0.0f;
   }
 
   for (int h = 0; h < sh.H; ++h) {

@@ -242,12 +242,13 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 }
 
 // ---- action sampling, 4 raw actions for dims 4g..4g+3 (0 beyond A) --------------------------
-__device__ __forceinline__ void raw_action4(const ActionSource& s, int A, int H, int h, int env_l, int cand_l,
-                                            long long row, long long R, int g, float (&out)[4]) {
-  // branch-free per element: indices are clamped into range and the result is masked, so the four
-  // independent load -> fma -> clip chains can overlap
-  const long long ms = ((long long)env_l * H + h) * A;
-  float z[4];
+// ms_mu / ms_sd: optional shared-memory copy of this tile's mean/std rows, already offset to
+// (env, h) (see the fused kernel's sampler); null -> coherent global loads (dep_load: the mean/std
+// were written by the refit kernel that precedes this launch).
+// raw_noise4: the draw itself (depends only on counters / the static injected buffer -- may run
+// before griddepcontrol.wait); apply_action4: mean/std/clip (reads the predecessor's refit).
+__device__ __forceinline__ void raw_noise4(const ActionSource& s, int A, int H, int h, int env_l, int cand_l,
+                                           long long row, long long R, int g, float (&z)[4]) {
   if (s.mode == MBRL_SAMPLE_INJECT_ACTIONS || s.mode == MBRL_SAMPLE_INJECT_NOISE) {
     const float* p = s.buf + ((long long)h * R + row) * A;
 #pragma unroll
@@ -264,15 +265,33 @@ __device__ __forceinline__ void raw_action4(const ActionSource& s, int A, int H,
       z[0] = u32_to_uniform(r.x); z[1] = u32_to_uniform(r.y); z[2] = u32_to_uniform(r.z); z[3] = u32_to_uniform(r.w);
     }
   }
+}
+__device__ __forceinline__ void apply_action4(const ActionSource& s, int A, int H, int h, int env_l, int g,
+                                              const float (&z)[4], float (&out)[4],
+                                              const float* ms_mu = nullptr, const float* ms_sd = nullptr) {
+  // branch-free per element: indices are clamped into range and the result is masked, so the four
+  // independent load -> fma -> clip chains can overlap
+  const long long ms = ((long long)env_l * H + h) * A;
   const bool affine = s.mode == MBRL_SAMPLE_INJECT_NOISE || s.mode == MBRL_SAMPLE_GAUSSIAN;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int a = 4 * g + j, ac = min(a, A - 1);
     float v = z[j];
-    if (affine) v = clipf(__fadd_rn(__ldg(s.mu + ms + ac), __fmul_rn(__ldg(s.sd + ms + ac), v)), s.lo, s.hi);
+    if (affine) {
+      const float mu = ms_mu ? ms_mu[ac] : dep_load(s.mu + ms + ac);
+      const float sd = ms_sd ? ms_sd[ac] : dep_load(s.sd + ms + ac);
+      v = clipf(__fadd_rn(mu, __fmul_rn(sd, v)), s.lo, s.hi);
+    }
     else if (s.mode == MBRL_SAMPLE_UNIFORM) v = __fadd_rn(s.lo, __fmul_rn(__fsub_rn(s.hi, s.lo), v));
     out[j] = a < A ? v : 0.f;
   }
+}
+__device__ __forceinline__ void raw_action4(const ActionSource& s, int A, int H, int h, int env_l, int cand_l,
+                                            long long row, long long R, int g, float (&out)[4],
+                                            const float* ms_mu = nullptr, const float* ms_sd = nullptr) {
+  float z[4];
+  raw_noise4(s, A, H, h, env_l, cand_l, row, R, g, z);
+  apply_action4(s, A, H, h, env_l, g, z, out, ms_mu, ms_sd);
 }
 
 // ---- the kernel ----------------------------------------------------------------------------
@@ -495,7 +514,7 @@ rollout_tc_kernel(TcGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Action
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int o = 8 * j + i;
-        xn[i] = (o < O && valid) ? (__ldg(s0 + (long long)env_l * O + o) - t_mu[o]) / t_sd[o] : 0.f;
+        xn[i] = (o < O && valid) ? (dep_load(s0 + (long long)env_l * O + o) - t_mu[o]) / t_sd[o] : 0.f;
       }
       uint4 pk;
       pk.x = pack2<FP16>(xn[0], xn[1]); pk.y = pack2<FP16>(xn[2], xn[3]);

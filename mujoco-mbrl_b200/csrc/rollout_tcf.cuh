@@ -28,6 +28,7 @@
 // The per-element epilogue math is written branch-free (zero-padded tables and masks): per-element
 // branches serialise the load -> fma -> sqrt chains and cost ~10x (measured).
 #pragma once
+#include <algorithm>
 #include <cstdlib>
 
 #include "rollout_tc.cuh"
@@ -43,6 +44,7 @@ struct TcfGeom {
   int Na;  // Np + Oy: N of GEMM-A
   int wa_off, waa_off, w1s_off, w2_off, w_bytes;
   int tab_off, xs_off, xa_off, bar_off, smem_bytes;
+  int ms_off, ms_floats;  // staging area for the sampling mean/std rows of the tile's environments
 };
 
 constexpr int kTcfSlots = 3;  // action tiles in flight: the sampler runs up to 3 steps ahead
@@ -73,6 +75,10 @@ inline bool tcf_geometry(int O, int A, int U, size_t max_smem, TcfGeom* g, std::
   g->bar_off = g->xa_off + kTcfSlots * g->Ka * kTcRows * 2;
   g->smem_bytes = g->bar_off + 8 * kTcfBarriers + 16;
   if ((size_t)g->smem_bytes > max_smem) { *why = "fused operands do not fit shared memory"; return false; }
+  // whatever is left (up to 16 KB) stages mean/std: [envs of the tile][H][A] x 2, fp32
+  g->ms_off = g->smem_bytes;
+  g->ms_floats = (int)std::min<size_t>((max_smem - (size_t)g->smem_bytes) / 4, 4096);
+  g->smem_bytes += 4 * g->ms_floats;
   return true;
 }
 
@@ -293,7 +299,25 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
     const float inv_beta = 1.0f / m.beta, cscale = valid ? m.beta2 / (float)A : 0.f;
     const int QA = (A + 8) >> 3;  // 8-wide chunks holding the actions and the constant 1
     float act_total = 0.f;
+    // (Drawing step 0's noise before this wait was tried: -2 % -- the extra live registers spill.)
     pdl_wait();
+
+    // The mean/std of the sampling distribution (written by the preceding refit) are re-read every
+    // step by every row: copy the rows of this tile's environments into shared memory once
+    // (coherent loads), so the per-step reads are not L2 round trips on the sampler's chain.
+    const bool gauss = src.mode == MBRL_SAMPLE_INJECT_NOISE || src.mode == MBRL_SAMPLE_GAUSSIAN;
+    const long long row_lo = (long long)blockIdx.x * kTcRows, row_hi = min(row_lo + kTcRows, R) - 1;
+    const int env_lo = (int)(row_lo / sh.N), env_hi = (int)(row_hi / sh.N);
+    const int ms_n = (env_hi - env_lo + 1) * H * A;
+    const bool staged = gauss && 2 * ms_n <= g.ms_floats;  // uniform over the CTA
+    float* const ms_mu = reinterpret_cast<float*>(smem + g.ms_off);
+    float* const ms_sd = ms_mu + ms_n;
+    if (staged) {
+      const long long base = (long long)env_lo * H * A;
+      for (int i = srow; i < ms_n; i += kTcRows) { ms_mu[i] = dep_load(src.mu + base + i); ms_sd[i] = dep_load(src.sd + base + i); }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    const int ms_env = (env_l - env_lo) * H * A;
 
     auto stage_actions = [&](int hs) {
       float acc = 0.f;
@@ -303,8 +327,10 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
         float v[8];
         {
           float t4[4], u4[4];
-          raw_action4(src, A, H, hs, env_l, cand_l, row, R, 2 * q, t4);
-          if (8 * q + 4 < A) raw_action4(src, A, H, hs, env_l, cand_l, row, R, 2 * q + 1, u4);
+          const float* pm = staged ? ms_mu + ms_env + hs * A : nullptr;
+          const float* ps = staged ? ms_sd + ms_env + hs * A : nullptr;
+          raw_action4(src, A, H, hs, env_l, cand_l, row, R, 2 * q, t4, pm, ps);
+          if (8 * q + 4 < A) raw_action4(src, A, H, hs, env_l, cand_l, row, R, 2 * q + 1, u4, pm, ps);
           else { u4[0] = u4[1] = u4[2] = u4[3] = 0.f; }
           v[0] = t4[0]; v[1] = t4[1]; v[2] = t4[2]; v[3] = t4[3];
           v[4] = u4[0]; v[5] = u4[1]; v[6] = u4[2]; v[7] = u4[3];
@@ -335,7 +361,7 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int o = 8 * j + i;
-        xn[i] = (o < O && valid) ? (__ldg(s0 + (long long)env_l * O + o) - t_mu[o]) / t_sd[o] - t_b3[o] : 0.f;
+        xn[i] = (o < O && valid) ? (dep_load(s0 + (long long)env_l * O + o) - t_mu[o]) / t_sd[o] - t_b3[o] : 0.f;
       }
       uint4 pk;
       pk.x = pack2<FP16>(xn[0], xn[1]); pk.y = pack2<FP16>(xn[2], xn[3]);

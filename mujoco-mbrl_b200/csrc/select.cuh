@@ -85,11 +85,11 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
   // four keys of indices i4..i4+3 (i4 multiple of 4); out-of-range -> 0xFFFFFFFF (masked by index)
   auto load4 = [&](int i4, uint32_t (&kk)[4]) {
     if (vec_ok && i4 + 3 < n) {
-      const float4 q = __ldg(reinterpret_cast<const float4*>(c + i4));
+      const float4 q = dep_load(reinterpret_cast<const float4*>(c + i4));
       kk[0] = cost_key(q.x); kk[1] = cost_key(q.y); kk[2] = cost_key(q.z); kk[3] = cost_key(q.w);
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) kk[j] = i4 + j < n ? cost_key(__ldg(c + i4 + j)) : 0xFFFFFFFFu;
+      for (int j = 0; j < 4; ++j) kk[j] = i4 + j < n ? cost_key(dep_load(c + i4 + j)) : 0xFFFFFFFFu;
     }
   };
   auto key4_at = [&](int i4, uint32_t (&kk)[4]) {
@@ -219,7 +219,7 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
             if (less || (eq && eq_before < take_eq)) {
               const uint32_t pos = less_before + (eq_before < take_eq ? eq_before : take_eq);
               elite_idx[(long long)seg * k + pos] = i;
-              if (elite_cost) elite_cost[(long long)seg * k + pos] = __ldg(c + i);
+              if (elite_cost) elite_cost[(long long)seg * k + pos] = dep_load(c + i);
             }
             less_before += less;
             eq_before += eq;
@@ -247,7 +247,7 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
     }
     if (lane == 0 && n > 0) {
       const int idx = (int)(uint32_t)(v & 0xFFFFFFFFull);
-      const float cmin = __ldg(c + idx);
+      const float cmin = dep_load(c + idx);
       if (best) { best[seg].best_cost = cmin; best[seg].best_iteration = iteration; best[seg].best_index = idx; best[seg].reserved = 0; }
       if (best_ever) {
         BestEver b = best_ever[seg];
@@ -260,19 +260,28 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
 
 // ---- refit ---------------------------------------------------------------------------
 constexpr int kRefitThreads = 1024;
+constexpr int kRefitChunk = 2 * kRefitThreads;  // elites per CTA
 
-// grid = (H * G, E): one CTA per (step, 4-wide action group, env).  Each thread regenerates
-// (or gathers) the 4 actions of its elites and accumulates shifted sums sum(d), sum(d^2) with
-// d = a - c, c = the old mean of that (h, a) (the draws are centred there, so the shifted
-// second moment does not cancel); a fixed shuffle tree + one shared-memory stage reduces them.
-// mean = c + sum(d)/k, std = sqrt(sum(d^2)/k - (sum(d)/k)^2)   (population std, unbiased=False).
+// grid = (H * G, E, chunks): one CTA per (step, 4-wide action group, env, chunk of 2048 elites).
+// Each thread regenerates (or gathers) the 4 actions of its elites and accumulates shifted sums
+// sum(d), sum(d^2) with d = a - c, c = the old mean of that (h, a) (the draws are centred there, so
+// the shifted second moment does not cancel); a fixed shuffle tree + one shared-memory stage
+// reduces them.  mean = c + sum(d)/k, std = sqrt(sum(d^2)/k - (sum(d)/k)^2)   (population std).
+// k > 2048 (large or population-sharded elite sets): the chunk CTAs run in parallel on otherwise
+// idle SMs, park their partial sums, and the last one to arrive adds them IN CHUNK ORDER -- the
+// result depends only on the elite list (ascending index), never on timing or on the sharding,
+// which is what keeps every rank's refit bit-identical to the unsharded one.
 __global__ void __launch_bounds__(kRefitThreads)
 refit_kernel(ActionSource src, Shape sh, int A, const int* __restrict__ elite_idx, int k,
-             float* __restrict__ mu_new, float* __restrict__ sd_new) {
+             float* __restrict__ mu_new, float* __restrict__ sd_new, float* __restrict__ part,
+             unsigned int* __restrict__ arrive) {
   __shared__ float red[kRefitThreads / 32][8];
+  __shared__ bool s_last;
   const int G = (A + 3) >> 2;
   const int h = blockIdx.x / G, g = blockIdx.x % G;
   const int env_l = blockIdx.y;
+  const int chunk = blockIdx.z, nchunks = gridDim.z;
+  const int e_end = min(k, (chunk + 1) * kRefitChunk);
   const long long R = sh.rows();
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const long long ms = ((long long)env_l * sh.H + h) * A;
@@ -284,12 +293,12 @@ refit_kernel(ActionSource src, Shape sh, int A, const int* __restrict__ elite_id
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int ac = min(4 * g + j, A - 1);
-    mu_old[j] = affine ? __ldg(src.mu + ms + ac) : 0.f;
-    sd_old[j] = affine ? __ldg(src.sd + ms + ac) : 0.f;
+    mu_old[j] = affine ? dep_load(src.mu + ms + ac) : 0.f;
+    sd_old[j] = affine ? dep_load(src.sd + ms + ac) : 0.f;
   }
   const uint2 key = make_uint2(src.seed_lo, src.seed_hi);
-  for (int e = t; e < k; e += kRefitThreads) {
-    const int cand_l = __ldg(elite_idx + (long long)env_l * k + e);
+  for (int e = chunk * kRefitChunk + t; e < e_end; e += kRefitThreads) {
+    const int cand_l = dep_load(elite_idx + (long long)env_l * k + e);
     float z[4];
     if (inject) {
       const long long row = (long long)env_l * sh.N + cand_l;
@@ -328,9 +337,32 @@ refit_kernel(ActionSource src, Shape sh, int A, const int* __restrict__ elite_id
     if (lane == 0) { red[warp][j] = s1[j]; red[warp][4 + j] = s2[j]; }
   }
   __syncthreads();
-  if (t < 4) {
-    float a1 = 0.f, a2 = 0.f;
+  float a1 = 0.f, a2 = 0.f;
+  if (t < 4)
     for (int w = 0; w < kRefitThreads / 32; ++w) { a1 += red[w][t]; a2 += red[w][4 + t]; }
+  if (nchunks > 1) {
+    const long long slot = (long long)env_l * gridDim.x + blockIdx.x;
+    float* mine = part + (slot * nchunks + chunk) * 8;
+    if (t < 4) { mine[t] = a1; mine[4 + t] = a2; }
+    __threadfence();
+    __syncthreads();
+    if (t == 0) {
+      const unsigned int n = atomicAdd(arrive + slot, 1u);
+      s_last = n == (unsigned int)nchunks - 1;
+      if (s_last) arrive[slot] = 0;  // ready for the next launch (stream order)
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (t < 4) {
+      a1 = 0.f; a2 = 0.f;
+      for (int c = 0; c < nchunks; ++c) {
+        a1 += __ldcg(part + (slot * nchunks + c) * 8 + t);
+        a2 += __ldcg(part + (slot * nchunks + c) * 8 + 4 + t);
+      }
+    }
+  }
+  if (t < 4) {
     const int a = 4 * g + t;
     const float c = t == 0 ? mu_old[0] : t == 1 ? mu_old[1] : t == 2 ? mu_old[2] : mu_old[3];
     if (a < A) {
@@ -349,8 +381,8 @@ __global__ void pack_elites_kernel(const float* __restrict__ elite_cost, const i
   pdl_trigger();
   pdl_wait();
   if (i < k_l) {
-    send[i] = __float_as_uint(elite_cost[i]);
-    send[k_l + i] = (uint32_t)(elite_idx[i] + idx_offset);
+    send[i] = __float_as_uint(dep_load(elite_cost + i));
+    send[k_l + i] = (uint32_t)(dep_load(elite_idx + i) + idx_offset);
   }
 }
 // ---- peer-memory (NVLink P2P) elite exchange ---------------------------------------------------
@@ -377,8 +409,8 @@ __global__ void p2p_scatter_kernel(const float* __restrict__ elite_cost, const i
   pdl_trigger();
   pdl_wait();
   if (i < k_l) {
-    const uint32_t c = __float_as_uint(elite_cost[i]);
-    const uint32_t g = (uint32_t)(elite_idx[i] + idx_offset);
+    const uint32_t c = __float_as_uint(dep_load(elite_cost + i));
+    const uint32_t g = (uint32_t)(dep_load(elite_idx + i) + idx_offset);
     const size_t off = ((size_t)parity * world + rank) * 2 * slot;
     for (int r = 0; r < world; ++r) {
       uint32_t* dst = peers.base[r] + off;
@@ -435,8 +467,8 @@ __global__ void unpack_gathered_kernel(const uint32_t* __restrict__ recv, int wo
   pdl_wait();
   if (i < world * k_l) {
     const int r = i / k_l, j = i - r * k_l;
-    gcost[i] = __uint_as_float(recv[(long long)r * 2 * k_l + j]);
-    gidx[i] = (int)recv[(long long)r * 2 * k_l + k_l + j];
+    gcost[i] = __uint_as_float(dep_load(recv + (long long)r * 2 * k_l + j));
+    gidx[i] = (int)dep_load(recv + (long long)r * 2 * k_l + k_l + j);
   }
 }
 // positions in the gathered list -> global candidate indices; best-ever bookkeeping in global indices
@@ -451,20 +483,20 @@ __global__ void remap_elites_kernel(const int* __restrict__ pos, const int* __re
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   pdl_trigger();
   pdl_wait();
-  if (i < k) elite_global[i] = gidx[pos[i]];
+  if (i < k) elite_global[i] = dep_load(gidx + dep_load(pos + i));
   if (i < world && k_s < k_full) {
     auto lower_bound = [&](int v) {
       int lo = 0, hi = k;
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (pos[mid] < v) lo = mid + 1; else hi = mid; }
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (dep_load(pos + mid) < v) lo = mid + 1; else hi = mid; }
       return lo;
     };
     if (lower_bound((i + 1) * k_s) - lower_bound(i * k_s) == k_s) atomicOr(trunc_flag, 1);
   }
   if (i == 0) {
-    const float cmin = best_now->best_cost;
+    const float cmin = dep_load(&best_now->best_cost);
     BestEver b = *best_ever;
     if (b.iteration < 0 || cmin < b.cost) {
-      b.cost = cmin; b.iteration = iteration; b.index = gidx[best_now->best_index];
+      b.cost = cmin; b.iteration = iteration; b.index = dep_load(gidx + dep_load(&best_now->best_index));
       *best_ever = b;
     }
   }

@@ -426,3 +426,30 @@ def test_warm_start_and_return_mean(native):
     np.testing.assert_allclose(outm["actions"][0], outm["mu"][0], atol=1e-7)
     st, _ = po.rollout_costs(p, s0, torch.from_numpy(outm["actions"][0]), H, 1)
     np.testing.assert_allclose(outm["states"][0], st.numpy(), rtol=1e-4, atol=1e-4)
+
+
+def test_refit_large_elite_set_chunked(native):
+    """k > 2048 elites: the refit runs as parallel 2048-elite chunks whose partial sums are added in
+    chunk order -- checked against the oracle refit and for run-to-run bit stability."""
+    p = po.synthetic_params(6, 5, 16)
+    H, n, E, k = 3, 9000, 2, 5000
+    h = _planner(native, p, H, n, E, 1, max_elites=k)
+    g = torch.Generator().manual_seed(5)
+    acts = torch.rand(H * E * n, 5, generator=g) * 2 - 1
+    elite = torch.stack([torch.randperm(n, generator=g)[:k].sort().values for _ in range(E)]).int()
+    mu, sd = h.refit(elite.cuda(), k, native.SAMPLE_INJECT_ACTIONS, d_injected=acts.cuda())
+    a4 = acts.view(H, E, n, 5)
+    for e in range(E):
+        m, s = po.refit(a4[:, e], elite[e].numpy())
+        np.testing.assert_allclose(mu[e].cpu().numpy(), m.numpy(), rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(sd[e].cpu().numpy(), s.numpy(), rtol=1e-5, atol=2e-6)
+    for _ in range(5):  # chunk CTAs finish in any order; the sum order must not depend on it
+        mu2, sd2 = h.refit(elite.cuda(), k, native.SAMPLE_INJECT_ACTIONS, d_injected=acts.cuda())
+        assert torch.equal(mu, mu2) and torch.equal(sd, sd2)
+    mu0 = (torch.rand(E, H, 5, generator=g) - 0.5).cuda()
+    sd0 = (torch.rand(E, H, 5, generator=g) + 0.2).cuda()
+    mat = h.sample(native.SAMPLE_GAUSSIAN, 11, 2, mu0, sd0)
+    m1, s1 = h.refit(elite.cuda(), k, native.SAMPLE_GAUSSIAN, 11, 2, d_mu=mu0, d_sd=sd0)
+    m2, s2 = h.refit(elite.cuda(), k, native.SAMPLE_INJECT_ACTIONS, d_injected=mat)
+    torch.testing.assert_close(m1, m2, rtol=0, atol=2e-6)
+    torch.testing.assert_close(s1, s2, rtol=1e-5, atol=2e-6)

@@ -174,3 +174,26 @@ def test_tc_cem_plan_consistent(native, engine, variant):
     np.testing.assert_allclose(out["info"]["best_cost"][0], c[0], rtol=TOL[engine]["cost"])
     np.testing.assert_allclose(out["states"][0], states.numpy(), rtol=1e-4, atol=1e-4)  # replay is fp32
     assert np.abs(out["actions"]).max() <= 1.0
+
+
+@pytest.mark.parametrize("engine", ["fp16", "fp32"])
+def test_plan_chain_has_no_launch_overlap_race(native, engine, variant):
+    """The kernels of a plan are chained with programmatic dependent launch: each may start while
+    its predecessor still runs and must read the predecessor's outputs (mean/std, elite indices,
+    costs, best-ever) only after griddepcontrol.wait, with coherent loads.  Regression test for a
+    hoisted non-coherent load of the sampling mean: the FIRST plan on a fresh handle (stale buffers
+    hold no plausible values) must equal later plans bit for bit, over several fresh handles."""
+    p = po.synthetic_params(17, 6, 200)
+    H, N, I, k = 30, 4096, 4, 409
+    s0 = po.synthetic_state(p, 2).numpy()
+    ref = None
+    for handle in range(3):
+        h = _planner(native, p, H, N, 1, I, engine=engine)
+        for call in range(3):
+            out = h.plan(s0, I, k, native.SAMPLE_GAUSSIAN, seed=9, want_dist=True)
+            sig = (int(out["info"]["best_iteration"][0]), int(out["info"]["best_index"][0]),
+                   out["info"]["best_cost"][0].tobytes(), out["mu"].tobytes(), out["sd"].tobytes(),
+                   out["actions"].tobytes(), out["states"].tobytes())
+            if ref is None:
+                ref = sig
+            assert sig == ref, f"handle {handle} call {call} differs from the first plan"
