@@ -110,11 +110,19 @@ class CEMPlanner(ModelPlanner):
     random shooting), keep the k = int(elite_frac*N) cheapest (ties -> lower index), refit
     mu/sd per (h, a) with the population std; return the best-ever candidate.
 
-    `initial_trajectory` (the warm start MPCPolicy passes, src/mbrl/agents.py:41-47) seeds the
-    mean with its action sequence when given."""
+    Warm start across MPC steps (`warm_start`).  MPCPolicy passes the previous plan
+    as `initial_trajectory` (None on the first step of an episode, src/mbrl/agents.py:38-47):
+      "trajectory" (default)  the mean is seeded with that action sequence as the reference hands it
+                              over (un-shifted: agents.py:45 slices the states but not the actions);
+      "shift_mean"            the mean is the previous call's FINAL CEM mean shifted by one step
+                              (last step repeated) -- the usual MPC-CEM warm start; the previous mean
+                              is kept with the cached handle and dropped when `initial_trajectory`
+                              is None (episode start);
+      "none"                  always start from the action-range midpoint.
+    `init_std` sets the std of a warm-started distribution (default: half the action range)."""
 
     defaults = dict(num_trajectories=16384, num_iterations=5, elite_frac=0.1, engine="fp16", seed=None, device=0,
-                    return_mean=False, init_std=None, return_states=True)
+                    return_mean=False, init_std=None, return_states=True, warm_start="trajectory")
 
     @staticmethod
     def plan(initial_state, model, cost, sample_action, horizon, initial_trajectory=None, **kwargs):
@@ -129,20 +137,31 @@ class CEMPlanner(ModelPlanner):
         if seed is None:
             seed = ent["calls"]
         ent["calls"] += 1
+        warm = kwargs.get("warm_start", d["warm_start"])
+        if warm not in ("trajectory", "shift_mean", "none"):
+            raise ValueError("warm_start must be 'trajectory', 'shift_mean' or 'none'")
         mu0 = sd0 = None
-        if initial_trajectory is not None:
+        if initial_trajectory is None:
+            ent["last_mu"] = None  # episode start (agents.py:38-40)
+        elif warm == "trajectory":
             acts = native._f32(_stack(initial_trajectory[1])).reshape(-1, prob.act_dim)
             mu0 = np.zeros((horizon, prob.act_dim), np.float32) + 0.5 * (prob.act_lo + prob.act_hi)
             m = min(horizon, acts.shape[0])
             mu0[:m] = acts[:m]
+        elif warm == "shift_mean" and ent.get("last_mu") is not None:
+            last = ent["last_mu"]
+            mu0 = np.concatenate([last[1:], last[-1:]], axis=0).astype(np.float32)
+        if mu0 is not None:
             init_std = kwargs.get("init_std", d["init_std"])
             sd0 = np.full((horizon, prob.act_dim), 0.5 * (prob.act_hi - prob.act_lo) if init_std is None else init_std,
                           np.float32)
         noise = kwargs.get("noise")  # [I, H*N, A] recorded N(0,1) draws (parity runs)
         mode = native.SAMPLE_GAUSSIAN if noise is None else native.SAMPLE_INJECT_NOISE
         out = h.plan(initial_state, iters, k, mode, seed, injected=noise, mu0=mu0, sd0=sd0,
-                     return_mean=kwargs.get("return_mean", d["return_mean"]),
+                     return_mean=kwargs.get("return_mean", d["return_mean"]), want_dist=warm == "shift_mean",
                      actions_only=not kwargs.get("return_states", d["return_states"]))
+        if warm == "shift_mean":
+            ent["last_mu"] = np.array(out["mu"][0], np.float32)
         return _as_torch(out["states"][0]), _as_torch(out["actions"][0])
 
 

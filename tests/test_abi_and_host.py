@@ -103,3 +103,52 @@ def test_synthetic_inputs_identical_for_product_and_oracle():
     for name in ("W1", "b1", "W2", "b2", "W3", "b3", "mu_s", "sd_s", "mu_a", "sd_a", "cost_w", "goal"):
         assert torch.equal(getattr(a, name), getattr(b, name)), name
     assert torch.equal(synthetic_state(a, 3), po.synthetic_state(b, 3))
+
+
+def test_cem_warm_start_modes_host_logic(monkeypatch):
+    """CEMPlanner's warm start is host logic over the C ABI: checked with a
+    recording stand-in for the native handle (no GPU)."""
+    import numpy as np
+    import torch
+    from mbrl_b200 import planners
+    from mbrl_b200.adaptor import PlanningProblem
+
+    H, A, O = 4, 2, 3
+    calls = []
+
+    class FakeHandle:
+        def plan(self, s0, iters, k, mode, seed, injected=None, mu0=None, sd0=None, return_mean=False,
+                 want_dist=False, actions_only=False):
+            calls.append(dict(mu0=None if mu0 is None else np.array(mu0), sd0=None if sd0 is None else np.array(sd0),
+                              want_dist=want_dist))
+            mu = np.arange(H * A, dtype=np.float32).reshape(1, H, A) / 10 + len(calls)
+            return dict(states=np.zeros((1, H, O), np.float32), actions=np.zeros((1, H, A), np.float32),
+                        mu=mu if want_dist else None, sd=None, info=None)
+
+    ent = dict(handle=FakeHandle(), calls=0)
+
+    class Prob:
+        act_dim, act_lo, act_hi = A, -1.0, 1.0
+
+    monkeypatch.setattr(planners, "_get_handle", lambda *a, **kw: (ent, Prob))
+    plan = planners.CEMPlanner.plan
+    prev = (torch.zeros(H - 1, O), torch.full((H, A), 0.25))
+    # shift_mean: first step of an episode has no previous mean; the second starts from the shifted final mean
+    plan(torch.zeros(O), None, None, None, H, None, warm_start="shift_mean", num_trajectories=8)
+    assert calls[-1]["mu0"] is None and calls[-1]["want_dist"]
+    plan(torch.zeros(O), None, None, None, H, prev, warm_start="shift_mean", num_trajectories=8, init_std=0.3)
+    first_mu = np.arange(H * A, dtype=np.float32).reshape(H, A) / 10 + 1
+    np.testing.assert_array_equal(calls[-1]["mu0"], np.concatenate([first_mu[1:], first_mu[-1:]]))
+    np.testing.assert_array_equal(calls[-1]["sd0"], np.full((H, A), 0.3, np.float32))
+    plan(torch.zeros(O), None, None, None, H, None, warm_start="shift_mean", num_trajectories=8)
+    assert calls[-1]["mu0"] is None  # episode start drops the remembered mean
+    # trajectory (default): the reference's handed-over action sequence seeds the mean
+    plan(torch.zeros(O), None, None, None, H, prev, num_trajectories=8)
+    np.testing.assert_array_equal(calls[-1]["mu0"], np.full((H, A), 0.25, np.float32))
+    np.testing.assert_array_equal(calls[-1]["sd0"], np.ones((H, A), np.float32))
+    # none: never warm-started
+    plan(torch.zeros(O), None, None, None, H, prev, warm_start="none", num_trajectories=8)
+    assert calls[-1]["mu0"] is None
+    import pytest
+    with pytest.raises(ValueError):
+        plan(torch.zeros(O), None, None, None, H, prev, warm_start="bogus", num_trajectories=8)
