@@ -62,6 +62,12 @@ extern "C" {
                                       (dm_control/suite/cartpole.py:216-226, utils/rewards.py:88-130);
                                       not used by the reference planner;
                                       fp32 engine only this round; weights/goal are ignored   */
+#define MBRL_COST_REWARD_HEAD 2 /* RewardAgent's cost (src/mbrl/agents.py:342-366): a second trunk
+                                      evaluation at (s_{h+1}, a_h) through ModelWithReward's
+                                      linear4 head, un-normalised with the reward statistics
+                                      (src/mbrl/models.py:125-163, data.py:255-257); minimised like
+                                      a cost, as the reference does.  Needs mbrl_set_reward_head;
+                                      fp32 engine only this round; weights/goal are ignored   */
 
 typedef struct MbrlPlanner MbrlPlanner;
 
@@ -126,6 +132,9 @@ int mbrl_set_cost(MbrlPlanner* p, int32_t kind, const float* h_weights, const fl
 /* bounds EnvWrapper._sample_action derives from the action spec
  * (src/mbrl/env_wrappers.py:52-55: dimension 0's bounds for every dim, clipped to +-3). */
 int mbrl_set_action_bounds(MbrlPlanner* p, float lo, float hi);
+/* ModelWithReward.linear4 (src/mbrl/models.py:132: weight [1, U], bias [1]) and the "rewards"
+ * entry of the dataset statistics that unnormalize_reward closes over (agents.py:347). */
+int mbrl_set_reward_head(MbrlPlanner* p, const float* h_W4, float b4, float reward_mean, float reward_std);
 
 /* One whole plan with HOST buffers: replaces RandomShootingPlanner.plan
  * (src/mbrl/planners.py:143-187) for iterations == 1 and adds CEM for iterations > 1.

@@ -42,7 +42,12 @@ class PlanningProblem:
     beta: float = 0.25
     act_lo: float = -1.0
     act_hi: float = 1.0
-    cost_kind: int = 0  # native.COST_*: 0 = SmoothAbs + Cosh (the reference's), 1 = dm_control cartpole swing-up
+    cost_kind: int = 0  # native.COST_*: 0 = SmoothAbs + Cosh (the reference's), 1 = dm_control cartpole swing-up,
+    #                     2 = ModelWithReward's reward head (RewardAgent)
+    W4: Any = None      # [1, U] linear4.weight / [1] bias / "rewards" statistics -- cost_kind 2 only
+    b4: Any = None
+    mu_r: Any = 0.0
+    sd_r: Any = 1.0
 
     @property
     def obs_dim(self) -> int:
@@ -76,11 +81,70 @@ def _linear_layers(module):
         raise TypeError(
             f"{type(module).__name__}: unsupported dynamics model (need linear1/linear2/linear3 as in "
             "src/mbrl/models.py:96-110); pass an explicit PlanningProblem instead")
-    if hasattr(module, "linear4"):
-        raise TypeError("ModelWithReward (reward-head cost, src/mbrl/models.py:125-163) is not supported yet")
     if getattr(module, "noise", None) is not None:
         raise TypeError("Model(noise=...) adds fresh Gaussian noise per forward (src/mbrl/models.py:110); unsupported")
     return [getattr(module, n) for n in names]
+
+
+def _composed(fn):
+    """RewardAgent wraps the wired ModelWithReward as compose(partial(...), itemgetter(i))
+    (src/mbrl/agents.py:290-295, 349-358): a closure over (a, b).  Returns (partial, index) or None."""
+    import operator
+    cells = getattr(fn, "__closure__", None)
+    if not cells:
+        return None
+    inner = index = None
+    for c in cells:
+        v = c.cell_contents
+        if isinstance(v, functools.partial):
+            inner = v
+        elif isinstance(v, operator.itemgetter):
+            probe = v(("state", "reward"))
+            index = 0 if probe == "state" else 1 if probe == "reward" else None
+    return (inner, index) if inner is not None and index is not None else None
+
+
+def _action_bounds(sample_action):
+    lo, hi = -1.0, 1.0
+    if isinstance(sample_action, functools.partial) and "action_spec" in (sample_action.keywords or {}):
+        spec = sample_action.keywords["action_spec"]
+        # EnvWrapper._sample_action: dimension 0's bounds for every dim, clipped to +-3
+        # (src/mbrl/env_wrappers.py:52-55)
+        lo, hi = max(float(spec.minimum[0]), -3.0), min(float(spec.maximum[0]), 3.0)
+    return lo, hi
+
+
+def _reward_problem(model, cost, sample_action):
+    """The RewardAgent wiring: model = compose(wired, itemgetter(0)), cost = compose(wired, itemgetter(1))."""
+    from . import native
+    (wired_m, i_m), (wired_c, i_c) = _composed(model), _composed(cost)
+    if (i_m, i_c) != (0, 1) or wired_m.func is not wired_c.func or not hasattr(wired_m.func, "linear4"):
+        raise TypeError("composed model/cost must be RewardAgent's (ModelWithReward, itemgetter(0)/(1)) pair "
+                        "(src/mbrl/agents.py:349-358)")
+    module = wired_m.func
+    l1, l2, l3 = _linear_layers(module)
+    l4 = module.linear4
+    kw = wired_m.keywords or {}
+    mu_s, sd_s, tok_s = _stats_of(kw.get("normalize_state"), "normalize_state")
+    mu_u, sd_u, tok_u = _stats_of(kw.get("unnormalize_state"), "unnormalize_state")
+    mu_a, sd_a, _ = _stats_of(kw.get("normalize_action"), "normalize_action")
+    mu_r, sd_r, _ = _stats_of(kw.get("unnormalize_reward"), "unnormalize_reward")
+    if (tok_s is None) != (tok_u is None) or (tok_s is not None and tok_s is not tok_u):
+        raise TypeError("normalize_state and unnormalize_state must use the same statistics entry")
+    lo, hi = _action_bounds(sample_action)
+    prob = PlanningProblem(
+        W1=l1.weight, b1=l1.bias, W2=l2.weight, b2=l2.bias, W3=l3.weight, b3=l3.bias,
+        mu_s=mu_s, sd_s=sd_s, mu_a=mu_a, sd_a=sd_a, act_lo=lo, act_hi=hi,
+        cost_kind=native.COST_REWARD_HEAD, W4=l4.weight, b4=l4.bias,
+        mu_r=0.0 if mu_r is None else mu_r, sd_r=1.0 if sd_r is None else sd_r,
+    )
+    params = [l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias, l4.weight, l4.bias]
+    fp = (
+        tuple((id(t), int(getattr(t, "_version", 0))) for t in params),
+        tuple((id(t), int(getattr(t, "_version", 0))) for t in (mu_s, sd_s, mu_a, sd_a, mu_r, sd_r) if t is not None),
+        "reward_head", lo, hi,
+    )
+    return prob, fp
 
 
 def problem_from_callables(model, cost, sample_action) -> Tuple[PlanningProblem, tuple]:
@@ -89,6 +153,11 @@ def problem_from_callables(model, cost, sample_action) -> Tuple[PlanningProblem,
     statistics entries (src/mbrl/data.py:244-249) or moves the goal (models.py:240-241)."""
     if isinstance(model, PlanningProblem):
         return model, ("explicit", id(model))
+    if _composed(model) is not None and _composed(cost) is not None:
+        return _reward_problem(model, cost, sample_action)
+    if isinstance(model, functools.partial) and hasattr(model.func, "linear4"):
+        raise TypeError("ModelWithReward must be wired as RewardAgent does (compose(..., itemgetter(0)) as model and "
+                        "compose(..., itemgetter(1)) as cost, src/mbrl/agents.py:349-358)")
     if not isinstance(model, functools.partial) or not hasattr(model.func, "parameters"):
         raise TypeError(
             "model must be functools.partial(<nn.Module>, normalize_state=..., normalize_action=..., "
@@ -111,12 +180,7 @@ def problem_from_callables(model, cost, sample_action) -> Tuple[PlanningProblem,
     if sc is None or ac is None or not all(hasattr(sc, a) for a in ("weights", "goal_state", "alpha")) or not hasattr(ac, "alpha"):
         raise TypeError("cost partial must carry state_cost (weights, goal_state, alpha) and action_cost (alpha)")
 
-    lo, hi = -1.0, 1.0
-    if isinstance(sample_action, functools.partial) and "action_spec" in (sample_action.keywords or {}):
-        spec = sample_action.keywords["action_spec"]
-        # EnvWrapper._sample_action: dimension 0's bounds for every dim, clipped to +-3
-        # (src/mbrl/env_wrappers.py:52-55)
-        lo, hi = max(float(spec.minimum[0]), -3.0), min(float(spec.maximum[0]), 3.0)
+    lo, hi = _action_bounds(sample_action)
 
     prob = PlanningProblem(
         W1=l1.weight, b1=l1.bias, W2=l2.weight, b2=l2.bias, W3=l3.weight, b3=l3.bias,

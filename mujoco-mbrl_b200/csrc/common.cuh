@@ -30,6 +30,8 @@ struct ModelDev {
   float alpha, alpha2;  // alpha2 = (float)(alpha_fp64^2), as torch folds the Python scalar
   float beta, beta2;
   int cost_kind;
+  const float* W4;  // [U] reward head (MBRL_COST_REWARD_HEAD), else null
+  float b4, mu_r, sd_r;
 };
 
 // Problem extents on this GPU: R = E*N rows, row r = env*N + cand.

@@ -124,6 +124,9 @@ struct MbrlPlanner {
   int* d_gidx = nullptr;        // [world*k_l]
   int* d_pos = nullptr;         // [kmax]
   MbrlPlanInfo* d_best_now = nullptr;
+  float* W4 = nullptr;  // reward head (mbrl_set_reward_head)
+  float b4 = 0.f, mu_r = 0.f, sd_r = 1.f;
+  bool have_reward_head = false;
   int* d_trunc = nullptr;       // truncation flag of the reduced-size elite gather
   float* d_refit_part = nullptr;           // [E][H*G][chunks][8] partial sums of the chunked refit
   unsigned int* d_refit_arrive = nullptr;  // [E][H*G] arrival counters (self-resetting)
@@ -146,6 +149,7 @@ static ModelDev model_view(const MbrlPlanner* p) {
   m.cost_w = p->cost_w; m.goal = p->goal;
   m.alpha = p->alpha; m.alpha2 = p->alpha2; m.beta = p->beta; m.beta2 = p->beta2;
   m.cost_kind = p->cost_kind;
+  m.W4 = p->W4; m.b4 = p->b4; m.mu_r = p->mu_r; m.sd_r = p->sd_r;
   return m;
 }
 
@@ -176,6 +180,7 @@ extern "C" int mbrl_destroy(MbrlPlanner* p) {
                   p->d_out_states, p->d_out_actions, p->d_injected};
   for (float* q : dev) if (q) cudaFree(q);
   if (p->d_elite) cudaFree(p->d_elite);
+  if (p->W4) cudaFree(p->W4);
   if (p->d_refit_part) cudaFree(p->d_refit_part);
   if (p->d_refit_arrive) cudaFree(p->d_refit_arrive);
   if (p->d_best_ever) cudaFree(p->d_best_ever);
@@ -332,13 +337,19 @@ extern "C" int mbrl_set_norm(MbrlPlanner* p, const float* mu_s, const float* sd_
 extern "C" int mbrl_set_cost(MbrlPlanner* p, int32_t kind, const float* w, const float* goal, double alpha,
                              double beta) {
   if (!p) return fail(MBRL_E_INVALID, "null planner");
-  MBRL_REQUIRE(kind == MBRL_COST_SMOOTHABS_COSH || kind == MBRL_COST_DMC_CARTPOLE_SWINGUP, "unknown cost kind");
+  MBRL_REQUIRE(kind == MBRL_COST_SMOOTHABS_COSH || kind == MBRL_COST_DMC_CARTPOLE_SWINGUP || kind == MBRL_COST_REWARD_HEAD,
+               "unknown cost kind");
   MBRL_CUDA(cudaSetDevice(p->cfg.device));
   MBRL_CUDA(cudaStreamSynchronize(p->stream));
   if (kind == MBRL_COST_DMC_CARTPOLE_SWINGUP) {
     MBRL_REQUIRE(p->O >= 5 && p->A >= 1, "cartpole cost needs the 5-d cartpole observation");
     if (p->cfg.engine != MBRL_ENGINE_SIMT_FP32)
       return fail(MBRL_E_UNSUPPORTED, "the dm_control task-cost epilogue is implemented for the fp32 engine only");
+  } else if (kind == MBRL_COST_REWARD_HEAD) {
+    MBRL_REQUIRE(p->have_reward_head, "mbrl_set_reward_head must be called before selecting the reward-head cost");
+    if (p->cfg.engine != MBRL_ENGINE_SIMT_FP32)
+      return fail(MBRL_E_UNSUPPORTED, "the reward-head cost is implemented for the fp32 engine only");
+    if (beta == 0.0) beta = 1.0;  // unused by this cost; keeps 1/beta finite
   } else {
     MBRL_REQUIRE(w && goal, "null cost pointer");
     MBRL_REQUIRE(beta != 0.0, "beta must be non-zero");
@@ -349,6 +360,18 @@ extern "C" int mbrl_set_cost(MbrlPlanner* p, int32_t kind, const float* w, const
   p->alpha = (float)alpha; p->alpha2 = (float)(alpha * alpha);
   p->beta = (float)beta; p->beta2 = (float)(beta * beta);
   p->have_cost = true;
+  return MBRL_OK;
+}
+
+extern "C" int mbrl_set_reward_head(MbrlPlanner* p, const float* h_W4, float b4, float reward_mean, float reward_std) {
+  if (!p) return fail(MBRL_E_INVALID, "null planner");
+  MBRL_REQUIRE(h_W4, "null reward-head weights");
+  MBRL_CUDA(cudaSetDevice(p->cfg.device));
+  MBRL_CUDA(cudaStreamSynchronize(p->stream));
+  if (!p->W4) MBRL_CUDA(dev_alloc(&p->W4, (size_t)p->U));
+  MBRL_CUDA(cudaMemcpy(p->W4, h_W4, sizeof(float) * p->U, cudaMemcpyHostToDevice));
+  p->b4 = b4; p->mu_r = reward_mean; p->sd_r = reward_std;
+  p->have_reward_head = true;
   return MBRL_OK;
 }
 

@@ -75,12 +75,13 @@ __device__ __forceinline__ void dense_layer(const float* __restrict__ Wt, const 
 }
 
 // Shared memory: bufA [KA][TM] (layer-1 input, then layer-2 output), bufB [U][TM]
-// (layer-1 output, then layer-3 output), bufS [O][TM] current un-normalised state.
+// (layer-1 output, then layer-3 output), bufS [O][TM] current un-normalised state, bufN [A][TM]
+// the step's normalised actions (kept for the reward-head cost's second trunk evaluation).
 template <int TM>
 __host__ __device__ inline size_t simt_smem_bytes(int O, int A, int U) {
   const int KA = (O + A) > U ? (O + A) : U;
   const int KB = U > O ? U : O;
-  return sizeof(float) * (size_t)TM * (KA + KB + O);
+  return sizeof(float) * (size_t)TM * (KA + KB + O + A);
 }
 
 template <int TM, int CPT>
@@ -98,6 +99,8 @@ rollout_simt_kernel(ModelDev m, ActionSource src, Shape sh, const float* __restr
   float* bufA = smem;
   float* bufB = bufA + KA * TM;
   float* bufS = bufB + KB * TM;
+  float* bufN = bufS + O * TM;
+  const bool reward_head = m.cost_kind == MBRL_COST_REWARD_HEAD;
 
   const long long R = sh.rows();
   const int t = threadIdx.x;
@@ -121,13 +124,15 @@ rollout_simt_kernel(ModelDev m, ActionSource src, Shape sh, const float* __restr
       if (valid) {
         float* aout = actions_out ? actions_out + ((long long)h * R + row) * A : nullptr;
         for_each_action(src, A, sh.H, h, env_l, cand_l, row, R, [&](int a, float v) {
-          bufA[(O + a) * TM + t] = __fdiv_rn(__fsub_rn(v, __ldg(m.mu_a + a)), __ldg(m.sd_a + a));
+          const float vn = __fdiv_rn(__fsub_rn(v, __ldg(m.mu_a + a)), __ldg(m.sd_a + a));
+          bufA[(O + a) * TM + t] = vn;
+          bufN[a * TM + t] = vn;
           act_cost = __fadd_rn(act_cost, cosh_term(v, m.beta));
           if (a == 0) a0 = v;
           if (aout) aout[a] = v;
         });
       } else {
-        for (int a = 0; a < A; ++a) bufA[(O + a) * TM + t] = 0.0f;
+        for (int a = 0; a < A; ++a) { bufA[(O + a) * TM + t] = 0.0f; bufN[a * TM + t] = 0.0f; }
       }
     }
     __syncthreads();
@@ -152,9 +157,31 @@ rollout_simt_kernel(ModelDev m, ActionSource src, Shape sh, const float* __restr
         // CoshLoss: beta^2 * mean_a(cosh(a/beta) - 1); row cost pairs s_{h+1} with a_h
         const float ac = __fmul_rn(m.beta2, __fdiv_rn(act_cost, (float)A));
         cost = __fadd_rn(cost, __fadd_rn(st_cost, ac));
-      } else {  // MBRL_COST_DMC_CARTPOLE_SWINGUP (O >= 5 checked by the host)
+      } else if (!reward_head) {  // MBRL_COST_DMC_CARTPOLE_SWINGUP (O >= 5 checked by the host)
         cost += dmc_cartpole_cost(bufS[0 * TM + t], bufS[1 * TM + t], bufS[4 * TM + t], a0);
       }
+    }
+    if (reward_head) {
+      // RewardAgent (src/mbrl/agents.py:349-358): cost(s_{h+1}, a_h) = unnormalize_reward(linear4(trunk(
+      // [normalize(s_{h+1}), normalize(a_h)]))) -- a second trunk evaluation (models.py:135-163).
+      // Layer 3 (the last reader of bufA) is behind the barrier above.
+      if (row_thread) {
+        for (int o = 0; o < O; ++o)
+          bufA[o * TM + t] = __fdiv_rn(__fsub_rn(bufS[o * TM + t], __ldg(m.mu_s + o)), __ldg(m.sd_s + o));
+        for (int a = 0; a < A; ++a) bufA[(O + a) * TM + t] = bufN[a * TM + t];
+      }
+      __syncthreads();
+      dense_layer<TM, CPT, true>(m.W1t, m.b1, bufA, bufB, D, U);
+      __syncthreads();
+      dense_layer<TM, CPT, true>(m.W2t, m.b2, bufB, bufA, U, U);
+      __syncthreads();
+      if (row_thread) {
+        float r = 0.0f;
+        for (int k = 0; k < U; ++k) r = fmaf(bufA[k * TM + t], __ldg(m.W4 + k), r);
+        r = __fadd_rn(r, m.b4);
+        cost = __fadd_rn(cost, __fadd_rn(__fmul_rn(r, m.sd_r), m.mu_r));  // unnormalize_field (data.py:255-257)
+      }
+      __syncthreads();  // bufA is rewritten by the row threads at the top of the next step
     }
     // bufA is rewritten by row threads next step: every warp has passed the barrier after
     // layer 3, which was the last reader of bufA.

@@ -18,12 +18,12 @@ LIB_PATH = os.path.join(_HERE, "libmbrl_b200.so")
 ENGINE_SIMT_FP32, ENGINE_TC_BF16, ENGINE_TC_FP16 = 0, 1, 2
 ENGINES = {"fp32": ENGINE_SIMT_FP32, "simt": ENGINE_SIMT_FP32, "bf16": ENGINE_TC_BF16, "fp16": ENGINE_TC_FP16}
 SAMPLE_INJECT_ACTIONS, SAMPLE_INJECT_NOISE, SAMPLE_GAUSSIAN, SAMPLE_UNIFORM = 0, 1, 2, 3
-COST_SMOOTHABS_COSH, COST_DMC_CARTPOLE_SWINGUP = 0, 1
+COST_SMOOTHABS_COSH, COST_DMC_CARTPOLE_SWINGUP, COST_REWARD_HEAD = 0, 1, 2
 
 # every symbol include/mbrl_b200.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
     "mbrl_abi_version", "mbrl_last_error", "mbrl_create", "mbrl_destroy", "mbrl_set_weights",
-    "mbrl_set_norm", "mbrl_set_cost", "mbrl_set_action_bounds", "mbrl_plan", "mbrl_plan_device",
+    "mbrl_set_norm", "mbrl_set_cost", "mbrl_set_action_bounds", "mbrl_set_reward_head", "mbrl_plan", "mbrl_plan_device",
     "mbrl_rollout", "mbrl_sample", "mbrl_philox_raw", "mbrl_topk", "mbrl_refit", "mbrl_emit",
     "mbrl_tc_debug", "mbrl_nccl_unique_id", "mbrl_comm_init", "mbrl_comm_destroy",
     "mbrl_p2p_export", "mbrl_p2p_attach",
@@ -87,6 +87,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         "mbrl_set_norm": [p] + [vp] * 4,
         "mbrl_set_cost": [p, i32, vp, vp, f64, f64],
         "mbrl_set_action_bounds": [p, f32, f32],
+        "mbrl_set_reward_head": [p, vp, f32, f32, f32],
         "mbrl_plan": [p, C.POINTER(MbrlPlanArgs), vp, vp, vp, vp, vp, vp],
         "mbrl_plan_device": [p, C.POINTER(MbrlPlanArgs), vp, vp, vp, vp, vp, vp],
         "mbrl_rollout": [p, i32, u64, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp, vp],
@@ -194,6 +195,14 @@ class NativePlanner:
             raise ValueError("cost weights/goal must have obs_dim entries")
         _check(self.lib.mbrl_set_cost(self._h, kind, _hp(w), _hp(g), float(alpha), float(beta)))
 
+    def set_reward_head(self, W4, b4, reward_mean=0.0, reward_std=1.0):
+        """ModelWithReward.linear4 + the "rewards" statistics (src/mbrl/models.py:132, agents.py:347)."""
+        w = _f32(W4).reshape(-1)
+        if w.shape != (self.U,):
+            raise ValueError(f"reward head must have {self.U} weights, got {w.shape}")
+        scalar = lambda v: float(_f32(v).reshape(-1)[0])
+        _check(self.lib.mbrl_set_reward_head(self._h, _hp(w), scalar(b4), scalar(reward_mean), scalar(reward_std)))
+
     def set_action_bounds(self, lo, hi):
         _check(self.lib.mbrl_set_action_bounds(self._h, float(lo), float(hi)))
 
@@ -201,6 +210,8 @@ class NativePlanner:
         """Upload a PlanningProblem (adaptor.py)."""
         self.set_weights(prob.W1, prob.b1, prob.W2, prob.b2, prob.W3, prob.b3)
         self.set_norm(prob.mu_s, prob.sd_s, prob.mu_a, prob.sd_a)
+        if getattr(prob, "W4", None) is not None:
+            self.set_reward_head(prob.W4, prob.b4, prob.mu_r, prob.sd_r)
         self.set_cost(prob.cost_w, prob.goal, prob.alpha, prob.beta, getattr(prob, "cost_kind", COST_SMOOTHABS_COSH))
         self.set_action_bounds(prob.act_lo, prob.act_hi)
 

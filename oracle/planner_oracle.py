@@ -42,6 +42,12 @@ class PlannerParams:
     beta: float = 0.25  #        CoshLoss.alpha                 src/mbrl/models.py:267
     act_lo: float = -1.0
     act_hi: float = 1.0
+    # ModelWithReward's reward head and the "rewards" statistics (src/mbrl/models.py:125-163,
+    # src/mbrl/agents.py:342-366); None for the plain dynamics Model
+    W4: Optional[torch.Tensor] = None  # [1, U]   linear4.weight
+    b4: Optional[torch.Tensor] = None  # [1]
+    mu_r: float = 0.0                   # stats["rewards"]["mean"]
+    sd_r: float = 1.0
 
     @property
     def obs_dim(self) -> int:
@@ -137,8 +143,21 @@ def state_action_cost(p: PlannerParams, state: torch.Tensor, action: torch.Tenso
 # --------------------------------------------------------------------------------------
 # Random shooting
 # --------------------------------------------------------------------------------------
+def reward_head_cost(p: PlannerParams, state: torch.Tensor, action: torch.Tensor) -> torch.Tensor:
+    """RewardAgent's cost callable: compose(partial(ModelWithReward, normalisers...), itemgetter(1))
+    (src/mbrl/agents.py:349-358): a SECOND trunk evaluation at the state it is handed (the planner
+    hands it the predicted next states, planners.py:210) with the same action, through the reward
+    head, un-normalised with the reward statistics (models.py:135-163).  The planner minimises it
+    as it would a cost (the reference's behaviour, kept).  Returns [B, 1] like the reference."""
+    x = torch.cat([normalize(state, p.mu_s, p.sd_s), normalize(action, p.mu_a, p.sd_a)], dim=1)
+    h1 = torch.relu(torch.nn.functional.linear(x, p.W1, p.b1))
+    h2 = torch.relu(torch.nn.functional.linear(h1, p.W2, p.b2))
+    r = torch.nn.functional.linear(h2, p.W4, p.b4)
+    return r * p.sd_r + p.mu_r  # unnormalize_field, data.py:255-257
+
+
 def rollout_costs(
-    p: PlannerParams, s0: torch.Tensor, actions: torch.Tensor, horizon: int, n: int
+    p: PlannerParams, s0: torch.Tensor, actions: torch.Tensor, horizon: int, n: int, cost: str = "goal"
 ) -> Tuple[torch.Tensor, np.ndarray]:
     """The hot loop of RandomShootingPlanner._generate_trajectories,
     src/mbrl/planners.py:199-210, for the dynamics MLP + SmoothAbs/Cosh cost.
@@ -154,7 +173,10 @@ def rollout_costs(
             else:
                 cur = states[(h - 1) * n: h * n]
             states[h * n: (h + 1) * n] = dynamics_forward(p, cur, actions[h * n: (h + 1) * n])
-        costs = state_action_cost(p, states, actions).view(horizon, n).sum(0).numpy()
+        if cost == "reward_head":
+            costs = reward_head_cost(p, states, actions).view(horizon, n).sum(0).numpy()
+        else:
+            costs = state_action_cost(p, states, actions).view(horizon, n).sum(0).numpy()
     return states, costs
 
 

@@ -17,6 +17,14 @@ def load_golden(name):
 
 def params_from_golden(g) -> PlannerParams:
     t = lambda k: torch.from_numpy(np.ascontiguousarray(g[k])).float()
+    if "W4" in g:  # ModelWithReward fixture: no SmoothAbs/Cosh parameters, a reward head instead
+        obs = g["W3"].shape[0]
+        return PlannerParams(
+            t("W1"), t("b1"), t("W2"), t("b2"), t("W3"), t("b3"),
+            t("mu_s"), t("sd_s"), t("mu_a"), t("sd_a"), torch.ones(obs), torch.zeros(obs),
+            act_lo=float(g["lo"]), act_hi=float(g["hi"]),
+            W4=t("W4"), b4=t("b4"), mu_r=float(g["mu_r"][0]), sd_r=float(g["sd_r"][0]),
+        )
     return PlannerParams(
         t("W1"), t("b1"), t("W2"), t("b2"), t("W3"), t("b3"),
         t("mu_s"), t("sd_s"), t("mu_a"), t("sd_a"), t("cost_w"), t("goal"),

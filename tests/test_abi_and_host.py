@@ -152,3 +152,66 @@ def test_cem_warm_start_modes_host_logic(monkeypatch):
     import pytest
     with pytest.raises(ValueError):
         plan(torch.zeros(O), None, None, None, H, prev, warm_start="bogus", num_trajectories=8)
+
+
+def _reward_agent_wiring(obs=4, act=2, hidden=8, seed=0):
+    """The callables RewardAgent hands to MPCPolicy (src/mbrl/agents.py:342-366), rebuilt with
+    stand-ins shaped like the reference's ModelWithReward / compose / normalize_field."""
+    from functools import partial
+    from operator import itemgetter
+    import torch
+
+    class ModelWithReward(torch.nn.Module):  # src/mbrl/models.py:125-163
+        def __init__(self):
+            super().__init__()
+            self.linear1 = torch.nn.Linear(obs + act, hidden)
+            self.linear2 = torch.nn.Linear(hidden, hidden)
+            self.linear3 = torch.nn.Linear(hidden, obs)
+            self.linear4 = torch.nn.Linear(hidden, 1)
+
+        def forward(self, state, action, normalize_state=None, unnormalize_state=None, normalize_action=None,
+                    unnormalize_reward=None):
+            x = torch.cat([normalize_state(state), normalize_action(action)], dim=1)
+            x = torch.relu(self.linear2(torch.relu(self.linear1(x))))
+            return unnormalize_state(self.linear3(x)), unnormalize_reward(self.linear4(x))
+
+    def normalize_field(x, field_name, stats):
+        return (x - stats[field_name]["mean"]) / stats[field_name]["std"]
+
+    def unnormalize_field(x, field_name, stats):
+        return x * stats[field_name]["std"] + stats[field_name]["mean"]
+
+    def compose(a, b):  # src/mbrl/agents.py:290-295
+        def ab(*args, **kwargs):
+            return b(a(*args, **kwargs))
+        return ab
+
+    torch.manual_seed(seed)
+    net = ModelWithReward()
+    stats = {"observations": {"mean": torch.randn(obs), "std": torch.rand(obs) + 0.5},
+             "actions": {"mean": torch.zeros(act), "std": torch.ones(act) * 0.6},
+             "rewards": {"mean": torch.tensor([0.3]), "std": torch.tensor([2.0])}}
+    wired = partial(net, normalize_state=partial(normalize_field, field_name="observations", stats=stats),
+                    normalize_action=partial(normalize_field, field_name="actions", stats=stats),
+                    unnormalize_state=partial(unnormalize_field, field_name="observations", stats=stats),
+                    unnormalize_reward=partial(unnormalize_field, field_name="rewards", stats=stats))
+    return net, stats, compose(wired, itemgetter(0)), compose(wired, itemgetter(1)), wired
+
+
+def test_adaptor_recognises_reward_agent_wiring():
+    import pytest
+    from mbrl_b200 import native
+    from mbrl_b200.adaptor import problem_from_callables
+    net, stats, model, cost, wired = _reward_agent_wiring()
+    prob, fp = problem_from_callables(model, cost, None)
+    assert prob.cost_kind == native.COST_REWARD_HEAD
+    assert prob.W4 is net.linear4.weight and prob.b4 is net.linear4.bias
+    assert prob.mu_r is stats["rewards"]["mean"] and prob.sd_r is stats["rewards"]["std"]
+    assert (prob.obs_dim, prob.act_dim, prob.hidden) == (4, 2, 8)
+    with torch.no_grad():
+        net.linear4.weight.add_(1.0)  # retraining in place changes the fingerprint (models.py:84-86)
+    assert problem_from_callables(model, cost, None)[1] != fp
+    with pytest.raises(TypeError):  # the bare partial is not how RewardAgent passes it
+        problem_from_callables(wired, cost, None)
+    with pytest.raises(TypeError):  # swapped itemgetters
+        problem_from_callables(cost, model, None)

@@ -453,3 +453,64 @@ def test_refit_large_elite_set_chunked(native):
     m2, s2 = h.refit(elite.cuda(), k, native.SAMPLE_INJECT_ACTIONS, d_injected=mat)
     torch.testing.assert_close(m1, m2, rtol=0, atol=2e-6)
     torch.testing.assert_close(s1, s2, rtol=1e-5, atol=2e-6)
+
+
+def test_reward_head_cost_matches_reference_fixture(native):
+    """RewardAgent's cost (ModelWithReward's reward head, a second trunk evaluation per step) on the
+    fp32 engine against the fixture produced by the reference's own planner
+    (tests/golden/make_golden.py::make_rs_reward): costs, argmin, the returned plan; then the Python
+    drop-in API with callables wired exactly like src/mbrl/agents.py:349-358."""
+    from functools import partial
+    from operator import itemgetter
+    from mbrl_b200 import RandomShootingPlanner, planners
+    g = load_golden("rs_reward_head.npz")
+    p = params_from_golden(g)
+    n, H = int(g["n"]), int(g["horizon"])
+    h = native.NativePlanner(p.obs_dim, p.act_dim, p.hidden, H, n, 1, 1, None, "fp32")
+    h.set_weights(p.W1, p.b1, p.W2, p.b2, p.W3, p.b3)
+    h.set_norm(p.mu_s, p.sd_s, p.mu_a, p.sd_a)
+    h.set_reward_head(p.W4, p.b4, p.mu_r, p.sd_r)
+    h.set_cost(kind=native.COST_REWARD_HEAD)
+    h.set_action_bounds(p.act_lo, p.act_hi)
+    costs, _, _ = h.rollout(_cuda(g["s0"][None]), native.SAMPLE_INJECT_ACTIONS, d_injected=_cuda(g["actions"]))
+    np.testing.assert_allclose(costs.cpu().numpy(), g["costs"], rtol=1e-5, atol=1e-4)
+    out = h.plan(g["s0"], 1, 1, native.SAMPLE_INJECT_ACTIONS, injected=g["actions"])
+    assert int(out["info"]["best_index"][0]) == int(g["idx"])
+    np.testing.assert_array_equal(out["actions"][0], g["plan_actions"])
+    np.testing.assert_allclose(out["states"][0], g["plan_states"], rtol=1e-5, atol=1e-5)
+    # tensor-core engines: refused loudly, not silently served by another path
+    tc = native.NativePlanner(p.obs_dim, p.act_dim, p.hidden, H, n, 1, 1, None, "fp16")
+    tc.set_reward_head(p.W4, p.b4, p.mu_r, p.sd_r)
+    with pytest.raises(RuntimeError):
+        tc.set_cost(kind=native.COST_REWARD_HEAD)
+
+    # drop-in API with the RewardAgent wiring
+    class ModelWithReward(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            U, O, A = p.hidden, p.obs_dim, p.act_dim
+            self.linear1, self.linear2 = torch.nn.Linear(O + A, U), torch.nn.Linear(U, U)
+            self.linear3, self.linear4 = torch.nn.Linear(U, O), torch.nn.Linear(U, 1)
+    net = ModelWithReward()
+    with torch.no_grad():
+        for lin, (w, b) in zip((net.linear1, net.linear2, net.linear3, net.linear4),
+                               ((p.W1, p.b1), (p.W2, p.b2), (p.W3, p.b3), (p.W4, p.b4))):
+            lin.weight.copy_(w); lin.bias.copy_(b)
+    stats = {"observations": {"mean": p.mu_s, "std": p.sd_s}, "actions": {"mean": p.mu_a, "std": p.sd_a},
+             "rewards": {"mean": torch.tensor([p.mu_r]), "std": torch.tensor([p.sd_r])}}
+    def field(x, field_name, stats):  # stands in for TransitionsDataset.(un)normalize_field
+        raise AssertionError("the GPU planner never calls the host callables")
+    def compose(a, b):
+        def ab(*args, **kwargs):
+            return b(a(*args, **kwargs))
+        return ab
+    wired = partial(net, normalize_state=partial(field, field_name="observations", stats=stats),
+                    normalize_action=partial(field, field_name="actions", stats=stats),
+                    unnormalize_state=partial(field, field_name="observations", stats=stats),
+                    unnormalize_reward=partial(field, field_name="rewards", stats=stats))
+    acts = torch.from_numpy(g["actions"])
+    s, a = RandomShootingPlanner.plan(torch.from_numpy(g["s0"]), compose(wired, itemgetter(0)), compose(wired, itemgetter(1)),
+                                      lambda batch_size: acts, H, None, num_trajectories=n, sampler="host", engine="fp32")
+    np.testing.assert_array_equal(a.numpy(), g["plan_actions"])
+    np.testing.assert_allclose(s.numpy(), g["plan_states"], rtol=1e-5, atol=1e-5)
+    planners.clear_handles()
