@@ -232,10 +232,20 @@ def main():
     if world > 1:
         # the sharded CEM loop runs on the stream inside the library; elite exchange over NVLink peer
         # memory (default) or an in-library ncclAllGather
-        if args.transport == "p2p":
+        transport = args.transport
+        if transport == "p2p":
+            # peer-memory exchange needs every GPU pair of this node to be P2P-accessible (rank r drives
+            # device r under torchrun); agree on it collectively, else every rank takes the NCCL transport
+            ok = all(torch.cuda.can_device_access_peer(local_rank, r) for r in range(world) if r != local_rank)
+            flag = torch.tensor([1 if ok else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                transport = "nccl"
+        if transport == "p2p":
             h.p2p_init(rank, world)
         else:
             h.comm_init(rank, world)
+        args.transport = transport
     states0 = torch.stack([synthetic_state(p, c) for c in range(args.warmup + args.steps)]).float()
     d_states0 = states0.to(dev)
     d_out_s = torch.empty(1, H, O, device=dev)
