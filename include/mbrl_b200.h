@@ -62,6 +62,10 @@ extern "C" {
                                       (dm_control/suite/cartpole.py:216-226, utils/rewards.py:88-130);
                                       not used by the reference planner;
                                       fp32 engine only this round; weights/goal are ignored   */
+#define MBRL_COST_DMC_HUMANOID_RUN 3 /* 1 - Humanoid.get_reward at move_speed 10 restated on the egocentric
+                                      observation (head_height obs[21], torso zz obs[36], com velocity
+                                      obs[37:39]) and the control (dm_control/suite/humanoid.py:172-211);
+                                      fp32 engine only this round; weights/goal are ignored   */
 #define MBRL_COST_REWARD_HEAD 2 /* RewardAgent's cost (src/mbrl/agents.py:342-366): a second trunk
                                       evaluation at (s_{h+1}, a_h) through ModelWithReward's
                                       linear4 head, un-normalised with the reward statistics

@@ -97,4 +97,22 @@ __device__ __forceinline__ float dmc_cartpole_cost(float x, float cosang, float 
   return 1.0f - upright * small_control * small_velocity * centered;
 }
 
+// 1 - Humanoid.get_reward, move_speed = 10 (dm_control/suite/humanoid.py:187-211): standing =
+// tolerance(head_height, [1.4, inf), margin 0.35, gaussian); upright = tolerance(torso zz, [0.9, inf),
+// margin 1.9, linear, value_at_margin 0); small_control = (4 + mean_a(1 - a^2 inside |a| < 1)) / 5;
+// move = (5 * tolerance(|com_vel_xy|, [10, inf), margin 10, linear, 0) + 1) / 6.
+__device__ __forceinline__ float dmc_humanoid_run_cost(float head, float zz, float vx, float vy, float ctl_mean) {
+  const float ln01 = -2.302585092994046f;
+  const float dh = (1.4f - head) * (1.0f / 0.35f);
+  const float standing = head >= 1.4f ? 1.0f : expf(ln01 * dh * dh);
+  const float du = (0.9f - zz) * (1.0f / 1.9f);
+  const float upright = zz >= 0.9f ? 1.0f : (du < 1.0f ? 1.0f - du : 0.0f);
+  const float small_control = 0.2f * (4.0f + ctl_mean);
+  const float speed = sqrtf(vx * vx + vy * vy);
+  const float dm = (10.0f - speed) * 0.1f;
+  const float move_raw = speed >= 10.0f ? 1.0f : (dm < 1.0f ? 1.0f - dm : 0.0f);
+  const float move = (5.0f * move_raw + 1.0f) * (1.0f / 6.0f);
+  return 1.0f - small_control * standing * upright * move;
+}
+
 }  // namespace mbrl

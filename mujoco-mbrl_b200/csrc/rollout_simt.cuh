@@ -116,7 +116,7 @@ rollout_simt_kernel(ModelDev m, ActionSource src, Shape sh, const float* __restr
   }
 
   for (int h = 0; h < sh.H; ++h) {
-    float act_cost = 0.0f, a0 = 0.0f;
+    float act_cost = 0.0f, a0 = 0.0f, ctl_sum = 0.0f;
     if (row_thread) {
       // normalize_state: (s - mean) / std   (data.py:258-260)
       for (int o = 0; o < O; ++o)
@@ -129,6 +129,7 @@ rollout_simt_kernel(ModelDev m, ActionSource src, Shape sh, const float* __restr
           bufN[a * TM + t] = vn;
           act_cost = __fadd_rn(act_cost, cosh_term(v, m.beta));
           if (a == 0) a0 = v;
+          ctl_sum += fabsf(v) < 1.0f ? 1.0f - v * v : 0.0f;  // quadratic tolerance of the control (task costs)
           if (aout) aout[a] = v;
         });
       } else {
@@ -157,8 +158,11 @@ rollout_simt_kernel(ModelDev m, ActionSource src, Shape sh, const float* __restr
         // CoshLoss: beta^2 * mean_a(cosh(a/beta) - 1); row cost pairs s_{h+1} with a_h
         const float ac = __fmul_rn(m.beta2, __fdiv_rn(act_cost, (float)A));
         cost = __fadd_rn(cost, __fadd_rn(st_cost, ac));
-      } else if (!reward_head) {  // MBRL_COST_DMC_CARTPOLE_SWINGUP (O >= 5 checked by the host)
+      } else if (m.cost_kind == MBRL_COST_DMC_CARTPOLE_SWINGUP) {  // O >= 5 checked by the host
         cost += dmc_cartpole_cost(bufS[0 * TM + t], bufS[1 * TM + t], bufS[4 * TM + t], a0);
+      } else if (m.cost_kind == MBRL_COST_DMC_HUMANOID_RUN) {  // O >= 40 checked by the host
+        cost += dmc_humanoid_run_cost(bufS[21 * TM + t], bufS[36 * TM + t], bufS[37 * TM + t], bufS[38 * TM + t],
+                                      ctl_sum / (float)A);
       }
     }
     if (reward_head) {

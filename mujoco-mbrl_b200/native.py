@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libmbrl_b200.so")
 ENGINE_SIMT_FP32, ENGINE_TC_BF16, ENGINE_TC_FP16 = 0, 1, 2
 ENGINES = {"fp32": ENGINE_SIMT_FP32, "simt": ENGINE_SIMT_FP32, "bf16": ENGINE_TC_BF16, "fp16": ENGINE_TC_FP16}
 SAMPLE_INJECT_ACTIONS, SAMPLE_INJECT_NOISE, SAMPLE_GAUSSIAN, SAMPLE_UNIFORM = 0, 1, 2, 3
-COST_SMOOTHABS_COSH, COST_DMC_CARTPOLE_SWINGUP, COST_REWARD_HEAD = 0, 1, 2
+COST_SMOOTHABS_COSH, COST_DMC_CARTPOLE_SWINGUP, COST_REWARD_HEAD, COST_DMC_HUMANOID_RUN = 0, 1, 2, 3
 
 # every symbol include/mbrl_b200.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [

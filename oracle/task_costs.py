@@ -59,3 +59,26 @@ def cartpole_swingup_cost(obs, act):
     small_control = (4 + tolerance(act[..., 0], margin=1, value_at_margin=0, sigmoid="quadratic")) / 5
     small_velocity = (1 + tolerance(obs[..., 4], margin=5)) / 2
     return 1.0 - upright * small_control * small_velocity * centered
+
+
+HUMANOID_STAND_HEIGHT = 1.4  # dm_control/suite/humanoid.py:36
+HUMANOID_RUN_SPEED = 10.0    # dm_control/suite/humanoid.py:40
+
+
+def humanoid_cost(obs, act, move_speed=HUMANOID_RUN_SPEED):
+    """1 - Humanoid.get_reward (dm_control/dm_control/suite/humanoid.py:187-211) from the
+    egocentric observation (humanoid.py:172-185): joint_angles[0:21], head_height[21],
+    extremities[22:34], torso_vertical[34:37] (zz = obs[36] is physics.torso_upright(),
+    humanoid.py:95-97), com_velocity[37:40], velocity[40:67]; control = the action.
+    move_speed > 0 (walk / run; the reference's stand task, move_speed == 0, is `dont_move`).
+    obs [..., 67], act [..., 21] -> cost [...]."""
+    obs = np.asarray(obs, dtype=np.float64)
+    act = np.asarray(act, dtype=np.float64)
+    standing = tolerance(obs[..., 21], bounds=(HUMANOID_STAND_HEIGHT, np.inf), margin=HUMANOID_STAND_HEIGHT / 4)
+    upright = tolerance(obs[..., 36], bounds=(0.9, np.inf), sigmoid="linear", margin=1.9, value_at_margin=0)
+    small_control = tolerance(act, margin=1, value_at_margin=0, sigmoid="quadratic").mean(axis=-1)
+    small_control = (4 + small_control) / 5
+    com_velocity = np.sqrt(obs[..., 37] ** 2 + obs[..., 38] ** 2)
+    move = tolerance(com_velocity, bounds=(move_speed, np.inf), margin=move_speed, value_at_margin=0, sigmoid="linear")
+    move = (5 * move + 1) / 6
+    return 1.0 - small_control * standing * upright * move

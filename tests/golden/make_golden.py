@@ -291,6 +291,27 @@ def make_tolerance():
     np.savez_compressed(os.path.join(OUT, "tolerance.npz"), x=x, cases=np.array(cases), values=np.array(vals))
     print("tolerance cases", len(cases))
 
+    # Humanoid.get_reward (dm_control/suite/humanoid.py:187-211) composed with the reference's own
+    # tolerance() on synthetic physics quantities (MuJoCo itself is not available): pins the
+    # restated humanoid task cost (oracle/task_costs.humanoid_cost).
+    rng = np.random.default_rng(7)
+    m = 512
+    head = rng.uniform(0.2, 1.8, m); zz = rng.uniform(-1.0, 1.0, m)
+    com = rng.normal(size=(m, 3)) * np.array([6.0, 3.0, 1.0]); ctrl = rng.uniform(-1.3, 1.3, size=(m, 21))
+    rew = np.empty(m)
+    for i in range(m):
+        standing = rewards.tolerance(head[i], bounds=(1.4, float("inf")), margin=1.4 / 4)
+        upright = rewards.tolerance(zz[i], bounds=(0.9, float("inf")), sigmoid="linear", margin=1.9, value_at_margin=0)
+        small_control = rewards.tolerance(ctrl[i], margin=1, value_at_margin=0, sigmoid="quadratic").mean()
+        small_control = (4 + small_control) / 5
+        com_velocity = np.linalg.norm(com[i][[0, 1]])
+        move = rewards.tolerance(com_velocity, bounds=(10, float("inf")), margin=10, value_at_margin=0, sigmoid="linear")
+        move = (5 * move + 1) / 6
+        rew[i] = small_control * standing * upright * move
+    np.savez_compressed(os.path.join(OUT, "humanoid_reward.npz"), head_height=head, torso_upright=zz, com_velocity=com,
+                        control=ctrl, reward=rew)
+    print("humanoid reward samples", m, "mean", rew.mean())
+
 
 if __name__ == "__main__":
     _install_stubs()

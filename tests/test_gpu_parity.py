@@ -514,3 +514,31 @@ def test_reward_head_cost_matches_reference_fixture(native):
     np.testing.assert_array_equal(a.numpy(), g["plan_actions"])
     np.testing.assert_allclose(s.numpy(), g["plan_states"], rtol=1e-5, atol=1e-5)
     planners.clear_handles()
+
+
+def test_dmc_humanoid_task_cost_epilogue(native):
+    """Humanoid-run task cost (dm_control/suite/humanoid.py:187-211 restated on
+    the 67-d egocentric observation and the 21-d control) at the cfg-5 model shape on the fp32
+    engine, against the oracle that is pinned to the reference's rewards.tolerance composition."""
+    from oracle import task_costs
+    p = po.synthetic_params(67, 21, 128, seed=4)
+    # statistics that put head height / uprightness / speed in the interesting range of the reward
+    p.mu_s[21], p.sd_s[21] = 1.2, 0.4
+    p.mu_s[36], p.sd_s[36] = 0.5, 0.6
+    p.mu_s[37], p.sd_s[37] = 4.0, 5.0
+    p.mu_s[38], p.sd_s[38] = 0.0, 3.0
+    H, n = 6, 300
+    h = _planner(native, p, H, n)
+    h.set_cost(kind=native.COST_DMC_HUMANOID_RUN)
+    g = torch.Generator().manual_seed(2)
+    s0 = po.synthetic_state(p, 3)
+    acts = torch.rand(H * n, 21, generator=g) * 2.6 - 1.3  # beyond +-1: the quadratic control tolerance saturates
+    h.set_action_bounds(-1.3, 1.3)
+    costs, states, _ = h.rollout(s0[None].cuda(), native.SAMPLE_INJECT_ACTIONS, d_injected=acts.cuda(), want_states=True)
+    st, _ = po.rollout_costs(p, s0, acts, H, n)
+    np.testing.assert_allclose(states.cpu().numpy(), st.numpy(), rtol=2e-4, atol=2e-4)
+    want = task_costs.humanoid_cost(st.numpy(), acts.numpy()).reshape(H, n).sum(0)
+    assert want.std() > 0.01  # the test exercises the reward's active range
+    np.testing.assert_allclose(costs.cpu().numpy(), want, rtol=1e-4, atol=1e-4)
+    with pytest.raises(native.MbrlError):
+        _planner(native, po.synthetic_params(17, 6, 64), H, n).set_cost(kind=native.COST_DMC_HUMANOID_RUN)  # obs too small

@@ -37,3 +37,16 @@ def test_cartpole_cost_range_and_optimum():
     rng = np.random.default_rng(0)
     c = tc.cartpole_swingup_cost(rng.normal(size=(1000, 5)).clip(-3, 3) * [1, 0.3, 0.3, 1, 3], rng.uniform(-1, 1, (1000, 1)))
     assert ((c >= 0) & (c <= 1.0 + 1e-12)).all()
+
+
+def test_humanoid_cost_matches_reference_composition():
+    """oracle humanoid cost == 1 - Humanoid.get_reward composed with the reference's own
+    rewards.tolerance (tests/golden/humanoid_reward.npz, humanoid.py:187-211, move_speed = 10)."""
+    g = load_golden("humanoid_reward.npz")
+    m = g["reward"].shape[0]
+    obs = np.zeros((m, 67))
+    obs[:, 21] = g["head_height"]
+    obs[:, 36] = g["torso_upright"]
+    obs[:, 37:40] = g["com_velocity"]
+    np.testing.assert_allclose(tc.humanoid_cost(obs, g["control"]), 1.0 - g["reward"], rtol=1e-12, atol=1e-14)
+    assert 0.0 <= (1.0 - g["reward"]).min() and (1.0 - g["reward"]).max() <= 1.0
