@@ -11,11 +11,12 @@ struct Op { int ts, N, dcol, count; };  // count MMAs of this kind in a row
 __global__ void __launch_bounds__(64, 1) ubench(long long* out, const Op* ops, int nops) {
   extern __shared__ __align__(1024) uint8_t sm[];
   __shared__ uint64_t bar;
+  __shared__ uint64_t bar2[8];
   __shared__ uint32_t slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < 200 * 1024 / 4; i += 64) reinterpret_cast<uint32_t*>(sm)[i] = 0x3c003c00u;
   if (warp == 0) {
-    if (lane == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (lane == 0) { mbar_init(smem_u32(&bar), 1); for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&bar2[i]), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncwarp();
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&slot)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -32,6 +33,7 @@ __global__ void __launch_bounds__(64, 1) ubench(long long* out, const Op* ops, i
         int first = 1;
         for (int o = 0; o < nops; ++o) {
           const Op op = ops[o];
+          if (op.N == 0) { tc_commit(smem_u32(&bar2[o & 7])); continue; }  // mid-stream commit on another barrier
           const uint32_t idesc = umma_idesc(op.N, true);
           for (int i = 0; i < op.count; ++i) {
             if (op.ts) mma_ts(tmem + op.dcol, tmem + 448 + 8 * (i & 7), bd0 + (uint64_t)(i & 7) * 32, idesc, first ? 0u : 1u);
@@ -65,6 +67,10 @@ int main() {
     {"13 TS N=208 @D0, 13 TS N=32 @D208 (separate y pass)", {{1, 208, 0, 13}, {1, 32, 208, 13}}},
     {"1 SS N=240, then 13 TS N=240 (action K-step first)", {{0, 240, 0, 1}, {1, 240, 0, 13}}},
     {"14 x TS N=240", {{1, 240, 0, 14}}},
+    {"13 TS N=208, COMMIT, 13 TS N=208 @D208", {{1, 208, 0, 13}, {1, 0, 0, 0}, {1, 208, 208, 13}}},
+    {"13 TS N=208, COMMIT, 13 TS N=208 same accumulator", {{1, 208, 0, 13}, {1, 0, 0, 0}, {1, 208, 0, 13}}},
+    {"8 TS N=208, 5 TS N=64 @D0, COMMIT, 5 TS N=144 @D64 (tail split as in the kernel)", {{1, 208, 0, 8}, {1, 64, 0, 5}, {1, 0, 0, 0}, {1, 144, 64, 5}}},
+    {"1 SS N=240, COMMIT, 13 TS N=240 (production GEMM-A)", {{0, 240, 0, 1}, {1, 0, 0, 0}, {1, 240, 0, 13}}},
     {"alternating TS N=64@D0 / N=144@D64, 13 pairs", {}},
   };
   for (int i = 0; i < 13; ++i) { cases.back().ops.push_back({1, 64, 0, 1}); cases.back().ops.push_back({1, 144, 64, 1}); }
