@@ -23,12 +23,15 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     O, A, U, H, I = 24, 6, 200, 30, 4  # walker-walk shape (BASELINE config 4)
-    n_local = 2048
-    n_total, k = n_local * world, int(0.1 * n_local * world)
     prob = synthetic_problem(O, A, U)
     s0 = synthetic_state(prob, 4).numpy()
-    for engine, force_kl, transport in (("fp32", None, "nccl"), ("fp16", None, "nccl"), ("fp16", "min", "nccl"),
-                                        ("fp16", None, "p2p"), ("fp16", "min", "p2p")):
+    # the last case is the full per-GPU size of BASELINE config 4 (16384 candidates per rank): the global
+    # elite set exceeds 2048, so the refit runs as chunk CTAs whose partial sums must add up in the same
+    # order on every rank and in the unsharded plan
+    for engine, force_kl, transport, n_local in (("fp32", None, "nccl", 2048), ("fp16", None, "nccl", 2048),
+                                                 ("fp16", "min", "nccl", 2048), ("fp16", None, "p2p", 2048),
+                                                 ("fp16", "min", "p2p", 2048), ("fp16", None, "p2p", 16384)):
+        n_total, k = n_local * world, int(0.1 * n_local * world)
         if force_kl is None:
             os.environ.pop("MBRL_SHARD_KL", None)
         else:  # a gather that is far too small: the on-device check must flag it and the plan is redone in full

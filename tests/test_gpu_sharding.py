@@ -103,3 +103,21 @@ def test_in_library_nccl_world1_equals_plain_plan(native):
         np.testing.assert_array_equal(got[key], want[key])
     for key in ("best_cost", "best_index", "best_iteration"):
         np.testing.assert_array_equal(got["info"][key], want["info"][key])
+
+
+def test_multi_gpu_population_sharding_is_bit_identical():
+    """Runs tests/multi_gpu_check.py under torchrun when this box has >= 2 GPUs (skipped on the
+    single-GPU test box): every rank's plan == the unsharded plan, both transports, incl. the full
+    per-GPU size of BASELINE config 4 with a chunked refit."""
+    import subprocess
+    import sys
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "multi_gpu_check.py")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29533", script]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert res.stdout.count("multi_gpu_check[") == 6, res.stdout[-2000:]
