@@ -5,6 +5,7 @@ one device, never as concurrently waiting kernels):
     from global elite indices equals the unsharded refit;
   * the host loop PopulationShardedCEM (world 1) reproduces NativePlanner.plan;
   * environment sharding: env_offset makes a shard of environments draw the same streams."""
+import os
 import numpy as np
 import pytest
 import torch
