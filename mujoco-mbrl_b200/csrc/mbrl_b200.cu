@@ -405,16 +405,16 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   cfg.attrs = attr; cfg.numAttrs = g_use_pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
-template <int TM, int CPT>
+template <int TM, int CPT, int CG>
 static cudaError_t launch_simt_t(const MbrlPlanner* p, const ActionSource& src, const float* d_s0,
                                  float* d_costs, float* d_states, float* d_actions, cudaStream_t st) {
   const size_t smem = simt_smem_bytes<TM>(p->O, p->A, p->U);
-  auto kern = rollout_simt_kernel<TM, CPT>;
+  auto kern = rollout_simt_kernel<TM, CPT, CG>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   Shape sh{p->H, p->N, p->E};
   const unsigned grid = (unsigned)((p->R + TM - 1) / TM);
-  kern<<<grid, TM * 4, smem, st>>>(model_view(p), src, sh, d_s0, d_costs, d_states, d_actions);
+  kern<<<grid, TM * 4 * CG, smem, st>>>(model_view(p), src, sh, d_s0, d_costs, d_states, d_actions);
   return cudaGetLastError();
 }
 
@@ -422,10 +422,17 @@ template <int TM>
 static cudaError_t launch_simt_cpt(const MbrlPlanner* p, const ActionSource& src, const float* d_s0,
                                    float* d_costs, float* d_states, float* d_actions, cudaStream_t st) {
   const int U = p->U;
-  if (U <= 64) return launch_simt_t<TM, 2>(p, src, d_s0, d_costs, d_states, d_actions, st);
-  if (U <= 128) return launch_simt_t<TM, 4>(p, src, d_s0, d_costs, d_states, d_actions, st);
-  if (U <= 224) return launch_simt_t<TM, 7>(p, src, d_s0, d_costs, d_states, d_actions, st);
-  return launch_simt_t<TM, 8>(p, src, d_s0, d_costs, d_states, d_actions, st);
+  // (columns per lane CPT, column groups CG): a pass covers 32*CPT*CG output columns.  Up to 256 hidden
+  // units one warp per 8-row strip with a wide register tile is fastest (cfg 3: 2.76 ms vs 4.31 ms with
+  // two column groups); wider layers shrink the row tile (shared memory) to 4 warps per CTA, and
+  // splitting the columns over CG warps per strip restores the occupancy (cfg 5: 524 ms vs 928 ms).
+  constexpr int kMaxCG = 1024 / (TM * 4);
+  static const bool narrow = std::getenv("MBRL_SIMT_CG1") != nullptr;  // A/B switch: always one warp per strip
+  if (U <= 64) return launch_simt_t<TM, 2, 1>(p, src, d_s0, d_costs, d_states, d_actions, st);
+  if (U <= 128) return launch_simt_t<TM, 4, 1>(p, src, d_s0, d_costs, d_states, d_actions, st);
+  if (U <= 224) return launch_simt_t<TM, 7, 1>(p, src, d_s0, d_costs, d_states, d_actions, st);
+  if (U <= 256 || narrow) return launch_simt_t<TM, 8, 1>(p, src, d_s0, d_costs, d_states, d_actions, st);
+  return launch_simt_t<TM, 4, (kMaxCG >= 4 ? 4 : kMaxCG)>(p, src, d_s0, d_costs, d_states, d_actions, st);
 }
 
 static int launch_rollout(MbrlPlanner* p, const ActionSource& src, const float* d_s0, float* d_costs,

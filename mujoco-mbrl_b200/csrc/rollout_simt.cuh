@@ -20,14 +20,17 @@
 namespace mbrl {
 
 // out[j][r] = act(bias[j] + sum_k in[k][r] * Wt[k][j]) for r in this warp's 8-row strip.
-// Thread (rg = warp, lane): rows rg*8..rg*8+7, columns c0 + c*32 + lane, c < CPT.
-template <int TM, int CPT, bool RELU>
+// Warp (rg, cg): rows rg*8..rg*8+7 (rg < TM/8), column group cg of CG -- the CG warps of a strip
+// split the output columns (passes of 32*CPT columns, interleaved over cg), so a wide layer keeps
+// CG times more warps in flight on the same shared-memory tile; lane: columns c0 + c*32 + lane, c < CPT.
+template <int TM, int CPT, int CG, bool RELU>
 __device__ __forceinline__ void dense_layer(const float* __restrict__ Wt, const float* __restrict__ bias,
                                             const float* __restrict__ in, float* __restrict__ out,
                                             int K, int Nout) {
-  const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rg = warp % (TM / 8), cg = warp / (TM / 8);
   const float* in_strip = in + rg * 8;
-  for (int c0 = 0; c0 < Nout; c0 += 32 * CPT) {
+  for (int c0 = cg * 32 * CPT; c0 < Nout; c0 += CG * 32 * CPT) {
     float acc[CPT][8];
 #pragma unroll
     for (int c = 0; c < CPT; ++c) {
@@ -84,8 +87,8 @@ __host__ __device__ inline size_t simt_smem_bytes(int O, int A, int U) {
   return sizeof(float) * (size_t)TM * (KA + KB + O + A);
 }
 
-template <int TM, int CPT>
-__global__ void __launch_bounds__(TM * 4)
+template <int TM, int CPT, int CG>
+__global__ void __launch_bounds__(TM * 4 * CG)
 rollout_simt_kernel(ModelDev m, ActionSource src, Shape sh, const float* __restrict__ s0,
                     float* __restrict__ costs, float* __restrict__ states_out,
                     float* __restrict__ actions_out) {
@@ -137,11 +140,11 @@ rollout_simt_kernel(ModelDev m, ActionSource src, Shape sh, const float* __restr
       }
     }
     __syncthreads();
-    dense_layer<TM, CPT, true>(m.W1t, m.b1, bufA, bufB, D, U);
+    dense_layer<TM, CPT, CG, true>(m.W1t, m.b1, bufA, bufB, D, U);
     __syncthreads();
-    dense_layer<TM, CPT, true>(m.W2t, m.b2, bufB, bufA, U, U);
+    dense_layer<TM, CPT, CG, true>(m.W2t, m.b2, bufB, bufA, U, U);
     __syncthreads();
-    dense_layer<TM, 1, false>(m.W3t, m.b3, bufA, bufB, U, O);
+    dense_layer<TM, 1, CG, false>(m.W3t, m.b3, bufA, bufB, U, O);
     __syncthreads();
     if (row_thread) {
       float st_cost = 0.0f;
@@ -175,9 +178,9 @@ rollout_simt_kernel(ModelDev m, ActionSource src, Shape sh, const float* __restr
         for (int a = 0; a < A; ++a) bufA[(O + a) * TM + t] = bufN[a * TM + t];
       }
       __syncthreads();
-      dense_layer<TM, CPT, true>(m.W1t, m.b1, bufA, bufB, D, U);
+      dense_layer<TM, CPT, CG, true>(m.W1t, m.b1, bufA, bufB, D, U);
       __syncthreads();
-      dense_layer<TM, CPT, true>(m.W2t, m.b2, bufB, bufA, U, U);
+      dense_layer<TM, CPT, CG, true>(m.W2t, m.b2, bufB, bufA, U, U);
       __syncthreads();
       if (row_thread) {
         float r = 0.0f;
