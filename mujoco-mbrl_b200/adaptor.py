@@ -75,8 +75,47 @@ def _stats_of(norm_partial, what: str) -> Tuple[Any, Any, Any]:
     return entry["mean"], entry["std"], entry
 
 
+_LINEAR_EMBEDDINGS: dict = {}
+
+
+def embed_linear_model(weight, bias):
+    """LinearModel (src/mbrl/models.py:113-122) is a single Linear(D, O).  It runs on the same
+    kernels as the 3-layer MLP through an exact ReLU embedding with hidden width 2D:
+        h1 = relu([x; -x])          W1 = [I; -I], b1 = 0
+        h2 = relu(I h1) = h1        W2 = I,       b2 = 0      (h1 >= 0 already)
+        y  = [W, -W] h2 + b         = W relu(x) - W relu(-x) + b = W x + b
+    Every product W[i,j]*x[j] appears once with its exact value (the other half contributes exact
+    zeros), so only the summation order differs from the reference's dot product.
+    Returns (W1, b1, W2, b2, W3, b3) as float32 numpy arrays; cached per (tensor, version)."""
+    key = (id(weight), int(getattr(weight, "_version", 0)), id(bias), int(getattr(bias, "_version", 0)))
+    hit = _LINEAR_EMBEDDINGS.get(key)
+    if hit is not None:
+        return hit
+    W = np.ascontiguousarray(weight.detach().cpu().numpy() if hasattr(weight, "detach") else weight, np.float32)
+    b = np.ascontiguousarray(bias.detach().cpu().numpy() if hasattr(bias, "detach") else bias, np.float32)
+    D = W.shape[1]
+    eye = np.eye(D, dtype=np.float32)
+    out = (np.concatenate([eye, -eye], 0), np.zeros(2 * D, np.float32), np.eye(2 * D, dtype=np.float32),
+           np.zeros(2 * D, np.float32), np.concatenate([W, -W], 1), b)
+    _LINEAR_EMBEDDINGS.clear()  # one live model is the normal case; do not accumulate stale versions
+    _LINEAR_EMBEDDINGS[key] = out
+    return out
+
+
+class _Layer:
+    """Minimal stand-in for nn.Linear carrying embedded weights."""
+
+    def __init__(self, weight, bias):
+        self.weight, self.bias = weight, bias
+
+
 def _linear_layers(module):
     names = ("linear1", "linear2", "linear3")
+    if hasattr(module, "linear1") and not hasattr(module, "linear2") and not hasattr(module, "linear3"):
+        if getattr(module, "noise", None) is not None:
+            raise TypeError("LinearModel(noise=...) adds fresh Gaussian noise per forward (src/mbrl/models.py:122); unsupported")
+        W1, b1, W2, b2, W3, b3 = embed_linear_model(module.linear1.weight, module.linear1.bias)
+        return [_Layer(W1, b1), _Layer(W2, b2), _Layer(W3, b3)]
     if not all(hasattr(module, n) for n in names):
         raise TypeError(
             f"{type(module).__name__}: unsupported dynamics model (need linear1/linear2/linear3 as in "
@@ -188,7 +227,7 @@ def problem_from_callables(model, cost, sample_action) -> Tuple[PlanningProblem,
         cost_w=sc.weights, goal=sc.goal_state, alpha=float(sc.alpha), beta=float(ac.alpha),
         act_lo=lo, act_hi=hi,
     )
-    params = [l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias]
+    params = list(module.parameters())  # the live tensors (the embedded copies of a LinearModel are derived from them)
     fp = (
         tuple((id(t), int(getattr(t, "_version", 0))) for t in params),
         tuple((id(t), int(getattr(t, "_version", 0))) for t in (mu_s, sd_s, mu_a, sd_a, sc.weights, sc.goal_state) if t is not None),

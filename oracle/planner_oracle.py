@@ -49,13 +49,15 @@ class PlannerParams:
     mu_r: float = 0.0                   # stats["rewards"]["mean"]
     sd_r: float = 1.0
 
+    # LinearModel (src/mbrl/models.py:113-122): W2/b2/W3/b3 are None and W1 is the single Linear(D, O)
+
     @property
     def obs_dim(self) -> int:
-        return int(self.W3.shape[0])
+        return int((self.W3 if self.W3 is not None else self.W1).shape[0])
 
     @property
     def act_dim(self) -> int:
-        return int(self.W1.shape[1] - self.W3.shape[0])
+        return int(self.W1.shape[1]) - self.obs_dim
 
     @property
     def hidden(self) -> int:
@@ -109,6 +111,8 @@ def unnormalize(x: torch.Tensor, mean: torch.Tensor, std: torch.Tensor) -> torch
 
 def mlp_forward(p: PlannerParams, x: torch.Tensor) -> torch.Tensor:
     """Model._forward, src/mbrl/models.py:106-110 (noise=None): relu(L1), relu(L2), L3."""
+    if p.W2 is None:  # LinearModel._forward, src/mbrl/models.py:119-122
+        return F.linear(x, p.W1, p.b1)
     h = torch.relu(F.linear(x, p.W1, p.b1))
     h = torch.relu(F.linear(h, p.W2, p.b2))
     return F.linear(h, p.W3, p.b3)

@@ -195,6 +195,59 @@ def make_rs_reward(name, obs, act, hidden, n, horizon):
     print(name, "argmin", int(arrays["idx"]), "min cost", float(np.min(costs)))
 
 
+def make_rs_linear(name, obs, act, n, horizon):
+    """LinearModel (src/mbrl/models.py:113-122, `--model lin`) wired like GoalStateAgent and run through
+    the reference's own RandomShootingPlanner with an injected sample."""
+    from src.mbrl.models import LinearModel, SmoothAbsLoss, CoshLoss
+    from src.mbrl.data import TransitionsDataset
+    from src.mbrl.agents import state_action_cost
+    from src.mbrl.planners import RandomShootingPlanner
+    from src.mbrl.env_wrappers import EnvWrapper
+
+    torch.manual_seed(11)
+    net = LinearModel(obs, act)
+    g = torch.Generator().manual_seed(31)
+    stats = {
+        "observations": {"mean": torch.randn(obs, generator=g), "std": torch.rand(obs, generator=g) + 0.5},
+        "actions": {"mean": 0.1 * torch.randn(act, generator=g), "std": torch.rand(act, generator=g) * 0.3 + 0.4},
+    }
+    weights = torch.rand(obs, generator=g) + 0.5
+    goal = 0.3 * torch.randn(obs, generator=g)
+    state_cost, action_cost = SmoothAbsLoss(weights=weights, goal_state=goal), CoshLoss()
+    model = partial(
+        net,
+        normalize_state=partial(TransitionsDataset.normalize_field, field_name="observations", stats=stats),
+        normalize_action=partial(TransitionsDataset.normalize_field, field_name="actions", stats=stats),
+        unnormalize_state=partial(TransitionsDataset.unnormalize_field, field_name="observations", stats=stats),
+    )
+    cost = partial(state_action_cost, state_cost=state_cost, action_cost=action_cost)
+    s0 = stats["observations"]["mean"] + stats["observations"]["std"] * torch.randn(obs, generator=g)
+    np.random.seed(987)
+    recorded = EnvWrapper._sample_action(_Spec(act), batch_size=n * horizon)
+
+    def injected(batch_size):
+        return recorded.clone()
+
+    trajs, costs = RandomShootingPlanner._generate_trajectories(
+        initial_state=s0, model=model, cost=cost, sample_action=injected, horizon=horizon, num_trajectories=n
+    )
+    plan_s, plan_a = RandomShootingPlanner.plan(s0, model, cost, injected, horizon, None, num_trajectories=n)
+    arrays = dict(
+        W1=net.linear1.weight, b1=net.linear1.bias,
+        mu_s=stats["observations"]["mean"], sd_s=stats["observations"]["std"],
+        mu_a=stats["actions"]["mean"], sd_a=stats["actions"]["std"], cost_w=weights, goal=goal, s0=s0,
+        alpha=torch.tensor(state_cost.alpha), beta=torch.tensor(action_cost.alpha),
+    )
+    arrays = {k: v.detach().numpy().copy() for k, v in arrays.items()}
+    arrays.update(
+        actions=recorded.numpy(), costs=np.asarray(costs, dtype=np.float32), idx=np.int64(np.argmin(costs)),
+        plan_states=plan_s.detach().numpy().copy(), plan_actions=plan_a.detach().numpy().copy(),
+        n=np.int64(n), horizon=np.int64(horizon), lo=np.float32(-1), hi=np.float32(1),
+    )
+    np.savez_compressed(os.path.join(OUT, name), **arrays)
+    print(name, "argmin", int(arrays["idx"]), "min cost", float(np.min(costs)))
+
+
 def make_cem(name, obs, act, hidden, n, horizon, iters, k):
     """Reference-composed CEM: the reference's _generate_trajectories per
     iteration with an injected Gaussian sampler; argsort/mean/std are the only lines that
@@ -322,3 +375,4 @@ if __name__ == "__main__":
     make_cem("cem_cartpole_small.npz", obs=5, act=1, hidden=50, n=512, horizon=30, iters=4, k=51)
     make_tolerance()
     make_rs_reward("rs_reward_head.npz", obs=17, act=6, hidden=50, n=256, horizon=20)
+    make_rs_linear("rs_linear_model.npz", obs=9, act=3, n=200, horizon=12)

@@ -17,6 +17,12 @@ def load_golden(name):
 
 def params_from_golden(g) -> PlannerParams:
     t = lambda k: torch.from_numpy(np.ascontiguousarray(g[k])).float()
+    if "W2" not in g:  # LinearModel fixture: a single Linear(D, O)
+        return PlannerParams(
+            t("W1"), t("b1"), None, None, None, None,
+            t("mu_s"), t("sd_s"), t("mu_a"), t("sd_a"), t("cost_w"), t("goal"),
+            alpha=float(g["alpha"]), beta=float(g["beta"]), act_lo=float(g["lo"]), act_hi=float(g["hi"]),
+        )
     if "W4" in g:  # ModelWithReward fixture: no SmoothAbs/Cosh parameters, a reward head instead
         obs = g["W3"].shape[0]
         return PlannerParams(

@@ -215,3 +215,39 @@ def test_adaptor_recognises_reward_agent_wiring():
         problem_from_callables(wired, cost, None)
     with pytest.raises(TypeError):  # swapped itemgetters
         problem_from_callables(cost, model, None)
+
+
+def test_linear_model_embedding_is_exact():
+    """LinearModel runs through an exact ReLU embedding (adaptor.embed_linear_model): the embedded
+    3-layer MLP reproduces W x + b to fp32 rounding of the summation order only."""
+    from functools import partial
+    from mbrl_b200.adaptor import embed_linear_model, problem_from_callables
+    torch.manual_seed(3)
+
+    class LinearModel(torch.nn.Module):  # src/mbrl/models.py:113-122
+        def __init__(self):
+            super().__init__()
+            self.linear1 = torch.nn.Linear(12, 9)
+            self.noise = None
+    net = LinearModel()
+    W1, b1, W2, b2, W3, b3 = (torch.from_numpy(a) for a in embed_linear_model(net.linear1.weight, net.linear1.bias))
+    x = torch.randn(64, 12) * 3
+    h = torch.relu(torch.nn.functional.linear(torch.relu(torch.nn.functional.linear(x, W1, b1)), W2, b2))
+    y = torch.nn.functional.linear(h, W3, b3)
+    torch.testing.assert_close(y, net.linear1(x).detach(), rtol=1e-6, atol=1e-6)
+
+    class Cost:
+        weights, goal_state, alpha = torch.ones(9), torch.zeros(9), 0.4
+    class ACost:
+        alpha = 0.25
+    stats = {"observations": {"mean": torch.zeros(9), "std": torch.ones(9)}, "actions": {"mean": torch.zeros(3), "std": torch.ones(3)}}
+    f = lambda x, field_name, stats: x
+    model = partial(net, normalize_state=partial(f, field_name="observations", stats=stats),
+                    normalize_action=partial(f, field_name="actions", stats=stats),
+                    unnormalize_state=partial(f, field_name="observations", stats=stats))
+    prob, fp = problem_from_callables(model, partial(f, state_cost=Cost, action_cost=ACost), None)
+    assert (prob.obs_dim, prob.act_dim, prob.hidden) == (9, 3, 24)
+    with torch.no_grad():
+        net.linear1.weight.mul_(2.0)  # retraining in place: new fingerprint, new embedding
+    prob2, fp2 = problem_from_callables(model, partial(f, state_cost=Cost, action_cost=ACost), None)
+    assert fp2 != fp and not np.array_equal(np.asarray(prob2.W3), np.asarray(prob.W3))

@@ -542,3 +542,46 @@ def test_dmc_humanoid_task_cost_epilogue(native):
     np.testing.assert_allclose(costs.cpu().numpy(), want, rtol=1e-4, atol=1e-4)
     with pytest.raises(native.MbrlError):
         _planner(native, po.synthetic_params(17, 6, 64), H, n).set_cost(kind=native.COST_DMC_HUMANOID_RUN)  # obs too small
+
+
+def test_linear_model_drop_in_matches_reference_fixture(native):
+    """`--model lin` (LinearModel, src/mbrl/models.py:113-122) through the drop-in planner API: the
+    adaptor's exact ReLU embedding on the fp32 engine reproduces the reference planner's plan."""
+    from functools import partial
+    from mbrl_b200 import RandomShootingPlanner, planners
+    g = load_golden("rs_linear_model.npz")
+    n, H = int(g["n"]), int(g["horizon"])
+    O, D = g["W1"].shape
+
+    class LinearModel(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.linear1 = torch.nn.Linear(D, O)
+            self.noise = None
+    net = LinearModel()
+    with torch.no_grad():
+        net.linear1.weight.copy_(torch.from_numpy(g["W1"])); net.linear1.bias.copy_(torch.from_numpy(g["b1"]))
+    t = lambda k: torch.from_numpy(g[k])
+    stats = {"observations": {"mean": t("mu_s"), "std": t("sd_s")}, "actions": {"mean": t("mu_a"), "std": t("sd_a")}}
+
+    def field(x, field_name, stats):
+        raise AssertionError("the GPU planner never calls the host callables")
+
+    class SC:
+        weights, goal_state, alpha = t("cost_w"), t("goal"), float(g["alpha"])
+
+    class AC:
+        alpha = float(g["beta"])
+    model = partial(net, normalize_state=partial(field, field_name="observations", stats=stats),
+                    normalize_action=partial(field, field_name="actions", stats=stats),
+                    unnormalize_state=partial(field, field_name="observations", stats=stats))
+    cost = partial(field, state_cost=SC, action_cost=AC)
+    acts = torch.from_numpy(g["actions"])
+    s, a = RandomShootingPlanner.plan(t("s0"), model, cost, lambda batch_size: acts, H, None, num_trajectories=n,
+                                      sampler="host", engine="fp32")
+    np.testing.assert_array_equal(a.numpy(), g["plan_actions"])
+    np.testing.assert_allclose(s.numpy(), g["plan_states"], rtol=1e-5, atol=1e-5)
+    s16, a16 = RandomShootingPlanner.plan(t("s0"), model, cost, lambda batch_size: acts, H, None, num_trajectories=n,
+                                          sampler="host", engine="fp16", return_states=True)
+    assert a16.shape == a.shape and torch.isfinite(s16).all()
+    planners.clear_handles()
