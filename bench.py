@@ -172,6 +172,54 @@ def run_reference(args, rank):
 # ------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------
+def python_api_latency(prob, w, engine, k, states0, warmup, steps):
+    """Plan latency through the reference-facing Python API: CEMPlanner.plan called the way
+    MPCPolicy.get_action calls it (src/mbrl/agents.py:48-55) with callables wired like GoalStateAgent
+    (agents.py:225-233) -- adaptor introspection, fingerprint check, ctypes call, host tensors back."""
+    import torch
+    from functools import partial
+    from mbrl_b200 import CEMPlanner, planners
+
+    class Net(torch.nn.Module):  # shaped like src/mbrl/models.py:96-104
+        def __init__(self):
+            super().__init__()
+            self.linear1 = torch.nn.Linear(w["O"] + w["A"], w["U"])
+            self.linear2 = torch.nn.Linear(w["U"], w["U"])
+            self.linear3 = torch.nn.Linear(w["U"], w["O"])
+            self.noise = None
+    net = Net()
+    with torch.no_grad():
+        for lin, (W, b) in zip((net.linear1, net.linear2, net.linear3),
+                               ((prob.W1, prob.b1), (prob.W2, prob.b2), (prob.W3, prob.b3))):
+            lin.weight.copy_(W); lin.bias.copy_(b)
+    stats = {"observations": {"mean": prob.mu_s, "std": prob.sd_s}, "actions": {"mean": prob.mu_a, "std": prob.sd_a}}
+
+    def field(x, field_name, stats):
+        raise RuntimeError("host callables are never invoked by the GPU planner")
+
+    class StateCost:
+        weights, goal_state, alpha = prob.cost_w, prob.goal, prob.alpha
+
+    class ActionCost:
+        alpha = prob.beta
+    model = partial(net, normalize_state=partial(field, field_name="observations", stats=stats),
+                    normalize_action=partial(field, field_name="actions", stats=stats),
+                    unnormalize_state=partial(field, field_name="observations", stats=stats))
+    cost = partial(field, state_cost=StateCost, action_cost=ActionCost)
+    lat = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, actions = CEMPlanner.plan(states0[i], model, cost, None, w["H"], None, num_trajectories=w["N"],
+                                     num_iterations=w["I"], num_elites=k, engine=engine, seed=i, return_states=False)
+        first_action = actions[0].flatten()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            lat.append(dt)
+    planners.clear_handles()
+    assert first_action.shape == (w["A"],)
+    return statistics.median(lat) * 1e3
+
+
 def pick_engine(native, w, requested):
     if requested != "auto":
         return requested
@@ -319,6 +367,9 @@ def main():
             dt = time.perf_counter() - t0
             if i >= args.warmup:
                 e2e_lat.append(dt)
+    py_api_ms = None
+    if world == 1:
+        py_api_ms = python_api_latency(prob, w, engine, k, states0, args.warmup, args.steps)
     e2e_total = torch.tensor([sum(e2e_lat)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
@@ -394,6 +445,7 @@ def main():
         e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=4 * O, d2h_bytes_per_step=4 * H * (O + A) + 16,
                  latency_ms_p50=statistics.median(e2e_lat) * 1e3,
                  latency_ms_p50_actions_only=(statistics.median(e2e_lat_actions) * 1e3 if e2e_lat_actions else None),
+                 python_api_first_action_latency_ms_p50=py_api_ms,
                  api="mbrl_plan (host buffers)" + ("" if world == 1 else ", population-sharded (in-library elite exchange: %s)" % args.transport)),
         gpu_launches=launches_per_plan * args.steps,
         roofline=roofline,
