@@ -16,7 +16,7 @@
 //     GEMM-B(h):   D_B[128 x Np] = h1(h) . W2p^T                  (TS)
 // Both hidden epilogues (TMEM fp32 -> relu -> 16 bit -> TMEM, each 16-column K-step packed into the
 // first half of its own columns, so no warp ever overwrites data another warp still has to read)
-// release the next GEMM's K-steps one by one through mbarriers, so the tensor pipe only idles for the first-chunk
+// release the next GEMM's K-steps in groups of 4 through mbarriers, so the tensor pipe only idles for the first-group
 // latency of each epilogue.  Step 0 uses a state tile (x0 - b3, so that b13 gives exactly b1)
 // with W1s as extra SS K-steps.
 //

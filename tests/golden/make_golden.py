@@ -7,11 +7,16 @@ container; it does not exist on the GPU box, which is why the outputs are commit
 
 What is imported from the reference (unmodified, from where it lies):
   src/mbrl/planners.py   RandomShootingPlanner.plan / _generate_trajectories
-  src/mbrl/models.py     Model, SmoothAbsLoss, CoshLoss
+  src/mbrl/models.py     Model, LinearModel, ModelWithReward, SmoothAbsLoss, CoshLoss
   src/mbrl/data.py       TransitionsDataset.normalize_field / unnormalize_field
-  src/mbrl/agents.py     MPCPolicy, state_action_cost        (needs the stubs below)
+  src/mbrl/agents.py     MPCPolicy, state_action_cost, compose   (needs the stubs below)
   src/mbrl/env_wrappers.py  EnvWrapper._sample_action        (needs the stubs below)
   dm_control/dm_control/utils/rewards.py  tolerance           (numpy only)
+
+Fixtures: ring_world, rs_cartpole, rs_cheetah_small (random shooting: costs, argmin, plan, first
+action through MPCPolicy), cem_cheetah_small, cem_cartpole_small (reference-composed CEM),
+rs_reward_head (RewardAgent wiring), rs_linear_model (--model lin), tolerance (rewards.tolerance
+grid), humanoid_reward (Humanoid.get_reward composed with the reference's tolerance).
 
 Third-party modules the reference imports at module scope but which are not installed
 here (tensorboardX, colorlog, dm_env, dm_control.suite, PIL) are stubbed in sys.modules;
