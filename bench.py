@@ -289,9 +289,9 @@ def main():
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             if int(flag.item()) == 0:
                 transport = "nccl"
-        if transport == "p2p":
-            h.p2p_init(rank, world)
-        else:
+        if transport == "p2p" and not h.p2p_init(rank, world):
+            transport = "nccl"  # some rank could not open a peer buffer: every rank detached, all take NCCL
+        if transport == "nccl":
             h.comm_init(rank, world)
         args.transport = transport
     states0 = torch.stack([synthetic_state(p, c) for c in range(args.warmup + args.steps)]).float()

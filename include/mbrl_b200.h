@@ -229,6 +229,9 @@ int mbrl_emit(MbrlPlanner* p, int32_t sample_mode, uint64_t seed, uint32_t cand_
  * Falls back to NCCL when no peer buffers are attached.                                        */
 int mbrl_p2p_export(MbrlPlanner* p, int32_t world, uint8_t* h_handle64);
 int mbrl_p2p_attach(MbrlPlanner* p, const uint8_t* h_handles, int32_t rank, int32_t world);
+/* Closes whatever peer buffers were opened (also after a failed attach) so that the handle can
+ * take the NCCL transport instead; the exported buffer stays allocated.  Idempotent. */
+int mbrl_p2p_detach(MbrlPlanner* p);
 int mbrl_nccl_unique_id(uint8_t* h_id128);
 int mbrl_comm_init(MbrlPlanner* p, const uint8_t* h_id128, int32_t rank, int32_t world);
 int mbrl_comm_destroy(MbrlPlanner* p);

@@ -659,17 +659,32 @@ extern "C" int mbrl_p2p_attach(MbrlPlanner* p, const uint8_t* h_handles, int32_t
                "p2p_attach: export first, with the same world size");
   MBRL_REQUIRE(!p->p2p_attached, "p2p already attached");
   MBRL_CUDA(cudaSetDevice(p->cfg.device));
+  if (const char* f = getenv("MBRL_TEST_P2P_FAIL_RANK"))  // tests: make one rank's attach fail (fallback path)
+    if (std::atoi(f) == rank) return fail(MBRL_E_CUDA, "p2p_attach: forced failure (MBRL_TEST_P2P_FAIL_RANK)");
+  for (int r = 0; r < world; ++r) p->p2p_peers.base[r] = nullptr;
+  p->rank = rank; p->world = world;
   for (int r = 0; r < world; ++r) {
     if (r == rank) { p->p2p_peers.base[r] = p->d_p2p_local; continue; }
     cudaIpcMemHandle_t hdl;
     std::memcpy(&hdl, h_handles + 64 * r, 64);
     void* ptr = nullptr;
-    MBRL_CUDA(cudaIpcOpenMemHandle(&ptr, hdl, cudaIpcMemLazyEnablePeerAccess));
+    MBRL_CUDA(cudaIpcOpenMemHandle(&ptr, hdl, cudaIpcMemLazyEnablePeerAccess));  // on failure: mbrl_p2p_detach cleans up
     p->p2p_peers.base[r] = (uint32_t*)ptr;
   }
-  p->rank = rank; p->world = world;
   p->p2p_attached = true;
   return alloc_shard_scratch(p, world);
+}
+
+extern "C" int mbrl_p2p_detach(MbrlPlanner* p) {
+  if (!p) return fail(MBRL_E_INVALID, "null planner");
+  MBRL_CUDA(cudaSetDevice(p->cfg.device));
+  MBRL_CUDA(cudaDeviceSynchronize());
+  for (int r = 0; r < p->p2p_world && r < 64; ++r) {
+    if (r != p->rank && p->p2p_peers.base[r]) cudaIpcCloseMemHandle(p->p2p_peers.base[r]);
+    p->p2p_peers.base[r] = nullptr;
+  }
+  p->p2p_attached = false;
+  return MBRL_OK;
 }
 
 extern "C" int mbrl_comm_init(MbrlPlanner* p, const uint8_t* h_id128, int32_t rank, int32_t world) {

@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "mbrl_set_norm", "mbrl_set_cost", "mbrl_set_action_bounds", "mbrl_set_reward_head", "mbrl_plan", "mbrl_plan_device",
     "mbrl_rollout", "mbrl_sample", "mbrl_philox_raw", "mbrl_topk", "mbrl_refit", "mbrl_emit",
     "mbrl_tc_debug", "mbrl_nccl_unique_id", "mbrl_comm_init", "mbrl_comm_destroy",
-    "mbrl_p2p_export", "mbrl_p2p_attach",
+    "mbrl_p2p_export", "mbrl_p2p_attach", "mbrl_p2p_detach",
 ]
 
 
@@ -102,6 +102,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         "mbrl_comm_destroy": [p],
         "mbrl_p2p_export": [p, i32, vp],
         "mbrl_p2p_attach": [p, vp, i32, i32],
+        "mbrl_p2p_detach": [p],
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)
@@ -313,22 +314,32 @@ class NativePlanner:
 
     def p2p_init(self, rank=None, world=None, group=None):
         """Peer-memory (NVLink P2P, CUDA IPC) transport for the sharded loop: export this rank's gather
-        buffer, all-gather the 64-byte IPC handles through torch.distributed, open the peers' buffers."""
+        buffer, all-gather the 64-byte IPC handles through torch.distributed, open the peers' buffers.
+        Collective and all-or-nothing: every rank takes part in both exchanges whatever happened
+        locally, and if ANY rank failed to export or attach, every rank detaches and the call returns
+        False (the caller then uses comm_init: a mix of transports would stall the elite exchange)."""
         import torch
         import torch.distributed as dist
         if world is None:
             world, rank = dist.get_world_size(group), dist.get_rank(group)
-        mine = np.zeros(64, np.uint8)
-        _check(self.lib.mbrl_p2p_export(self._h, world, _hp(mine)))
-        t = torch.from_numpy(mine)
         on_gpu = dist.get_backend(group) == "nccl"
-        if on_gpu:
-            t = t.cuda(self.device)
-        allh = torch.empty(world * 64, dtype=torch.uint8, device=t.device)
-        dist.all_gather_into_tensor(allh, t, group=group)
-        handles = np.ascontiguousarray(allh.cpu().numpy())
-        _check(self.lib.mbrl_p2p_attach(self._h, _hp(handles), rank, world))
+        dev = torch.device("cuda", self.device) if on_gpu else torch.device("cpu")
+        mine = np.zeros(64, np.uint8)
+        ok = self.lib.mbrl_p2p_export(self._h, world, _hp(mine)) == 0
+        allh = torch.empty(world * 64, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, torch.from_numpy(mine).to(dev), group=group)
+        if ok:
+            handles = np.ascontiguousarray(allh.cpu().numpy())
+            ok = self.lib.mbrl_p2p_attach(self._h, _hp(handles), rank, world) == 0
+        err = None if ok else self.lib.mbrl_last_error().decode(errors="replace")
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            self.lib.mbrl_p2p_detach(self._h)
+            self.p2p_error = err
+            return False
         self.rank, self.world = rank, world
+        return True
 
     def tc_debug(self, enable=True, fetch=False):
         """Diagnostic: arm / fetch the raw accumulator dump of tile 0, step 0 ([3,128,256]);

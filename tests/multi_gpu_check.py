@@ -39,7 +39,7 @@ def main():
         h = native.NativePlanner(O, A, U, H, n_local, 1, I, k, engine, local)
         h.load_problem(prob)
         if transport == "p2p":
-            h.p2p_init(rank, world)   # NVLink peer stores + sequence flags instead of ncclAllGather
+            assert h.p2p_init(rank, world)   # NVLink peer stores + sequence flags instead of ncclAllGather
         else:
             h.comm_init(rank, world)
         for rep in range(3):          # repeated plans: sequence numbers / double buffering keep working
