@@ -66,6 +66,15 @@ extern "C" {
                                       observation (head_height obs[21], torso zz obs[36], com velocity
                                       obs[37:39]) and the control (dm_control/suite/humanoid.py:172-211);
                                       fp32 engine only this round; weights/goal are ignored   */
+#define MBRL_COST_DMC_CHEETAH_RUN 4 /* 1 - Cheetah.get_reward (dm_control/suite/cheetah.py:91-97): linear
+                                      tolerance of the forward speed up to 10 m/s.  The reward's
+                                      torso_subtreelinvel sensor is not part of the observation
+                                      (cheetah.py:59-61,83-89): the root-x joint velocity obs[8] stands in
+                                      for it (a documented PROXY); weights/goal ignored */
+#define MBRL_COST_DMC_WALKER_WALK 5 /* 1 - PlanarWalker.get_reward at move_speed 1 (walker.py:135-158):
+                                      torso height obs[14], torso zz obs[0] (planar: xx == zz), and the
+                                      root-x joint velocity obs[16] as PROXY for the unobserved
+                                      horizontal-velocity sensor; weights/goal ignored               */
 #define MBRL_COST_REWARD_HEAD 2 /* RewardAgent's cost (src/mbrl/agents.py:342-366): a second trunk
                                       evaluation at (s_{h+1}, a_h) through ModelWithReward's
                                       linear4 head, un-normalised with the reward statistics
@@ -237,9 +246,9 @@ int mbrl_comm_init(MbrlPlanner* p, const uint8_t* h_id128, int32_t rank, int32_t
 int mbrl_comm_destroy(MbrlPlanner* p);
 
 /* Diagnostic for the tensor-core engines (tests only): enable != 0 arms a dump of the raw
- * fp32 accumulators of row tile 0 at step 0 ([3 layers][128 rows][256 cols] floats) followed
+ * fp32 accumulators of row tile 0 at step 0 ([3 layers][128 rows][512 cols] floats) followed
  * by a clock64() timeline of tile 1 ([64 steps][32 events] int64) by the next mbrl_rollout;
- * h_out != NULL copies the dump (3*128*256*4 + 64*32*8 bytes) to the host after a sync. */
+ * h_out != NULL copies the dump (3*128*512*4 + 64*32*8 bytes) to the host after a sync. */
 int mbrl_tc_debug(MbrlPlanner* p, int32_t enable, float* h_out);
 
 #ifdef __cplusplus

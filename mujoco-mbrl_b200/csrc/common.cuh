@@ -115,4 +115,52 @@ __device__ __forceinline__ float dmc_humanoid_run_cost(float head, float zz, flo
   return 1.0f - small_control * standing * upright * move;
 }
 
+// 1 - Cheetah.get_reward (dm_control/suite/cheetah.py:91-97): tolerance(speed, [10, inf), margin 10,
+// linear, value_at_margin 0).  physics.speed() is the torso_subtreelinvel sensor, which is NOT in the
+// observation (cheetah.py:59-61): the documented proxy is the root-x joint velocity obs[8]
+// (obs = qpos[1:] | qvel, cheetah.py:83-89).
+__device__ __forceinline__ float dmc_cheetah_run_cost(float speed) {
+  const float d = (10.0f - speed) * 0.1f;
+  const float r = speed >= 10.0f ? 1.0f : (d < 1.0f ? 1.0f - d : 0.0f);
+  return 1.0f - r;
+}
+
+// 1 - PlanarWalker.get_reward at move_speed 1 (walker-walk; dm_control/suite/walker.py:135-158):
+// standing = tolerance(torso_height, [1.2, inf), margin 0.6, gaussian); upright = (1 + torso zz) / 2;
+// stand = (3 standing + upright) / 4; move = tolerance(v, [1, inf), margin 0.5, linear, value_at_margin
+// 0.5); reward = stand * (5 move + 1) / 6.  torso_height = obs[14], zz = obs[0] (planar: xx == zz);
+// the horizontal-velocity sensor is not observed: proxy = root-x joint velocity obs[16]
+// (walker.py:88-102, qvel order rootz, rootx, rooty).
+__device__ __forceinline__ float dmc_walker_walk_cost(float height, float zz, float v) {
+  const float ln01 = -2.302585092994046f;
+  const float dh = (1.2f - height) * (1.0f / 0.6f);
+  const float standing = height >= 1.2f ? 1.0f : expf(ln01 * dh * dh);
+  const float upright = 0.5f * (1.0f + zz);
+  const float stand = 0.25f * (3.0f * standing + upright);
+  const float sx = (1.0f - v);  // d / margin * (1 - value_at_margin) = (1 - v) / 0.5 * 0.5
+  const float move = v >= 1.0f ? 1.0f : (sx < 1.0f ? 1.0f - sx : 0.0f);
+  return 1.0f - stand * (5.0f * move + 1.0f) * (1.0f / 6.0f);
+}
+
+// The dm_control task costs read at most four entries of the un-normalised predicted state: the
+// tensor-core engines pick them out of the output epilogue instead of keeping the whole state.
+__host__ __device__ inline void task_pick_indices(int kind, int (&idx)[4]) {
+  idx[0] = idx[1] = idx[2] = idx[3] = -1;
+  if (kind == MBRL_COST_DMC_CARTPOLE_SWINGUP) { idx[0] = 0; idx[1] = 1; idx[2] = 4; }
+  else if (kind == MBRL_COST_DMC_HUMANOID_RUN) { idx[0] = 21; idx[1] = 36; idx[2] = 37; idx[3] = 38; }
+  else if (kind == MBRL_COST_DMC_CHEETAH_RUN) { idx[0] = 8; }
+  else if (kind == MBRL_COST_DMC_WALKER_WALK) { idx[0] = 14; idx[1] = 0; idx[2] = 16; }
+}
+// a0: the step's first control; ctl_mean: mean_a(1 - a^2 inside |a| < 1) of the step's controls.
+__device__ __forceinline__ float task_cost(int kind, const float (&p)[4], float a0, float ctl_mean) {
+  if (kind == MBRL_COST_DMC_CARTPOLE_SWINGUP) return dmc_cartpole_cost(p[0], p[1], p[2], a0);
+  if (kind == MBRL_COST_DMC_HUMANOID_RUN) return dmc_humanoid_run_cost(p[0], p[1], p[2], p[3], ctl_mean);
+  if (kind == MBRL_COST_DMC_CHEETAH_RUN) return dmc_cheetah_run_cost(p[0]);
+  return dmc_walker_walk_cost(p[0], p[1], p[2]);
+}
+__host__ __device__ inline bool is_task_cost(int kind) {
+  return kind == MBRL_COST_DMC_CARTPOLE_SWINGUP || kind == MBRL_COST_DMC_HUMANOID_RUN ||
+         kind == MBRL_COST_DMC_CHEETAH_RUN || kind == MBRL_COST_DMC_WALKER_WALK;
+}
+
 }  // namespace mbrl

@@ -337,20 +337,18 @@ extern "C" int mbrl_set_norm(MbrlPlanner* p, const float* mu_s, const float* sd_
 extern "C" int mbrl_set_cost(MbrlPlanner* p, int32_t kind, const float* w, const float* goal, double alpha,
                              double beta) {
   if (!p) return fail(MBRL_E_INVALID, "null planner");
-  MBRL_REQUIRE(kind == MBRL_COST_SMOOTHABS_COSH || kind == MBRL_COST_DMC_CARTPOLE_SWINGUP || kind == MBRL_COST_REWARD_HEAD ||
-                   kind == MBRL_COST_DMC_HUMANOID_RUN,
-               "unknown cost kind");
+  MBRL_REQUIRE(kind == MBRL_COST_SMOOTHABS_COSH || kind == MBRL_COST_REWARD_HEAD || is_task_cost(kind), "unknown cost kind");
   MBRL_CUDA(cudaSetDevice(p->cfg.device));
   MBRL_CUDA(cudaStreamSynchronize(p->stream));
-  if (kind == MBRL_COST_DMC_CARTPOLE_SWINGUP) {
-    MBRL_REQUIRE(p->O >= 5 && p->A >= 1, "cartpole cost needs the 5-d cartpole observation");
-    if (p->cfg.engine != MBRL_ENGINE_SIMT_FP32)
-      return fail(MBRL_E_UNSUPPORTED, "the dm_control task-cost epilogue is implemented for the fp32 engine only");
-  } else if (kind == MBRL_COST_DMC_HUMANOID_RUN) {
-    MBRL_REQUIRE(p->O >= 40 && p->A >= 1, "humanoid cost needs the 67-d egocentric humanoid observation (>= 40 dims)");
-    if (p->cfg.engine != MBRL_ENGINE_SIMT_FP32)
-      return fail(MBRL_E_UNSUPPORTED, "the dm_control task-cost epilogue is implemented for the fp32 engine only");
-    if (beta == 0.0) beta = 1.0;
+  if (is_task_cost(kind)) {
+    int pick[4];
+    task_pick_indices(kind, pick);
+    const int need = std::max(std::max(pick[0], pick[1]), std::max(pick[2], pick[3])) + 1;
+    MBRL_REQUIRE(p->O >= need && p->A >= 1, "observation too short for this dm_control task cost "
+                 "(cartpole 5, cheetah 9, walker 17, humanoid 39 leading entries are read)");
+    if (p->cfg.engine != MBRL_ENGINE_SIMT_FP32 && !tc_supports_task_cost(&p->tc))
+      return fail(MBRL_E_UNSUPPORTED, "the dm_control task-cost epilogue is not implemented for this tensor-core kernel variant");
+    if (beta == 0.0) beta = 1.0;  // unused by these costs; keeps 1/beta finite
   } else if (kind == MBRL_COST_REWARD_HEAD) {
     MBRL_REQUIRE(p->have_reward_head, "mbrl_set_reward_head must be called before selecting the reward-head cost");
     if (p->cfg.engine != MBRL_ENGINE_SIMT_FP32)

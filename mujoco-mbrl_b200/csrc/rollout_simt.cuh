@@ -161,11 +161,13 @@ rollout_simt_kernel(ModelDev m, ActionSource src, Shape sh, const float* __restr
         // CoshLoss: beta^2 * mean_a(cosh(a/beta) - 1); row cost pairs s_{h+1} with a_h
         const float ac = __fmul_rn(m.beta2, __fdiv_rn(act_cost, (float)A));
         cost = __fadd_rn(cost, __fadd_rn(st_cost, ac));
-      } else if (m.cost_kind == MBRL_COST_DMC_CARTPOLE_SWINGUP) {  // O >= 5 checked by the host
-        cost += dmc_cartpole_cost(bufS[0 * TM + t], bufS[1 * TM + t], bufS[4 * TM + t], a0);
-      } else if (m.cost_kind == MBRL_COST_DMC_HUMANOID_RUN) {  // O >= 40 checked by the host
-        cost += dmc_humanoid_run_cost(bufS[21 * TM + t], bufS[36 * TM + t], bufS[37 * TM + t], bufS[38 * TM + t],
-                                      ctl_sum / (float)A);
+      } else if (is_task_cost(m.cost_kind)) {  // the host checked that O covers the picked entries
+        int pick[4];
+        task_pick_indices(m.cost_kind, pick);
+        float p4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) p4[q] = pick[q] >= 0 ? bufS[pick[q] * TM + t] : 0.0f;
+        cost += task_cost(m.cost_kind, p4, a0, ctl_sum / (float)A);
       }
     }
     if (reward_head) {

@@ -314,7 +314,8 @@ __device__ __forceinline__ float cosh_m1_fast(float t) {
 
 // Diagnostic timeline (tests/profiling only): when the debug buffer is armed, tile 1 records
 // clock64() at the hand-over points of every step: slot [h][e], e = 0..15.
-constexpr int kTcDbgFloats = 3 * kTcRows * 256;
+constexpr int kTcDbgCols = 512;  // dump row pitch (the wide engine has 512 hidden columns)
+constexpr int kTcDbgFloats = 3 * kTcRows * kTcDbgCols;
 constexpr int kTcTimelineSteps = 64, kTcTimelineEvents = 32;
 __device__ __forceinline__ void tc_stamp(float* dbg, int h, int e) {
   if (dbg && blockIdx.x == 1 && h < kTcTimelineSteps)
@@ -552,8 +553,8 @@ rollout_tc_kernel(TcGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Action
           if (dbg && blockIdx.x == 0 && h == 0) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              if (full || i < 16) dbg[(layer * kTcRows + trow) * 256 + 32 * c + i] = __uint_as_float(v[i]);
-              if (has2 && (full2 || i < 16)) dbg[(layer * kTcRows + trow) * 256 + 32 * c2 + i] = __uint_as_float(v2[i]);
+              if (full || i < 16) dbg[(layer * kTcRows + trow) * kTcDbgCols + 32 * c + i] = __uint_as_float(v[i]);
+              if (has2 && (full2 || i < 16)) dbg[(layer * kTcRows + trow) * kTcDbgCols + 32 * c2 + i] = __uint_as_float(v2[i]);
             }
           }
 #pragma unroll
@@ -602,7 +603,7 @@ rollout_tc_kernel(TcGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Action
         }
         if (dbg && blockIdx.x == 0 && h == 0 && col0 < g.Op) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) dbg[(2 * kTcRows + trow) * 256 + col0 + i] = __uint_as_float(v[i]);
+          for (int i = 0; i < 16; ++i) dbg[(2 * kTcRows + trow) * kTcDbgCols + col0 + i] = __uint_as_float(v[i]);
         }
         // branch-free: padded table entries are zero, padded outputs are masked by select
         float y[16], term[16];

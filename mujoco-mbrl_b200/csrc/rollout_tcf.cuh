@@ -32,6 +32,7 @@
 #include <cstdlib>
 
 #include "rollout_tc.cuh"
+#include "rollout_tcw.cuh"
 
 namespace mbrl {
 
@@ -404,7 +405,7 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
         tmem_ld_wait();
         if (DBG && dbg && blockIdx.x == 0 && j == 1) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) dbg[(2 * kTcRows + crow) * 256 + 16 * cc + i] = __uint_as_float(v[i]);
+          for (int i = 0; i < 16; ++i) dbg[(2 * kTcRows + crow) * kTcDbgCols + 16 * cc + i] = __uint_as_float(v[i]);
         }
         float term[16];
 #pragma unroll
@@ -453,7 +454,7 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
           tmem_ld_wait();
           if (DBG && dbg && blockIdx.x == 0 && h == 0) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) dbg[(layer * kTcRows + trow) * 256 + 16 * ks + i] = __uint_as_float(v[i]);
+            for (int i = 0; i < 16; ++i) dbg[(layer * kTcRows + trow) * kTcDbgCols + 16 * ks + i] = __uint_as_float(v[i]);
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) pk[i] = pack_relu<FP16>(v[2 * i], v[2 * i + 1]);
@@ -486,12 +487,15 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
 }
 
 // ---- host side of the tensor-core engines ---------------------------------------------------
+enum TcKind { kTcFused = 0, kTcUnfused = 1, kTcWide = 2 };
+
 struct TcModel {
   int ready = 0;
   bool fp16 = true;
-  bool fused = true;   // rollout_tcf_kernel; false -> rollout_tc_kernel (unfused fallback)
+  int kind = kTcFused;  // rollout_tcf_kernel; rollout_tc_kernel (unfused fallback); rollout_tcw_kernel (hidden > 255)
   TcGeom g{};
   TcfGeom fg{};
+  TcwGeom wg{};
   int w_bytes = 0;
   uint8_t* d_wimg = nullptr;
   float* d_dbg = nullptr;  // optional accumulator dump + timeline (tests / profiling)
@@ -500,17 +504,31 @@ struct TcModel {
 inline bool tc_init(TcModel* t, int O, int A, int U, bool fp16, size_t max_smem, std::string* why) {
   t->fp16 = fp16;
   const char* force = getenv("MBRL_TC_UNFUSED");
-  std::string why_f;
-  t->fused = !(force && force[0] == '1') && tcf_geometry(O, A, U, max_smem, &t->fg, &why_f);
-  if (!t->fused && !tc_geometry(O, A, U, max_smem, &t->g, why)) {
+  const char* wide = getenv("MBRL_TC_WIDE");  // tests: run small shapes through the streaming kernel
+  std::string why_f, why_u;
+  if (wide && wide[0] == '1') {
+    if (!tcw_geometry(O, A, U, max_smem, &t->wg, why)) return false;
+    t->kind = kTcWide;
+  } else if (!(force && force[0] == '1') && tcf_geometry(O, A, U, max_smem, &t->fg, &why_f)) {
+    t->kind = kTcFused;
+  } else if (tc_geometry(O, A, U, max_smem, &t->g, &why_u)) {
+    t->kind = kTcUnfused;
+  } else if (tcw_geometry(O, A, U, max_smem, &t->wg, why)) {
+    t->kind = kTcWide;
+  } else {
+    if (!why_u.empty()) *why += "; resident-weight kernel: " + why_u;
     if (!why_f.empty()) *why += "; fused: " + why_f;
     return false;
   }
-  t->w_bytes = t->fused ? t->fg.w_bytes : t->g.w_bytes;
+  t->w_bytes = t->kind == kTcFused ? t->fg.w_bytes : (t->kind == kTcUnfused ? t->g.w_bytes : t->wg.w_bytes);
   if (cudaMalloc((void**)&t->d_wimg, t->w_bytes) != cudaSuccess) { *why = "cudaMalloc failed"; return false; }
   t->ready = 1;
   return true;
 }
+
+// dm_control task-cost epilogues (cost threads pick the entries, sampler threads hand over the
+// control terms): built into the wide kernel.
+inline bool tc_supports_task_cost(const TcModel* t) { return t->kind == kTcWide; }
 
 inline void tc_free(TcModel* t) {
   if (t->d_wimg) cudaFree(t->d_wimg);
@@ -521,8 +539,9 @@ inline void tc_free(TcModel* t) {
 inline bool tc_set_weights(TcModel* t, const float* W1, const float* b1, const float* W2, const float* b2,
                            const float* W3, const float* b3, std::string* why) {
   std::vector<uint16_t> img;
-  if (t->fused) tcf_pack(t->fg, t->fp16, W1, b1, W2, b2, W3, b3, &img);
-  else tc_pack(t->g, t->fp16, W1, b1, W2, b2, W3, &img);  // b3 is added in fp32 in the last epilogue
+  if (t->kind == kTcFused) tcf_pack(t->fg, t->fp16, W1, b1, W2, b2, W3, b3, &img);
+  else if (t->kind == kTcUnfused) tc_pack(t->g, t->fp16, W1, b1, W2, b2, W3, &img);  // b3 is added in fp32 in the last epilogue
+  else tcw_pack(t->wg, t->fp16, W1, b1, W2, b2, W3, &img);
   if (cudaMemcpy(t->d_wimg, img.data(), t->w_bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
     *why = "cudaMemcpy of packed operands failed";
     return false;
@@ -554,15 +573,24 @@ inline cudaError_t tc_launch_rollout(TcModel* t, const ModelDev& m, const Action
                                      cudaStream_t st) {
   (void)num_sms;
   if (!t->ready) return cudaErrorNotReady;
-  if (t->fused) {
-    const bool dbg = t->d_dbg != nullptr;
-    if (t->fp16 && !dbg) return tc_launch_one(rollout_tcf_kernel<true, false>, t->fg, t->fg.smem_bytes, kTcfThreads, t, m, src, sh, d_s0, d_costs, d_states, d_actions, st);
-    if (t->fp16) return tc_launch_one(rollout_tcf_kernel<true, true>, t->fg, t->fg.smem_bytes, kTcfThreads, t, m, src, sh, d_s0, d_costs, d_states, d_actions, st);
-    if (!dbg) return tc_launch_one(rollout_tcf_kernel<false, false>, t->fg, t->fg.smem_bytes, kTcfThreads, t, m, src, sh, d_s0, d_costs, d_states, d_actions, st);
-    return tc_launch_one(rollout_tcf_kernel<false, true>, t->fg, t->fg.smem_bytes, kTcfThreads, t, m, src, sh, d_s0, d_costs, d_states, d_actions, st);
+  const bool dbg = t->d_dbg != nullptr;
+#define MBRL_TC_LAUNCH(KERN, GEOM, THREADS) \
+  return tc_launch_one(KERN, GEOM, (GEOM).smem_bytes, THREADS, t, m, src, sh, d_s0, d_costs, d_states, d_actions, st)
+  if (t->kind == kTcFused) {
+    if (t->fp16 && !dbg) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, false>), t->fg, kTcfThreads);
+    if (t->fp16) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, true>), t->fg, kTcfThreads);
+    if (!dbg) MBRL_TC_LAUNCH((rollout_tcf_kernel<false, false>), t->fg, kTcfThreads);
+    MBRL_TC_LAUNCH((rollout_tcf_kernel<false, true>), t->fg, kTcfThreads);
   }
-  if (t->fp16) return tc_launch_one(rollout_tc_kernel<true>, t->g, t->g.smem_bytes, kTcThreads, t, m, src, sh, d_s0, d_costs, d_states, d_actions, st);
-  return tc_launch_one(rollout_tc_kernel<false>, t->g, t->g.smem_bytes, kTcThreads, t, m, src, sh, d_s0, d_costs, d_states, d_actions, st);
+  if (t->kind == kTcWide) {
+    if (t->fp16 && !dbg) MBRL_TC_LAUNCH((rollout_tcw_kernel<true, false>), t->wg, kTcwThreads);
+    if (t->fp16) MBRL_TC_LAUNCH((rollout_tcw_kernel<true, true>), t->wg, kTcwThreads);
+    if (!dbg) MBRL_TC_LAUNCH((rollout_tcw_kernel<false, false>), t->wg, kTcwThreads);
+    MBRL_TC_LAUNCH((rollout_tcw_kernel<false, true>), t->wg, kTcwThreads);
+  }
+  if (t->fp16) MBRL_TC_LAUNCH(rollout_tc_kernel<true>, t->g, kTcThreads);
+  MBRL_TC_LAUNCH(rollout_tc_kernel<false>, t->g, kTcThreads);
+#undef MBRL_TC_LAUNCH
 }
 
 }  // namespace mbrl

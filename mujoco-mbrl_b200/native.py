@@ -19,6 +19,7 @@ ENGINE_SIMT_FP32, ENGINE_TC_BF16, ENGINE_TC_FP16 = 0, 1, 2
 ENGINES = {"fp32": ENGINE_SIMT_FP32, "simt": ENGINE_SIMT_FP32, "bf16": ENGINE_TC_BF16, "fp16": ENGINE_TC_FP16}
 SAMPLE_INJECT_ACTIONS, SAMPLE_INJECT_NOISE, SAMPLE_GAUSSIAN, SAMPLE_UNIFORM = 0, 1, 2, 3
 COST_SMOOTHABS_COSH, COST_DMC_CARTPOLE_SWINGUP, COST_REWARD_HEAD, COST_DMC_HUMANOID_RUN = 0, 1, 2, 3
+COST_DMC_CHEETAH_RUN, COST_DMC_WALKER_WALK = 4, 5
 
 # every symbol include/mbrl_b200.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
@@ -342,14 +343,16 @@ class NativePlanner:
         return True
 
     def tc_debug(self, enable=True, fetch=False):
-        """Diagnostic: arm / fetch the raw accumulator dump of tile 0, step 0 ([3,128,256]);
-        the clock64 timeline of tile 1 ([64,32] int64) is left in `self.tc_timeline`."""
-        buf = np.zeros(3 * 128 * 256 * 4 + 64 * 32 * 8, np.uint8) if fetch else None
+        """Diagnostic: arm / fetch the raw accumulator dump of tile 0, step 0 ([3,128,512]: three
+        layers, 128 rows, 512-column pitch); the clock64 timeline of tile 1 ([64,32] int64) is left
+        in `self.tc_timeline`."""
+        nb = 3 * 128 * 512 * 4
+        buf = np.zeros(nb + 64 * 32 * 8, np.uint8) if fetch else None
         _check(self.lib.mbrl_tc_debug(self._h, int(enable), _hp(buf)))
         if buf is None:
             return None
-        self.tc_timeline = buf[3 * 128 * 256 * 4:].view(np.int64).reshape(64, 32).copy()
-        return buf[:3 * 128 * 256 * 4].view(np.float32).reshape(3, 128, 256).copy()
+        self.tc_timeline = buf[nb:].view(np.int64).reshape(64, 32).copy()
+        return buf[:nb].view(np.float32).reshape(3, 128, 512).copy()
 
     def emit(self, d_s0, d_best, d_mu_hist, d_sd_hist, iterations, mode, seed=0, d_injected=None, return_mean=False,
              cand_offset=0, env_offset=0):

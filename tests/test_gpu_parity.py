@@ -168,7 +168,7 @@ def test_rollout_ragged_rows_and_batched_envs(native):
 
 def test_humanoid_shape_batched_envs_fp32_engine(native):
     """BASELINE config 5 shape (obs 67, act 21, hidden 512, batched independent environments) on
-    the fp32 engine -- the tensor-core engines do not cover hidden > 255 yet and must say so."""
+    the fp32 engine (tests/test_gpu_tc.py runs the same shape on the weight-streaming tcgen05 kernel)."""
     p = po.synthetic_params(67, 21, 512, seed=9)
     H, n, E = 6, 96, 3
     h = _planner(native, p, H, n, E, iters=2)
@@ -187,7 +187,7 @@ def test_humanoid_shape_batched_envs_fp32_engine(native):
         _, c = po.rollout_costs(p, s0[e], torch.from_numpy(out["actions"][e]), H, 1)
         np.testing.assert_allclose(out["info"]["best_cost"][e], c[0], rtol=5e-5)
     with pytest.raises(native.MbrlError, match="hidden"):
-        native.NativePlanner(67, 21, 512, H, n, E, engine="fp16")
+        native.NativePlanner(67, 21, 600, H, n, E, engine="fp16")  # > 512 hidden units: no tensor-core kernel
 
 
 # ---------------------------------------------------------------------------------------
