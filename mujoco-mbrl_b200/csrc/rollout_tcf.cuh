@@ -506,19 +506,30 @@ inline bool tc_init(TcModel* t, int O, int A, int U, bool fp16, size_t max_smem,
   const char* force = getenv("MBRL_TC_UNFUSED");
   const char* wide = getenv("MBRL_TC_WIDE");  // tests: run small shapes through the streaming kernel
   std::string why_f, why_u;
+  int stage_bytes = 0;  // geometry default
+  if (const char* sk = getenv("MBRL_TCW_STAGE_KB")) { const int v = std::atoi(sk); if (v == 16 || v == 32) stage_bytes = v * 1024; }
   if (wide && wide[0] == '1') {
-    if (!tcw_geometry(O, A, U, max_smem, &t->wg, why)) return false;
+    if (!tcw_geometry(O, A, U, max_smem, &t->wg, why, stage_bytes)) return false;
     t->kind = kTcWide;
   } else if (!(force && force[0] == '1') && tcf_geometry(O, A, U, max_smem, &t->fg, &why_f)) {
     t->kind = kTcFused;
   } else if (tc_geometry(O, A, U, max_smem, &t->g, &why_u)) {
     t->kind = kTcUnfused;
-  } else if (tcw_geometry(O, A, U, max_smem, &t->wg, why)) {
+  } else if (tcw_geometry(O, A, U, max_smem, &t->wg, why, stage_bytes)) {
     t->kind = kTcWide;
   } else {
     if (!why_u.empty()) *why += "; resident-weight kernel: " + why_u;
     if (!why_f.empty()) *why += "; fused: " + why_f;
     return false;
+  }
+  if (t->kind == kTcWide) {
+    // CTAs per cluster sharing one multicast weight stream (MBRL_TCW_CLUSTER=1|2|4 overrides)
+    t->wg.cluster = kTcwDefaultCluster;
+    if (const char* x = getenv("MBRL_TCW_EXP")) t->wg.exp = std::atoi(x);
+    if (const char* c = getenv("MBRL_TCW_CLUSTER")) {
+      const int v = std::atoi(c);
+      if (v == 1 || v == 2 || v == 4) t->wg.cluster = v;
+    }
   }
   t->w_bytes = t->kind == kTcFused ? t->fg.w_bytes : (t->kind == kTcUnfused ? t->g.w_bytes : t->wg.w_bytes);
   if (cudaMalloc((void**)&t->d_wimg, t->w_bytes) != cudaSuccess) { *why = "cudaMalloc failed"; return false; }
@@ -552,17 +563,27 @@ inline bool tc_set_weights(TcModel* t, const float* W1, const float* b1, const f
 template <class Kern, class Geom>
 inline cudaError_t tc_launch_one(Kern kern, const Geom& g, int smem_bytes, int threads, TcModel* t, const ModelDev& m,
                                  const ActionSource& src, const Shape& sh, const float* d_s0, float* d_costs,
-                                 float* d_states, float* d_actions, cudaStream_t st) {
+                                 float* d_states, float* d_actions, cudaStream_t st, int cluster = 1) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return e;
   const unsigned grid = (unsigned)((sh.rows() + kTcRows - 1) / kTcRows);
   // programmatic dependent launch: the prologue (barriers, TMEM, weight TMA) overlaps the predecessor
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = (size_t)smem_bytes; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = getenv("MBRL_NO_PDL") ? 0 : 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (!getenv("MBRL_NO_PDL")) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cluster > 1) {  // weight-streaming kernel: CTAs of a cluster share one multicast weight stream
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = (unsigned)cluster; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+    cfg.gridDim = dim3((grid + cluster - 1) / cluster * cluster);  // surplus CTAs own no valid row but keep the ring protocol
+  }
+  cfg.attrs = attr; cfg.numAttrs = na;
   const uint8_t* wimg = t->d_wimg;
   float* dbg = t->d_dbg;
   return cudaLaunchKernelEx(&cfg, kern, g, wimg, m, src, sh, d_s0, d_costs, d_states, d_actions, dbg);
@@ -575,7 +596,8 @@ inline cudaError_t tc_launch_rollout(TcModel* t, const ModelDev& m, const Action
   if (!t->ready) return cudaErrorNotReady;
   const bool dbg = t->d_dbg != nullptr;
 #define MBRL_TC_LAUNCH(KERN, GEOM, THREADS) \
-  return tc_launch_one(KERN, GEOM, (GEOM).smem_bytes, THREADS, t, m, src, sh, d_s0, d_costs, d_states, d_actions, st)
+  return tc_launch_one(KERN, GEOM, (GEOM).smem_bytes, THREADS, t, m, src, sh, d_s0, d_costs, d_states, d_actions, st, \
+                       t->kind == kTcWide ? t->wg.cluster : 1)
   if (t->kind == kTcFused) {
     if (t->fp16 && !dbg) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, false>), t->fg, kTcfThreads);
     if (t->fp16) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, true>), t->fg, kTcfThreads);
@@ -583,10 +605,17 @@ inline cudaError_t tc_launch_rollout(TcModel* t, const ModelDev& m, const Action
     MBRL_TC_LAUNCH((rollout_tcf_kernel<false, true>), t->fg, kTcfThreads);
   }
   if (t->kind == kTcWide) {
-    if (t->fp16 && !dbg) MBRL_TC_LAUNCH((rollout_tcw_kernel<true, false>), t->wg, kTcwThreads);
-    if (t->fp16) MBRL_TC_LAUNCH((rollout_tcw_kernel<true, true>), t->wg, kTcwThreads);
-    if (!dbg) MBRL_TC_LAUNCH((rollout_tcw_kernel<false, false>), t->wg, kTcwThreads);
-    MBRL_TC_LAUNCH((rollout_tcw_kernel<false, true>), t->wg, kTcwThreads);
+    const bool spec = tcw_matches_spec(t->wg) && !getenv("MBRL_TCW_NO_SPEC");
+    if (spec) {
+      if (t->fp16 && !dbg) MBRL_TC_LAUNCH((rollout_tcw_kernel<true, false, true>), t->wg, kTcwThreads);
+      if (t->fp16) MBRL_TC_LAUNCH((rollout_tcw_kernel<true, true, true>), t->wg, kTcwThreads);
+      if (!dbg) MBRL_TC_LAUNCH((rollout_tcw_kernel<false, false, true>), t->wg, kTcwThreads);
+      MBRL_TC_LAUNCH((rollout_tcw_kernel<false, true, true>), t->wg, kTcwThreads);
+    }
+    if (t->fp16 && !dbg) MBRL_TC_LAUNCH((rollout_tcw_kernel<true, false, false>), t->wg, kTcwThreads);
+    if (t->fp16) MBRL_TC_LAUNCH((rollout_tcw_kernel<true, true, false>), t->wg, kTcwThreads);
+    if (!dbg) MBRL_TC_LAUNCH((rollout_tcw_kernel<false, false, false>), t->wg, kTcwThreads);
+    MBRL_TC_LAUNCH((rollout_tcw_kernel<false, true, false>), t->wg, kTcwThreads);
   }
   if (t->fp16) MBRL_TC_LAUNCH(rollout_tc_kernel<true>, t->g, kTcThreads);
   MBRL_TC_LAUNCH(rollout_tc_kernel<false>, t->g, kTcThreads);

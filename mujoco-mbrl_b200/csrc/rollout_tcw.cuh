@@ -42,8 +42,10 @@ constexpr int kTcwTmaWarp = kTcwMmaWarp + 1;
 constexpr int kTcwThreads = (kTcwTmaWarp + 1) * 32;
 constexpr int kTcwAccCol = 256;      // TMEM column of the chunk accumulator
 constexpr int kTcwMaxStages = 8;
-constexpr int kTcwStageBytes = 16384;
+constexpr int kTcwStageBytes = 16384;  // default ring stage (MBRL_TCW_STAGE_KB overrides: 16 or 32)
+constexpr int kTcwDefaultCluster = 1;  // CTAs per cluster sharing one weight stream (see tc_init)
 constexpr int kTcwBarriers = 2 * kTcwMaxStages + 6;  // full[8], empty[8], x, acc, e0, e1, l1, y
+constexpr int kTcwMaxKx = 16;  // layer-1 K-steps (Kx <= 32 + 128 + 15)
 
 struct TcwGeom {
   int O, A, U;
@@ -58,11 +60,18 @@ struct TcwGeom {
   int tps_h, tps_y;    // tiles per ring stage
   int p1_bytes, p2_bytes, p3_bytes, w_bytes;
   int stages, ycol;
+  int cluster;  // CTAs per thread-block cluster sharing one weight stream (1, 2 or 4)
+  int stage_bytes;  // ring stage size
+  int exp;      // profiling experiments (MBRL_TCW_EXP bit mask; results are garbage when non-zero)
   int tab_off, xa_off, xs_off, one_off, h2_off, ring_off, bar_off, ms_off, ms_floats, smem_bytes;
 };
 
-inline bool tcw_geometry(int O, int A, int U, size_t max_smem, TcwGeom* g, std::string* why) {
+inline bool tcw_geometry(int O, int A, int U, size_t max_smem, TcwGeom* g, std::string* why, int stage_bytes = 0) {
   g->O = O; g->A = A; g->U = U;
+  // A ring stage should hold >= 4 hidden K-step tiles: the MMA thread's per-stage bookkeeping (~150
+  // cycles) then hides behind the MMAs it has queued (measured: 16 KB stages 11.4 ms, 32 KB 9.2 ms at cfg 5).
+  if (stage_bytes == 0) stage_bytes = round_up(U, 64) / 2 * 32 * 4 > kTcwStageBytes ? 2 * kTcwStageBytes : kTcwStageBytes;
+  g->stage_bytes = stage_bytes;
   g->Ka = round_up(A + 1, 8);
   g->Kx = round_up(g->Ka + O, 16);
   g->Np = round_up(U, 64);
@@ -75,27 +84,30 @@ inline bool tcw_geometry(int O, int A, int U, size_t max_smem, TcwGeom* g, std::
   g->SC = (g->Kx - g->Ka) / 8;
   g->tile_h = g->Nc * 32;
   g->tile_y = g->Op * 32;
-  g->tps_h = kTcwStageBytes / g->tile_h;
-  g->tps_y = kTcwStageBytes / g->tile_y;
+  g->tps_h = stage_bytes / g->tile_h;
+  g->tps_y = stage_bytes / g->tile_y;
   g->p1_bytes = (g->Kx / 16) * g->tile_h;
   g->p2_bytes = (g->KH + 1) * g->tile_h;
   g->p3_bytes = g->KH * g->tile_y;
   g->w_bytes = 2 * g->p1_bytes + 2 * g->p2_bytes + g->p3_bytes;
   g->ycol = 256 - g->Op;
-  // fp32 tables: 6 of Op (b3, P, Q, sd, mu, mask), 2 of kMaxAct, cost partials [2][128], task-cost
-  // exchange [2 step parities][a0, ctl][128]
+  g->cluster = 1;
+  g->exp = 0;
+  // fp32 tables: 6 of Op (b3, P, Q, sd, mu, mask), 2 of kMaxAct, cost partials [6][128] (five column
+  // shares of the state cost + the action cost), task-cost exchange [2 step parities][a0, ctl][128]
+  // and picked state entries [2 step parities][4][128]
   g->tab_off = 0;
-  g->xa_off = round_up((6 * g->Op + 2 * kMaxAct + 2 * kTcRows + 4 * kTcRows) * 4, 128);
+  g->xa_off = round_up((6 * g->Op + 2 * kMaxAct + 6 * kTcRows + 4 * kTcRows + 8 * kTcRows) * 4, 128);
   g->xs_off = g->xa_off + 2 * g->QA * 2048;
   g->one_off = g->xs_off + g->SC * 2048;
   g->h2_off = g->one_off + 4096;
   g->ring_off = g->h2_off + g->Nc * 256;
-  const long long fixed = (long long)g->ring_off + 8 * kTcwBarriers + 16;
+  const long long fixed = (long long)g->ring_off + 8 * kTcwBarriers + 16 + 8 * kTcwMaxKx;
   const long long room = (long long)max_smem - fixed;
-  g->stages = (int)std::min<long long>(kTcwMaxStages, room / kTcwStageBytes);
+  g->stages = (int)std::min<long long>(kTcwMaxStages, room / stage_bytes);
   if (g->stages < 3) { *why = "not enough shared memory for the weight ring"; return false; }
-  g->bar_off = g->ring_off + g->stages * kTcwStageBytes;
-  g->smem_bytes = g->bar_off + 8 * kTcwBarriers + 16;
+  g->bar_off = g->ring_off + g->stages * stage_bytes;
+  g->smem_bytes = g->bar_off + 8 * kTcwBarriers + 16 + 8 * kTcwMaxKx;  // barriers, TMEM slot, layer-1 A-descriptor table
   g->ms_off = g->smem_bytes;
   g->ms_floats = (int)std::min<size_t>((max_smem - (size_t)g->smem_bytes) / 4, 4096);
   g->smem_bytes += 4 * g->ms_floats;
@@ -128,7 +140,71 @@ inline void tcw_pack(const TcwGeom& g, bool fp16, const float* W1, const float* 
     for (int k = 0; k < U; ++k) tc_put(img, off3, g.Op, o, k, W3[(size_t)o * U + k], fp16);
 }
 
+// ---- thread-block-cluster variants of the ring primitives ------------------------------------
+// With a cluster of C CTAs every CTA copies 1/C of each stage and MULTICASTS it into the same
+// ring slot of all C CTAs (the data and the mbarrier complete_tx land at the same CTA-relative
+// offsets in every destination), so the stream is read from L2 once per cluster instead of once per
+// CTA; a slot is handed back to all C producers at once by a multicast tcgen05.commit.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+
+// One 16-column half of a hidden-epilogue unit: fp32 accumulators -> relu -> 16 bit -> 8 packed words,
+// stored to TMEM (the next layer's A operand) or, for layer 2 / chunk 0, to h2's shared-memory A tile
+// (two 16-byte row chunks of 8 hidden units each).
 template <bool FP16, bool DBG>
+__device__ __forceinline__ void tcw_epi_half(const uint32_t (&v)[16], int q, uint32_t tmem_dst, uint8_t* smem_dst, float* dbg, int h,
+                                             int trow, int dbg_col) {
+  if (DBG && dbg && blockIdx.x == 0 && h == 0) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dbg[((q >> 1) * kTcRows + trow) * kTcDbgCols + dbg_col + i] = __uint_as_float(v[i]);
+  }
+  uint32_t pk[16];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) pk[i] = pack_relu<FP16>(v[2 * i], v[2 * i + 1]);
+  if (q == 2) {
+    *reinterpret_cast<uint4*>(smem_dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    *reinterpret_cast<uint4*>(smem_dst + 2048) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  } else {
+    tmem_st8(tmem_dst, pk);
+  }
+}
+
+// non-blocking probe of an mbarrier phase
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok;
+}
+
+// SPEC: the geometry class of BASELINE cfg 5 (humanoid-run: Kx = 96, hidden 449..512, Op = 80, 32 KB ring
+// stages, 3 stages) as compile-time constants.  What limits this kernel is the dependent-instruction
+// chain of the ONE thread that issues the MMAs; with constant trip counts and tile sizes its loops
+// unroll into straight-line code whose operand addresses are immediates (the micro-benchmark
+// profiles/ubench_ring.cu reaches the 128-cycle floor per N=256 MMA exactly that way, while generic
+// loops with run-time geometry cost 150-250 cycles per MMA).  tcw_matches_spec() selects it.
+constexpr int kSpecKx = 96, kSpecNp = 512, kSpecOp = 80, kSpecStage = 32768, kSpecStages = 3, kSpecQA = 3, kSpecSC = 9;
+inline bool tcw_matches_spec(const TcwGeom& g) {
+  return g.Kx == kSpecKx && g.Np == kSpecNp && g.Op == kSpecOp && g.stage_bytes == kSpecStage && g.stages == kSpecStages &&
+         g.QA == kSpecQA && g.SC == kSpecSC;
+}
+
+template <bool FP16, bool DBG, bool SPEC>
 __global__ void __launch_bounds__(kTcwThreads, 1)
 rollout_tcw_kernel(TcwGeom g, const uint8_t* __restrict__ wimg, ModelDev m, ActionSource src, Shape sh,
                    const float* __restrict__ s0, float* __restrict__ costs, float* __restrict__ states_out,
@@ -139,29 +215,34 @@ rollout_tcw_kernel(TcwGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
   pdl_trigger();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int O = g.O, A = g.A, H = sh.H;
-  const int KS_X = g.Kx >> 4, KH = g.KH, KC = g.Nc >> 4, NU = g.Nc >> 5;
-  const int QA = g.QA, SC = g.SC, S = g.stages;
+  const int KS_X = SPEC ? kSpecKx >> 4 : g.Kx >> 4, KH = SPEC ? kSpecNp >> 4 : g.KH, KC = SPEC ? kSpecNp >> 5 : g.Nc >> 4;
+  const int NU = SPEC ? kSpecNp >> 6 : g.Nc >> 5;
+  const int QA = SPEC ? kSpecQA : g.QA, SC = SPEC ? kSpecSC : g.SC, S = SPEC ? kSpecStages : g.stages;
+  const int NcC = SPEC ? kSpecNp / 2 : g.Nc, OpC = SPEC ? kSpecOp : g.Op, ycolC = SPEC ? 256 - kSpecOp : g.ycol;
+  const int CL = g.cluster;
+  const uint16_t cl_mask = (uint16_t)((1u << CL) - 1u);
   const bool smooth = m.cost_kind == MBRL_COST_SMOOTHABS_COSH;
 
   float* tab = reinterpret_cast<float*>(smem + g.tab_off);
   float *t_b3 = tab, *t_P = tab + g.Op, *t_Q = tab + 2 * g.Op, *t_sd = tab + 3 * g.Op, *t_mu = tab + 4 * g.Op;
   float *t_M = tab + 5 * g.Op;
   float *t_ainv = tab + 6 * g.Op, *t_aoff = t_ainv + kMaxAct, *costp = t_aoff + kMaxAct;
-  float* xch = costp + 2 * kTcRows;  // [parity][0: a0, 1: ctl_mean][row]
+  float* xch = costp + 6 * kTcRows;  // [parity][0: a0, 1: ctl_mean][row], then picks [parity][4][row]
   uint8_t* const xa = smem + g.xa_off;
   uint8_t* const xs = smem + g.xs_off;
   uint8_t* const h2lo = smem + g.h2_off;
   const int xa_bytes = QA * 2048;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.bar_off);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + g.bar_off + 8 * kTcwBarriers);
+  uint32_t* xdesc = tmem_slot + 4;  // [2 action-tile parities][kTcwMaxKx] low words of the layer-1 A descriptors
   const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kTcwMaxStages;
   const uint32_t bar_x = bar_empty + 8 * kTcwMaxStages, bar_acc = bar_x + 8, bar_e0 = bar_x + 16, bar_e1 = bar_x + 24;
   const uint32_t bar_l1 = bar_x + 32, bar_y = bar_x + 40;
 
   if (warp == kTcwMmaWarp) {
     if (lane == 0) {
-      for (int s = 0; s < kTcwMaxStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-      mbar_init(bar_x, 2);  // sampler group + cost group
+      for (int s = 0; s < kTcwMaxStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL); }  // empty: one commit per CTA of the cluster
+      mbar_init(bar_x, 1 + kTcwCostWarp0 + 4);  // sampler group + the 20 warps that write the state tile
       mbar_init(bar_acc, 1); mbar_init(bar_e0, kTcwEpiWarps); mbar_init(bar_e1, kTcwEpiWarps);
       mbar_init(bar_l1, 1); mbar_init(bar_y, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -192,15 +273,17 @@ rollout_tcw_kernel(TcwGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
   }
   fence_proxy_async();
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all();  // every CTA's barriers are initialised before any peer signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const long long R = sh.rows();
 
   if (warp == kTcwTmaWarp) {
     // ================= weight producer =================
-    if (elect_one()) {
+    if (!(g.exp & 1) && elect_one()) {
       const uint32_t ring = smem_u32(smem + g.ring_off);
+      const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
       uint32_t st = 0, ph = 0;
       for (int h = 0; h < H; ++h) {
         uint32_t off = 0;
@@ -212,8 +295,13 @@ rollout_tcw_kernel(TcwGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
           for (uint32_t done = 0; done < total; done += per) {
             const uint32_t n = min(per, total - done);
             mbar_wait(bar_empty + 8 * st, ph ^ 1);  // first lap: passes at once on a fresh barrier
-            mbar_arrive_expect_tx(bar_full + 8 * st, n);
-            bulk_g2s(ring + st * kTcwStageBytes, wimg + off, n, bar_full + 8 * st);
+            mbar_arrive_expect_tx(bar_full + 8 * st, n);  // the whole stage: own slice + the peers' multicasts
+            if (CL > 1) {
+              const uint32_t slice = n / (uint32_t)CL;  // stage sizes are multiples of 512 bytes
+              bulk_g2s_mc(ring + st * (uint32_t)g.stage_bytes + crank * slice, wimg + off + crank * slice, slice, bar_full + 8 * st, cl_mask);
+            } else {
+              bulk_g2s(ring + st * (uint32_t)g.stage_bytes, wimg + off, n, bar_full + 8 * st);
+            }
             off += n;
             if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
           }
@@ -222,108 +310,157 @@ rollout_tcw_kernel(TcwGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
     }
     __syncwarp();
   } else if (warp == kTcwMmaWarp) {
-    // ================= MMA issuer warp (converged; one elected lane issues) =================
-    const uint32_t idesc_h = umma_idesc(g.Nc, FP16), idesc_y = umma_idesc(g.Op, FP16);
-    const uint32_t ring = smem_u32(smem + g.ring_off);
-    const uint64_t d_ring_h = umma_desc(ring, (uint32_t)g.Nc * 16, 128);
-    const uint64_t d_ring_y = umma_desc(ring, (uint32_t)g.Op * 16, 128);
-    const uint64_t d_one = umma_desc(smem_u32(smem + g.one_off), 2048, 128);
-    const uint64_t d_h2 = umma_desc(smem_u32(h2lo), 2048, 128);
-    const uint32_t xa0 = smem_u32(xa), xs0 = smem_u32(xs);
-    const uint32_t tm_h = tmem, tm_acc = tmem + kTcwAccCol, tm_y = tmem + (uint32_t)g.ycol;
-    uint32_t st = 0, ph = 0, e0_cnt = 0, e1_cnt = 0;
-    auto wait_epi = [&](int r) {
-      if (r == 0) { mbar_wait(bar_e0, e0_cnt & 1); ++e0_cnt; }
-      else { mbar_wait(bar_e1, e1_cnt & 1); ++e1_cnt; }
-      tc_fence_after();
-    };
-    auto advance = [&]() { if (++st == (uint32_t)S) { st = 0; ph ^= 1; } };
+    // ================= MMA issuer: ONE elected lane runs the whole loop =================
+    // tcgen05.mma issue blocks the issuing thread for about the MMA's own duration (queue depth ~2), so
+    // whatever this thread does between two MMAs beyond ~one MMA time leaves the tensor pipe idle.
+    // Measured on the first version of this loop (per stage: warp-converged wait, elect, 64-bit
+    // descriptor adds, runtime-trip-count loops, __syncwarp): ~300 cycles per ring stage on top of its
+    // two 128-cycle MMAs, tensor pipe 35 % busy.  Hence: descriptors as (lo, hi) words (only the
+    // 14-bit start-address field of the low word changes), incremental ring bookkeeping, compile-time
+    // unrolled stages on the hot layer-2 path, and the next stage's full barrier is PROBED
+    // (mbarrier.test_wait) before the current stage's MMAs are issued, so its latency hides behind them.
+    if (elect_one()) {
+      const uint32_t idesc_h = umma_idesc(NcC, FP16), idesc_y = umma_idesc(OpC, FP16);
+      const uint32_t dhi = (128u >> 4) | (1u << 14);  // SBO = 128 bytes; descriptor version 1 (bit 46)
+      auto dlo = [](uint32_t saddr, uint32_t lbo_bytes) { return ((saddr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16); };
+      auto d64 = [dhi](uint32_t lo) { return ((uint64_t)dhi << 32) | lo; };
+      const uint32_t lo_ring_h = dlo(smem_u32(smem + g.ring_off), (uint32_t)NcC * 16);
+      const uint32_t lo_ring_y = dlo(smem_u32(smem + g.ring_off), (uint32_t)OpC * 16);
+      const uint32_t lo_one = dlo(smem_u32(smem + g.one_off), 2048), lo_h2 = dlo(smem_u32(h2lo), 2048);
+      const uint32_t xa0 = smem_u32(xa), xs0 = smem_u32(xs);
+      // The 512-column allocation necessarily starts at TMEM address 0 (checked below): using the literal
+      // keeps every MMA operand address in uniform registers instead of behind the shared-memory load
+      // of the allocation slot (one R2UR move per operand per MMA otherwise).
+      if (tmem != 0u) __trap();
+      const uint32_t tm_h = 0u, tm_acc = kTcwAccCol, tm_y = (uint32_t)ycolC;
+      const uint32_t tile_h16 = SPEC ? (uint32_t)(kSpecNp / 2 * 32) >> 4 : (uint32_t)g.tile_h >> 4;
+      const uint32_t tile_y16 = SPEC ? (uint32_t)(kSpecOp * 32) >> 4 : (uint32_t)g.tile_y >> 4;
+      const int tps_h = SPEC ? kSpecStage / (kSpecNp / 2 * 32) : g.tps_h, tps_y = SPEC ? kSpecStage / (kSpecOp * 32) : g.tps_y;
+      const uint32_t stage16 = SPEC ? (uint32_t)kSpecStage >> 4 : (uint32_t)g.stage_bytes >> 4;
+      const bool use_ring = !(g.exp & 1);
+      uint32_t st = 0, ph = 0, off16 = 0, ready = 0;  // ring stage, phase, offset in 16-byte units, "already full" probe
+      uint32_t e0_ph = 0, e1_ph = 0;
+      // layer-1 A descriptors: K-step ks of the input tile = its 8-wide chunks 2ks, 2ks+1; the action
+      // chunks live in the double-buffered action tile, the state chunks in the state tile, and the
+      // descriptor's LBO is simply the distance between the two chunks
+      for (int par = 0; par < 2; ++par)
+        for (int ks = 0; ks < KS_X; ++ks) {
+          const int c0 = 2 * ks, c1 = c0 + 1;
+          const uint32_t xa_cur = xa0 + (uint32_t)(par * xa_bytes);
+          const uint32_t a0 = c0 < QA ? xa_cur + (uint32_t)c0 * 2048u : xs0 + (uint32_t)(c0 - QA) * 2048u;
+          const uint32_t a1 = c1 < QA ? xa_cur + (uint32_t)c1 * 2048u : xs0 + (uint32_t)(c1 - QA) * 2048u;
+          xdesc[par * kTcwMaxKx + ks] = dlo(a0, a1 - a0);
+        }
+      auto wait_epi = [&]() {  // both release rounds of the running epilogue chunk
+        mbar_wait(bar_e0, e0_ph); e0_ph ^= 1;
+        mbar_wait(bar_e1, e1_ph); e1_ph ^= 1;
+        tc_fence_after();
+      };
+      auto acquire = [&]() {
+        if (use_ring && !ready) mbar_wait(bar_full + 8 * st, ph);
+        tc_fence_after();
+        const bool wrap = st + 1 == (uint32_t)S;
+        ready = use_ring ? mbar_test(bar_full + (wrap ? 0u : 8 * st + 8), wrap ? ph ^ 1 : ph) : 1u;
+      };
+      auto release = [&]() {
+        if (use_ring) { if (CL > 1) tc_commit_mc(bar_empty + 8 * st, cl_mask); else tc_commit(bar_empty + 8 * st); }
+        if (++st == (uint32_t)S) { st = 0; off16 = 0; ph ^= 1; } else off16 += stage16;
+      };
 
-    for (int h = 0; h < H; ++h) {
-      mbar_wait(bar_x, h & 1);
-      tc_fence_after();
-      const uint32_t xa_cur = xa0 + (uint32_t)((h & 1) * xa_bytes);
-      // ---- layer 1, two chunks: ACC = x . W1[chunk]^T ----
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        if (c == 1) { wait_epi(0); wait_epi(1); }  // ACC drained by the epilogue of chunk 0
-#pragma unroll 1
-        for (int t0 = 0; t0 < KS_X; t0 += g.tps_h) {
-          const int n = min(g.tps_h, KS_X - t0);
-          mbar_wait(bar_full + 8 * st, ph);
-          tc_fence_after();
-          if (elect_one()) {
-            for (int i = 0; i < n; ++i) {
-              // K-step ks of the input tile = its 8-wide chunks 2ks, 2ks+1; the action chunks live in
-              // the double-buffered action tile, the state chunks in the state tile: LBO is simply
-              // the distance between the two chunks
-              const int ks = t0 + i, c0 = 2 * ks, c1 = c0 + 1;
-              const uint32_t a0 = c0 < QA ? xa_cur + (uint32_t)c0 * 2048u : xs0 + (uint32_t)(c0 - QA) * 2048u;
-              const uint32_t a1 = c1 < QA ? xa_cur + (uint32_t)c1 * 2048u : xs0 + (uint32_t)(c1 - QA) * 2048u;
-              const uint64_t bd = d_ring_h + (uint64_t)((st * kTcwStageBytes + (uint32_t)(i * g.tile_h)) >> 4);
-              mma_ss(tm_acc, umma_desc(a0, a1 - a0, 128), bd, idesc_h, ks > 0);
+      for (int h = 0; h < H; ++h) {
+        mbar_wait(bar_x, h & 1);
+        tc_fence_after();
+        if (DBG) tc_stamp(dbg, h, 0);
+        const uint32_t* xd = xdesc + (h & 1) * kTcwMaxKx;
+        // ---- layer 1, two chunks: ACC = x . W1[chunk]^T ----
+#pragma unroll (SPEC ? 16 : 1)
+        for (int c = 0; c < 2; ++c) {
+          if (c == 1) wait_epi();  // ACC drained by the epilogue of chunk 0
+          if (DBG) tc_stamp(dbg, h, 1 + 2 * c);
+#pragma unroll (SPEC ? 16 : 1)
+          for (int t0 = 0; t0 < KS_X; t0 += tps_h) {
+            const int n = min(tps_h, KS_X - t0);
+            acquire();
+            uint32_t blo = lo_ring_h + off16;
+#pragma unroll (SPEC ? 4 : 1)
+            for (int i = 0; i < n; ++i, blo += tile_h16)
+              mma_ss(tm_acc, d64(xd[t0 + i]), d64(blo), idesc_h, (t0 + i) > 0);
+            release();
+          }
+          tc_commit(bar_acc);
+          if (c == 1) tc_commit(bar_l1);  // the action tile of this step is free again
+          if (DBG) tc_stamp(dbg, h, 2 + 2 * c);
+        }
+        // ---- layer 2, two chunks: ACC = h1 . W2[chunk]^T + b2 (KH TS K-steps, then the b2 K-step) ----
+#pragma unroll (SPEC ? 16 : 1)
+        for (int c = 0; c < 2; ++c) {
+          wait_epi();  // c == 0: h1 complete in TMEM; c == 1: h2's lower half in shared memory
+          if (DBG) tc_stamp(dbg, h, 5 + 2 * c);
+          int ks = 0;
+          uint32_t a = tm_h;
+          if (tps_h == 2) {  // hidden 512: two 8 KB tiles per stage, straight-line
+#pragma unroll (SPEC ? 16 : 1)
+            for (; ks + 2 <= KH; ks += 2, a += 16) {
+              acquire();
+              const uint32_t blo = lo_ring_h + off16;
+              mma_ts(tm_acc, a, d64(blo), idesc_h, ks > 0);
+              mma_ts(tm_acc, a + 8, d64(blo + tile_h16), idesc_h, 1);
+              release();
             }
-            tc_commit(bar_empty + 8 * st);
-            if (t0 + n == KS_X) {
-              tc_commit(bar_acc);
-              if (c == 1) tc_commit(bar_l1);  // the action tile of this step is free again
+          } else if (tps_h == 4) {
+#pragma unroll (SPEC ? 16 : 1)
+            for (; ks + 4 <= KH; ks += 4, a += 32) {
+              acquire();
+              const uint32_t blo = lo_ring_h + off16;
+              mma_ts(tm_acc, a, d64(blo), idesc_h, ks > 0);
+              mma_ts(tm_acc, a + 8, d64(blo + tile_h16), idesc_h, 1);
+              mma_ts(tm_acc, a + 16, d64(blo + 2 * tile_h16), idesc_h, 1);
+              mma_ts(tm_acc, a + 24, d64(blo + 3 * tile_h16), idesc_h, 1);
+              release();
             }
           }
-          __syncwarp();
-          advance();
-        }
-      }
-      // ---- layer 2, two chunks: ACC = h1 . W2[chunk]^T + b2 ----
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        wait_epi(0); wait_epi(1);  // c == 0: h1 complete in TMEM; c == 1: h2's lower half in shared memory
-#pragma unroll 1
-        for (int t0 = 0; t0 <= KH; t0 += g.tps_h) {
-          const int n = min(g.tps_h, KH + 1 - t0);
-          mbar_wait(bar_full + 8 * st, ph);
-          tc_fence_after();
-          if (elect_one()) {
-            for (int i = 0; i < n; ++i) {
-              const int ks = t0 + i;
-              const uint64_t bd = d_ring_h + (uint64_t)((st * kTcwStageBytes + (uint32_t)(i * g.tile_h)) >> 4);
-              if (ks < KH) mma_ts(tm_acc, tm_h + 8u * (uint32_t)ks, bd, idesc_h, ks > 0);
-              else mma_ss(tm_acc, d_one, bd, idesc_h, 1);
+#pragma unroll (SPEC ? 16 : 1)
+          while (ks <= KH) {  // remaining stages (always the one that ends with the b2 tile)
+            const int n = min(tps_h, KH + 1 - ks);
+            acquire();
+            uint32_t blo = lo_ring_h + off16;
+#pragma unroll (SPEC ? 4 : 1)
+            for (int i = 0; i < n; ++i, ++ks, blo += tile_h16) {
+              if (ks < KH) { mma_ts(tm_acc, a, d64(blo), idesc_h, ks > 0); a += 8; }
+              else mma_ss(tm_acc, d64(lo_one), d64(blo), idesc_h, 1);
             }
-            tc_commit(bar_empty + 8 * st);
-            if (t0 + n == KH + 1) tc_commit(bar_acc);
+            release();
           }
-          __syncwarp();
-          advance();
+          tc_commit(bar_acc);
+          if (DBG) tc_stamp(dbg, h, 6 + 2 * c);
         }
-      }
-      // ---- layer 3: y = h2 . W3^T; lower half from shared memory, upper half from TMEM as released ----
-      {
-        bool w0 = false, w1 = false;
-#pragma unroll 1
-        for (int t0 = 0; t0 < KH; t0 += g.tps_y) {
-          const int n = min(g.tps_y, KH - t0);
-          mbar_wait(bar_full + 8 * st, ph);
-          tc_fence_after();
-          const int last_ks = t0 + n - 1;
-          if (!w0 && last_ks >= KC) { wait_epi(0); w0 = true; }
-          if (!w1 && last_ks >= KC + 8) { wait_epi(1); w1 = true; }
-          if (elect_one()) {
-            for (int i = 0; i < n; ++i) {
-              const int ks = t0 + i;
-              const uint64_t bd = d_ring_y + (uint64_t)((st * kTcwStageBytes + (uint32_t)(i * g.tile_y)) >> 4);
-              if (ks < KC) mma_ss(tm_y, d_h2 + (uint64_t)(ks * (4096 >> 4)), bd, idesc_y, ks > 0);
-              else mma_ts(tm_y, tm_h + 8u * (uint32_t)(ks - KC), bd, idesc_y, 1);
-            }
-            tc_commit(bar_empty + 8 * st);
-            if (t0 + n == KH) tc_commit(bar_y);
-          }
-          __syncwarp();
-          advance();
+        // ---- layer 3: y = h2 . W3^T; lower half from shared memory, upper half from TMEM as released ----
+        {
+          // N = Op MMAs are short (~26 + 0.43*Op cycles): the per-MMA bookkeeping is one counter
+          int ks = 0, rem = KH, left = 0;
+          uint32_t alo = lo_h2, a = tm_h, blo = 0;
+          auto tile_begin = [&]() { if (left == 0) { acquire(); left = min(tps_y, rem); rem -= left; blo = lo_ring_y + off16; } };
+          auto tile_end = [&]() { blo += tile_y16; if (--left == 0) release(); };
+#pragma unroll (SPEC ? 16 : 1)
+          for (; ks < KC; ++ks, alo += 4096u >> 4) { tile_begin(); mma_ss(tm_y, d64(alo), d64(blo), idesc_y, ks > 0); tile_end(); }
+          // the chunk-1 epilogue releases h2's upper half in two rounds: K-steps [KC, KC+8) and the rest
+          if (DBG) tc_stamp(dbg, h, 26);
+          mbar_wait(bar_e0, e0_ph); e0_ph ^= 1; tc_fence_after();
+          if (DBG) tc_stamp(dbg, h, 27);
+          const int r0_end = min(KC + 8, KH);
+#pragma unroll (SPEC ? 16 : 1)
+          for (; ks < r0_end; ++ks, a += 8) { tile_begin(); mma_ts(tm_y, a, d64(blo), idesc_y, 1); tile_end(); }
+          if (DBG) tc_stamp(dbg, h, 28);
+          mbar_wait(bar_e1, e1_ph); e1_ph ^= 1; tc_fence_after();  // (a round without units still completes)
+          if (DBG) tc_stamp(dbg, h, 29);
+#pragma unroll (SPEC ? 16 : 1)
+          for (; ks < KH; ++ks, a += 8) { tile_begin(); mma_ts(tm_y, a, d64(blo), idesc_y, 1); tile_end(); }
+          tc_commit(bar_y);
+          if (DBG) tc_stamp(dbg, h, 9);
         }
-        if (!w0) wait_epi(0);
-        if (!w1) wait_epi(1);  // (a round without units still completes: keep the phases in step)
       }
     }
+    __syncwarp();
   } else if (warp >= kTcwSampWarp0) {
     // ================= sampler threads (one per row) =================
     const int srow = tid - kTcwSampWarp0 * 32;
@@ -355,6 +492,7 @@ rollout_tcw_kernel(TcwGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
       // layer 1 of step hs-1 has finished reading action tile (hs-1)&1; tile hs&1 was last read by
       // step hs-2, and the exchange slot hs&1 by the cost threads of step hs-2
       if (hs >= 1) mbar_wait(bar_l1, (hs - 1) & 1);
+      if (DBG && srow == 0) tc_stamp(dbg, hs, 13);
       float acc = 0.f, ctl = 0.f, first = 0.f;
       float* aout = (actions_out && valid) ? actions_out + ((long long)hs * R + row) * A : nullptr;
       uint8_t* xt = xa + (hs & 1) * xa_bytes;
@@ -364,9 +502,11 @@ rollout_tcw_kernel(TcwGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
         float v[8];
         {
           float t4[4], u4[4];
-          if (8 * q < A) raw_action4(src, A, H, hs, env_l, cand_l, row, R, 2 * q, t4, pm, ps);
+          if (g.exp & 4) { t4[0] = t4[1] = t4[2] = t4[3] = 0.25f; }
+          else if (8 * q < A) raw_action4(src, A, H, hs, env_l, cand_l, row, R, 2 * q, t4, pm, ps);
           else { t4[0] = t4[1] = t4[2] = t4[3] = 0.f; }
-          if (8 * q + 4 < A) raw_action4(src, A, H, hs, env_l, cand_l, row, R, 2 * q + 1, u4, pm, ps);
+          if (g.exp & 4) { u4[0] = u4[1] = u4[2] = u4[3] = 0.25f; }
+          else if (8 * q + 4 < A) raw_action4(src, A, H, hs, env_l, cand_l, row, R, 2 * q + 1, u4, pm, ps);
           else { u4[0] = u4[1] = u4[2] = u4[3] = 0.f; }
           v[0] = t4[0]; v[1] = t4[1]; v[2] = t4[2]; v[3] = t4[3];
           v[4] = u4[0]; v[5] = u4[1]; v[6] = u4[2]; v[7] = u4[3];
@@ -396,154 +536,196 @@ rollout_tcw_kernel(TcwGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
       xch[((hs & 1) * 2 + 1) * kTcRows + srow] = ctl * inv_A;
       fence_proxy_async();   // generic-proxy tile writes -> visible to the MMA (async proxy)
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (srow == 0) mbar_arrive(bar_x);
+      if (srow == 0) { mbar_arrive(bar_x); if (DBG) tc_stamp(dbg, hs, 14); }
     }
-    costp[kTcRows + srow] = act_total;
-  } else if (warp >= kTcwCostWarp0) {
-    // ================= cost threads (one per row) =================
-    const int crow = tid - kTcwCostWarp0 * 32;
-    const long long row = (long long)blockIdx.x * kTcRows + crow;
+    costp[5 * kTcRows + srow] = act_total;
+  } else {
+    // ================= hidden-epilogue warps 0-15 and cost warps 16-19 =================
+    // All 20 warps share the OUTPUT epilogue: five warps own each TMEM lane quarter (warp & 3) and
+    // split the y columns in 16-column groups (group index = warp >> 2, +5, ...), so the y -> cost ->
+    // next-input-tile hand-over -- which sits on the step's critical path -- costs one group per
+    // thread instead of all Op columns in one thread.
+    const int yw = warp >> 2, quarter = warp & 3;
+    const int trow = quarter * 32 + lane;
+    const long long row = (long long)blockIdx.x * kTcRows + trow;
     const bool valid = row < R;
     const int env_l = valid ? (int)(row / sh.N) : 0;
-    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    int pick[4];
-    task_pick_indices(m.cost_kind, pick);
+    const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
+    const int NG = OpC >> 4;
     float st_total = 0.f;
     pdl_wait();
-    // step 0: the normalised initial state
-    for (int j = 0; j < SC; ++j) {
-      float xn[8];
+    // step 0: the normalised initial state, this warp's chunks of the state tile
+    for (int gi = yw; gi < NG; gi += 5) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int o = 8 * j + i;
-        xn[i] = (o < O && valid) ? (dep_load(s0 + (long long)env_l * O + o) - t_mu[o]) / t_sd[o] : 0.f;
+      for (int jj = 0; jj < 2; ++jj) {
+        const int j = 2 * gi + jj;
+        if (j < SC) {
+          float xn[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int o = 8 * j + i;
+            xn[i] = (o < O && valid) ? (dep_load(s0 + (long long)env_l * O + o) - t_mu[o]) / t_sd[o] : 0.f;
+          }
+          uint4 pk;
+          pk.x = pack2<FP16>(xn[0], xn[1]); pk.y = pack2<FP16>(xn[2], xn[3]);
+          pk.z = pack2<FP16>(xn[4], xn[5]); pk.w = pack2<FP16>(xn[6], xn[7]);
+          *reinterpret_cast<uint4*>(xs + j * 2048 + trow * 16) = pk;
+        }
       }
-      uint4 pk;
-      pk.x = pack2<FP16>(xn[0], xn[1]); pk.y = pack2<FP16>(xn[2], xn[3]);
-      pk.z = pack2<FP16>(xn[4], xn[5]); pk.w = pack2<FP16>(xn[6], xn[7]);
-      *reinterpret_cast<uint4*>(xs + j * 2048 + crow * 16) = pk;
     }
     fence_proxy_async();
-    asm volatile("bar.sync 2, 128;" ::: "memory");
-    if (crow == 0) mbar_arrive(bar_x);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_x);
 
     for (int h = 0; h < H; ++h) {
+      if (warp < kTcwEpiWarps) {
+        const int wg = yw;
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {  // L1 chunk 0, L1 chunk 1, L2 chunk 0, L2 chunk 1
+          mbar_wait(bar_acc, q & 1);  // accumulator completion #(4h + q)
+          tc_fence_after();
+          if (DBG && tid == 0) tc_stamp(dbg, h, 16 + 2 * q);
+          {
+            // This warp's two 32-column units of the chunk (release rounds 0 and 1), processed as four
+            // 16-column halves through two register buffers so that a TMEM load is always in flight
+            // while the previous half is converted and stored.
+            const int u0 = wg, u1 = 4 + wg;
+            const bool has0 = u0 < NU && !(g.exp & 2), has1 = u1 < NU && !(g.exp & 2);
+            const uint32_t src0 = lane_base + (uint32_t)(kTcwAccCol + 32 * u0), src1 = lane_base + (uint32_t)(kTcwAccCol + 32 * u1);
+            const uint32_t dst = lane_base + (uint32_t)(q == 1 ? NcC >> 1 : 0);
+            uint32_t va[16], vb[16];
+            if (has0) { tmem_ld16(src0, va); tmem_ld16(src0 + 16, vb); tmem_ld_wait(); }
+            if (has0) {
+              tcw_epi_half<FP16, DBG>(va, q, dst + 16 * u0, h2lo + (4 * u0) * 2048 + trow * 16, dbg, h, trow, (q & 1) * NcC + 32 * u0);
+              if (has1) tmem_ld16(src1, va);
+              tcw_epi_half<FP16, DBG>(vb, q, dst + 16 * u0 + 8, h2lo + (4 * u0 + 2) * 2048 + trow * 16, dbg, h, trow, (q & 1) * NcC + 32 * u0 + 16);
+              if (has1) tmem_ld16(src1 + 16, vb);
+              if (q == 2) fence_proxy_async(); else tmem_st_wait();
+              tc_fence_before();
+            } else if (has1) { tmem_ld16(src1, va); tmem_ld16(src1 + 16, vb); }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_e0);
+            if (has1) {
+              tmem_ld_wait();
+              tcw_epi_half<FP16, DBG>(va, q, dst + 16 * u1, h2lo + (4 * u1) * 2048 + trow * 16, dbg, h, trow, (q & 1) * NcC + 32 * u1);
+              tcw_epi_half<FP16, DBG>(vb, q, dst + 16 * u1 + 8, h2lo + (4 * u1 + 2) * 2048 + trow * 16, dbg, h, trow, (q & 1) * NcC + 32 * u1 + 16);
+              if (q == 2) fence_proxy_async(); else tmem_st_wait();
+              tc_fence_before();
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_e1);
+          }
+          if (DBG && tid == 0) tc_stamp(dbg, h, 17 + 2 * q);
+        }
+      }
+      // ---- output epilogue: y + b3 (fp32), un-normalise, cost, next input tile ----
       mbar_wait(bar_y, h & 1);
       tc_fence_after();
-      float* sout = (states_out && valid) ? states_out + ((long long)h * R + row) * O : nullptr;
-      float p4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (DBG && tid == 0) tc_stamp(dbg, h, 11);
+      float* pk_slot = xch + 4 * kTcRows + (h & 1) * 4 * kTcRows;  // task-cost picks [parity][4][row]
+      // Critical path first: y -> next step's state tile -> x-ready; the cost of step h is accumulated
+      // afterwards, under the next step's layer-1 MMAs.  (Rows of W3 beyond O are zero and b3 is
+      // zero-padded, so padded y columns are exactly 0 without a mask.)
+      const bool one_group = NG <= 5;  // every warp owns at most one 16-column group: keep its y in registers
+      uint32_t v[16];
+      if (one_group) {
+        if (yw < NG) {
+          tmem_ld16(lane_base + (uint32_t)(ycolC + 16 * yw), v);
+          tmem_ld_wait();
+        }
+      }
+      if (h + 1 < H) {
 #pragma unroll 1
-      for (int cc = 0; cc < (g.Op >> 4); ++cc) {
-        uint32_t v[32];
-        tmem_ld16(lane_base + (uint32_t)(g.ycol + 16 * cc), v);
-        tmem_ld_wait();
-        if (DBG && dbg && blockIdx.x == 0 && h == 0) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) dbg[(2 * kTcRows + crow) * kTcDbgCols + 16 * cc + i] = __uint_as_float(v[i]);
-        }
-        float y[16], term[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int o = 16 * cc + i;  // < Op: tables are Op long, padded entries are zero / masked
-          const float raw = __uint_as_float(v[i]);
-          y[i] = (raw + t_b3[o]) * t_M[o];              // normalised prediction == next input
-          const float x = fmaf(raw, t_P[o], t_Q[o]);    // (s - goal) * w with s = y*sd + mu
-          term[i] = (fast_sqrt(fmaf(x, x, m.alpha2)) - m.alpha) * t_M[o];
-        }
-        if (smooth)
-          st_total += ((term[0] + term[1]) + (term[2] + term[3])) + ((term[4] + term[5]) + (term[6] + term[7])) +
-                      (((term[8] + term[9]) + (term[10] + term[11])) + ((term[12] + term[13]) + (term[14] + term[15])));
-        else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int o = 16 * cc + i;
-            const float s = fmaf(y[i], t_sd[o], t_mu[o]);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) p4[q] = (o == pick[q]) ? s : p4[q];
-          }
-        }
-        if (sout) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int o = 16 * cc + i;
-            if (o < O) sout[o] = fmaf(y[i], t_sd[o], t_mu[o]);  // unnormalize_state (data.py:255-257)
-          }
-        }
-        if (h + 1 < H) {
+        for (int gi = yw; gi < NG; gi += 5) {
+          if (!one_group) { tmem_ld16(lane_base + (uint32_t)(ycolC + 16 * gi), v); tmem_ld_wait(); }
 #pragma unroll
           for (int jj = 0; jj < 2; ++jj) {
-            const int j = 2 * cc + jj;
+            const int j = 2 * gi + jj;
             if (j < SC) {
+              const float4 ba = *reinterpret_cast<const float4*>(t_b3 + 16 * gi + 8 * jj), bb = *reinterpret_cast<const float4*>(t_b3 + 16 * gi + 8 * jj + 4);
               uint4 pk;
-              pk.x = pack2<FP16>(y[8 * jj + 0], y[8 * jj + 1]); pk.y = pack2<FP16>(y[8 * jj + 2], y[8 * jj + 3]);
-              pk.z = pack2<FP16>(y[8 * jj + 4], y[8 * jj + 5]); pk.w = pack2<FP16>(y[8 * jj + 6], y[8 * jj + 7]);
-              *reinterpret_cast<uint4*>(xs + j * 2048 + crow * 16) = pk;
+              pk.x = pack2<FP16>(__uint_as_float(v[8 * jj + 0]) + ba.x, __uint_as_float(v[8 * jj + 1]) + ba.y);
+              pk.y = pack2<FP16>(__uint_as_float(v[8 * jj + 2]) + ba.z, __uint_as_float(v[8 * jj + 3]) + ba.w);
+              pk.z = pack2<FP16>(__uint_as_float(v[8 * jj + 4]) + bb.x, __uint_as_float(v[8 * jj + 5]) + bb.y);
+              pk.w = pack2<FP16>(__uint_as_float(v[8 * jj + 6]) + bb.z, __uint_as_float(v[8 * jj + 7]) + bb.w);
+              *reinterpret_cast<uint4*>(xs + j * 2048 + trow * 16) = pk;
             }
           }
         }
-      }
-      if (!smooth)
-        st_total += task_cost(m.cost_kind, p4, xch[((h & 1) * 2 + 0) * kTcRows + crow], xch[((h & 1) * 2 + 1) * kTcRows + crow]);
-      if (h + 1 < H) {
         fence_proxy_async();   // generic-proxy writes of the state tile -> visible to the MMA
-        tc_fence_before();     // our tcgen05.ld of y is ordered before the columns are reused
-        asm volatile("bar.sync 2, 128;" ::: "memory");
-        if (crow == 0) mbar_arrive(bar_x);
-      }
-    }
-    costp[crow] = valid ? st_total : 0.f;
-  } else {
-    // ================= hidden-epilogue threads =================
-    const int wg = warp >> 2, quarter = warp & 3;
-    const int trow = quarter * 32 + lane;
-    const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
-    uint32_t acc_cnt = 0;
-    for (int h = 0; h < H; ++h) {
-#pragma unroll 1
-      for (int q = 0; q < 4; ++q) {  // L1 chunk 0, L1 chunk 1, L2 chunk 0, L2 chunk 1
-        mbar_wait(bar_acc, acc_cnt & 1);
-        ++acc_cnt;
-        tc_fence_after();
-#pragma unroll 1
-        for (int r = 0; r < 2; ++r) {
-          const int u = 4 * r + wg;  // 32-column unit of the chunk
-          if (u < NU) {
-            uint32_t v[32], pk[16];
-            tmem_ld32(lane_base + (uint32_t)(kTcwAccCol + 32 * u), v);
-            tmem_ld_wait();
-            if (DBG && dbg && blockIdx.x == 0 && h == 0) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                dbg[((q >> 1) * kTcRows + trow) * kTcDbgCols + (q & 1) * g.Nc + 32 * u + i] = __uint_as_float(v[i]);
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) pk[i] = pack_relu<FP16>(v[2 * i], v[2 * i + 1]);
-            if (q == 2) {
-              // h2's lower half: canonical A tile in shared memory, 8 hidden units per 16-byte row chunk
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                *reinterpret_cast<uint4*>(h2lo + (4 * u + j) * 2048 + trow * 16) =
-                    make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-              fence_proxy_async();
-            } else {
-              tmem_st16(lane_base + (uint32_t)((q == 1 ? g.Nc >> 1 : 0) + 16 * u), pk);
-              tmem_st_wait();
-            }
-            tc_fence_before();
-          }
+        if (one_group) {
+          tc_fence_before();   // our tcgen05.ld of y is ordered before the columns are reused
           __syncwarp();
-          if (lane == 0) mbar_arrive(r == 0 ? bar_e0 : bar_e1);
+          if (lane == 0) mbar_arrive(bar_x);
+          if (DBG && tid == 0) tc_stamp(dbg, h, 12);
+        }
+      }
+#pragma unroll 1
+      for (int gi = yw; gi < NG; gi += 5) {
+        if (!one_group) { tmem_ld16(lane_base + (uint32_t)(ycolC + 16 * gi), v); tmem_ld_wait(); }
+        if (DBG && dbg && blockIdx.x == 0 && h == 0) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) dbg[(2 * kTcRows + trow) * kTcDbgCols + 16 * gi + i] = __uint_as_float(v[i]);
+        }
+        if (smooth) {
+          float term[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int o = 16 * gi + i;  // < Op: tables are Op long, padded entries are zero / masked
+            const float x = fmaf(__uint_as_float(v[i]), t_P[o], t_Q[o]);  // (s - goal) * w with s = (y_raw + b3)*sd + mu
+            term[i] = (fast_sqrt(fmaf(x, x, m.alpha2)) - m.alpha) * t_M[o];
+          }
+          st_total += ((term[0] + term[1]) + (term[2] + term[3])) + ((term[4] + term[5]) + (term[6] + term[7])) +
+                      (((term[8] + term[9]) + (term[10] + term[11])) + ((term[12] + term[13]) + (term[14] + term[15])));
+        } else {
+          int pick[4];
+          task_pick_indices(m.cost_kind, pick);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int o = 16 * gi + i;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (o == pick[q]) pk_slot[q * kTcRows + trow] = fmaf(__uint_as_float(v[i]) + t_b3[o], t_sd[o], t_mu[o]);
+          }
+        }
+        if (states_out && valid) {
+          float* sout = states_out + ((long long)h * R + row) * O;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int o = 16 * gi + i;
+            if (o < O) sout[o] = fmaf(__uint_as_float(v[i]) + t_b3[o], t_sd[o], t_mu[o]);  // unnormalize_state (data.py:255-257)
+          }
+        }
+      }
+      if (h + 1 < H && !one_group) {
+        tc_fence_before();     // our tcgen05.ld of y is ordered before the columns are reused
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_x);
+        if (DBG && tid == 0) tc_stamp(dbg, h, 12);
+      }
+      if (!smooth) {
+        // the five warps of this lane quarter have stored the picked state entries of step h
+        asm volatile("bar.sync %0, 160;" ::"r"(3 + quarter) : "memory");
+        if (yw == 4) {
+          int pick[4];
+          task_pick_indices(m.cost_kind, pick);
+          float p4[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) p4[q] = pick[q] >= 0 ? pk_slot[q * kTcRows + trow] : 0.f;
+          st_total += task_cost(m.cost_kind, p4, xch[((h & 1) * 2 + 0) * kTcRows + trow], xch[((h & 1) * 2 + 1) * kTcRows + trow]);
         }
       }
     }
+    costp[yw * kTcRows + trow] = valid ? st_total : 0.f;
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no CTA exits while a peer may still signal its ring barriers
+  else __syncthreads();
   tc_fence_after();
   if (tid < kTcRows) {
     const long long row = (long long)blockIdx.x * kTcRows + tid;
-    if (row < R) costs[row] = costp[tid] + costp[kTcRows + tid];
+    if (row < R) costs[row] = (((costp[tid] + costp[kTcRows + tid]) + (costp[2 * kTcRows + tid] + costp[3 * kTcRows + tid])) + costp[4 * kTcRows + tid]) + costp[5 * kTcRows + tid];
   }
   if (warp == kTcwMmaWarp) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");

@@ -41,7 +41,7 @@ static int check_tcw_stream(int O, int A, int U, size_t max_smem) {
     for (int t0 = 0; t0 < T; t0 += tps) {
       const int n_t = std::min(tps, T - t0);
       const int stage_bytes = std::min(tps * tile, total - consumed);  // what the producer copies into this stage
-      if (stage_bytes != n_t * tile || stage_bytes > kTcwStageBytes || stage_bytes % 16) { std::printf("FAIL stage size part %d\n", part); ++fails; }
+      if (stage_bytes != n_t * tile || stage_bytes > g.stage_bytes || stage_bytes % 16) { std::printf("FAIL stage size part %d\n", part); ++fails; }
       for (int i = 0; i < n_t; ++i) {
         const int ks = t0 + i;
         for (int n = 0; n < rows; ++n)
@@ -102,9 +102,9 @@ int main() {
           CHECK(w.Ka % 8 == 0 && w.Ka > A && w.Kx % 16 == 0 && w.Kx >= w.Ka + O && w.Op % 16 == 0 && w.Op >= O && w.Op <= 128, "K/N padding");
           CHECK(w.QA * 8 == w.Ka && w.SC * 8 == w.Kx - w.Ka && w.SC * 8 >= O, "input tile chunks");
           CHECK(kTcwAccCol + w.Nc <= 512 && w.Nc <= 256 && w.ycol >= w.Nc / 2 && w.ycol + w.Op <= kTcwAccCol, "TMEM columns: y at %d", w.ycol);
-          CHECK(w.tps_h >= 1 && w.tps_y >= 1 && w.tps_h * w.tile_h <= kTcwStageBytes && w.tps_y * w.tile_y <= kTcwStageBytes, "stage tiles");
+          CHECK(w.tps_h >= 1 && w.tps_y >= 1 && w.tps_h * w.tile_h <= w.stage_bytes && w.tps_y * w.tile_y <= w.stage_bytes, "stage tiles");
           CHECK(w.xa_off % 128 == 0 && w.xs_off % 128 == 0 && w.one_off % 128 == 0 && w.h2_off % 128 == 0 && w.ring_off % 128 == 0 && w.bar_off % 8 == 0, "offsets");
-          CHECK(w.xa_off >= (6 * w.Op + 2 * kMaxAct + 6 * kTcRows) * 4 && w.xs_off > w.xa_off, "tables / tile order (LBO = xs - xa must be positive)");
+          CHECK(w.xa_off >= (6 * w.Op + 2 * kMaxAct + 18 * kTcRows) * 4 && w.xs_off > w.xa_off, "tables / tile order (LBO = xs - xa must be positive)");
           CHECK(w.stages >= 3 && w.stages <= kTcwMaxStages && (size_t)w.smem_bytes <= max_smem && w.ms_off + 4 * w.ms_floats == w.smem_bytes, "smem %d", w.smem_bytes);
           CHECK(w.w_bytes == 2 * w.p1_bytes + 2 * w.p2_bytes + w.p3_bytes && w.w_bytes % 16 == 0, "image size");
         } else {
