@@ -119,7 +119,15 @@ inline void tcf_pack(const TcfGeom& g, bool fp16, const float* W1, const float* 
 
 // DBG: accumulator dump + clock64 timeline instrumentation (tests / profiling only); the
 // production instantiation carries none of it.
-template <bool FP16, bool DBG>
+// SPEC: the geometry class of BASELINE cfgs 3 and 4 (cheetah-run O=17 / walker-walk O=24, A=6, hidden 200:
+// Np = 208, Oy = 32, Ka = 16, Ks = 32) as compile-time constants, so that the single MMA-issuing thread
+// runs straight-line code with immediate operand offsets (see rollout_tcw.cuh for the measurements).
+constexpr int kTcfSpecNp = 208, kTcfSpecOy = 32, kTcfSpecKa = 16, kTcfSpecKs = 32;
+inline bool tcf_matches_spec(const TcfGeom& g) {
+  return g.Np == kTcfSpecNp && g.Oy == kTcfSpecOy && g.Ka == kTcfSpecKa && g.Ks == kTcfSpecKs;
+}
+
+template <bool FP16, bool DBG, bool SPEC>
 __global__ void __launch_bounds__(kTcfThreads, 1)
 rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, ActionSource src, Shape sh,
                    const float* __restrict__ s0, float* __restrict__ costs, float* __restrict__ states_out,
@@ -133,8 +141,9 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
   pdl_trigger();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int O = g.O, A = g.A, H = sh.H;
-  const int KS_H = g.Np >> 4;        // K-steps over a hidden operand
-  const int KS_A = g.Ka >> 4, KS_S = g.Ks >> 4;
+  const int NpC = SPEC ? kTcfSpecNp : g.Np, OyC = SPEC ? kTcfSpecOy : g.Oy, NaC = NpC + OyC;
+  const int KS_H = NpC >> 4;        // K-steps over a hidden operand
+  const int KS_A = SPEC ? kTcfSpecKa >> 4 : g.Ka >> 4, KS_S = SPEC ? kTcfSpecKs >> 4 : g.Ks >> 4;
 
   float* tab = reinterpret_cast<float*>(smem + g.tab_off);
   float *t_b3 = tab, *t_P = tab + g.Oy, *t_Q = tab + 2 * g.Oy, *t_sd = tab + 3 * g.Oy, *t_mu = tab + 4 * g.Oy;
@@ -191,105 +200,94 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
   const long long R = sh.rows();
 
   if (warp == kTcfMmaWarp) {
-    // ================= MMA issuer warp =================
-    // The whole warp stays converged and waits on the barriers; every tcgen05 instruction is
-    // issued by one elected lane (see elect_one()).
+    // ================= MMA issuer: ONE elected lane runs the whole loop =================
+    // tcgen05.mma issue blocks the issuing thread for about the MMA's own duration, so the thread's own
+    // bookkeeping between MMAs is tensor-pipe idle time.  The loops below are written for full unrolling
+    // in the SPEC instantiation (compile-time geometry of the cheetah / walker shape class): descriptors
+    // as (lo, hi) words whose start-address field takes immediate offsets, the TMEM base as the literal
+    // 0 (a 512-column allocation starts there; checked), no per-group elect / __syncwarp.
     if (elect_one()) {
       mbar_arrive_expect_tx(bar_w, (uint32_t)g.w_bytes);
       bulk_g2s(smem_u32(smem), wimg, (uint32_t)g.w_bytes, bar_w);
-    }
-    const uint32_t idesc_a = umma_idesc(g.Na, FP16), idesc_h = umma_idesc(g.Np, FP16), idesc_y = umma_idesc(g.Oy, FP16);
-    const uint32_t lbo_a = (uint32_t)g.Na * 16, lbo_h = (uint32_t)g.Np * 16, lbo_x = kTcRows * 16;
-    // Descriptors are loop invariant; a K-step advances the 14-bit start-address field by
-    // 2*LBO/16 (smem addresses stay below 256 KB, so the add never carries out of the field).
-    const uint64_t d_wa = umma_desc(smem_u32(smem + g.wa_off), lbo_a, 128);
-    const uint64_t d_wy = umma_desc(smem_u32(smem + g.wa_off) + (uint32_t)g.Np * 16, lbo_a, 128);  // rows Np.. of [W13;W3]
-    const uint64_t d_waa = umma_desc(smem_u32(smem + g.waa_off), lbo_a, 128);
-    const uint64_t d_w1s = umma_desc(smem_u32(smem + g.w1s_off), lbo_h, 128);
-    const uint64_t d_w2 = umma_desc(smem_u32(smem + g.w2_off), lbo_h, 128);
-    const uint64_t d_xs = umma_desc(smem_u32(xs), lbo_x, 128);
-    const uint64_t d_xa0 = umma_desc(smem_u32(xa), lbo_x, 128);
-    const uint64_t xa_step = (uint64_t)(xa_bytes >> 4);  // next action tile
-    const uint64_t step_a = (2 * lbo_a) >> 4, step_h = (2 * lbo_h) >> 4, step_x = (2 * lbo_x) >> 4;
-    const uint32_t tm_a = tmem, tm_b = tmem + kTcD2Col;
-    mbar_wait(bar_w, 0);
+      if (tmem != 0u) __trap();
+      const uint32_t idesc_a = umma_idesc(NaC, FP16), idesc_h = umma_idesc(NpC, FP16), idesc_y = umma_idesc(OyC, FP16);
+      const uint32_t dhi = (128u >> 4) | (1u << 14);  // SBO = 128 bytes; descriptor version 1 (bit 46)
+      auto dlo = [](uint32_t saddr, uint32_t lbo_bytes) { return ((saddr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16); };
+      auto d64 = [dhi](uint32_t lo) { return ((uint64_t)dhi << 32) | lo; };
+      const uint32_t lbo_a = (uint32_t)NaC * 16, lbo_h = (uint32_t)NpC * 16, lbo_x = kTcRows * 16;
+      // a K-step advances the 14-bit start-address field by 2*LBO/16 (smem addresses stay below 256 KB)
+      const uint32_t lo_wa = dlo(smem_u32(smem + g.wa_off), lbo_a);
+      const uint32_t lo_wy = dlo(smem_u32(smem + g.wa_off) + (uint32_t)NpC * 16, lbo_a);  // rows Np.. of [W13;W3]
+      const uint32_t lo_waa = dlo(smem_u32(smem + g.waa_off), lbo_a);
+      const uint32_t lo_w1s = dlo(smem_u32(smem + g.w1s_off), lbo_h);
+      const uint32_t lo_w2 = dlo(smem_u32(smem + g.w2_off), lbo_h);
+      const uint32_t lo_xs = dlo(smem_u32(xs), lbo_x), lo_xa0 = dlo(smem_u32(xa), lbo_x);
+      const uint32_t xa_step = (uint32_t)(xa_bytes >> 4);  // next action tile
+      const uint32_t step_a = (2 * lbo_a) >> 4, step_h = (2 * lbo_h) >> 4, step_x = (2 * lbo_x) >> 4;
+      const uint32_t tm_a = 0u, tm_b = kTcD2Col;
+      mbar_wait(bar_w, 0);
 
-    // ---- step 0: D_A = a(0).[W1a|b13]^T + (x0 - b3).W1s^T ----
-    mbar_wait(bar_xa, 0);
-    tc_fence_after();
-    if (elect_one()) {
-      uint64_t ad = d_xa0, bd = d_waa;
-      mma_ss(tm_a, ad, bd, idesc_a, 0);
-      for (int ks = 1; ks < KS_A; ++ks) { ad += step_x; bd += step_a; mma_ss(tm_a, ad, bd, idesc_a, 1); }
+      // ---- step 0: D_A = a(0).[W1a|b13]^T + (x0 - b3).W1s^T ----
+      mbar_wait(bar_xa, 0);
+      tc_fence_after();
+#pragma unroll (SPEC ? 4 : 1)
+      for (int ks = 0; ks < KS_A; ++ks) mma_ss(tm_a, d64(lo_xa0 + ks * step_x), d64(lo_waa + ks * step_a), idesc_a, ks > 0);
       tc_commit(bar_xf);  // slot 0 is free again once these MMAs have read it
-      ad = d_xs; bd = d_w1s;
-      for (int ks = 0; ks < KS_S; ++ks) { mma_ss(tm_a, ad, bd, idesc_h, 1); ad += step_x; bd += step_h; }
+#pragma unroll (SPEC ? 4 : 1)
+      for (int ks = 0; ks < KS_S; ++ks) mma_ss(tm_a, d64(lo_xs + ks * step_x), d64(lo_w1s + ks * step_h), idesc_h, 1);
       tc_commit(bar_dA);
-    }
-    __syncwarp();
 
-    for (int h = 0; h < H; ++h) {
-      const uint32_t ph = h & 1;
-      // ---- GEMM-B(h): D_B = h1(h) . W2p^T, K-steps released by epilogue A ----
-      {
-        // K-step ks of h1 (16 hidden units) is packed into the first 8 of its own 16 fp32 columns
-        // and released on its own barrier as soon as one warpgroup has converted it
-        uint64_t bd = d_w2;
-        uint32_t a = tm_a;
+      uint32_t slot = 0, slot_ph = 0;  // action-tile slot of step h+1 and its phase
+      for (int h = 0; h < H; ++h) {
+        const uint32_t ph = h & 1;
+        // ---- GEMM-B(h): D_B = h1(h) . W2p^T, K-steps released by epilogue A ----
+        // K-step ks of h1 (16 hidden units) is packed into the first 8 of its own 16 fp32 columns; a
+        // group of 4 K-steps is released on its barrier as soon as the four warpgroups have converted it
+#pragma unroll (SPEC ? 4 : 1)
         for (int ks = 0; ks < KS_H; ks += 4) {
           mbar_wait(bar_hA + 2 * ks, ph);  // barrier of the K-step group ks/4
           tc_fence_after();
-          if (lane == 0 && (ks == 0 || ks + 4 >= KS_H)) if (DBG) tc_stamp(dbg, h, ks == 0 ? 1 : 2);
-          if (elect_one()) {
+          if (DBG && (ks == 0 || ks + 4 >= KS_H)) tc_stamp(dbg, h, ks == 0 ? 1 : 2);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if (ks + i < KS_H) mma_ts(tm_b, a + 16 * i, bd + i * step_h, idesc_h, (ks + i) > 0);
-            if (ks + 4 >= KS_H) tc_commit(bar_dB);
-          }
-          __syncwarp();
-          bd += 4 * step_h; a += 64;
+          for (int i = 0; i < 4; ++i)
+            if (ks + i < KS_H) mma_ts(tm_b, tm_a + 16 * (ks + i), d64(lo_w2 + (ks + i) * step_h), idesc_h, (ks + i) > 0);
         }
-      }
-      // ---- GEMM-A(h+1) (or, after the last step, only the y columns) ----
-      const bool last = h + 1 == H;
-      if (h >= 1) { mbar_wait(bar_y, (h - 1) & 1); }  // y(h-1) in D_A has been consumed
-      uint32_t acc = 0;
-      if (!last) {
-        const int slot = (h + 1) % kTcfSlots;
-        mbar_wait(bar_xa + 8 * slot, ((h + 1) / kTcfSlots) & 1);
-        tc_fence_after();
-        if (lane == 0) if (DBG) tc_stamp(dbg, h, 3);
-        if (elect_one()) {
-          uint64_t ad = d_xa0 + slot * xa_step, bd = d_waa;
-          mma_ss(tm_a, ad, bd, idesc_a, 0);
-          for (int ks = 1; ks < KS_A; ++ks) { ad += step_x; bd += step_a; mma_ss(tm_a, ad, bd, idesc_a, 1); }
-          tc_commit(bar_xf + 8 * slot);
-        }
-        __syncwarp();
-        acc = 1;
-      }
-      {
-        uint64_t bd = last ? d_wy : d_wa;
-        const uint32_t d = last ? tm_a + (uint32_t)g.Np : tm_a;
-        const uint32_t idesc = last ? idesc_y : idesc_a;
-        uint32_t a = tm_b;
-        if (lane == 0) if (DBG) tc_stamp(dbg, h, 18);
-        for (int ks = 0; ks < KS_H; ks += 4) {
-          mbar_wait(bar_hB + 2 * ks, ph);
+        tc_commit(bar_dB);
+        // ---- GEMM-A(h+1) (or, after the last step, only the y columns) ----
+        const bool last = h + 1 == H;
+        if (h >= 1) mbar_wait(bar_y, (h - 1) & 1);  // y(h-1) in D_A has been consumed
+        uint32_t acc = 0;
+        if (!last) {
+          if (++slot == kTcfSlots) { slot = 0; slot_ph ^= 1; }  // slot (h+1) % kTcfSlots, phase ((h+1) / kTcfSlots) & 1
+          mbar_wait(bar_xa + 8 * slot, slot_ph);
           tc_fence_after();
-          if (lane == 0 && (ks == 0 || ks + 4 >= KS_H)) if (DBG) tc_stamp(dbg, h, ks == 0 ? 16 : 17);
-          if (elect_one()) {
+          if (DBG) tc_stamp(dbg, h, 3);
+          const uint32_t lo_xa = lo_xa0 + slot * xa_step;
+#pragma unroll (SPEC ? 4 : 1)
+          for (int ks = 0; ks < KS_A; ++ks) mma_ss(tm_a, d64(lo_xa + ks * step_x), d64(lo_waa + ks * step_a), idesc_a, ks > 0);
+          tc_commit(bar_xf + 8 * slot);
+          acc = 1;
+        }
+        {
+          const uint32_t lo_b = last ? lo_wy : lo_wa;
+          const uint32_t d = last ? tm_a + (uint32_t)NpC : tm_a;
+          const uint32_t idesc = last ? idesc_y : idesc_a;
+          if (DBG) tc_stamp(dbg, h, 18);
+#pragma unroll (SPEC ? 4 : 1)
+          for (int ks = 0; ks < KS_H; ks += 4) {
+            mbar_wait(bar_hB + 2 * ks, ph);
+            tc_fence_after();
+            if (DBG && (ks == 0 || ks + 4 >= KS_H)) tc_stamp(dbg, h, ks == 0 ? 16 : 17);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              if (ks + i < KS_H) mma_ts(d, a + 16 * i, bd + i * step_a, idesc, (ks + i) > 0 ? 1u : acc);
-            if (ks + 4 >= KS_H) tc_commit(bar_dA);
+              if (ks + i < KS_H) mma_ts(d, tm_b + 16 * (ks + i), d64(lo_b + (ks + i) * step_a), idesc, (ks + i) > 0 ? 1u : acc);
           }
-          __syncwarp();
-          bd += 4 * step_a; a += 64;
+          tc_commit(bar_dA);
         }
+        if (DBG) tc_stamp(dbg, h + 1, 0);
       }
-      if (lane == 0) if (DBG) tc_stamp(dbg, h + 1, 0);
     }
+    __syncwarp();
   } else if (warp >= kTcfSampWarp0) {
     // ================= sampler threads (one per row) =================
     const int srow = tid - kTcfSampWarp0 * 32;
@@ -399,9 +397,9 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
       if (crow == 0) if (DBG) tc_stamp(dbg, j - 1, 14);
       float* sout = (states_out && valid) ? states_out + ((long long)(j - 1) * R + row) * O : nullptr;
 #pragma unroll 1
-      for (int cc = 0; cc < (g.Oy >> 4); ++cc) {
+      for (int cc = 0; cc < (OyC >> 4); ++cc) {
         uint32_t v[32];
-        tmem_ld16(lane_base + (uint32_t)(g.Np + 16 * cc), v);
+        tmem_ld16(lane_base + (uint32_t)(NpC + 16 * cc), v);
         tmem_ld_wait();
         if (DBG && dbg && blockIdx.x == 0 && j == 1) {
 #pragma unroll
@@ -599,10 +597,17 @@ inline cudaError_t tc_launch_rollout(TcModel* t, const ModelDev& m, const Action
   return tc_launch_one(KERN, GEOM, (GEOM).smem_bytes, THREADS, t, m, src, sh, d_s0, d_costs, d_states, d_actions, st, \
                        t->kind == kTcWide ? t->wg.cluster : 1)
   if (t->kind == kTcFused) {
-    if (t->fp16 && !dbg) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, false>), t->fg, kTcfThreads);
-    if (t->fp16) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, true>), t->fg, kTcfThreads);
-    if (!dbg) MBRL_TC_LAUNCH((rollout_tcf_kernel<false, false>), t->fg, kTcfThreads);
-    MBRL_TC_LAUNCH((rollout_tcf_kernel<false, true>), t->fg, kTcfThreads);
+    const bool spec = tcf_matches_spec(t->fg) && !getenv("MBRL_TCF_NO_SPEC");
+    if (spec) {
+      if (t->fp16 && !dbg) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, false, true>), t->fg, kTcfThreads);
+      if (t->fp16) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, true, true>), t->fg, kTcfThreads);
+      if (!dbg) MBRL_TC_LAUNCH((rollout_tcf_kernel<false, false, true>), t->fg, kTcfThreads);
+      MBRL_TC_LAUNCH((rollout_tcf_kernel<false, true, true>), t->fg, kTcfThreads);
+    }
+    if (t->fp16 && !dbg) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, false, false>), t->fg, kTcfThreads);
+    if (t->fp16) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, true, false>), t->fg, kTcfThreads);
+    if (!dbg) MBRL_TC_LAUNCH((rollout_tcf_kernel<false, false, false>), t->fg, kTcfThreads);
+    MBRL_TC_LAUNCH((rollout_tcf_kernel<false, true, false>), t->fg, kTcfThreads);
   }
   if (t->kind == kTcWide) {
     const bool spec = tcw_matches_spec(t->wg) && !getenv("MBRL_TCW_NO_SPEC");
