@@ -64,6 +64,36 @@ def main():
                   f"{out['info']['best_cost'][0]:.4f} idx {out['info']['best_index'][0]} it {out['info']['best_iteration'][0]}")
         dist.barrier()
         h.close()
+    # random shooting (I = 1, k = 1: the reference's planner, src/mbrl/planners.py:166-187) over a sharded
+    # population: one (cost, index) pair per rank is exchanged and the global argmin (ties -> lower global
+    # index, as np.argmin) must be the unsharded one; uniform sampler as EnvWrapper._sample_action
+    for engine, transport in (("fp32", "nccl"), ("fp16", "p2p")):
+        n_local = 4096
+        h = native.NativePlanner(O, A, U, H, n_local, 1, 1, 1, engine, local)
+        h.load_problem(prob)
+        if transport == "p2p":
+            assert h.p2p_init(rank, world)
+        else:
+            h.comm_init(rank, world)
+        for rep in range(2):
+            out = h.plan(s0, 1, 1, native.SAMPLE_UNIFORM, seed=30 + rep)
+        mine = torch.from_numpy(np.concatenate([out["actions"].ravel(), out["states"].ravel(), out["info"]["best_cost"],
+                                                out["info"]["best_index"].astype(np.float32)])).cuda()
+        ref = mine.clone()
+        dist.broadcast(ref, src=0)
+        assert torch.equal(mine, ref), f"rank {rank}: RS plan differs from rank 0 ({engine})"
+        if rank == 0:
+            full = native.NativePlanner(O, A, U, H, n_local * world, 1, 1, 1, engine, local)
+            full.load_problem(prob)
+            want = full.plan(s0, 1, 1, native.SAMPLE_UNIFORM, seed=31)
+            for key in ("actions", "states"):
+                np.testing.assert_array_equal(out[key], want[key], err_msg=f"RS {engine} {key}")
+            for key in ("best_cost", "best_index"):
+                np.testing.assert_array_equal(out["info"][key], want["info"][key], err_msg=f"RS {engine} {key}")
+            print(f"multi_gpu_check[RS, {engine}, {transport}]: {world} ranks == unsharded N={n_local * world}: "
+                  f"argmin {out['info']['best_index'][0]} cost {out['info']['best_cost'][0]:.4f}")
+        dist.barrier()
+        h.close()
     dist.destroy_process_group()
 
 
