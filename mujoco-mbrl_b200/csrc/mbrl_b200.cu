@@ -346,7 +346,7 @@ extern "C" int mbrl_set_cost(MbrlPlanner* p, int32_t kind, const float* w, const
     const int need = std::max(std::max(pick[0], pick[1]), std::max(pick[2], pick[3])) + 1;
     MBRL_REQUIRE(p->O >= need && p->A >= 1, "observation too short for this dm_control task cost "
                  "(cartpole 5, cheetah 9, walker 17, humanoid 39 leading entries are read)");
-    if (p->cfg.engine != MBRL_ENGINE_SIMT_FP32 && !tc_supports_task_cost(&p->tc))
+    if (p->cfg.engine != MBRL_ENGINE_SIMT_FP32 && !tc_supports_task_cost(&p->tc, kind))
       return fail(MBRL_E_UNSUPPORTED, "the dm_control task-cost epilogue is not implemented for this tensor-core kernel variant");
     if (beta == 0.0) beta = 1.0;  // unused by these costs; keeps 1/beta finite
   } else if (kind == MBRL_COST_REWARD_HEAD) {

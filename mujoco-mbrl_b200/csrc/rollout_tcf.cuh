@@ -46,9 +46,11 @@ struct TcfGeom {
   int wa_off, waa_off, w1s_off, w2_off, w_bytes;
   int tab_off, xs_off, xa_off, bar_off, smem_bytes;
   int ms_off, ms_floats;  // staging area for the sampling mean/std rows of the tile's environments
+  int xch_off;  // task costs: per-step control terms (a0, ctl_mean) handed from the sampler to the cost threads; -1 = no room
 };
 
 constexpr int kTcfSlots = 3;  // action tiles in flight: the sampler runs up to 3 steps ahead
+constexpr int kTcfXchSlots = 8;  // control-term slots (the cost threads lag the sampler by at most 4 steps)
 constexpr int kTcfMaxKSteps = 16;  // hidden K-steps (Np <= 256)
 constexpr int kTcfBarriers = 4 + 2 * kTcfSlots + kTcfMaxKSteps;  // w, dA, dB, y, xa[3], xf[3], hA[8], hB[8]
 constexpr int kTcfEpiGroups = 4;                      // hidden-epilogue warpgroups (4 warps each)
@@ -76,6 +78,13 @@ inline bool tcf_geometry(int O, int A, int U, size_t max_smem, TcfGeom* g, std::
   g->bar_off = g->xa_off + kTcfSlots * g->Ka * kTcRows * 2;
   g->smem_bytes = g->bar_off + 8 * kTcfBarriers + 16;
   if ((size_t)g->smem_bytes > max_smem) { *why = "fused operands do not fit shared memory"; return false; }
+  // dm_control task costs that depend on the control (cartpole, humanoid): the sampler hands (a0,
+  // ctl_mean) of every step to the cost threads through kTcfXchSlots slots -- only when shared memory
+  // has the room (small models; the cheetah / walker shapes do not need it: their task costs read the
+  // state only)
+  g->xch_off = -1;
+  const int xch_bytes = kTcfXchSlots * 2 * kTcRows * 4;
+  if ((size_t)g->smem_bytes + xch_bytes + 4096 <= max_smem) { g->xch_off = g->smem_bytes; g->smem_bytes += xch_bytes; }
   // whatever is left (up to 16 KB) stages mean/std: [envs of the tile][H][A] x 2, fp32
   g->ms_off = g->smem_bytes;
   g->ms_floats = (int)std::min<size_t>((max_smem - (size_t)g->smem_bytes) / 4, 4096);
@@ -127,7 +136,9 @@ inline bool tcf_matches_spec(const TcfGeom& g) {
   return g.Np == kTcfSpecNp && g.Oy == kTcfSpecOy && g.Ka == kTcfSpecKa && g.Ks == kTcfSpecKs;
 }
 
-template <bool FP16, bool DBG, bool SPEC>
+// TASK: a dm_control task cost instead of SmoothAbs + Cosh (compiled out of the default-cost kernel: the
+// extra registers and branches in the sampler / cost threads cost the default path 12 % when left in).
+template <bool FP16, bool DBG, bool SPEC, bool TASK>
 __global__ void __launch_bounds__(kTcfThreads, 1)
 rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, ActionSource src, Shape sh,
                    const float* __restrict__ s0, float* __restrict__ costs, float* __restrict__ states_out,
@@ -142,6 +153,8 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int O = g.O, A = g.A, H = sh.H;
   const int NpC = SPEC ? kTcfSpecNp : g.Np, OyC = SPEC ? kTcfSpecOy : g.Oy, NaC = NpC + OyC;
+  constexpr bool smooth = !TASK;
+  float* const xch = (TASK && g.xch_off >= 0) ? reinterpret_cast<float*>(smem + g.xch_off) : nullptr;  // [slot][a0, ctl][row]
   const int KS_H = NpC >> 4;        // K-steps over a hidden operand
   const int KS_A = SPEC ? kTcfSpecKa >> 4 : g.Ka >> 4, KS_S = SPEC ? kTcfSpecKs >> 4 : g.Ks >> 4;
 
@@ -180,7 +193,7 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
     const bool in = i < O;
     t_M[i] = in ? 1.f : 0.f;
     const float b3 = in ? __ldg(m.b3 + i) : 0.f, sd = in ? __ldg(m.sd_s + i) : 1.f, mu = in ? __ldg(m.mu_s + i) : 0.f;
-    const float w = in ? __ldg(m.cost_w + i) : 0.f, goal = in ? __ldg(m.goal + i) : 0.f;
+    const float w = (in && smooth) ? __ldg(m.cost_w + i) : 0.f, goal = (in && smooth) ? __ldg(m.goal + i) : 0.f;
     t_b3[i] = b3; t_sd[i] = sd; t_mu[i] = mu;
     t_P[i] = sd * w;
     t_Q[i] = (b3 * sd + mu - goal) * w;
@@ -295,7 +308,7 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
     const bool valid = row < R;
     const int env_l = valid ? (int)(row / sh.N) : 0;
     const int cand_l = valid ? (int)(row - (long long)env_l * sh.N) : 0;
-    const float inv_beta = 1.0f / m.beta, cscale = valid ? m.beta2 / (float)A : 0.f;
+    const float inv_beta = 1.0f / m.beta, cscale = (valid && smooth) ? m.beta2 / (float)A : 0.f;
     const int QA = (A + 8) >> 3;  // 8-wide chunks holding the actions and the constant 1
     float act_total = 0.f;
     // (Drawing step 0's noise before this wait was tried: -2 % -- the extra live registers spill.)
@@ -335,6 +348,16 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
           v[4] = u4[0]; v[5] = u4[1]; v[6] = u4[2]; v[7] = u4[3];
         }
         // branch-free: raw_action4 returns 0 beyond A (cosh(0) - 1 == 0), tables are zero-padded
+        if (xch && !smooth) {
+          // task costs: this step's first control and mean_a(quadratic tolerance of the control), accumulated
+          // in the step's exchange slot (no live registers on the default-cost path)
+          float c8 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) c8 += (8 * q + i < A && fabsf(v[i]) < 1.0f) ? 1.0f - v[i] * v[i] : 0.0f;
+          float* slot = xch + ((hs % kTcfXchSlots) * 2) * kTcRows + srow;
+          if (q == 0) { slot[0] = v[0]; slot[kTcRows] = c8 / (float)A; }
+          else slot[kTcRows] += c8 / (float)A;
+        }
         float xn[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -396,6 +419,7 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
       tc_fence_after();
       if (crow == 0) if (DBG) tc_stamp(dbg, j - 1, 14);
       float* sout = (states_out && valid) ? states_out + ((long long)(j - 1) * R + row) * O : nullptr;
+      float p4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int cc = 0; cc < (OyC >> 4); ++cc) {
         uint32_t v[32];
@@ -405,15 +429,28 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
 #pragma unroll
           for (int i = 0; i < 16; ++i) dbg[(2 * kTcRows + crow) * kTcDbgCols + 16 * cc + i] = __uint_as_float(v[i]);
         }
-        float term[16];
+        if (smooth) {
+          float term[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int o = 16 * cc + i;  // < Oy: tables are Oy long; padded entries are zero / masked
-          const float x = fmaf(__uint_as_float(v[i]), t_P[o], t_Q[o]);  // (s - goal) * w, s = (y_raw + b3)*sd + mu
-          term[i] = (fast_sqrt(fmaf(x, x, m.alpha2)) - m.alpha) * t_M[o];
+          for (int i = 0; i < 16; ++i) {
+            const int o = 16 * cc + i;  // < Oy: tables are Oy long; padded entries are zero / masked
+            const float x = fmaf(__uint_as_float(v[i]), t_P[o], t_Q[o]);  // (s - goal) * w, s = (y_raw + b3)*sd + mu
+            term[i] = (fast_sqrt(fmaf(x, x, m.alpha2)) - m.alpha) * t_M[o];
+          }
+          st_total += ((term[0] + term[1]) + (term[2] + term[3])) + ((term[4] + term[5]) + (term[6] + term[7])) +
+                      (((term[8] + term[9]) + (term[10] + term[11])) + ((term[12] + term[13]) + (term[14] + term[15])));
+        } else {
+          // dm_control task cost: pick the (at most four) un-normalised state entries it reads
+          int pick[4];
+          task_pick_indices(m.cost_kind, pick);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int o = 16 * cc + i;
+            const float sv = fmaf(__uint_as_float(v[i]) + t_b3[o], t_sd[o], t_mu[o]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) p4[q] = (o == pick[q]) ? sv : p4[q];
+          }
         }
-        st_total += ((term[0] + term[1]) + (term[2] + term[3])) + ((term[4] + term[5]) + (term[6] + term[7])) +
-                    (((term[8] + term[9]) + (term[10] + term[11])) + ((term[12] + term[13]) + (term[14] + term[15])));
         if (sout) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -422,6 +459,12 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
             if (o < O) sout[o] = fmaf(__uint_as_float(v[i]) + t_b3[o], t_sd[o], t_mu[o]);
           }
         }
+      }
+      if (!smooth) {
+        // step j-1's control terms: written by the sampler before the action MMAs of that step were issued
+        const int xs_slot = (j - 1) % kTcfXchSlots;
+        const float a0 = xch ? xch[(xs_slot * 2 + 0) * kTcRows + crow] : 0.f, ctl = xch ? xch[(xs_slot * 2 + 1) * kTcRows + crow] : 0.f;
+        st_total += task_cost(m.cost_kind, p4, a0, ctl);
       }
       if (j < H) {
         tc_fence_before();  // our tcgen05.ld of y is ordered before GEMM-A(j+1) overwrites it
@@ -536,8 +579,14 @@ inline bool tc_init(TcModel* t, int O, int A, int U, bool fp16, size_t max_smem,
 }
 
 // dm_control task-cost epilogues (cost threads pick the entries, sampler threads hand over the
-// control terms): built into the wide kernel.
-inline bool tc_supports_task_cost(const TcModel* t) { return t->kind == kTcWide; }
+// control terms): built into the wide and the fused kernel (the fused one needs shared-memory room for
+// the control-term slots when the cost depends on the control).
+inline bool tc_supports_task_cost(const TcModel* t, int kind) {
+  if (t->kind == kTcWide) return true;
+  if (t->kind != kTcFused) return false;
+  const bool needs_control = kind == MBRL_COST_DMC_CARTPOLE_SWINGUP || kind == MBRL_COST_DMC_HUMANOID_RUN;
+  return !needs_control || t->fg.xch_off >= 0;
+}
 
 inline void tc_free(TcModel* t) {
   if (t->d_wimg) cudaFree(t->d_wimg);
@@ -598,16 +647,23 @@ inline cudaError_t tc_launch_rollout(TcModel* t, const ModelDev& m, const Action
                        t->kind == kTcWide ? t->wg.cluster : 1)
   if (t->kind == kTcFused) {
     const bool spec = tcf_matches_spec(t->fg) && !getenv("MBRL_TCF_NO_SPEC");
-    if (spec) {
-      if (t->fp16 && !dbg) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, false, true>), t->fg, kTcfThreads);
-      if (t->fp16) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, true, true>), t->fg, kTcfThreads);
-      if (!dbg) MBRL_TC_LAUNCH((rollout_tcf_kernel<false, false, true>), t->fg, kTcfThreads);
-      MBRL_TC_LAUNCH((rollout_tcf_kernel<false, true, true>), t->fg, kTcfThreads);
+    if (m.cost_kind != MBRL_COST_SMOOTHABS_COSH) {  // dm_control task cost (no debug-dump variant)
+      if (dbg) return cudaErrorNotSupported;
+      if (spec && t->fp16) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, false, true, true>), t->fg, kTcfThreads);
+      if (spec) MBRL_TC_LAUNCH((rollout_tcf_kernel<false, false, true, true>), t->fg, kTcfThreads);
+      if (t->fp16) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, false, false, true>), t->fg, kTcfThreads);
+      MBRL_TC_LAUNCH((rollout_tcf_kernel<false, false, false, true>), t->fg, kTcfThreads);
     }
-    if (t->fp16 && !dbg) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, false, false>), t->fg, kTcfThreads);
-    if (t->fp16) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, true, false>), t->fg, kTcfThreads);
-    if (!dbg) MBRL_TC_LAUNCH((rollout_tcf_kernel<false, false, false>), t->fg, kTcfThreads);
-    MBRL_TC_LAUNCH((rollout_tcf_kernel<false, true, false>), t->fg, kTcfThreads);
+    if (spec) {
+      if (t->fp16 && !dbg) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, false, true, false>), t->fg, kTcfThreads);
+      if (t->fp16) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, true, true, false>), t->fg, kTcfThreads);
+      if (!dbg) MBRL_TC_LAUNCH((rollout_tcf_kernel<false, false, true, false>), t->fg, kTcfThreads);
+      MBRL_TC_LAUNCH((rollout_tcf_kernel<false, true, true, false>), t->fg, kTcfThreads);
+    }
+    if (t->fp16 && !dbg) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, false, false, false>), t->fg, kTcfThreads);
+    if (t->fp16) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, true, false, false>), t->fg, kTcfThreads);
+    if (!dbg) MBRL_TC_LAUNCH((rollout_tcf_kernel<false, false, false, false>), t->fg, kTcfThreads);
+    MBRL_TC_LAUNCH((rollout_tcf_kernel<false, true, false, false>), t->fg, kTcfThreads);
   }
   if (t->kind == kTcWide) {
     const bool spec = tcw_matches_spec(t->wg) && !getenv("MBRL_TCW_NO_SPEC");

@@ -82,3 +82,35 @@ def humanoid_cost(obs, act, move_speed=HUMANOID_RUN_SPEED):
     move = tolerance(com_velocity, bounds=(move_speed, np.inf), margin=move_speed, value_at_margin=0, sigmoid="linear")
     move = (5 * move + 1) / 6
     return 1.0 - small_control * standing * upright * move
+
+
+CHEETAH_RUN_SPEED = 10.0  # dm_control/suite/cheetah.py:36
+
+
+def cheetah_run_cost(obs):
+    """1 - Cheetah.get_reward (dm_control/dm_control/suite/cheetah.py:91-97): linear tolerance of the forward
+    speed up to 10 m/s.  physics.speed() is the torso_subtreelinvel sensor (cheetah.py:59-61), which is NOT
+    part of the observation (qpos[1:] | qvel, cheetah.py:83-89): the root-x joint velocity obs[8] stands in
+    for it -- a documented PROXY, pinned here only through tolerance() itself.
+    obs [..., 17] -> cost [...]."""
+    obs = np.asarray(obs, dtype=np.float64)
+    r = tolerance(obs[..., 8], bounds=(CHEETAH_RUN_SPEED, np.inf), margin=CHEETAH_RUN_SPEED, value_at_margin=0, sigmoid="linear")
+    return 1.0 - r
+
+
+WALKER_STAND_HEIGHT = 1.2  # dm_control/suite/walker.py:37
+WALKER_WALK_SPEED = 1.0    # dm_control/suite/walker.py:40
+
+
+def walker_walk_cost(obs, move_speed=WALKER_WALK_SPEED):
+    """1 - PlanarWalker.get_reward (dm_control/dm_control/suite/walker.py:135-158) at move_speed 1 from the
+    observation (walker.py:127-133): orientations[0:14] (xx, xz of every body; torso first, and in this
+    planar model xx == zz == physics.torso_upright()), height[14] (torso_height), velocity[15:24] (qvel:
+    rootz, rootx, rooty, joints).  The horizontal-velocity sensor is not observed: the root-x joint
+    velocity obs[16] is the documented PROXY.  obs [..., 24] -> cost [...]."""
+    obs = np.asarray(obs, dtype=np.float64)
+    standing = tolerance(obs[..., 14], bounds=(WALKER_STAND_HEIGHT, np.inf), margin=WALKER_STAND_HEIGHT / 2)
+    upright = (1 + obs[..., 0]) / 2
+    stand_reward = (3 * standing + upright) / 4
+    move = tolerance(obs[..., 16], bounds=(move_speed, np.inf), margin=move_speed / 2, value_at_margin=0.5, sigmoid="linear")
+    return 1.0 - stand_reward * (5 * move + 1) / 6

@@ -16,7 +16,8 @@ What is imported from the reference (unmodified, from where it lies):
 Fixtures: ring_world, rs_cartpole, rs_cheetah_small (random shooting: costs, argmin, plan, first
 action through MPCPolicy), cem_cheetah_small, cem_cartpole_small (reference-composed CEM),
 rs_reward_head (RewardAgent wiring), rs_linear_model (--model lin), tolerance (rewards.tolerance
-grid), humanoid_reward (Humanoid.get_reward composed with the reference's tolerance).
+grid), humanoid_reward (Humanoid.get_reward composed with the reference's tolerance), locomotion_reward
+(Cheetah.get_reward and walker-walk PlanarWalker.get_reward, same construction).
 
 Third-party modules the reference imports at module scope but which are not installed
 here (tensorboardX, colorlog, dm_env, dm_control.suite, PIL) are stubbed in sys.modules;
@@ -369,6 +370,24 @@ def make_tolerance():
     np.savez_compressed(os.path.join(OUT, "humanoid_reward.npz"), head_height=head, torso_upright=zz, com_velocity=com,
                         control=ctrl, reward=rew)
     print("humanoid reward samples", m, "mean", rew.mean())
+
+    # Cheetah.get_reward (dm_control/suite/cheetah.py:91-97) and PlanarWalker.get_reward at move_speed 1
+    # (walker-walk, dm_control/suite/walker.py:135-158) composed with the reference's own tolerance() on
+    # synthetic physics quantities: pins oracle/task_costs.cheetah_run_cost / walker_walk_cost.
+    rng = np.random.default_rng(11)
+    speed = rng.uniform(-4.0, 14.0, m)
+    rew_c = np.array([rewards.tolerance(v, bounds=(10, float("inf")), margin=10, value_at_margin=0, sigmoid="linear") for v in speed])
+    height = rng.uniform(0.2, 1.6, m); zz = rng.uniform(-1.0, 1.0, m); vel = rng.uniform(-1.5, 2.5, m)
+    rew_w = np.empty(m)
+    for i in range(m):
+        standing = rewards.tolerance(height[i], bounds=(1.2, float("inf")), margin=1.2 / 2)
+        upright = (1 + zz[i]) / 2
+        stand_reward = (3 * standing + upright) / 4
+        move_reward = rewards.tolerance(vel[i], bounds=(1, float("inf")), margin=1 / 2, value_at_margin=0.5, sigmoid="linear")
+        rew_w[i] = stand_reward * (5 * move_reward + 1) / 6
+    np.savez_compressed(os.path.join(OUT, "locomotion_reward.npz"), cheetah_speed=speed, cheetah_reward=rew_c,
+                        walker_height=height, walker_upright=zz, walker_velocity=vel, walker_reward=rew_w)
+    print("cheetah / walker reward samples", m, "means", rew_c.mean(), rew_w.mean())
 
 
 if __name__ == "__main__":

@@ -91,6 +91,7 @@ int main() {
           CHECK(g.xs_off % 128 == 0 && g.xa_off % 16 == 0 && g.bar_off % 8 == 0 && g.ms_off % 4 == 0, "tile / barrier offsets");
           CHECK(g.tab_off >= g.w_bytes && g.xs_off >= g.tab_off + (6 * g.Oy + 2 * kMaxAct + 2 * kTcRows) * 4, "table region");
           CHECK((size_t)g.smem_bytes <= max_smem && g.ms_floats >= 0 && g.ms_off + 4 * g.ms_floats == g.smem_bytes, "smem %d", g.smem_bytes);
+          CHECK(g.xch_off == -1 || (g.xch_off % 4 == 0 && g.xch_off + kTcfXchSlots * 2 * kTcRows * 4 == g.ms_off), "control-term slots");
         } else {
           CHECK(!why.empty(), "rejected without a reason O=%d A=%d U=%d", O, A, U);
         }

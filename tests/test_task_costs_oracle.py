@@ -50,3 +50,19 @@ def test_humanoid_cost_matches_reference_composition():
     obs[:, 37:40] = g["com_velocity"]
     np.testing.assert_allclose(tc.humanoid_cost(obs, g["control"]), 1.0 - g["reward"], rtol=1e-12, atol=1e-14)
     assert 0.0 <= (1.0 - g["reward"]).min() and (1.0 - g["reward"]).max() <= 1.0
+
+
+def test_cheetah_and_walker_costs_match_reference_composition():
+    """oracle cheetah-run / walker-walk costs == 1 - the tasks' get_reward composed with the reference's own
+    rewards.tolerance (tests/golden/locomotion_reward.npz; cheetah.py:91-97, walker.py:135-158) with the
+    speed proxies in the documented observation slots."""
+    g = load_golden("locomotion_reward.npz")
+    m = g["cheetah_reward"].shape[0]
+    obs_c = np.zeros((m, 17))
+    obs_c[:, 8] = g["cheetah_speed"]
+    np.testing.assert_allclose(tc.cheetah_run_cost(obs_c), 1.0 - g["cheetah_reward"], rtol=1e-12, atol=1e-14)
+    obs_w = np.zeros((m, 24))
+    obs_w[:, 14], obs_w[:, 0], obs_w[:, 16] = g["walker_height"], g["walker_upright"], g["walker_velocity"]
+    np.testing.assert_allclose(tc.walker_walk_cost(obs_w), 1.0 - g["walker_reward"], rtol=1e-12, atol=1e-14)
+    for c in (1.0 - g["cheetah_reward"], 1.0 - g["walker_reward"]):
+        assert 0.0 <= c.min() and c.max() <= 1.0 and c.std() > 0.05
