@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MBRL_ABI_VERSION 1
+#define MBRL_ABI_VERSION 2
 
 /* error codes */
 #define MBRL_OK 0
@@ -111,8 +111,18 @@ typedef struct MbrlPlanArgs {
   int32_t actions_only; /* 1: emit only the action sequence; the fp32 replay that produces the
                            predicted states is skipped and out_states is zero-filled.  MPCPolicy
                            only consumes plan[1][0] (src/mbrl/agents.py:56)                      */
+  int32_t warm_start;   /* MBRL_WARM_* bit mask: warm start across MPC steps with the sampling mean
+                           RESIDENT ON THE DEVICE (MPCPolicy hands the previous plan to the next call,
+                           src/mbrl/agents.py:41-47).  Ignored when h_mu0 is given. */
+  float warm_std;       /* std of a warm-started distribution; <= 0 -> (hi-lo)/2                 */
   int32_t reserved;
 } MbrlPlanArgs;
+
+#define MBRL_WARM_USE 1  /* seed the mean with the previous plan's final mean shifted by one step (last
+                            step repeated), if the handle holds one; std = warm_std                */
+#define MBRL_WARM_KEEP 2 /* refit after the last iteration and keep this plan's final mean in the
+                            handle for the next call (without this bit the stored mean is dropped:
+                            episode start, agents.py:38-40)                                        */
 
 typedef struct MbrlPlanInfo {
   float best_cost;

@@ -101,6 +101,8 @@ struct MbrlPlanner {
   float* d_costs = nullptr;     // [R]
   float* d_mu_hist = nullptr;   // [(Imax+1), E, H, A]
   float* d_sd_hist = nullptr;
+  float* d_mu_last = nullptr;   // [E,H,A] final mean of the previous plan (MBRL_WARM_KEEP), resident for the next call's warm start
+  bool have_last = false;
   int* d_elite = nullptr;       // [E, kmax]
   BestEver* d_best_ever = nullptr;  // [E]
   float* d_out_states = nullptr;    // [E,H,O]
@@ -130,7 +132,8 @@ struct MbrlPlanner {
   int* d_trunc = nullptr;       // truncation flag of the reduced-size elite gather
   float* d_refit_part = nullptr;           // [E][H*G][chunks][8] partial sums of the chunked refit
   unsigned int* d_refit_arrive = nullptr;  // [E][H*G] arrival counters (self-resetting)
-  bool full_gather = false;     // force worst-case-size gathers (set after a flagged plan)
+  bool full_gather = false;     // force worst-case-size gathers (while a flagged plan is redone)
+  int scratch_world = 0;        // world size the sharding scratch buffers were allocated for (0 = none)
   // peer-memory transport (mbrl_p2p_export / mbrl_p2p_attach)
   uint32_t* d_p2p_local = nullptr;  // exported: [2][world][2*slot] data + [world] flags
   int p2p_slot = 0, p2p_world = 0;
@@ -176,7 +179,7 @@ extern "C" int mbrl_destroy(MbrlPlanner* p) {
   if (!p) return MBRL_OK;
   cudaSetDevice(p->cfg.device);
   float* dev[] = {p->W1t, p->b1, p->W2t, p->b2, p->W3t, p->b3, p->mu_s, p->sd_s, p->mu_a, p->sd_a,
-                  p->cost_w, p->goal, p->d_s0, p->d_costs, p->d_mu_hist, p->d_sd_hist,
+                  p->cost_w, p->goal, p->d_s0, p->d_costs, p->d_mu_hist, p->d_sd_hist, p->d_mu_last,
                   p->d_out_states, p->d_out_actions, p->d_injected};
   for (float* q : dev) if (q) cudaFree(q);
   if (p->d_elite) cudaFree(p->d_elite);
@@ -250,6 +253,7 @@ extern "C" int mbrl_create(const MbrlConfig* cfg, MbrlPlanner** out) {
   A_(dev_alloc(&p->d_s0, (size_t)E * O)); A_(dev_alloc(&p->d_costs, (size_t)p->R));
   A_(dev_alloc(&p->d_mu_hist, EHA * (cfg->max_iterations + 1)));
   A_(dev_alloc(&p->d_sd_hist, EHA * (cfg->max_iterations + 1)));
+  A_(dev_alloc(&p->d_mu_last, EHA));
   A_(dev_alloc(&p->d_elite, (size_t)E * cfg->max_elites));
   {
     const size_t slots = (size_t)E * H * ((A + 3) / 4), chunks = (size_t)(cfg->max_elites + kRefitChunk - 1) / kRefitChunk;
@@ -302,7 +306,7 @@ extern "C" int mbrl_set_weights(MbrlPlanner* p, const float* W1, const float* b1
   if (!p) return fail(MBRL_E_INVALID, "null planner");
   MBRL_REQUIRE(W1 && b1 && W2 && b2 && W3 && b3, "null weight pointer");
   MBRL_CUDA(cudaSetDevice(p->cfg.device));
-  MBRL_CUDA(cudaStreamSynchronize(p->stream));
+  MBRL_CUDA(cudaDeviceSynchronize());  // a plan may be in flight on ANY stream (mbrl_plan_device runs on the caller's)
   std::vector<float> t;
   transpose_to(t, W1, p->U, p->D);
   MBRL_CUDA(cudaMemcpy(p->W1t, t.data(), sizeof(float) * t.size(), cudaMemcpyHostToDevice));
@@ -325,7 +329,7 @@ extern "C" int mbrl_set_norm(MbrlPlanner* p, const float* mu_s, const float* sd_
                              const float* sd_a) {
   if (!p) return fail(MBRL_E_INVALID, "null planner");
   MBRL_CUDA(cudaSetDevice(p->cfg.device));
-  MBRL_CUDA(cudaStreamSynchronize(p->stream));
+  MBRL_CUDA(cudaDeviceSynchronize());  // a plan may be in flight on ANY stream (mbrl_plan_device runs on the caller's)
   std::vector<float> zeros(kMaxObs, 0.f), ones(kMaxObs, 1.f);
   MBRL_CUDA(cudaMemcpy(p->mu_s, mu_s ? mu_s : zeros.data(), sizeof(float) * p->O, cudaMemcpyHostToDevice));
   MBRL_CUDA(cudaMemcpy(p->sd_s, sd_s ? sd_s : ones.data(), sizeof(float) * p->O, cudaMemcpyHostToDevice));
@@ -339,7 +343,7 @@ extern "C" int mbrl_set_cost(MbrlPlanner* p, int32_t kind, const float* w, const
   if (!p) return fail(MBRL_E_INVALID, "null planner");
   MBRL_REQUIRE(kind == MBRL_COST_SMOOTHABS_COSH || kind == MBRL_COST_REWARD_HEAD || is_task_cost(kind), "unknown cost kind");
   MBRL_CUDA(cudaSetDevice(p->cfg.device));
-  MBRL_CUDA(cudaStreamSynchronize(p->stream));
+  MBRL_CUDA(cudaDeviceSynchronize());  // a plan may be in flight on ANY stream (mbrl_plan_device runs on the caller's)
   if (is_task_cost(kind)) {
     int pick[4];
     task_pick_indices(kind, pick);
@@ -371,7 +375,7 @@ extern "C" int mbrl_set_reward_head(MbrlPlanner* p, const float* h_W4, float b4,
   if (!p) return fail(MBRL_E_INVALID, "null planner");
   MBRL_REQUIRE(h_W4, "null reward-head weights");
   MBRL_CUDA(cudaSetDevice(p->cfg.device));
-  MBRL_CUDA(cudaStreamSynchronize(p->stream));
+  MBRL_CUDA(cudaDeviceSynchronize());  // a plan may be in flight on ANY stream (mbrl_plan_device runs on the caller's)
   if (!p->W4) MBRL_CUDA(dev_alloc(&p->W4, (size_t)p->U));
   MBRL_CUDA(cudaMemcpy(p->W4, h_W4, sizeof(float) * p->U, cudaMemcpyHostToDevice));
   p->b4 = b4; p->mu_r = reward_mean; p->sd_r = reward_std;
@@ -614,18 +618,37 @@ extern "C" int mbrl_comm_destroy(MbrlPlanner* p) {
   return MBRL_OK;
 }
 
+static unsigned long long p2p_timeout_ns() {
+  static const unsigned long long ns = [] {
+    const char* e = getenv("MBRL_P2P_TIMEOUT_S");
+    const double sec = e ? std::atof(e) : 120.0;
+    return (unsigned long long)((sec > 0.0 ? sec : 120.0) * 1e9);
+  }();
+  return ns;
+}
+
 static int alloc_shard_scratch(MbrlPlanner* p, int world) {
-  if (p->d_ecost) return MBRL_OK;
+  if (p->scratch_world == world) return MBRL_OK;
+  // (re)allocate for this world size; commit only when every allocation succeeded
+  void* old[] = {p->d_ecost, p->d_send, p->d_recv, p->d_gcost, p->d_gidx, p->d_pos, p->d_best_now, p->d_trunc};
+  for (void* q : old) if (q) cudaFree(q);
+  p->d_ecost = nullptr; p->d_send = nullptr; p->d_recv = nullptr; p->d_gcost = nullptr; p->d_gidx = nullptr;
+  p->d_pos = nullptr; p->d_best_now = nullptr; p->d_trunc = nullptr; p->scratch_world = 0;
   const size_t kl = (size_t)std::min(p->cfg.max_elites, p->N);
-  MBRL_CUDA(dev_alloc(&p->d_ecost, kl));
-  MBRL_CUDA(dev_alloc(&p->d_send, 2 * kl));
-  MBRL_CUDA(dev_alloc(&p->d_recv, 2 * kl * world));
-  MBRL_CUDA(dev_alloc(&p->d_gcost, kl * world));
-  MBRL_CUDA(dev_alloc(&p->d_gidx, kl * world));
-  MBRL_CUDA(dev_alloc(&p->d_pos, (size_t)p->cfg.max_elites));
-  MBRL_CUDA(dev_alloc(&p->d_best_now, 1));
-  MBRL_CUDA(dev_alloc(&p->d_trunc, 1));
-  MBRL_CUDA(cudaMemset(p->d_trunc, 0, sizeof(int)));
+  bool ok = dev_alloc(&p->d_ecost, kl) == cudaSuccess && dev_alloc(&p->d_send, 2 * kl) == cudaSuccess &&
+            dev_alloc(&p->d_recv, 2 * kl * world) == cudaSuccess && dev_alloc(&p->d_gcost, kl * world) == cudaSuccess &&
+            dev_alloc(&p->d_gidx, kl * world) == cudaSuccess && dev_alloc(&p->d_pos, (size_t)p->cfg.max_elites) == cudaSuccess &&
+            dev_alloc(&p->d_best_now, 1) == cudaSuccess && dev_alloc(&p->d_trunc, 1) == cudaSuccess &&
+            cudaMemset(p->d_trunc, 0, sizeof(int)) == cudaSuccess;
+  if (!ok) {
+    void* part[] = {p->d_ecost, p->d_send, p->d_recv, p->d_gcost, p->d_gidx, p->d_pos, p->d_best_now, p->d_trunc};
+    for (void* q : part) if (q) cudaFree(q);
+    p->d_ecost = nullptr; p->d_send = nullptr; p->d_recv = nullptr; p->d_gcost = nullptr; p->d_gidx = nullptr;
+    p->d_pos = nullptr; p->d_best_now = nullptr; p->d_trunc = nullptr;
+    cudaGetLastError();
+    return fail(MBRL_E_CUDA, "out of device memory allocating the population-sharding scratch buffers");
+  }
+  p->scratch_world = world;
   return MBRL_OK;
 }
 
@@ -633,17 +656,36 @@ extern "C" int mbrl_p2p_export(MbrlPlanner* p, int32_t world, uint8_t* h_handle6
   if (!p) return fail(MBRL_E_INVALID, "null planner");
   MBRL_REQUIRE(h_handle64 && world >= 1 && world <= 64, "p2p_export: bad argument");
   MBRL_REQUIRE(p->E == 1, "population sharding needs num_envs == 1");
-  MBRL_REQUIRE(!p->d_p2p_local, "p2p buffer already exported");
+  MBRL_REQUIRE(!p->p2p_attached, "detach the peer buffers (mbrl_p2p_detach) before exporting again");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   MBRL_CUDA(cudaSetDevice(p->cfg.device));
-  p->p2p_slot = std::min(p->cfg.max_elites, p->N);
+  const int slot = std::min(p->cfg.max_elites, p->N);
+  const size_t words = (size_t)2 * world * 2 * slot + world;
+  if (p->d_p2p_local && p->p2p_world != world) {  // another world size: a new buffer
+    MBRL_CUDA(cudaDeviceSynchronize());
+    cudaFree(p->d_p2p_local); p->d_p2p_local = nullptr;
+  }
+  if (!p->d_p2p_local) {
+    uint32_t* buf = nullptr;
+    unsigned int* counter = p->d_p2p_counter;
+    int* err = p->d_p2p_error;
+    bool ok = dev_alloc(&buf, words) == cudaSuccess && (counter || dev_alloc(&counter, 1) == cudaSuccess) &&
+              (err || dev_alloc(&err, 1) == cudaSuccess);
+    if (!ok) {  // nothing half-initialised is left behind: a retry starts from scratch
+      if (buf) cudaFree(buf);
+      if (counter && counter != p->d_p2p_counter) cudaFree(counter);
+      if (err && err != p->d_p2p_error) cudaFree(err);
+      cudaGetLastError();
+      return fail(MBRL_E_CUDA, "out of device memory allocating the peer-memory gather buffer");
+    }
+    p->d_p2p_local = buf; p->d_p2p_counter = counter; p->d_p2p_error = err;
+  }
+  // (re-)export: flags, sequence number and arrival counter restart from zero on every rank
+  p->p2p_slot = slot;
   p->p2p_world = world;
-  const size_t words = (size_t)2 * world * 2 * p->p2p_slot + world;
-  MBRL_CUDA(dev_alloc(&p->d_p2p_local, words));
+  p->p2p_seq = 0;
   MBRL_CUDA(cudaMemset(p->d_p2p_local, 0, sizeof(uint32_t) * words));
-  MBRL_CUDA(dev_alloc(&p->d_p2p_counter, 1));
   MBRL_CUDA(cudaMemset(p->d_p2p_counter, 0, sizeof(unsigned int)));
-  MBRL_CUDA(dev_alloc(&p->d_p2p_error, 1));
   MBRL_CUDA(cudaMemset(p->d_p2p_error, 0, sizeof(int)));
   cudaIpcMemHandle_t hdl;
   MBRL_CUDA(cudaIpcGetMemHandle(&hdl, p->d_p2p_local));
@@ -745,15 +787,25 @@ static int enqueue_plan(MbrlPlanner* p, const MbrlPlanArgs* a, const float* d_s0
                         cudaStream_t st) {
   const int I = a->iterations;
   MBRL_REQUIRE(I >= 1 && I <= p->cfg.max_iterations, "iterations out of range [1, max_iterations]");
+  need_final_dist = need_final_dist || (a->warm_start & MBRL_WARM_KEEP) != 0;  // the kept mean is the refit after the last iteration
   const int k = (I == 1 && !need_final_dist) ? 1 : a->elites;
   MBRL_REQUIRE(k >= 1 && k <= p->cfg.max_elites, "elites out of range [1, max_elites]");
   const size_t EHA = (size_t)p->E * p->H * p->A;
   const long long HRA = (long long)p->H * p->R * p->A;
 
+  MBRL_REQUIRE((a->warm_start & ~(MBRL_WARM_USE | MBRL_WARM_KEEP)) == 0, "unknown warm_start bits");
+  const bool warm_keep = (a->warm_start & MBRL_WARM_KEEP) != 0;
   if (a->h_mu0 && a->h_sd0) {
     MBRL_CUDA(cudaMemcpyAsync(p->d_mu_hist, a->h_mu0, sizeof(float) * EHA, cudaMemcpyHostToDevice, st));
     MBRL_CUDA(cudaMemcpyAsync(p->d_sd_hist, a->h_sd0, sizeof(float) * EHA, cudaMemcpyHostToDevice, st));
     init_plan_kernel<<<(unsigned)((p->E + 255) / 256), 256, 0, st>>>(nullptr, nullptr, 0, p->lo, p->hi, p->d_best_ever, p->E);
+  } else if ((a->warm_start & MBRL_WARM_USE) && p->have_last) {
+    // device-resident warm start: no host round trip of the mean between MPC steps
+    MBRL_REQUIRE(!a->h_mu0 && !a->h_sd0, "mu0 and sd0 must be given together");
+    const float std = a->warm_std > 0.f ? a->warm_std : 0.5f * (p->hi - p->lo);
+    const long long n = (long long)EHA > p->E ? (long long)EHA : p->E;
+    warm_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p->d_mu_hist, p->d_sd_hist, p->d_mu_last, p->E, p->H, p->A, std,
+                                                                  p->lo, p->hi, p->d_best_ever);
   } else {
     MBRL_REQUIRE(!a->h_mu0 && !a->h_sd0, "mu0 and sd0 must be given together");
     const long long n = (long long)EHA > p->E ? (long long)EHA : p->E;
@@ -762,6 +814,7 @@ static int enqueue_plan(MbrlPlanner* p, const MbrlPlanArgs* a, const float* d_s0
   MBRL_CUDA(cudaGetLastError());
 
   const bool sharded = p->comm != nullptr || p->p2p_attached;
+  if (p->p2p_attached) MBRL_CUDA(cudaMemsetAsync(p->d_p2p_error, 0, sizeof(int), st));  // one late rank must not poison later plans
   if (sharded) {
     MBRL_REQUIRE(a->sample_mode == MBRL_SAMPLE_GAUSSIAN || a->sample_mode == MBRL_SAMPLE_UNIFORM,
                  "population sharding supports the Philox sample modes only");
@@ -801,7 +854,7 @@ static int enqueue_plan(MbrlPlanner* p, const MbrlPlanArgs* a, const float* d_s0
                              (int)cand_offset, p->p2p_peers, p->rank, p->world, p->p2p_slot, (int)(seq & 1), seq,
                              p->d_p2p_counter));
         MBRL_CUDA(launch_pdl(p2p_wait_unpack_kernel, dim3((ng + 255) / 256), dim3(256), 0, st, p->d_p2p_local, p->world,
-                             p->p2p_slot, kl, (int)(seq & 1), seq, p->d_gcost, p->d_gidx, p->d_p2p_error));
+                             p->p2p_slot, kl, (int)(seq & 1), seq, p->d_gcost, p->d_gidx, p->d_p2p_error, p2p_timeout_ns()));
       } else {
         pack_elites_kernel<<<(kl + 255) / 256, 256, 0, st>>>(p->d_ecost, p->d_elite, kl, (int)cand_offset, p->d_send);
         MBRL_NCCL(g_nccl.AllGather(p->d_send, p->d_recv, (size_t)2 * kl, kNcclUint32, p->comm, st));
@@ -831,9 +884,17 @@ static int enqueue_plan(MbrlPlanner* p, const MbrlPlanArgs* a, const float* d_s0
                          p->d_mu_hist, p->d_sd_hist, I, a->return_mean, a->actions_only, p->d_best_ever, d_out_states,
                          d_out_actions, d_info, st);
   if (rc) return rc;
-  if (sharded && d_info) {  // info.reserved = 1: the reduced-size elite gather was not provably exact
-    MBRL_CUDA(cudaMemcpyAsync(&d_info[0].reserved, p->d_trunc, sizeof(int), cudaMemcpyDeviceToDevice, st));
-    MBRL_CUDA(cudaMemsetAsync(p->d_trunc, 0, sizeof(int), st));
+  if (warm_keep) {
+    MBRL_CUDA(cudaMemcpyAsync(p->d_mu_last, p->d_mu_hist + (size_t)I * EHA, sizeof(float) * EHA, cudaMemcpyDeviceToDevice, st));
+    p->have_last = true;
+  } else {
+    p->have_last = false;  // episode start (or a caller that does not warm start): forget the stored mean
+  }
+  if (sharded) {
+    // info.reserved bit 0: the reduced-size elite gather was not provably exact; bit 1: the peer-memory
+    // exchange timed out.  The truncation flag is reset here even when the caller passed no info buffer.
+    MBRL_CUDA(launch_pdl(shard_flags_kernel, dim3(1), dim3(32), 0, st, d_info, p->d_trunc,
+                         p->p2p_attached ? (const int*)p->d_p2p_error : (const int*)nullptr));
   }
   return MBRL_OK;
 }
@@ -886,16 +947,16 @@ extern "C" int mbrl_plan(MbrlPlanner* p, const MbrlPlanArgs* args, const float* 
     MBRL_CUDA(cudaMemcpyAsync(p->h_sd, p->d_sd_hist + (size_t)args->iterations * EHA, sizeof(float) * EHA, cudaMemcpyDeviceToHost, st));
   }
   MBRL_CUDA(cudaStreamSynchronize(st));
-  if (p->p2p_attached) {
-    int perr = 0;
-    MBRL_CUDA(cudaMemcpy(&perr, p->d_p2p_error, sizeof(int), cudaMemcpyDeviceToHost));
-    if (perr) return fail(MBRL_E_CUDA, "peer-memory elite exchange timed out waiting for another rank");
-  }
-  if ((p->comm || p->p2p_attached) && p->h_info[0].reserved != 0 && !p->full_gather) {
+  if (p->p2p_attached && (p->h_info[0].reserved & 2))
+    return fail(MBRL_E_CUDA, "peer-memory elite exchange timed out waiting for another rank (MBRL_P2P_TIMEOUT_S); the ranks' "
+                             "sequence numbers are out of step now: mbrl_p2p_detach, then export / attach again (or mbrl_comm_init)");
+  if ((p->comm || p->p2p_attached) && (p->h_info[0].reserved & 1) && !p->full_gather) {
     // Practically unreachable (the shards are i.i.d.): some rank's reduced elite list was used up.
     // The flag derives from the gathered data, so every rank sees it and redoes the plan in lockstep.
     p->full_gather = true;
-    return mbrl_plan(p, args, h_s0, h_out_states, h_out_actions, h_info, h_out_mu, h_out_sd);
+    const int rc2 = mbrl_plan(p, args, h_s0, h_out_states, h_out_actions, h_info, h_out_mu, h_out_sd);
+    p->full_gather = false;  // the redo succeeded (or failed for another reason): back to reduced-size gathers
+    return rc2;
   }
   std::memcpy(h_out_actions, p->h_out_actions, sizeof(float) * EHA);
   std::memcpy(h_out_states, p->h_out_states, sizeof(float) * E * H * O);

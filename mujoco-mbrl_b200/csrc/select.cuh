@@ -431,10 +431,18 @@ __global__ void p2p_scatter_kernel(const float* __restrict__ elite_cost, const i
   }
 }
 // Consumer: acquire every rank's flag (>= seq), then unpack [parity][r][..] into contiguous costs /
-// global indices in rank order.  A rank that never shows up trips the timeout: *error = 1.
+// global indices in rank order.  A rank that never shows up within `timeout_ns` (wall clock, default
+// 120 s, MBRL_P2P_TIMEOUT_S) trips the timeout: *error = 1 and the gathered arrays are filled with
+// (+inf, -1) sentinels instead of the previous iteration's data, so that whatever runs next is
+// deterministic garbage that the plan reports (info.reserved bit 1) rather than a plausible wrong plan.
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __global__ void p2p_wait_unpack_kernel(const uint32_t* __restrict__ local, int world, int slot, int k_l, int parity,
                                        uint32_t seq, float* __restrict__ gcost, int* __restrict__ gidx,
-                                       int* __restrict__ error) {
+                                       int* __restrict__ error, unsigned long long timeout_ns) {
   __shared__ int s_ok;
   pdl_trigger();
   pdl_wait();
@@ -442,19 +450,36 @@ __global__ void p2p_wait_unpack_kernel(const uint32_t* __restrict__ local, int w
   __syncthreads();
   if (threadIdx.x < world) {
     const uint32_t* flag = local + (size_t)2 * world * 2 * slot + threadIdx.x;
-    const long long t0 = clock64();
+    const unsigned long long t0 = globaltimer_ns();
+    unsigned int spins = 0;
     while ((int)(ld_acquire_sys(flag) - seq) < 0) {
-      if (clock64() - t0 > 20000000000ll) { s_ok = 0; break; }  // ~10 s
+      if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > timeout_ns) { s_ok = 0; break; }
     }
   }
   __syncthreads();
-  if (!s_ok) { if (threadIdx.x == 0 && blockIdx.x == 0) *error = 1; return; }
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (!s_ok) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *error = 1;
+    if (i < world * k_l) { gcost[i] = __int_as_float(0x7f800000); gidx[i] = -1; }
+    return;
+  }
   if (i < world * k_l) {
     const int r = i / k_l, j = i - r * k_l;
     const uint32_t* src = local + ((size_t)parity * world + r) * 2 * slot;
     gcost[i] = __uint_as_float(__ldcg(src + j));
     gidx[i] = (int)__ldcg(src + k_l + j);
+  }
+}
+
+// End of a sharded plan: info.reserved = (reduced-gather-not-provably-exact) | (exchange timed out) << 1;
+// the truncation flag is reset for the next plan whether or not the caller passed an info buffer.
+__global__ void shard_flags_kernel(MbrlPlanInfo* __restrict__ info, int* __restrict__ trunc, const int* __restrict__ p2p_error) {
+  pdl_trigger();
+  pdl_wait();
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const int t = dep_load(trunc) != 0, e = p2p_error ? (dep_load(p2p_error) != 0) : 0;
+    if (info) info[0].reserved = t | (e << 1);
+    *trunc = 0;
   }
 }
 
@@ -509,6 +534,25 @@ __global__ void init_plan_kernel(float* __restrict__ mu, float* __restrict__ sd,
   pdl_trigger();
   pdl_wait();
   if (mu && i < n) { mu[i] = 0.5f * (lo + hi); sd[i] = 0.5f * (hi - lo); }
+  if (best_ever && i < E) best_ever[i] = BestEver{0.f, -1, -1, 0};
+}
+
+// Warm start resident on the device (MBRL_WARM_USE): the new mean is the previous plan's final mean
+// shifted by one step with the last step repeated (the MPC receding-horizon shift of
+// MPCPolicy's hand-over, src/mbrl/agents.py:41-47), std = `std`; best-ever reset.
+__global__ void warm_init_kernel(float* __restrict__ mu, float* __restrict__ sd, const float* __restrict__ last_mu,
+                                 int E, int H, int A, float std, float lo, float hi, BestEver* __restrict__ best_ever) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  pdl_trigger();
+  pdl_wait();
+  const long long n = (long long)E * H * A;
+  if (i < n) {
+    const int a = (int)(i % A), h = (int)((i / A) % H);
+    const long long e = i / ((long long)A * H);
+    const int hs = h + 1 < H ? h + 1 : H - 1;
+    mu[i] = clipf(dep_load(last_mu + (e * H + hs) * A + a), lo, hi);
+    sd[i] = std;
+  }
   if (best_ever && i < E) best_ever[i] = BestEver{0.f, -1, -1, 0};
 }
 

@@ -64,6 +64,13 @@ def register_planners(experiment_module, enum_name: str = "Planner"):
     if not (isinstance(enum_cls, type) and issubclass(enum_cls, Enum)):
         raise TypeError(f"{experiment_module.__name__}.{enum_name} is not an Enum")
     members = {value: _add_member(enum_cls, _MEMBER_NAMES[value], value) for value in PLANNERS}
+    # MPCPolicy consumes only plan[1][0], the first action (src/mbrl/agents.py:56): planners selected
+    # through the reference's CLI skip the fp32 replay that produces the predicted states (zeros are
+    # returned in their place; the next call's warm start ignores the states anyway) and CEM keeps its
+    # sampling mean resident on the device between MPC steps.  configure(..., return_states=True) undoes it.
+    RandomShootingPlanner.defaults["return_states"] = False
+    CEMPlanner.defaults["return_states"] = False
+    CEMPlanner.defaults["warm_start"] = "shift_mean"
     if not getattr(enum_cls.construct, "_b200_patched", False):
         original = enum_cls.construct
 

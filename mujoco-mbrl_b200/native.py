@@ -20,6 +20,7 @@ ENGINES = {"fp32": ENGINE_SIMT_FP32, "simt": ENGINE_SIMT_FP32, "bf16": ENGINE_TC
 SAMPLE_INJECT_ACTIONS, SAMPLE_INJECT_NOISE, SAMPLE_GAUSSIAN, SAMPLE_UNIFORM = 0, 1, 2, 3
 COST_SMOOTHABS_COSH, COST_DMC_CARTPOLE_SWINGUP, COST_REWARD_HEAD, COST_DMC_HUMANOID_RUN = 0, 1, 2, 3
 COST_DMC_CHEETAH_RUN, COST_DMC_WALKER_WALK = 4, 5
+WARM_USE, WARM_KEEP = 1, 2
 
 # every symbol include/mbrl_b200.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
@@ -42,7 +43,7 @@ class MbrlPlanArgs(C.Structure):
         ("iterations", C.c_int32), ("elites", C.c_int32), ("sample_mode", C.c_int32), ("return_mean", C.c_int32),
         ("seed", C.c_uint64), ("cand_offset", C.c_uint32), ("env_offset", C.c_uint32),
         ("h_injected", C.c_void_p), ("h_mu0", C.c_void_p), ("h_sd0", C.c_void_p),
-        ("actions_only", C.c_int32), ("reserved", C.c_int32),
+        ("actions_only", C.c_int32), ("warm_start", C.c_int32), ("warm_std", C.c_float), ("reserved", C.c_int32),
     ]
 
 
@@ -219,10 +220,11 @@ class NativePlanner:
 
     # ---- whole plans -----------------------------------------------------------------
     def _args(self, iterations, elites, mode, seed, return_mean, cand_offset, env_offset, injected, mu0, sd0,
-              actions_only=False):
+              actions_only=False, warm_start=0, warm_std=0.0):
         keep = []
         a = MbrlPlanArgs()
         a.actions_only = int(actions_only)
+        a.warm_start, a.warm_std = int(warm_start), float(warm_std)
         a.iterations, a.elites, a.sample_mode, a.return_mean = iterations, elites, mode, int(return_mean)
         a.seed, a.cand_offset, a.env_offset = int(seed) & (2 ** 64 - 1), cand_offset, env_offset
         for name, val, n in (("h_injected", injected, iterations * self.H * self.R * self.A),
@@ -236,12 +238,13 @@ class NativePlanner:
         return a, keep
 
     def plan(self, s0, iterations=1, elites=1, mode=SAMPLE_GAUSSIAN, seed=0, injected=None, mu0=None, sd0=None,
-             return_mean=False, want_dist=False, cand_offset=0, env_offset=0, actions_only=False):
+             return_mean=False, want_dist=False, cand_offset=0, env_offset=0, actions_only=False, warm_start=0,
+             warm_std=0.0):
         """mbrl_plan with host buffers.  s0: [O] or [E,O].  Returns a dict of numpy arrays:
         states [E,H,O], actions [E,H,A], info (structured [E]), optionally mu/sd [E,H,A]."""
         s0 = _f32(s0).reshape(self.E, self.O)
         args, keep = self._args(iterations, elites, mode, seed, return_mean, cand_offset, env_offset, injected, mu0, sd0,
-                                actions_only)
+                                actions_only, warm_start, warm_std)
         states = np.empty((self.E, self.H, self.O), np.float32)
         actions = np.empty((self.E, self.H, self.A), np.float32)
         info = np.zeros(self.E, PLAN_INFO_DTYPE)
@@ -254,10 +257,10 @@ class NativePlanner:
 
     def plan_device(self, d_s0, d_out_states, d_out_actions, d_info=None, iterations=1, elites=1,
                     mode=SAMPLE_GAUSSIAN, seed=0, d_injected=None, return_mean=False, cand_offset=0, env_offset=0,
-                    actions_only=False):
+                    actions_only=False, warm_start=0, warm_std=0.0):
         """mbrl_plan_device: everything resident in HBM, enqueued on torch's current stream."""
         args, keep = self._args(iterations, elites, mode, seed, return_mean, cand_offset, env_offset, None, None, None,
-                                actions_only)
+                                actions_only, warm_start, warm_std)
         _check(self.lib.mbrl_plan_device(self._h, C.byref(args), _dp(d_s0), _dp(d_injected), _dp(d_out_states),
                                          _dp(d_out_actions), _dp(d_info), _stream_ptr()))
 

@@ -17,9 +17,22 @@ from typing import Dict, Optional, Tuple
 import numpy as np
 
 from . import native
-from .adaptor import PlanningProblem, problem_from_callables
+from .adaptor import PlanningProblem, problem_from_callables, problem_from_callables_cached
 
 _HANDLES: Dict[tuple, dict] = {}
+_HANDLES_PID = None  # the process that built the cache: a forked child must not reuse the parent's CUDA handles
+_SEED_SALT = None    # per-process salt of the default seed stream (parallel rollout workers explore differently)
+
+
+def _default_seed(ent):
+    """seed=None: a per-handle call counter on top of a per-process random salt, so that the reference's
+    parallel rollout workers (src/mbrl/parallel.py:20-38), which all start their counters at zero, do not
+    evaluate identical Philox candidate sets at the same MPC step."""
+    global _SEED_SALT
+    if _SEED_SALT is None:
+        import os
+        _SEED_SALT = int.from_bytes(os.urandom(6), "little") << 16
+    return _SEED_SALT + ent["calls"]
 
 
 def _as_torch(x):
@@ -27,8 +40,34 @@ def _as_torch(x):
     return torch.from_numpy(np.ascontiguousarray(x))
 
 
+def _check_process():
+    """Handles hold CUDA state that does not survive fork(): each process builds its own cache, and a
+    forked child of a parent that had already initialised CUDA gets a clear error instead of a cryptic
+    CUDA initialisation failure inside mbrl_create (use the 'spawn' or 'forkserver' start method, as the
+    reference's entry point does: src/mbrl/experiment.py:203)."""
+    global _HANDLES_PID
+    import os
+    pid = os.getpid()
+    if _HANDLES_PID is None:
+        _HANDLES_PID = pid
+    elif _HANDLES_PID != pid:
+        _HANDLES.clear()  # the parent's handles are not ours to destroy: just forget them
+        _HANDLES_PID = pid
+        try:
+            import torch
+            bad_fork = getattr(torch.cuda, "_is_in_bad_fork", None)
+            if (bad_fork() if bad_fork else torch.cuda.is_initialized()):
+                raise native.MbrlError(
+                    "this process was fork()ed from a parent that had already initialised CUDA; CUDA cannot be "
+                    "used in such a child.  Start rollout workers with the 'spawn' or 'forkserver' method "
+                    "(torch.multiprocessing.set_start_method), as src/mbrl/experiment.py:203 does")
+        except ImportError:
+            pass
+
+
 def _get_handle(model, cost, sample_action, horizon, n, max_iters, engine, device):
-    prob, fp = problem_from_callables(model, cost, sample_action)
+    _check_process()
+    prob, fp = problem_from_callables_cached(model, cost, sample_action)
     owner = model.func if hasattr(model, "func") else model
     key = (id(owner), prob.obs_dim, prob.act_dim, prob.hidden, horizon, n, max_iters, engine, device)
     ent = _HANDLES.get(key)
@@ -90,7 +129,7 @@ class RandomShootingPlanner(ModelPlanner):
         h = ent["handle"]
         seed = kwargs.get("seed", d["seed"])
         if seed is None:
-            seed = ent["calls"]
+            seed = _default_seed(ent)
         ent["calls"] += 1
         if sampler == "host":
             out = h.plan(initial_state, 1, 1, native.SAMPLE_INJECT_ACTIONS, seed,
@@ -115,9 +154,9 @@ class CEMPlanner(ModelPlanner):
       "trajectory" (default)  the mean is seeded with that action sequence as the reference hands it
                               over (un-shifted: agents.py:45 slices the states but not the actions);
       "shift_mean"            the mean is the previous call's FINAL CEM mean shifted by one step
-                              (last step repeated) -- the usual MPC-CEM warm start; the previous mean
-                              is kept with the cached handle and dropped when `initial_trajectory`
-                              is None (episode start);
+                              (last step repeated) -- the usual MPC-CEM warm start.  The mean stays
+                              RESIDENT ON THE DEVICE between calls (MbrlPlanArgs.warm_start) and is
+                              dropped when `initial_trajectory` is None (episode start);
       "none"                  always start from the action-range midpoint.
     `init_std` sets the std of a warm-started distribution (default: half the action range)."""
 
@@ -135,33 +174,32 @@ class CEMPlanner(ModelPlanner):
         h = ent["handle"]
         seed = kwargs.get("seed", d["seed"])
         if seed is None:
-            seed = ent["calls"]
+            seed = _default_seed(ent)
         ent["calls"] += 1
         warm = kwargs.get("warm_start", d["warm_start"])
         if warm not in ("trajectory", "shift_mean", "none"):
             raise ValueError("warm_start must be 'trajectory', 'shift_mean' or 'none'")
         mu0 = sd0 = None
-        if initial_trajectory is None:
-            ent["last_mu"] = None  # episode start (agents.py:38-40)
-        elif warm == "trajectory":
+        init_std = kwargs.get("init_std", d["init_std"])
+        warm_flags = 0
+        if warm == "shift_mean":
+            # device-resident: the handle keeps the final mean of this plan (KEEP) and seeds the next call
+            # with it, shifted by one step on the device (USE) -- no D2H / H2D of the mean between MPC
+            # steps.  initial_trajectory is None at the start of an episode (agents.py:38-40): cold start.
+            warm_flags = native.WARM_KEEP | (native.WARM_USE if initial_trajectory is not None else 0)
+        elif warm == "trajectory" and initial_trajectory is not None:
             acts = native._f32(_stack(initial_trajectory[1])).reshape(-1, prob.act_dim)
             mu0 = np.zeros((horizon, prob.act_dim), np.float32) + 0.5 * (prob.act_lo + prob.act_hi)
             m = min(horizon, acts.shape[0])
             mu0[:m] = acts[:m]
-        elif warm == "shift_mean" and ent.get("last_mu") is not None:
-            last = ent["last_mu"]
-            mu0 = np.concatenate([last[1:], last[-1:]], axis=0).astype(np.float32)
-        if mu0 is not None:
-            init_std = kwargs.get("init_std", d["init_std"])
             sd0 = np.full((horizon, prob.act_dim), 0.5 * (prob.act_hi - prob.act_lo) if init_std is None else init_std,
                           np.float32)
         noise = kwargs.get("noise")  # [I, H*N, A] recorded N(0,1) draws (parity runs)
         mode = native.SAMPLE_GAUSSIAN if noise is None else native.SAMPLE_INJECT_NOISE
         out = h.plan(initial_state, iters, k, mode, seed, injected=noise, mu0=mu0, sd0=sd0,
-                     return_mean=kwargs.get("return_mean", d["return_mean"]), want_dist=warm == "shift_mean",
-                     actions_only=not kwargs.get("return_states", d["return_states"]))
-        if warm == "shift_mean":
-            ent["last_mu"] = np.array(out["mu"][0], np.float32)
+                     return_mean=kwargs.get("return_mean", d["return_mean"]),
+                     actions_only=not kwargs.get("return_states", d["return_states"]),
+                     warm_start=warm_flags, warm_std=0.0 if init_std is None else float(init_std))
         return _as_torch(out["states"][0]), _as_torch(out["actions"][0])
 
 

@@ -21,14 +21,14 @@ def test_library_exports_every_header_symbol():
     assert declared == set(native.ABI_SYMBOLS), declared ^ set(native.ABI_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.mbrl_abi_version() == 1
+    assert lib.mbrl_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
     from mbrl_b200 import native
     assert ctypes.sizeof(native.MbrlConfig) == 40
     assert ctypes.sizeof(native.MbrlPlanInfo) == 16 == native.PLAN_INFO_DTYPE.itemsize
-    assert ctypes.sizeof(native.MbrlPlanArgs) == 64
+    assert ctypes.sizeof(native.MbrlPlanArgs) == 72
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
@@ -109,8 +109,9 @@ def test_cem_warm_start_modes_host_logic(monkeypatch):
     """CEMPlanner's warm start is host logic over the C ABI: checked with a
     recording stand-in for the native handle (no GPU)."""
     import numpy as np
+    import pytest
     import torch
-    from mbrl_b200 import planners
+    from mbrl_b200 import native, planners
     from mbrl_b200.adaptor import PlanningProblem
 
     H, A, O = 4, 2, 3
@@ -118,12 +119,11 @@ def test_cem_warm_start_modes_host_logic(monkeypatch):
 
     class FakeHandle:
         def plan(self, s0, iters, k, mode, seed, injected=None, mu0=None, sd0=None, return_mean=False,
-                 want_dist=False, actions_only=False):
+                 want_dist=False, actions_only=False, warm_start=0, warm_std=0.0):
             calls.append(dict(mu0=None if mu0 is None else np.array(mu0), sd0=None if sd0 is None else np.array(sd0),
-                              want_dist=want_dist))
-            mu = np.arange(H * A, dtype=np.float32).reshape(1, H, A) / 10 + len(calls)
+                              want_dist=want_dist, warm_start=warm_start, warm_std=warm_std))
             return dict(states=np.zeros((1, H, O), np.float32), actions=np.zeros((1, H, A), np.float32),
-                        mu=mu if want_dist else None, sd=None, info=None)
+                        mu=None, sd=None, info=None)
 
     ent = dict(handle=FakeHandle(), calls=0)
 
@@ -133,23 +133,22 @@ def test_cem_warm_start_modes_host_logic(monkeypatch):
     monkeypatch.setattr(planners, "_get_handle", lambda *a, **kw: (ent, Prob))
     plan = planners.CEMPlanner.plan
     prev = (torch.zeros(H - 1, O), torch.full((H, A), 0.25))
-    # shift_mean: first step of an episode has no previous mean; the second starts from the shifted final mean
+    # shift_mean keeps the mean RESIDENT ON THE DEVICE: nothing is uploaded or read back; the first step of an
+    # episode (initial_trajectory None) only asks the handle to keep its final mean, later steps also use it
     plan(torch.zeros(O), None, None, None, H, None, warm_start="shift_mean", num_trajectories=8)
-    assert calls[-1]["mu0"] is None and calls[-1]["want_dist"]
+    assert calls[-1]["mu0"] is None and not calls[-1]["want_dist"] and calls[-1]["warm_start"] == native.WARM_KEEP
     plan(torch.zeros(O), None, None, None, H, prev, warm_start="shift_mean", num_trajectories=8, init_std=0.3)
-    first_mu = np.arange(H * A, dtype=np.float32).reshape(H, A) / 10 + 1
-    np.testing.assert_array_equal(calls[-1]["mu0"], np.concatenate([first_mu[1:], first_mu[-1:]]))
-    np.testing.assert_array_equal(calls[-1]["sd0"], np.full((H, A), 0.3, np.float32))
+    assert calls[-1]["mu0"] is None and calls[-1]["warm_start"] == native.WARM_KEEP | native.WARM_USE
+    assert calls[-1]["warm_std"] == pytest.approx(0.3)
     plan(torch.zeros(O), None, None, None, H, None, warm_start="shift_mean", num_trajectories=8)
-    assert calls[-1]["mu0"] is None  # episode start drops the remembered mean
+    assert calls[-1]["warm_start"] == native.WARM_KEEP  # episode start drops the remembered mean
     # trajectory (default): the reference's handed-over action sequence seeds the mean
     plan(torch.zeros(O), None, None, None, H, prev, num_trajectories=8)
     np.testing.assert_array_equal(calls[-1]["mu0"], np.full((H, A), 0.25, np.float32))
     np.testing.assert_array_equal(calls[-1]["sd0"], np.ones((H, A), np.float32))
     # none: never warm-started
     plan(torch.zeros(O), None, None, None, H, prev, warm_start="none", num_trajectories=8)
-    assert calls[-1]["mu0"] is None
-    import pytest
+    assert calls[-1]["mu0"] is None and calls[-1]["warm_start"] == 0
     with pytest.raises(ValueError):
         plan(torch.zeros(O), None, None, None, H, prev, warm_start="bogus", num_trajectories=8)
 

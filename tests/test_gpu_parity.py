@@ -531,6 +531,30 @@ def test_warm_start_and_return_mean(native):
     np.testing.assert_allclose(outm["states"][0], st.numpy(), rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("engine", ["fp32", "fp16"])
+def test_device_resident_warm_start_equals_host_round_trip(native, engine):
+    """MBRL_WARM_KEEP / MBRL_WARM_USE (the mean stays on the device between MPC steps,
+    src/mbrl/agents.py:41-47): plan 2 warm-started on the device equals, bit for bit, plan 2 seeded from the
+    host with plan 1's final mean shifted by one step; and a call without MBRL_WARM_KEEP forgets the mean."""
+    p = po.synthetic_params(17, 6, 200)
+    H, N, I, k = 12, 1024, 3, 102
+    s0a, s0b = po.synthetic_state(p, 1).numpy(), po.synthetic_state(p, 2).numpy()
+    h = _planner(native, p, H, N, 1, I, engine=engine)
+    first = h.plan(s0a, I, k, native.SAMPLE_GAUSSIAN, seed=1, want_dist=True, warm_start=native.WARM_KEEP)
+    dev = h.plan(s0b, I, k, native.SAMPLE_GAUSSIAN, seed=2, want_dist=True, warm_start=native.WARM_KEEP | native.WARM_USE, warm_std=0.4)
+    mu0 = np.concatenate([first["mu"][0][1:], first["mu"][0][-1:]])[None]
+    h2 = _planner(native, p, H, N, 1, I, engine=engine)
+    host = h2.plan(s0b, I, k, native.SAMPLE_GAUSSIAN, seed=2, want_dist=True, mu0=mu0, sd0=np.full_like(mu0, 0.4))
+    for key in ("actions", "states", "mu", "sd"):
+        np.testing.assert_array_equal(dev[key], host[key], err_msg=key)
+    assert dev["info"]["best_cost"][0] == host["info"]["best_cost"][0]
+    # a plan without KEEP drops the stored mean: the next USE call is a cold start
+    h.plan(s0a, I, k, native.SAMPLE_GAUSSIAN, seed=3)
+    cold = h.plan(s0b, I, k, native.SAMPLE_GAUSSIAN, seed=2, want_dist=True, warm_start=native.WARM_USE)
+    ref = h2.plan(s0b, I, k, native.SAMPLE_GAUSSIAN, seed=2, want_dist=True)
+    np.testing.assert_array_equal(cold["actions"], ref["actions"])
+
+
 def test_refit_large_elite_set_chunked(native):
     """k > 2048 elites: the refit runs as parallel 2048-elite chunks whose partial sums are added in
     chunk order -- checked against the oracle refit and for run-to-run bit stability."""

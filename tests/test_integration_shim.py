@@ -11,6 +11,17 @@ from enum import Enum
 import pytest
 
 
+@pytest.fixture(autouse=True)
+def _restore_planner_defaults():
+    """register_planners / configure edit the planner classes' `defaults` in place (the reference's own
+    hyper-parameter pattern); keep the edits from leaking into other tests of the session."""
+    from mbrl_b200 import CEMPlanner, RandomShootingPlanner
+    saved = dict(CEMPlanner.defaults), dict(RandomShootingPlanner.defaults)
+    yield
+    CEMPlanner.defaults.clear(); CEMPlanner.defaults.update(saved[0])
+    RandomShootingPlanner.defaults.clear(); RandomShootingPlanner.defaults.update(saved[1])
+
+
 def _replica_module():
     mod = types.ModuleType("replica_experiment")
 
@@ -48,6 +59,9 @@ def test_register_on_replica_enum():
     assert mod.Planner("cem-b200").construct() is CEMPlanner
     assert mod.Planner("rs-b200").construct() is RandomShootingPlanner
     assert mod.Planner("rs").construct() == "ref-rs"          # reference members untouched
+    # MPC use (MPCPolicy reads only the first action): no state replay, device-resident CEM warm start
+    assert CEMPlanner.defaults["return_states"] is False and RandomShootingPlanner.defaults["return_states"] is False
+    assert CEMPlanner.defaults["warm_start"] == "shift_mean"
     assert _parse(mod, ["--planner", "cem-b200"]).planner is mod.Planner.CEMB200
     with pytest.raises(SystemExit):
         _parse(mod, ["--planner", "nope"])
