@@ -142,6 +142,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "WAIT_DONE:\n\t"
       "}\n" ::"r"(bar), "r"(parity), "r"(0x989680) : "memory");
 }
+// try_wait WITHOUT a suspend-time hint: the instruction itself blocks in hardware until the phase completes
+// or an implementation-defined time limit passes (the CUTLASS ClusterBarrier::wait loop).
+__device__ __forceinline__ void mbar_wait_nohint(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
 // One elected lane of a fully converged warp (what cute::elect_one_sync emits).  Code guarded by
 // this predicate is known to the compiler to run in exactly one thread, so warp-level
 // instructions (UTCHMMA, UTCBAR, UBLKCP) are emitted once with uniform-register operands instead
