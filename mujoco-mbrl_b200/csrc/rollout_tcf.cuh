@@ -46,6 +46,7 @@ struct TcfGeom {
   int wa_off, waa_off, w1s_off, w2_off, w_bytes;
   int tab_off, xs_off, xa_off, bar_off, smem_bytes;
   int ms_off, ms_floats;  // staging area for the sampling mean/std rows of the tile's environments
+  int exp;      // profiling experiments (MBRL_TCF_EXP bit mask)
   int xch_off;  // task costs: per-step control terms (a0, ctl_mean) handed from the sampler to the cost threads; -1 = no room
 };
 
@@ -83,6 +84,7 @@ inline bool tcf_geometry(int O, int A, int U, size_t max_smem, TcfGeom* g, std::
   // has the room (small models; the cheetah / walker shapes do not need it: their task costs read the
   // state only)
   g->xch_off = -1;
+  g->exp = 0;
   const int xch_bytes = kTcfXchSlots * 2 * kTcRows * 4;
   if ((size_t)g->smem_bytes + xch_bytes + 4096 <= max_smem) { g->xch_off = g->smem_bytes; g->smem_bytes += xch_bytes; }
   // whatever is left (up to 16 KB) stages mean/std: [envs of the tile][H][A] x 2, fp32
@@ -258,7 +260,7 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
         // group of 4 K-steps is released on its barrier as soon as the four warpgroups have converted it
 #pragma unroll (SPEC ? 4 : 1)
         for (int ks = 0; ks < KS_H; ks += 4) {
-          mbar_wait(bar_hA + 2 * ks, ph);  // barrier of the K-step group ks/4
+          if (g.exp & 2) mbar_wait_nohint(bar_hA + 2 * ks, ph); else mbar_wait(bar_hA + 2 * ks, ph);  // barrier of the K-step group ks/4
           tc_fence_after();
           if (DBG && (ks == 0 || ks + 4 >= KS_H)) tc_stamp(dbg, h, ks == 0 ? 1 : 2);
 #pragma unroll
@@ -288,7 +290,7 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
           if (DBG) tc_stamp(dbg, h, 18);
 #pragma unroll (SPEC ? 4 : 1)
           for (int ks = 0; ks < KS_H; ks += 4) {
-            mbar_wait(bar_hB + 2 * ks, ph);
+            if (g.exp & 2) mbar_wait_nohint(bar_hB + 2 * ks, ph); else mbar_wait(bar_hB + 2 * ks, ph);
             tc_fence_after();
             if (DBG && (ks == 0 || ks + 4 >= KS_H)) tc_stamp(dbg, h, ks == 0 ? 16 : 17);
 #pragma unroll
@@ -483,31 +485,62 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
 #pragma unroll 1
       for (int layer = 0; layer < 2; ++layer) {
         const uint32_t dcol = layer == 0 ? 0u : (uint32_t)kTcD2Col;
-        mbar_wait(layer == 0 ? bar_dA : bar_dB, ph);
+        if (g.exp & 1) mbar_wait_nohint(layer == 0 ? bar_dA : bar_dB, ph); else mbar_wait(layer == 0 ? bar_dA : bar_dB, ph);
         tc_fence_after();
         if (tid == 0) if (DBG) tc_stamp(dbg, h, 4 + 2 * layer);
         const uint32_t bar_rel = layer == 0 ? bar_hA : bar_hB;
-#pragma unroll 1
-        for (int ks = wg; ks < KS_H; ks += kTcfEpiGroups) {
-          // one K-step: 16 fp32 columns -> 8 packed words in the first half of the same columns
-          uint32_t v[32], pk[16];
-          tmem_ld16(lane_base + dcol + 16 * ks, v);
-          tmem_ld_wait();
+        // This warp's K-steps ks = wg, wg+4, wg+8, wg+12 (release groups 0..3), two at a time through two
+        // register buffers: while one K-step is converted and stored, the TMEM load of the one after next
+        // is already in flight, and a pair shares one wait::st / fence / arrive sequence.  (One K-step at a
+        // time -- ld, wait, cvt, st, wait, fence, arrive: ~420 cycles each -- paced the MMAs at 1,690 cycles
+        // per GEMM against 1,500 of MMA time; measured with profiles/tc_timeline.py.)
+        auto convert_store = [&](const uint32_t (&v)[16], int ks) {
           if (DBG && dbg && blockIdx.x == 0 && h == 0) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) dbg[(layer * kTcRows + trow) * kTcDbgCols + 16 * ks + i] = __uint_as_float(v[i]);
           }
+          uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 8; ++i) pk[i] = pack_relu<FP16>(v[2 * i], v[2 * i + 1]);
-          tmem_st8(lane_base + dcol + 16 * ks, pk);
+          tmem_st8(lane_base + dcol + 16 * ks, pk);  // 8 packed words in the first half of the K-step's own columns
+        };
+        uint32_t va[16], vb[16];
+        const int k0 = wg, k1 = wg + 4, k2 = wg + 8, k3 = wg + 12;
+        if (k0 < KS_H) tmem_ld16(lane_base + dcol + 16 * k0, va);
+        if (k1 < KS_H) tmem_ld16(lane_base + dcol + 16 * k1, vb);
+        tmem_ld_wait();
+        if (k0 < KS_H) convert_store(va, k0);
+        if (k2 < KS_H) tmem_ld16(lane_base + dcol + 16 * k2, va);
+        if (!(g.exp & 4)) {  // release the first K-step group on its own, as early as possible (96.9 -> 93.8 us)
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_rel + 8 * (ks >> 2));
-          if (DBG && lane == 0 && ks == wg) {  // first unit of this warp: own stamp for warps 0/15, latest over all 16
-            if (warp == 0 || warp == 15) tc_stamp(dbg, h, (warp == 0 ? 19 : 21) + layer);
-            if (dbg && blockIdx.x == 1 && h < kTcTimelineSteps)
-              atomicMax(reinterpret_cast<long long*>(dbg + kTcDbgFloats) + h * kTcTimelineEvents + 23 + layer, clock64());
+          if (lane == 0 && k0 < KS_H) mbar_arrive(bar_rel);
+        }
+        if (k1 < KS_H) convert_store(vb, k1);
+        if (k3 < KS_H) tmem_ld16(lane_base + dcol + 16 * k3, vb);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if ((g.exp & 4) && k0 < KS_H) mbar_arrive(bar_rel);
+          if (k1 < KS_H) mbar_arrive(bar_rel + 8);
+        }
+        if (DBG && lane == 0) {  // first pair of this warp: own stamp for warps 0/15, latest over all 16
+          if (warp == 0 || warp == 15) tc_stamp(dbg, h, (warp == 0 ? 19 : 21) + layer);
+          if (dbg && blockIdx.x == 1 && h < kTcTimelineSteps)
+            atomicMax(reinterpret_cast<long long*>(dbg + kTcDbgFloats) + h * kTcTimelineEvents + 23 + layer, clock64());
+        }
+        if (k2 < KS_H) {
+          tmem_ld_wait();
+          convert_store(va, k2);
+          if (k3 < KS_H) convert_store(vb, k3);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(bar_rel + 16);
+            if (k3 < KS_H) mbar_arrive(bar_rel + 24);
           }
         }
         if (tid == 0) if (DBG) tc_stamp(dbg, h, 5 + 2 * layer);
@@ -572,6 +605,7 @@ inline bool tc_init(TcModel* t, int O, int A, int U, bool fp16, size_t max_smem,
       if (v == 1 || v == 2 || v == 4) t->wg.cluster = v;
     }
   }
+  if (t->kind == kTcFused) { if (const char* x = getenv("MBRL_TCF_EXP")) t->fg.exp = std::atoi(x); }
   t->w_bytes = t->kind == kTcFused ? t->fg.w_bytes : (t->kind == kTcUnfused ? t->g.w_bytes : t->wg.w_bytes);
   if (cudaMalloc((void**)&t->d_wimg, t->w_bytes) != cudaSuccess) { *why = "cudaMalloc failed"; return false; }
   t->ready = 1;
