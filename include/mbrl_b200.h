@@ -61,11 +61,11 @@ extern "C" {
                                       [x, cos, sin, x_dot, theta_dot] and the control
                                       (dm_control/suite/cartpole.py:216-226, utils/rewards.py:88-130);
                                       not used by the reference planner;
-                                      fp32 engine only this round; weights/goal are ignored   */
+                                      every engine; weights/goal are ignored                   */
 #define MBRL_COST_DMC_HUMANOID_RUN 3 /* 1 - Humanoid.get_reward at move_speed 10 restated on the egocentric
                                       observation (head_height obs[21], torso zz obs[36], com velocity
                                       obs[37:39]) and the control (dm_control/suite/humanoid.py:172-211);
-                                      fp32 engine only this round; weights/goal are ignored   */
+                                      every engine; weights/goal are ignored                   */
 #define MBRL_COST_DMC_CHEETAH_RUN 4 /* 1 - Cheetah.get_reward (dm_control/suite/cheetah.py:91-97): linear
                                       tolerance of the forward speed up to 10 m/s.  The reward's
                                       torso_subtreelinvel sensor is not part of the observation
@@ -80,7 +80,9 @@ extern "C" {
                                       linear4 head, un-normalised with the reward statistics
                                       (src/mbrl/models.py:125-163, data.py:255-257); minimised like
                                       a cost, as the reference does.  Needs mbrl_set_reward_head;
-                                      fp32 engine only this round; weights/goal are ignored   */
+                                      weights/goal are ignored.  On the tensor-core engines the handle
+                                      switches to the weight-streaming kernel (hidden <= 512), which
+                                      runs the second trunk pass on the tensor cores              */
 
 typedef struct MbrlPlanner MbrlPlanner;
 

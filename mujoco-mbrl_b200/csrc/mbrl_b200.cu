@@ -96,6 +96,7 @@ struct MbrlPlanner {
   bool have_weights = false, have_cost = false;
   // tensor-core engine state (packed 16-bit operand images), owned by rollout_tc.cuh
   TcModel tc{};
+  std::vector<float> hW1, hb1, hW2, hb2, hW3, hb3;  // host copies: the tensor-core operand image is re-packed when the kernel variant changes
   // scratch
   float* d_s0 = nullptr;        // [E,O]
   float* d_costs = nullptr;     // [R]
@@ -320,6 +321,9 @@ extern "C" int mbrl_set_weights(MbrlPlanner* p, const float* W1, const float* b1
   if (p->cfg.engine != MBRL_ENGINE_SIMT_FP32) {
     std::string why;
     if (!tc_set_weights(&p->tc, W1, b1, W2, b2, W3, b3, &why)) return fail(MBRL_E_CUDA, why);
+    p->hW1.assign(W1, W1 + (size_t)p->U * p->D); p->hb1.assign(b1, b1 + p->U);
+    p->hW2.assign(W2, W2 + (size_t)p->U * p->U); p->hb2.assign(b2, b2 + p->U);
+    p->hW3.assign(W3, W3 + (size_t)p->O * p->U); p->hb3.assign(b3, b3 + p->O);
   }
   p->have_weights = true;
   return MBRL_OK;
@@ -355,8 +359,20 @@ extern "C" int mbrl_set_cost(MbrlPlanner* p, int32_t kind, const float* w, const
     if (beta == 0.0) beta = 1.0;  // unused by these costs; keeps 1/beta finite
   } else if (kind == MBRL_COST_REWARD_HEAD) {
     MBRL_REQUIRE(p->have_reward_head, "mbrl_set_reward_head must be called before selecting the reward-head cost");
-    if (p->cfg.engine != MBRL_ENGINE_SIMT_FP32)
-      return fail(MBRL_E_UNSUPPORTED, "the reward-head cost is implemented for the fp32 engine only");
+    if (p->cfg.engine != MBRL_ENGINE_SIMT_FP32 && !p->tc.head) {
+      // RewardAgent's second trunk pass + linear4 head live in the weight-streaming kernel: switch this
+      // handle to it (hidden <= 512) and re-pack the operand image
+      std::string why;
+      TcModel fresh{};
+      if (!tc_init(&fresh, p->O, p->A, p->U, p->cfg.engine == MBRL_ENGINE_TC_FP16, p->max_smem, &why, true))
+        return fail(MBRL_E_UNSUPPORTED, "reward-head cost on the tensor-core engine: " + why);
+      fresh.d_dbg = p->tc.d_dbg; p->tc.d_dbg = nullptr;
+      tc_free(&p->tc);
+      p->tc = fresh;
+      if (p->have_weights && !tc_set_weights(&p->tc, p->hW1.data(), p->hb1.data(), p->hW2.data(), p->hb2.data(), p->hW3.data(),
+                                             p->hb3.data(), &why))
+        return fail(MBRL_E_CUDA, why);
+    }
     if (beta == 0.0) beta = 1.0;  // unused by this cost; keeps 1/beta finite
   } else {
     MBRL_REQUIRE(w && goal, "null cost pointer");

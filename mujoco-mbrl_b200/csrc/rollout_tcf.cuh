@@ -570,20 +570,22 @@ struct TcModel {
   TcGeom g{};
   TcfGeom fg{};
   TcwGeom wg{};
+  bool head = false;  // weight-streaming kernel with the reward-head region (RewardAgent's cost)
   int w_bytes = 0;
   uint8_t* d_wimg = nullptr;
   float* d_dbg = nullptr;  // optional accumulator dump + timeline (tests / profiling)
 };
 
-inline bool tc_init(TcModel* t, int O, int A, int U, bool fp16, size_t max_smem, std::string* why) {
+inline bool tc_init(TcModel* t, int O, int A, int U, bool fp16, size_t max_smem, std::string* why, bool head = false) {
   t->fp16 = fp16;
+  t->head = head;
   const char* force = getenv("MBRL_TC_UNFUSED");
   const char* wide = getenv("MBRL_TC_WIDE");  // tests: run small shapes through the streaming kernel
   std::string why_f, why_u;
   int stage_bytes = 0;  // geometry default
   if (const char* sk = getenv("MBRL_TCW_STAGE_KB")) { const int v = std::atoi(sk); if (v == 16 || v == 32) stage_bytes = v * 1024; }
-  if (wide && wide[0] == '1') {
-    if (!tcw_geometry(O, A, U, max_smem, &t->wg, why, stage_bytes)) return false;
+  if ((wide && wide[0] == '1') || head) {  // the reward head is built into the weight-streaming kernel only
+    if (!tcw_geometry(O, A, U, max_smem, &t->wg, why, stage_bytes, head)) return false;
     t->kind = kTcWide;
   } else if (!(force && force[0] == '1') && tcf_geometry(O, A, U, max_smem, &t->fg, &why_f)) {
     t->kind = kTcFused;

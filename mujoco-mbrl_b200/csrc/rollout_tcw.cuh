@@ -64,9 +64,12 @@ struct TcwGeom {
   int stage_bytes;  // ring stage size
   int exp;      // profiling experiments (MBRL_TCW_EXP bit mask; results are garbage when non-zero)
   int tab_off, xa_off, xs_off, one_off, h2_off, ring_off, bar_off, ms_off, ms_floats, smem_bytes;
+  int head_off;  // reward-head cost: fp32 W4 [Np] + per-row partial sums [16 slots][128]; -1 when not enabled
 };
 
-inline bool tcw_geometry(int O, int A, int U, size_t max_smem, TcwGeom* g, std::string* why, int stage_bytes = 0) {
+constexpr int kTcwHeadSlots = 16;  // reward-head partial sums: [layer-2 chunk][32-column unit]
+
+inline bool tcw_geometry(int O, int A, int U, size_t max_smem, TcwGeom* g, std::string* why, int stage_bytes = 0, bool head = false) {
   g->O = O; g->A = A; g->U = U;
   // A ring stage should hold >= 4 hidden K-step tiles: the MMA thread's per-stage bookkeeping (~150
   // cycles) then hides behind the MMAs it has queued (measured: 16 KB stages 11.4 ms, 32 KB 9.2 ms at cfg 5).
@@ -101,7 +104,10 @@ inline bool tcw_geometry(int O, int A, int U, size_t max_smem, TcwGeom* g, std::
   g->xs_off = g->xa_off + 2 * g->QA * 2048;
   g->one_off = g->xs_off + g->SC * 2048;
   g->h2_off = g->one_off + 4096;
-  g->ring_off = g->h2_off + g->Nc * 256;
+  g->head_off = -1;
+  int after_h2 = g->h2_off + g->Nc * 256;
+  if (head) { g->head_off = after_h2; after_h2 += round_up((g->Np + kTcwHeadSlots * kTcRows) * 4, 128); }
+  g->ring_off = after_h2;
   const long long fixed = (long long)g->ring_off + 8 * kTcwBarriers + 16 + 8 * kTcwMaxKx;
   const long long room = (long long)max_smem - fixed;
   g->stages = (int)std::min<long long>(kTcwMaxStages, room / stage_bytes);
@@ -164,19 +170,33 @@ __device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
 }
 
 // One 16-column half of a hidden-epilogue unit: fp32 accumulators -> relu -> 16 bit -> 8 packed words,
-// stored to TMEM (the next layer's A operand) or, for layer 2 / chunk 0, to h2's shared-memory A tile
-// (two 16-byte row chunks of 8 hidden units each).
+// stored to TMEM (mode 0: the next layer's A operand) or to h2's shared-memory A tile (mode 1: two 16-byte
+// row chunks of 8 hidden units each); mode 2 is the reward head (ModelWithReward.linear4,
+// src/mbrl/models.py:135-141): relu in fp32 and a dot product with 16 entries of W4 instead of a store.
 template <bool FP16, bool DBG>
-__device__ __forceinline__ void tcw_epi_half(const uint32_t (&v)[16], int q, uint32_t tmem_dst, uint8_t* smem_dst, float* dbg, int h,
-                                             int trow, int dbg_col) {
-  if (DBG && dbg && blockIdx.x == 0 && h == 0) {
+__device__ __forceinline__ void tcw_epi_half(const uint32_t (&v)[16], int mode, uint32_t tmem_dst, uint8_t* smem_dst, float* dbg,
+                                             int h, int trow, int dbg_layer, int dbg_col, const float* w4, float& head_acc) {
+  if (DBG && dbg && blockIdx.x == 0 && h == 0 && dbg_layer >= 0) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) dbg[((q >> 1) * kTcRows + trow) * kTcDbgCols + dbg_col + i] = __uint_as_float(v[i]);
+    for (int i = 0; i < 16; ++i) dbg[(dbg_layer * kTcRows + trow) * kTcDbgCols + dbg_col + i] = __uint_as_float(v[i]);
+  }
+  if (mode == 2) {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      const float4 w = *reinterpret_cast<const float4*>(w4 + i);
+      acc = fmaf(fmaxf(__uint_as_float(v[i + 0]), 0.f), w.x, acc);
+      acc = fmaf(fmaxf(__uint_as_float(v[i + 1]), 0.f), w.y, acc);
+      acc = fmaf(fmaxf(__uint_as_float(v[i + 2]), 0.f), w.z, acc);
+      acc = fmaf(fmaxf(__uint_as_float(v[i + 3]), 0.f), w.w, acc);
+    }
+    head_acc += acc;
+    return;
   }
   uint32_t pk[16];
 #pragma unroll
   for (int i = 0; i < 8; ++i) pk[i] = pack_relu<FP16>(v[2 * i], v[2 * i + 1]);
-  if (q == 2) {
+  if (mode == 1) {
     *reinterpret_cast<uint4*>(smem_dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     *reinterpret_cast<uint4*>(smem_dst + 2048) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
   } else {
@@ -222,6 +242,10 @@ rollout_tcw_kernel(TcwGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
   const int CL = g.cluster;
   const uint16_t cl_mask = (uint16_t)((1u << CL) - 1u);
   const bool smooth = m.cost_kind == MBRL_COST_SMOOTHABS_COSH;
+  const bool head = m.cost_kind == MBRL_COST_REWARD_HEAD && g.head_off >= 0;  // RewardAgent: second trunk pass + linear4 head
+  const bool task = is_task_cost(m.cost_kind);
+  float* const t_w4 = head ? reinterpret_cast<float*>(smem + g.head_off) : nullptr;  // [Np] fp32, zero padded
+  float* const red = head ? t_w4 + g.Np : nullptr;                                    // [kTcwHeadSlots][128] per-row partial sums
 
   float* tab = reinterpret_cast<float*>(smem + g.tab_off);
   float *t_b3 = tab, *t_P = tab + g.Op, *t_Q = tab + 2 * g.Op, *t_sd = tab + 3 * g.Op, *t_mu = tab + 4 * g.Op;
@@ -266,6 +290,10 @@ rollout_tcw_kernel(TcwGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
     t_ainv[i] = inv;
     t_aoff[i] = i < A ? __ldg(m.mu_a + i) * inv : (i == A ? -1.f : 0.f);
   }
+  if (head) {
+    for (int i = tid; i < g.Np; i += kTcwThreads) t_w4[i] = i < g.U ? __ldg(m.W4 + i) : 0.f;
+    for (int i = tid; i < kTcwHeadSlots * kTcRows; i += kTcwThreads) red[i] = 0.f;  // slots of absent units stay zero
+  }
   // the constant A tile of the b2 K-step: element (row, k = 0) = 1, everything else 0
   for (int i = tid; i < 256; i += kTcwThreads) {
     const uint32_t one = FP16 ? 0x3C00u : 0x3F80u;
@@ -288,7 +316,9 @@ rollout_tcw_kernel(TcwGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
       for (int h = 0; h < H; ++h) {
         uint32_t off = 0;
 #pragma unroll 1
-        for (int part = 0; part < 5; ++part) {
+        for (int pp = 0; pp < (head ? 9 : 5); ++pp) {  // reward head: W1 / W2 are streamed a second time for the reward trunk pass
+          const int part = pp < 5 ? pp : pp - 5;
+          if (pp == 5) off = 0;
           const uint32_t total = (uint32_t)(part < 2 ? g.p1_bytes : (part < 4 ? g.p2_bytes : g.p3_bytes));
           const uint32_t per = (uint32_t)(part < 4 ? g.tps_h * g.tile_h : g.tps_y * g.tile_y);
 #pragma unroll 1
@@ -369,16 +399,28 @@ rollout_tcw_kernel(TcwGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
         if (++st == (uint32_t)S) { st = 0; off16 = 0; ph ^= 1; } else off16 += stage16;
       };
 
+      const int passes = head ? 2 : 1;
       for (int h = 0; h < H; ++h) {
-        mbar_wait(bar_x, h & 1);
-        tc_fence_after();
-        if (DBG) tc_stamp(dbg, h, 0);
+       // pass 0: the dynamics step.  pass 1 (reward head only): RewardAgent's cost (src/mbrl/agents.py:349-358),
+       // the trunk evaluated AGAIN at (s_{h+1}, a_h) -- the input tile is the action chunks of THIS step
+       // (parity h) with the state chunks the output epilogue has just written -- followed by
+       // ModelWithReward's linear4 head (models.py:135-141), a dot product in the layer-2 epilogue (fp32).
+#pragma unroll 1
+       for (int pass = 0; pass < passes; ++pass) {
+        const bool dynamics = pass == 0;
+        if (dynamics && head && h > 0) {
+          wait_epi();  // x of this step was awaited by the reward pass of step h-1; ACC drained by its last epilogue
+        } else {
+          mbar_wait(bar_x, (h + pass) & 1);
+          tc_fence_after();
+        }
+        if (DBG && dynamics) tc_stamp(dbg, h, 0);
         const uint32_t* xd = xdesc + (h & 1) * kTcwMaxKx;
         // ---- layer 1, two chunks: ACC = x . W1[chunk]^T ----
 #pragma unroll (SPEC ? 16 : 1)
         for (int c = 0; c < 2; ++c) {
           if (c == 1) wait_epi();  // ACC drained by the epilogue of chunk 0
-          if (DBG) tc_stamp(dbg, h, 1 + 2 * c);
+          if (DBG && dynamics) tc_stamp(dbg, h, 1 + 2 * c);
 #pragma unroll (SPEC ? 16 : 1)
           for (int t0 = 0; t0 < KS_X; t0 += tps_h) {
             const int n = min(tps_h, KS_X - t0);
@@ -390,17 +432,17 @@ rollout_tcw_kernel(TcwGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
             release();
           }
           tc_commit(bar_acc);
-          if (c == 1) tc_commit(bar_l1);  // the action tile of this step is free again
-          if (DBG) tc_stamp(dbg, h, 2 + 2 * c);
+          if (c == 1 && dynamics) tc_commit(bar_l1);  // the action tile of this step is free again
+          if (DBG && dynamics) tc_stamp(dbg, h, 2 + 2 * c);
         }
         // ---- layer 2, two chunks: ACC = h1 . W2[chunk]^T + b2 (KH TS K-steps, then the b2 K-step) ----
 #pragma unroll (SPEC ? 16 : 1)
         for (int c = 0; c < 2; ++c) {
-          wait_epi();  // c == 0: h1 complete in TMEM; c == 1: h2's lower half in shared memory
-          if (DBG) tc_stamp(dbg, h, 5 + 2 * c);
+          wait_epi();  // c == 0: h1 complete in TMEM; c == 1: ACC drained (dynamics: h2's lower half is in shared memory)
+          if (DBG && dynamics) tc_stamp(dbg, h, 5 + 2 * c);
           int ks = 0;
           uint32_t a = tm_h;
-          if (tps_h == 2) {  // hidden 512: two 8 KB tiles per stage, straight-line
+          if (tps_h == 2) {  // two 8 KB tiles per stage, straight-line
 #pragma unroll (SPEC ? 16 : 1)
             for (; ks + 2 <= KH; ks += 2, a += 16) {
               acquire();
@@ -434,8 +476,9 @@ rollout_tcw_kernel(TcwGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
             release();
           }
           tc_commit(bar_acc);
-          if (DBG) tc_stamp(dbg, h, 6 + 2 * c);
+          if (DBG && dynamics) tc_stamp(dbg, h, 6 + 2 * c);
         }
+        if (!dynamics) continue;
         // ---- layer 3: y = h2 . W3^T; lower half from shared memory, upper half from TMEM as released ----
         {
           // N = Op MMAs are short (~26 + 0.43*Op cycles): the per-MMA bookkeeping is one counter
@@ -460,6 +503,7 @@ rollout_tcw_kernel(TcwGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
           tc_commit(bar_y);
           if (DBG) tc_stamp(dbg, h, 9);
         }
+       }
       }
     }
     __syncwarp();
@@ -540,6 +584,7 @@ rollout_tcw_kernel(TcwGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (srow == 0) { mbar_arrive(bar_x); if (DBG) tc_stamp(dbg, hs, 14); }
     }
+    if (head && srow == 0) mbar_arrive(bar_x);  // the reward pass of the last step waits for one more x phase
     costp[5 * kTcRows + srow] = act_total;
   } else {
     // ================= hidden-epilogue warps 0-15 and cost warps 16-19 =================
@@ -579,46 +624,87 @@ rollout_tcw_kernel(TcwGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_x);
 
+    // One accumulator chunk (256 columns at hidden 512) through this warp's two 32-column units (release
+    // rounds 0 and 1), processed as four 16-column halves through two register buffers so that a TMEM load
+    // is always in flight while the previous half is converted and stored.
+    //   mode 0: relu -> 16 bit -> TMEM columns dstcol.. (the next layer's A operand)
+    //   mode 1: relu -> 16 bit -> h2's shared-memory A tile
+    //   mode 2: reward head: per-row partial dot products with W4[wcol..] into red[slot0 + unit]
+    auto hidden_chunk = [&](int h, int parity, int mode, int dstcol, int dbg_layer, int dbg_col0, int wcol, int slot0, int ev) {
+      const int wg = yw;
+      if (g.exp & 16) mbar_wait_nohint(bar_acc, parity); else mbar_wait(bar_acc, parity);
+      tc_fence_after();
+      if (DBG && tid == 0 && ev >= 0) tc_stamp(dbg, h, ev);
+      const int u0 = wg, u1 = 4 + wg;
+      const bool has0 = u0 < NU && !(g.exp & 2), has1 = u1 < NU && !(g.exp & 2);
+      const uint32_t src0 = lane_base + (uint32_t)(kTcwAccCol + 32 * u0), src1 = lane_base + (uint32_t)(kTcwAccCol + 32 * u1);
+      const uint32_t dst = lane_base + (uint32_t)dstcol;
+      const float* w4 = t_w4 + wcol;
+      uint32_t va[16], vb[16];
+      float hacc = 0.f;
+      if (has0) { tmem_ld16(src0, va); tmem_ld16(src0 + 16, vb); tmem_ld_wait(); }
+      if (has0) {
+        tcw_epi_half<FP16, DBG>(va, mode, dst + 16 * u0, h2lo + (4 * u0) * 2048 + trow * 16, dbg, h, trow, dbg_layer, dbg_col0 + 32 * u0, w4 + 32 * u0, hacc);
+        if (has1) tmem_ld16(src1, va);
+        tcw_epi_half<FP16, DBG>(vb, mode, dst + 16 * u0 + 8, h2lo + (4 * u0 + 2) * 2048 + trow * 16, dbg, h, trow, dbg_layer, dbg_col0 + 32 * u0 + 16, w4 + 32 * u0 + 16, hacc);
+        if (has1) tmem_ld16(src1 + 16, vb);
+        if (mode == 2) { red[(slot0 + u0) * kTcRows + trow] = hacc; hacc = 0.f; }
+        else if (mode == 1) fence_proxy_async();
+        else tmem_st_wait();
+        tc_fence_before();
+      } else if (has1) { tmem_ld16(src1, va); tmem_ld16(src1 + 16, vb); }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_e0);
+      if (has1) {
+        tmem_ld_wait();
+        tcw_epi_half<FP16, DBG>(va, mode, dst + 16 * u1, h2lo + (4 * u1) * 2048 + trow * 16, dbg, h, trow, dbg_layer, dbg_col0 + 32 * u1, w4 + 32 * u1, hacc);
+        tcw_epi_half<FP16, DBG>(vb, mode, dst + 16 * u1 + 8, h2lo + (4 * u1 + 2) * 2048 + trow * 16, dbg, h, trow, dbg_layer, dbg_col0 + 32 * u1 + 16, w4 + 32 * u1 + 16, hacc);
+        if (mode == 2) red[(slot0 + u1) * kTcRows + trow] = hacc;
+        else if (mode == 1) fence_proxy_async();
+        else tmem_st_wait();
+        tc_fence_before();
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_e1);
+      if (DBG && tid == 0 && ev >= 0) tc_stamp(dbg, h, ev + 1);
+    };
+    float head_total = 0.f;  // reward-head cost accumulated by the cost warps
+
     for (int h = 0; h < H; ++h) {
-      if (warp < kTcwEpiWarps) {
-        const int wg = yw;
+     // pass 0: the dynamics step (4 accumulator chunks, then the output epilogue); pass 1 (reward head only):
+     // the reward trunk pass (4 more chunks: L1' packs h1', L2' feeds the linear4 dot product)
 #pragma unroll 1
-        for (int q = 0; q < 4; ++q) {  // L1 chunk 0, L1 chunk 1, L2 chunk 0, L2 chunk 1
-          if (g.exp & 16) mbar_wait_nohint(bar_acc, q & 1); else mbar_wait(bar_acc, q & 1);  // accumulator completion #(4h + q)
-          tc_fence_after();
-          if (DBG && tid == 0) tc_stamp(dbg, h, 16 + 2 * q);
-          {
-            // This warp's two 32-column units of the chunk (release rounds 0 and 1), processed as four
-            // 16-column halves through two register buffers so that a TMEM load is always in flight
-            // while the previous half is converted and stored.
-            const int u0 = wg, u1 = 4 + wg;
-            const bool has0 = u0 < NU && !(g.exp & 2), has1 = u1 < NU && !(g.exp & 2);
-            const uint32_t src0 = lane_base + (uint32_t)(kTcwAccCol + 32 * u0), src1 = lane_base + (uint32_t)(kTcwAccCol + 32 * u1);
-            const uint32_t dst = lane_base + (uint32_t)(q == 1 ? NcC >> 1 : 0);
-            uint32_t va[16], vb[16];
-            if (has0) { tmem_ld16(src0, va); tmem_ld16(src0 + 16, vb); tmem_ld_wait(); }
-            if (has0) {
-              tcw_epi_half<FP16, DBG>(va, q, dst + 16 * u0, h2lo + (4 * u0) * 2048 + trow * 16, dbg, h, trow, (q & 1) * NcC + 32 * u0);
-              if (has1) tmem_ld16(src1, va);
-              tcw_epi_half<FP16, DBG>(vb, q, dst + 16 * u0 + 8, h2lo + (4 * u0 + 2) * 2048 + trow * 16, dbg, h, trow, (q & 1) * NcC + 32 * u0 + 16);
-              if (has1) tmem_ld16(src1 + 16, vb);
-              if (q == 2) fence_proxy_async(); else tmem_st_wait();
-              tc_fence_before();
-            } else if (has1) { tmem_ld16(src1, va); tmem_ld16(src1 + 16, vb); }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_e0);
-            if (has1) {
-              tmem_ld_wait();
-              tcw_epi_half<FP16, DBG>(va, q, dst + 16 * u1, h2lo + (4 * u1) * 2048 + trow * 16, dbg, h, trow, (q & 1) * NcC + 32 * u1);
-              tcw_epi_half<FP16, DBG>(vb, q, dst + 16 * u1 + 8, h2lo + (4 * u1 + 2) * 2048 + trow * 16, dbg, h, trow, (q & 1) * NcC + 32 * u1 + 16);
-              if (q == 2) fence_proxy_async(); else tmem_st_wait();
-              tc_fence_before();
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_e1);
-          }
-          if (DBG && tid == 0) tc_stamp(dbg, h, 17 + 2 * q);
+     for (int pass = 0; pass < (head ? 2 : 1); ++pass) {
+      if (warp < kTcwEpiWarps) {
+        // accumulator completions come in fours (L1 chunk 0, L1 chunk 1, L2 chunk 0, L2 chunk 1): parity q & 1
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+          // mode: L1 chunks and the dynamics L2 chunk 1 pack into TMEM, the dynamics L2 chunk 0 into h2's
+          // shared-memory tile, the reward pass's L2 chunks feed the head
+          const int mode = q < 2 ? 0 : (pass == 1 ? 2 : (q == 2 ? 1 : 0));
+          const int dstcol = q == 1 ? NcC >> 1 : 0;
+          // the cost warp of this lane quarter has consumed the head partial sums of step h-1
+          if (pass == 1 && q == 2 && h > 0) asm volatile("bar.sync %0, 160;" ::"r"(7 + quarter) : "memory");
+          hidden_chunk(h, q & 1, mode, dstcol, pass == 0 ? (q >> 1) : -1, (q & 1) * NcC, (q & 1) * NcC, (q & 1) * (kTcwHeadSlots / 2),
+                       pass == 0 ? 16 + 2 * q : -1);
         }
+      }
+      if (pass == 1) {
+        // ---- RewardAgent's cost: linear4 head of the second trunk pass (agents.py:349-358, models.py:135-141) ----
+        // Producer / consumer named barriers per lane quarter (4 epilogue warps + 1 cost warp = 160 threads): the
+        // side that only SIGNALS uses bar.arrive -- a cost warp blocked in bar.sync on the "consumed" barrier
+        // could not take part in the next step's output epilogue, and the step would never get its x-ready.
+        if (yw == 4) {
+          asm volatile("bar.sync %0, 160;" ::"r"(3 + quarter) : "memory");  // the quarter's partial sums of step h are written
+          float r = 0.f;
+#pragma unroll
+          for (int sl = 0; sl < kTcwHeadSlots; ++sl) r += red[sl * kTcRows + trow];
+          head_total += fmaf(r + m.b4, m.sd_r, m.mu_r);  // unnormalize_field(linear4(h2)) (data.py:255-257); minimised as the reference does
+          if (h + 1 < H) asm volatile("bar.arrive %0, 160;" ::"r"(7 + quarter) : "memory");  // consumed
+        } else {
+          asm volatile("bar.arrive %0, 160;" ::"r"(3 + quarter) : "memory");
+        }
+        continue;
       }
       // ---- output epilogue: y + b3 (fp32), un-normalise, cost, next input tile ----
       if (g.exp & 16) mbar_wait_nohint(bar_y, h & 1); else mbar_wait(bar_y, h & 1);
@@ -636,7 +722,7 @@ rollout_tcw_kernel(TcwGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
           tmem_ld_wait();
         }
       }
-      if (h + 1 < H) {
+      if (h + 1 < H || head) {  // (the reward pass of the last step still needs the state tile)
 #pragma unroll 1
         for (int gi = yw; gi < NG; gi += 5) {
           if (!one_group) { tmem_ld16(lane_base + (uint32_t)(ycolC + 16 * gi), v); tmem_ld_wait(); }
@@ -679,7 +765,7 @@ rollout_tcw_kernel(TcwGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
           }
           st_total += ((term[0] + term[1]) + (term[2] + term[3])) + ((term[4] + term[5]) + (term[6] + term[7])) +
                       (((term[8] + term[9]) + (term[10] + term[11])) + ((term[12] + term[13]) + (term[14] + term[15])));
-        } else {
+        } else if (task) {
           int pick[4];
           task_pick_indices(m.cost_kind, pick);
 #pragma unroll
@@ -699,13 +785,13 @@ rollout_tcw_kernel(TcwGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
           }
         }
       }
-      if (h + 1 < H && !one_group) {
+      if ((h + 1 < H || head) && !one_group) {
         tc_fence_before();     // our tcgen05.ld of y is ordered before the columns are reused
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_x);
         if (DBG && tid == 0) tc_stamp(dbg, h, 12);
       }
-      if (!smooth) {
+      if (task) {
         // the five warps of this lane quarter have stored the picked state entries of step h
         asm volatile("bar.sync %0, 160;" ::"r"(3 + quarter) : "memory");
         if (yw == 4) {
@@ -717,8 +803,9 @@ rollout_tcw_kernel(TcwGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
           st_total += task_cost(m.cost_kind, p4, xch[((h & 1) * 2 + 0) * kTcRows + trow], xch[((h & 1) * 2 + 1) * kTcRows + trow]);
         }
       }
+     }
     }
-    costp[yw * kTcRows + trow] = valid ? st_total : 0.f;
+    costp[yw * kTcRows + trow] = valid ? st_total + head_total : 0.f;
   }
 
   tc_fence_before();

@@ -584,7 +584,7 @@ def test_refit_large_elite_set_chunked(native):
 
 def test_reward_head_cost_matches_reference_fixture(native):
     """RewardAgent's cost (ModelWithReward's reward head, a second trunk evaluation per step) on the
-    fp32 engine against the fixture produced by the reference's own planner
+    fp32 engine and on the tensor-core engines against the fixture produced by the reference's own planner
     (tests/golden/make_golden.py::make_rs_reward): costs, argmin, the returned plan; then the Python
     drop-in API with callables wired exactly like src/mbrl/agents.py:349-358."""
     from functools import partial
@@ -605,11 +605,24 @@ def test_reward_head_cost_matches_reference_fixture(native):
     assert int(out["info"]["best_index"][0]) == int(g["idx"])
     np.testing.assert_array_equal(out["actions"][0], g["plan_actions"])
     np.testing.assert_allclose(out["states"][0], g["plan_states"], rtol=1e-5, atol=1e-5)
-    # tensor-core engines: refused loudly, not silently served by another path
-    tc = native.NativePlanner(p.obs_dim, p.act_dim, p.hidden, H, n, 1, 1, None, "fp16")
-    tc.set_reward_head(p.W4, p.b4, p.mu_r, p.sd_r)
-    with pytest.raises(RuntimeError):
+    # tensor-core engines: the handle switches to the weight-streaming kernel, which runs the second trunk
+    # pass on the tensor cores (16-bit operands: costs within the engine's tolerance of the reference's;
+    # the candidate it picks is a minimiser of the reference's cost array up to that tolerance)
+    for engine, tol in (("fp16", 2e-3), ("bf16", 1e-2)):
+        tc = native.NativePlanner(p.obs_dim, p.act_dim, p.hidden, H, n, 1, 1, None, engine)
+        tc.set_reward_head(p.W4, p.b4, p.mu_r, p.sd_r)
+        tc.set_weights(p.W1, p.b1, p.W2, p.b2, p.W3, p.b3)   # weights before the cost kind: the image is re-packed on the switch
+        tc.set_norm(p.mu_s, p.sd_s, p.mu_a, p.sd_a)
         tc.set_cost(kind=native.COST_REWARD_HEAD)
+        tc.set_action_bounds(p.act_lo, p.act_hi)
+        c16, _, _ = tc.rollout(_cuda(g["s0"][None]), native.SAMPLE_INJECT_ACTIONS, d_injected=_cuda(g["actions"]))
+        err = np.abs(c16.cpu().numpy() - g["costs"]).max()
+        scale = np.abs(g["costs"]).max()
+        print(f"reward head on {engine}: max abs cost err {err:.3e} (scale {scale:.3f})")
+        assert err <= tol * scale + tol, (engine, err)
+        o16 = tc.plan(g["s0"], 1, 1, native.SAMPLE_INJECT_ACTIONS, injected=g["actions"])
+        assert g["costs"][int(o16["info"]["best_index"][0])] <= g["costs"].min() + 2 * (tol * scale + tol)
+        tc.close()
 
     # drop-in API with the RewardAgent wiring
     class ModelWithReward(torch.nn.Module):

@@ -297,3 +297,27 @@ def test_dmc_humanoid_task_cost_at_cfg5_shape(native, engine):
     assert want.std() > 0.01
     tol = 1e-4 if engine == "fp32" else 3e-3  # fp16: 5e-4 state error through tolerance() slopes of O(1/margin)
     np.testing.assert_allclose(costs.cpu().numpy(), want, rtol=tol, atol=tol)
+
+
+def test_reward_head_at_cfg5_shape_matches_fp32_engine(native):
+    """RewardAgent's cost at hidden 512 (obs 67, act 21), device sampler, several CEM-style steps: the
+    weight-streaming kernel's second trunk pass + linear4 head (fp16 operands) against the fp32 engine on the
+    same Philox stream; ragged tile and two environments."""
+    p = po.synthetic_params(67, 21, 512, seed=6)
+    g = torch.Generator().manual_seed(3)
+    W4 = (torch.rand(1, 512, generator=g) * 2 - 1) / 512 ** 0.5
+    H, n, E = 12, 300, 2
+    s0 = torch.stack([po.synthetic_state(p, c) for c in range(E)]).cuda()
+    mu = (torch.rand(E, H, 21) * 0.2 - 0.1).cuda()
+    sd = (torch.rand(E, H, 21) * 0.5 + 0.5).cuda()
+    outs = {}
+    for engine in ("fp32", "fp16"):
+        h = _planner(native, p, H, n, E, engine=engine)
+        h.set_reward_head(W4, 0.3, 1.5, 2.0)
+        h.set_cost(kind=native.COST_REWARD_HEAD)
+        outs[engine] = h.rollout(s0, native.SAMPLE_GAUSSIAN, 9, 1, d_mu=mu, d_sd=sd)[0].cpu().numpy()
+    err = np.abs(outs["fp16"] - outs["fp32"]).max()
+    scale = np.abs(outs["fp32"]).max()
+    print(f"reward head hidden 512: fp16 vs fp32 engine max abs err {err:.3e} (scale {scale:.3f}, spread {outs['fp32'].std():.3f})")
+    assert outs["fp32"].std() > 1e-3
+    assert err <= 2e-3 * scale + 2e-3
