@@ -179,6 +179,28 @@ int mbrl_plan_device(MbrlPlanner* p, const MbrlPlanArgs* args, const float* d_s0
                      const float* d_injected, float* d_out_states, float* d_out_actions,
                      MbrlPlanInfo* d_info, void* stream);
 
+/* Batched GradientDescentPlanner (src/mbrl/planners.py:28-137): Adam on `restarts` independent action
+ * sequences, back-propagation through the H-step model rollout, the reference's early stop.  Uses the
+ * handle's fp32 model / normalisers / SmoothAbs + Cosh cost (any engine; num_envs must be 1).
+ *   h_s0            [O]               initial state, shared by all restarts
+ *   h_init_actions  [restarts, H, A]  initial sequences (the reference draws one with sample_action,
+ *                                     planners.py:88-100, or takes initial_trajectory's)
+ *   h_out_states    [restarts, H+1, O]  s_0 first, then the states of the LAST forward pass -- computed with
+ *                                     the actions before the final Adam step, as the reference returns them
+ *   h_out_actions   [restarts, H, A]  the updated actions
+ *   h_out_cost      [restarts]        nullable: loss of that last forward pass
+ *   h_out_iters     [restarts]        nullable: iterations run (early stop)                          */
+typedef struct MbrlGdArgs {
+  int32_t restarts;
+  int32_t iterations;   /* num_iterations (planners.py:29: 40)                     */
+  float lr;             /* Adam learning rate (planners.py:114: 0.01)              */
+  float stop_condition; /* mean |a_old - a_new| below which it stops (planners.py:29: 0.002) */
+  float beta1, beta2, eps; /* torch.optim.Adam defaults: 0.9, 0.999, 1e-8         */
+  int32_t reserved;
+} MbrlGdArgs;
+int mbrl_plan_gd(MbrlPlanner* p, const MbrlGdArgs* args, const float* h_s0, const float* h_init_actions,
+                 float* h_out_states, float* h_out_actions, float* h_out_cost, int32_t* h_out_iters);
+
 /* ---- building blocks on device buffers (parity tests, sharded host loops) ---- */
 
 /* The hot loop of _generate_trajectories (src/mbrl/planners.py:199-210) fused with

@@ -9,10 +9,10 @@ planning requires the built library and a CUDA device.
 """
 from .adaptor import PlanningProblem, problem_from_callables  # noqa: F401
 from .native import NativePlanner, load_library  # noqa: F401
-from .planners import CEMPlanner, ModelPlanner, RandomShootingPlanner  # noqa: F401
+from .planners import CEMPlanner, GradientDescentPlanner, ModelPlanner, RandomShootingPlanner  # noqa: F401
 from .integration import configure, register_planners  # noqa: F401
 
 __all__ = [
-    "CEMPlanner", "ModelPlanner", "RandomShootingPlanner", "NativePlanner", "PlanningProblem",
+    "CEMPlanner", "GradientDescentPlanner", "ModelPlanner", "RandomShootingPlanner", "NativePlanner", "PlanningProblem",
     "problem_from_callables", "load_library", "configure", "register_planners",
 ]

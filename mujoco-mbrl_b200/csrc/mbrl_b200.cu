@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "gd.cuh"
 #include "philox.cuh"
 #include "replay.cuh"
 #include "rollout_simt.cuh"
@@ -912,6 +913,52 @@ static int enqueue_plan(MbrlPlanner* p, const MbrlPlanArgs* a, const float* d_s0
     MBRL_CUDA(launch_pdl(shard_flags_kernel, dim3(1), dim3(32), 0, st, d_info, p->d_trunc,
                          p->p2p_attached ? (const int*)p->d_p2p_error : (const int*)nullptr));
   }
+  return MBRL_OK;
+}
+
+extern "C" int mbrl_plan_gd(MbrlPlanner* p, const MbrlGdArgs* a, const float* h_s0, const float* h_init_actions,
+                            float* h_out_states, float* h_out_actions, float* h_out_cost, int32_t* h_out_iters) {
+  if (!p || !a) return fail(MBRL_E_INVALID, "null planner/args");
+  MBRL_REQUIRE(h_s0 && h_init_actions && h_out_states && h_out_actions, "null host buffer");
+  MBRL_REQUIRE(a->restarts >= 1 && a->restarts <= 65535, "restarts out of range [1, 65535]");
+  MBRL_REQUIRE(a->iterations >= 1 && a->iterations <= 100000, "iterations out of range");
+  MBRL_REQUIRE(a->lr > 0.f && a->beta1 >= 0.f && a->beta1 < 1.f && a->beta2 >= 0.f && a->beta2 < 1.f && a->eps > 0.f, "bad Adam parameters");
+  MBRL_REQUIRE(p->E == 1, "the gradient planner plans for one environment (num_envs == 1)");
+  if (!p->have_weights || !p->have_cost) return fail(MBRL_E_STATE, "mbrl_set_weights and mbrl_set_cost must be called before planning");
+  if (p->cost_kind != MBRL_COST_SMOOTHABS_COSH)
+    return fail(MBRL_E_UNSUPPORTED, "the gradient planner differentiates the SmoothAbs + Cosh cost only");
+  MBRL_CUDA(cudaSetDevice(p->cfg.device));
+  const GdLayout L = gd_layout(p->O, p->A, p->U, p->H);
+  const size_t smem = sizeof(float) * (size_t)L.total;
+  if (smem > p->max_smem)
+    return fail(MBRL_E_UNSUPPORTED, "horizon x hidden too large for the gradient planner: it keeps every step's activations "
+                                    "(H*(O+A+2*hidden) floats) in shared memory");
+  const int B = a->restarts, HA = p->H * p->A, HO1 = (p->H + 1) * p->O;
+  float *d_s0 = nullptr, *d_init = nullptr, *d_st = nullptr, *d_ac = nullptr, *d_cost = nullptr;
+  int* d_it = nullptr;
+  auto cleanup = [&]() { for (void* q : {(void*)d_s0, (void*)d_init, (void*)d_st, (void*)d_ac, (void*)d_cost, (void*)d_it}) if (q) cudaFree(q); };
+  cudaError_t e = cudaSuccess;
+  auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; return r == cudaSuccess; };
+  ok(dev_alloc(&d_s0, (size_t)p->O)); ok(dev_alloc(&d_init, (size_t)B * HA)); ok(dev_alloc(&d_st, (size_t)B * HO1));
+  ok(dev_alloc(&d_ac, (size_t)B * HA)); ok(dev_alloc(&d_cost, (size_t)B)); ok(dev_alloc(&d_it, (size_t)B));
+  cudaStream_t st = p->stream;
+  if (e == cudaSuccess) {
+    ok(cudaMemcpyAsync(d_s0, h_s0, sizeof(float) * p->O, cudaMemcpyHostToDevice, st));
+    ok(cudaMemcpyAsync(d_init, h_init_actions, sizeof(float) * (size_t)B * HA, cudaMemcpyHostToDevice, st));
+    ok(cudaFuncSetAttribute(gd_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  if (e == cudaSuccess) {
+    GdParams gp{p->H, a->iterations, a->lr, a->stop_condition, a->beta1, a->beta2, a->eps};
+    gd_plan_kernel<<<B, kGdThreads, smem, st>>>(model_view(p), gp, d_s0, d_init, d_st, d_ac, d_cost, d_it);
+    ok(cudaGetLastError());
+    ok(cudaMemcpyAsync(h_out_states, d_st, sizeof(float) * (size_t)B * HO1, cudaMemcpyDeviceToHost, st));
+    ok(cudaMemcpyAsync(h_out_actions, d_ac, sizeof(float) * (size_t)B * HA, cudaMemcpyDeviceToHost, st));
+    if (h_out_cost) ok(cudaMemcpyAsync(h_out_cost, d_cost, sizeof(float) * B, cudaMemcpyDeviceToHost, st));
+    if (h_out_iters) ok(cudaMemcpyAsync(h_out_iters, d_it, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    ok(cudaStreamSynchronize(st));
+  }
+  cleanup();
+  if (e != cudaSuccess) return fail(MBRL_E_CUDA, std::string("mbrl_plan_gd: ") + cudaGetErrorString(e));
   return MBRL_OK;
 }
 

@@ -21,10 +21,10 @@ from __future__ import annotations
 from enum import Enum
 from typing import Dict
 
-from .planners import CEMPlanner, RandomShootingPlanner
+from .planners import CEMPlanner, GradientDescentPlanner, RandomShootingPlanner
 
-PLANNERS: Dict[str, type] = {"rs-b200": RandomShootingPlanner, "cem-b200": CEMPlanner}
-_MEMBER_NAMES = {"rs-b200": "RandomShootingB200", "cem-b200": "CEMB200"}
+PLANNERS: Dict[str, type] = {"rs-b200": RandomShootingPlanner, "cem-b200": CEMPlanner, "grad-b200": GradientDescentPlanner}
+_MEMBER_NAMES = {"rs-b200": "RandomShootingB200", "cem-b200": "CEMB200", "grad-b200": "GradientDescentB200"}
 
 
 def configure(planner, **hyper):

@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "mbrl_set_norm", "mbrl_set_cost", "mbrl_set_action_bounds", "mbrl_set_reward_head", "mbrl_plan", "mbrl_plan_device",
     "mbrl_rollout", "mbrl_sample", "mbrl_philox_raw", "mbrl_topk", "mbrl_refit", "mbrl_emit",
     "mbrl_tc_debug", "mbrl_nccl_unique_id", "mbrl_comm_init", "mbrl_comm_destroy",
-    "mbrl_p2p_export", "mbrl_p2p_attach", "mbrl_p2p_detach",
+    "mbrl_p2p_export", "mbrl_p2p_attach", "mbrl_p2p_detach", "mbrl_plan_gd",
 ]
 
 
@@ -45,6 +45,11 @@ class MbrlPlanArgs(C.Structure):
         ("h_injected", C.c_void_p), ("h_mu0", C.c_void_p), ("h_sd0", C.c_void_p),
         ("actions_only", C.c_int32), ("warm_start", C.c_int32), ("warm_std", C.c_float), ("reserved", C.c_int32),
     ]
+
+
+class MbrlGdArgs(C.Structure):
+    _fields_ = [("restarts", C.c_int32), ("iterations", C.c_int32), ("lr", C.c_float), ("stop_condition", C.c_float),
+                ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("reserved", C.c_int32)]
 
 
 class MbrlPlanInfo(C.Structure):
@@ -92,6 +97,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         "mbrl_set_reward_head": [p, vp, f32, f32, f32],
         "mbrl_plan": [p, C.POINTER(MbrlPlanArgs), vp, vp, vp, vp, vp, vp],
         "mbrl_plan_device": [p, C.POINTER(MbrlPlanArgs), vp, vp, vp, vp, vp, vp],
+        "mbrl_plan_gd": [p, C.POINTER(MbrlGdArgs), vp, vp, vp, vp, vp, vp],
         "mbrl_rollout": [p, i32, u64, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp, vp],
         "mbrl_sample": [p, i32, u64, u32, u32, u32, vp, vp, vp, vp],
         "mbrl_philox_raw": [vp, vp, vp, i64, vp],
@@ -263,6 +269,20 @@ class NativePlanner:
                                 actions_only, warm_start, warm_std)
         _check(self.lib.mbrl_plan_device(self._h, C.byref(args), _dp(d_s0), _dp(d_injected), _dp(d_out_states),
                                          _dp(d_out_actions), _dp(d_info), _stream_ptr()))
+
+    def plan_gd(self, s0, init_actions, iterations=40, stop_condition=0.002, lr=0.01, betas=(0.9, 0.999), eps=1e-8):
+        """mbrl_plan_gd: the batched GradientDescentPlanner.  init_actions [B,H,A] (or [H,A]).  Returns a dict of
+        numpy arrays: states [B,H+1,O], actions [B,H,A], cost [B], iterations [B]."""
+        s0 = _f32(s0).reshape(self.O)
+        init = _f32(init_actions).reshape(-1, self.H, self.A)
+        B = init.shape[0]
+        args = MbrlGdArgs(B, int(iterations), float(lr), float(stop_condition), float(betas[0]), float(betas[1]), float(eps), 0)
+        states = np.empty((B, self.H + 1, self.O), np.float32)
+        actions = np.empty((B, self.H, self.A), np.float32)
+        cost = np.empty(B, np.float32)
+        iters = np.empty(B, np.int32)
+        _check(self.lib.mbrl_plan_gd(self._h, C.byref(args), _hp(s0), _hp(init), _hp(states), _hp(actions), _hp(cost), _hp(iters)))
+        return dict(states=states, actions=actions, cost=cost, iterations=iters)
 
     # ---- building blocks (device tensors) --------------------------------------------
     def rollout(self, d_s0, mode, seed=0, iteration=0, d_injected=None, d_mu=None, d_sd=None, want_states=False,

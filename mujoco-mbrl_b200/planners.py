@@ -203,6 +203,38 @@ class CEMPlanner(ModelPlanner):
         return _as_torch(out["states"][0]), _as_torch(out["actions"][0])
 
 
+class GradientDescentPlanner(ModelPlanner):
+    """GPU GradientDescentPlanner (src/mbrl/planners.py:28-137): Adam(lr 0.01) on the action sequence with
+    back-propagation through the H-step model rollout, `num_iterations` (40) iterations at most, stopping when
+    mean|a_old - a_new| < `stop_condition` (0.002).  Returns, like the reference, H+1 states (s_0 first; the
+    states of the last forward pass) and H actions as lists of [1, .] tensors.
+
+    Batched: `num_restarts` > 1 optimises that many independently drawn initial sequences at once (one CTA
+    each) and returns the one whose last forward pass had the lowest loss; restart 0 is always the
+    reference's own start (initial_trajectory's actions, or one sample_action(batch_size=horizon) call)."""
+
+    defaults = dict(num_iterations=40, stop_condition=0.002, num_restarts=1, lr=0.01, engine="fp32", device=0)
+
+    @staticmethod
+    def plan(initial_state, model, cost, sample_action, horizon, initial_trajectory=None, **kwargs):
+        import torch
+        d = GradientDescentPlanner.defaults
+        ent, prob = _get_handle(model, cost, sample_action, horizon, 1, 1, kwargs.get("engine", d["engine"]),
+                                kwargs.get("device", d["device"]))
+        restarts = int(kwargs.get("num_restarts", d["num_restarts"]))
+        if initial_trajectory is not None:
+            first = native._f32(_stack(initial_trajectory[1])).reshape(-1, prob.act_dim)[:horizon]
+        else:
+            first = native._f32(sample_action(batch_size=horizon)).reshape(horizon, prob.act_dim)
+        init = [first] + [native._f32(sample_action(batch_size=horizon)).reshape(horizon, prob.act_dim) for _ in range(restarts - 1)]
+        out = ent["handle"].plan_gd(initial_state, np.stack(init), kwargs.get("num_iterations", d["num_iterations"]),
+                                    kwargs.get("stop_condition", d["stop_condition"]), kwargs.get("lr", d["lr"]))
+        ent["calls"] += 1
+        best = int(np.argmin(out["cost"])) if restarts > 1 else 0
+        states, actions = torch.from_numpy(out["states"][best]), torch.from_numpy(out["actions"][best])
+        return list(states.split(1, 0)), list(actions.split(1, 0))
+
+
 def _stack(seq):
     import torch
     if isinstance(seq, (list, tuple)):

@@ -305,3 +305,35 @@ def cem_plan(
         mu, sd = refit(acts.view(horizon, n, -1), elite)
         hist.append(dict(costs=costs, elite=elite, mu=mu.clone(), sd=sd.clone(), actions=acts))
     return dict(best=best, mu=mu, sd=sd, history=hist)
+
+
+# --------------------------------------------------------------------------------------
+# GradientDescentPlanner (src/mbrl/planners.py:28-137)
+# --------------------------------------------------------------------------------------
+def gd_plan(p: PlannerParams, s0: torch.Tensor, init_actions: torch.Tensor, horizon: int, num_iterations: int = 40,
+            stop_condition: float = 0.002, lr: float = 0.01):
+    """Restates GradientDescentPlanner._optimize_trajectory (planners.py:101-137) on the explicit problem:
+    Adam(lr) on the [H, A] action tensor, loss = sum over steps of state_action_cost(s_{h+1}, a_h) with
+    s_{h+1} = DynamicsModel.forward(s_h, a_h) (full back-propagation through time), stop as soon as
+    mean|a_old - a_new| < stop_condition.  Like the reference it returns the states of the LAST forward
+    pass (computed with the actions before the final Adam step, planners.py:121-135) together with the
+    updated actions.  Returns (states [H+1, O], actions [H, A], iterations run)."""
+    states = torch.zeros((horizon + 1, s0.shape[-1]))
+    states[0] = s0
+    actions = init_actions.clone().detach().reshape(horizon, -1)
+    actions.requires_grad = True
+    opt = torch.optim.Adam([actions], lr=lr)
+    ran = 0
+    for _ in range(num_iterations):
+        opt.zero_grad()
+        for i in range(horizon):
+            states[i + 1] = dynamics_forward(p, states[i:i + 1], actions[i:i + 1])
+        loss = torch.sum(state_action_cost(p, states[1:], actions))
+        loss.backward(retain_graph=True)
+        old = actions.clone().detach()
+        opt.step()
+        ran += 1
+        change = torch.mean(torch.abs(old - actions)).detach().numpy()
+        if change < stop_condition:
+            break
+    return states.detach().clone(), actions.detach().clone(), ran

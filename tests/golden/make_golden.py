@@ -17,7 +17,8 @@ Fixtures: ring_world, rs_cartpole, rs_cheetah_small (random shooting: costs, arg
 action through MPCPolicy), cem_cheetah_small, cem_cartpole_small (reference-composed CEM),
 rs_reward_head (RewardAgent wiring), rs_linear_model (--model lin), tolerance (rewards.tolerance
 grid), humanoid_reward (Humanoid.get_reward composed with the reference's tolerance), locomotion_reward
-(Cheetah.get_reward and walker-walk PlanarWalker.get_reward, same construction).
+(Cheetah.get_reward and walker-walk PlanarWalker.get_reward, same construction), gd_small / gd_early_stop /
+gd_cheetah (the reference's GradientDescentPlanner run as shipped).
 
 Third-party modules the reference imports at module scope but which are not installed
 here (tensorboardX, colorlog, dm_env, dm_control.suite, PIL) are stubbed in sys.modules;
@@ -144,6 +145,42 @@ def make_rs(name, obs, act, hidden, n, horizon, keep_states_of=None):
     )
     np.savez_compressed(os.path.join(OUT, name), **arrays)
     print(name, "argmin", int(arrays["idx"]), "min cost", float(np.min(costs)))
+
+
+def make_gd(name, obs, act, hidden, horizon, iters, stop):
+    """The reference's GradientDescentPlanner (src/mbrl/planners.py:28-137: Adam(lr 0.01) on one action
+    sequence, backprop through the H-step model rollout, early stop on mean |delta a|) run as shipped on a
+    recorded initial action sequence.  Records the initial actions, the returned (states, actions) and the
+    number of iterations it took (by counting model calls)."""
+    from src.mbrl.planners import GradientDescentPlanner
+    from src.mbrl.env_wrappers import EnvWrapper
+
+    net, model, cost, s0, arrays = _reference_problem(obs, act, hidden, seed=3)
+    np.random.seed(77)
+    init = EnvWrapper._sample_action(_Spec(act), batch_size=horizon)   # [H, A], the reference sampler
+    calls = [0]
+
+    def counting_model(states, actions):
+        calls[0] += 1
+        return model(states, actions)
+
+    def injected(batch_size):
+        assert batch_size == horizon
+        return init.clone()
+
+    states, actions = GradientDescentPlanner.plan(s0, counting_model, cost, injected, horizon, None,
+                                                   num_iterations=iters, stop_condition=stop)
+    n_calls = calls[0] - horizon  # _initialise_trajectory rolls the model once (planners.py:88-100)
+    assert n_calls % horizon == 0
+    st = torch.cat([s.reshape(1, -1) for s in states], 0).detach()
+    ac = torch.cat([a.reshape(1, -1) for a in actions], 0).detach()
+    with torch.no_grad():
+        final_cost = float(torch.sum(cost(st[1:], ac)))
+    arrays.update(init_actions=init.numpy(), states=st.numpy().copy(), actions=ac.numpy().copy(),
+                  iterations_run=np.int64(n_calls // horizon), iters=np.int64(iters), stop=np.float32(stop),
+                  horizon=np.int64(horizon), cost_of_returned=np.float32(final_cost), lo=np.float32(-1), hi=np.float32(1))
+    np.savez_compressed(os.path.join(OUT, name), **arrays)
+    print(name, "iterations run", n_calls // horizon, "cost of returned pair", final_cost)
 
 
 def make_rs_reward(name, obs, act, hidden, n, horizon):
@@ -400,3 +437,6 @@ if __name__ == "__main__":
     make_tolerance()
     make_rs_reward("rs_reward_head.npz", obs=17, act=6, hidden=50, n=256, horizon=20)
     make_rs_linear("rs_linear_model.npz", obs=9, act=3, n=200, horizon=12)
+    make_gd("gd_small.npz", obs=9, act=3, hidden=64, horizon=12, iters=25, stop=0.002)
+    make_gd("gd_early_stop.npz", obs=9, act=3, hidden=64, horizon=12, iters=40, stop=0.0095)
+    make_gd("gd_cheetah.npz", obs=17, act=6, hidden=200, horizon=30, iters=40, stop=0.002)

@@ -735,3 +735,61 @@ def test_linear_model_drop_in_matches_reference_fixture(native):
     if int(match[0]) == int(g["idx"]):
         np.testing.assert_allclose(s16.numpy(), g["plan_states"], rtol=1e-5, atol=1e-5)
     planners.clear_handles()
+
+
+# ---------------------------------------------------------------------------------------
+# GradientDescentPlanner
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["gd_small.npz", "gd_early_stop.npz", "gd_cheetah.npz"])
+def test_gradient_descent_planner_matches_reference_fixture(native, name):
+    """The batched GPU GradientDescentPlanner against the reference's own planner run as shipped
+    (src/mbrl/planners.py:28-137; tests/golden/make_golden.py::make_gd): same iteration count (incl. the early
+    stop), returned actions and states.  Tolerance: Adam normalises the gradient, so a step is ~lr * sign(g)
+    whatever the gradient's magnitude; fp32 summation-order differences (analytic back-propagation vs torch
+    autograd + MKL) stay far below lr = 0.01 -- actions within 2e-4, states within 1e-3."""
+    g = load_golden(name)
+    p = params_from_golden(g)
+    H = int(g["horizon"])
+    h = _planner(native, p, H, 1, 1, 1, engine="fp32")
+    out = h.plan_gd(g["s0"], g["init_actions"][None], iterations=int(g["iters"]), stop_condition=float(g["stop"]))
+    assert int(out["iterations"][0]) == int(g["iterations_run"])
+    err_a = np.abs(out["actions"][0] - g["actions"]).max()
+    err_s = np.abs(out["states"][0] - g["states"]).max()
+    print(f"GD planner {name}: iterations {int(out['iterations'][0])}, max |action err| {err_a:.2e}, max |state err| {err_s:.2e}")
+    assert err_a <= 2e-4 and err_s <= 1e-3
+    np.testing.assert_array_equal(out["states"][0][0], g["s0"])
+
+
+def test_gradient_descent_planner_batched_restarts_and_api(native):
+    """Batched restarts: every restart is optimised independently (restart 0 equals the single-restart run bit for
+    bit), the loss goes down, and the Python drop-in class returns the reference's list-of-[1, .]-tensors shape
+    (planners.py:137) with the best restart."""
+    from functools import partial
+    from mbrl_b200 import GradientDescentPlanner, planners
+    g = load_golden("gd_small.npz")
+    p = params_from_golden(g)
+    H, A, O = int(g["horizon"]), p.act_dim, p.obs_dim
+    h = _planner(native, p, H, 1, 1, 1, engine="fp32")
+    rng = np.random.default_rng(0)
+    init = np.concatenate([g["init_actions"][None], rng.uniform(-1, 1, (6, H, A)).astype(np.float32)])
+    one = h.plan_gd(g["s0"], init[:1], iterations=25)
+    many = h.plan_gd(g["s0"], init, iterations=25)
+    np.testing.assert_array_equal(many["actions"][0], one["actions"][0])
+    for b in range(init.shape[0]):
+        _, c0 = po.rollout_costs(p, torch.from_numpy(g["s0"]), torch.from_numpy(init[b]), H, 1)
+        assert many["cost"][b] < c0[0], "25 Adam iterations must lower the trajectory cost"
+    # drop-in class, callables wired like GoalStateAgent (agents.py:225-233)
+    model, cost, _, _ = _reference_style_callables(p, None)
+    calls = []
+
+    def sample(batch_size):
+        calls.append(batch_size)
+        return torch.from_numpy(init[len(calls) - 1])
+    states, actions = GradientDescentPlanner.plan(torch.from_numpy(g["s0"]), model, cost, sample, H, None, num_iterations=25,
+                                                  num_restarts=4)
+    assert calls == [H] * 4 and len(states) == H + 1 and len(actions) == H
+    assert states[0].shape == (1, O) and actions[0].shape == (1, A)
+    best = int(np.argmin(many["cost"][:4]))
+    np.testing.assert_allclose(torch.cat(actions).numpy(), many["actions"][best], rtol=0, atol=1e-6)
+    assert actions[0].flatten().shape == (A,)  # what MPCPolicy.get_action returns (agents.py:56)
+    planners.clear_handles()

@@ -55,7 +55,7 @@ def test_register_on_replica_enum():
     mod = _replica_module()
     register_planners(mod)
     register_planners(mod)  # idempotent
-    assert [str(m) for m in mod.Planner] == ["rs", "grad", "rs-b200", "cem-b200"]
+    assert [str(m) for m in mod.Planner] == ["rs", "grad", "rs-b200", "cem-b200", "grad-b200"]
     assert mod.Planner("cem-b200").construct() is CEMPlanner
     assert mod.Planner("rs-b200").construct() is RandomShootingPlanner
     assert mod.Planner("rs").construct() == "ref-rs"          # reference members untouched
