@@ -530,6 +530,30 @@ def main():
             full.close()
         D.barrier()
 
+    gd = None
+    if world == 1 and not env_mode and not args.no_extras:
+        # the batched GradientDescentPlanner (planners.py:28-137), 40 Adam iterations with
+        # back-propagation through the H-step rollout, for 1 and for 128 restarts; CPU: the oracle port, 1 restart
+        rng = np.random.default_rng(0)
+        init = rng.uniform(-1, 1, (128, H, A)).astype(np.float32)
+        s0g = states0[0, 0].numpy()
+        for B in (1, 128):
+            h.plan_gd(s0g, init[:B], iterations=40, stop_condition=0.0)
+        tg = {}
+        for B in (1, 128):
+            ts = []
+            for _ in range(5):
+                t0 = time.perf_counter(); h.plan_gd(s0g, init[:B], iterations=40, stop_condition=0.0); ts.append(time.perf_counter() - t0)
+            tg[B] = statistics.median(ts) * 1e3
+        gd = dict(workload=f"GradientDescentPlanner, {w['name'].split(' CEM')[0]} shape, H={H}, 40 Adam iterations (no early stop)",
+                  ms_per_plan_1_restart=tg[1], ms_per_plan_128_restarts=tg[128], api="mbrl_plan_gd (host buffers)")
+        if not args.no_cpu_baseline:
+            from oracle import planner_oracle as po
+            pp = po.synthetic_params(O, A, U)
+            t0 = time.perf_counter()
+            po.gd_plan(pp, po.synthetic_state(pp, 0), torch.from_numpy(init[0]), H, 40, 0.0)
+            gd["cpu_oracle_ms_per_plan_1_restart"] = (time.perf_counter() - t0) * 1e3
+
     cfg4 = cfg5 = None
     if not args.no_extras and not env_mode:
         D.barrier()
@@ -627,7 +651,7 @@ def main():
         gpu_launches=launches_per_plan * args.steps,
         roofline=roofline, hbm_kernels=hbm_kernels, cpu_baseline=cpu,
         sharded_equals_unsharded=(None if equal is None else bool(equal.get("ranks_identical") and equal.get("rank0_equals_unsharded_plan"))),
-        sharded_check=equal, cfg4_strong=cfg4, cfg5_env=cfg5,
+        sharded_check=equal, cfg4_strong=cfg4, cfg5_env=cfg5, gradient_planner=gd,
     )
     print(json.dumps(line), flush=True)
     if world > 1:
