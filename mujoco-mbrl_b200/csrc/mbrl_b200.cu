@@ -505,7 +505,7 @@ static int launch_refit(const MbrlPlanner* p, const ActionSource& src, const int
   const int G = (p->A + 3) / 4;
   Shape sh{p->H, p->N, p->E};
   dim3 grid(p->H * G, p->E, (k + kRefitChunk - 1) / kRefitChunk);
-  MBRL_CUDA(launch_pdl(refit_kernel, grid, dim3(kRefitThreads), 0, st, src, sh, p->A, d_elite, k, d_mu_new, d_sd_new,
+  MBRL_CUDA(launch_pdl(refit_kernel, grid, dim3(refit_threads(k)), 0, st, src, sh, p->A, d_elite, k, d_mu_new, d_sd_new,
                        p->d_refit_part, p->d_refit_arrive));
   MBRL_CUDA(cudaGetLastError());
   return MBRL_OK;

@@ -261,6 +261,11 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
 // ---- refit ---------------------------------------------------------------------------
 constexpr int kRefitThreads = 1024;
 constexpr int kRefitChunk = 2 * kRefitThreads;  // elites per CTA
+// CTA width for k elites: one elite per thread up to 1024 (a function of k alone, so the summation
+// order -- and with it the bit pattern of the refit -- does not depend on how the population is
+// sharded).  Small elite sets (k = 204 at the cfg-5 shard) would otherwise pay for 1024-thread CTAs
+// that are 80 % idle: 38 400 of them took 0.8 ms per iteration.
+inline int refit_threads(int k) { return k >= kRefitThreads ? kRefitThreads : (k < 1 ? 1 : k + 31) / 32 * 32; }
 
 // grid = (H * G, E, chunks): one CTA per (step, 4-wide action group, env, chunk of 2048 elites).
 // Each thread regenerates (or gathers) the 4 actions of its elites and accumulates shifted sums
@@ -283,7 +288,7 @@ refit_kernel(ActionSource src, Shape sh, int A, const int* __restrict__ elite_id
   const int chunk = blockIdx.z, nchunks = gridDim.z;
   const int e_end = min(k, (chunk + 1) * kRefitChunk);
   const long long R = sh.rows();
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nthreads = blockDim.x;
   const long long ms = ((long long)env_l * sh.H + h) * A;
   const bool inject = src.mode == MBRL_SAMPLE_INJECT_ACTIONS || src.mode == MBRL_SAMPLE_INJECT_NOISE;
   const bool affine = src.mode == MBRL_SAMPLE_INJECT_NOISE || src.mode == MBRL_SAMPLE_GAUSSIAN;
@@ -297,7 +302,7 @@ refit_kernel(ActionSource src, Shape sh, int A, const int* __restrict__ elite_id
     sd_old[j] = affine ? dep_load(src.sd + ms + ac) : 0.f;
   }
   const uint2 key = make_uint2(src.seed_lo, src.seed_hi);
-  for (int e = chunk * kRefitChunk + t; e < e_end; e += kRefitThreads) {
+  for (int e = chunk * kRefitChunk + t; e < e_end; e += nthreads) {
     const int cand_l = dep_load(elite_idx + (long long)env_l * k + e);
     float z[4];
     if (inject) {
@@ -339,7 +344,7 @@ refit_kernel(ActionSource src, Shape sh, int A, const int* __restrict__ elite_id
   __syncthreads();
   float a1 = 0.f, a2 = 0.f;
   if (t < 4)
-    for (int w = 0; w < kRefitThreads / 32; ++w) { a1 += red[w][t]; a2 += red[w][4 + t]; }
+    for (int w = 0; w < nthreads / 32; ++w) { a1 += red[w][t]; a2 += red[w][4 + t]; }
   if (nchunks > 1) {
     const long long slot = (long long)env_l * gridDim.x + blockIdx.x;
     float* mine = part + (slot * nchunks + chunk) * 8;

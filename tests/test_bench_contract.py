@@ -1,10 +1,12 @@
 """CPU test of bench.py's reference arm (`--impl reference`): the JSON line carries every key the
 driver's contract names.  (The B200 arm needs a GPU; its line is checked by the same key list in
-profiles/bench_r1_1gpu.json, which a GPU run of bench.py produced.)"""
+profiles/bench_r2_1gpu.json, which a GPU run of bench.py produced.)"""
 import json
 import os
 import subprocess
 import sys
+
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
@@ -31,8 +33,9 @@ def test_reference_arm_line():
     assert line["e2e"]["value"] == line["value"] == line["cpu_baseline"]["value"]
 
 
-def test_committed_b200_line_has_the_contract_keys():
-    with open(os.path.join(ROOT, "profiles", "bench_r1_1gpu.json")) as f:
+@pytest.mark.parametrize("name", ["bench_r1_1gpu.json", "bench_r2_1gpu.json"])
+def test_committed_b200_line_has_the_contract_keys(name):
+    with open(os.path.join(ROOT, "profiles", name)) as f:
         line = json.loads(f.read().strip().splitlines()[-1])
     _check_common(line)
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(line["roofline"])
