@@ -482,21 +482,30 @@ static int launch_rollout(MbrlPlanner* p, const ActionSource& src, const float* 
   return MBRL_OK;
 }
 
-static int launch_topk(const float* d_costs, int segments, int n, int k, int* d_idx, float* d_cost,
-                       MbrlPlanInfo* d_best, BestEver* d_best_ever, int iteration, cudaStream_t st) {
+template <int MODE>
+static int launch_topk_mode(const float* d_costs, int segments, int n, int k, int* d_idx, float* d_cost,
+                            MbrlPlanInfo* d_best, BestEver* d_best_ever, int iteration, const SelShard& sh, cudaStream_t st) {
   MBRL_REQUIRE(segments >= 1 && n >= 1, "topk: empty input");
   MBRL_REQUIRE(k >= 1 && k <= n, "topk: k out of range [1,n]");
   if (n <= kSelectStageMax) {
     const size_t smem = sizeof(uint32_t) * (size_t)((n + 3) & ~3);
-    MBRL_CUDA(cudaFuncSetAttribute(topk_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MBRL_CUDA(launch_pdl(topk_select_kernel<true>, dim3(segments), dim3(kSelectThreads), smem, st, d_costs, n, k, d_idx, d_cost,
-                         d_best, d_best_ever, iteration));
+    MBRL_CUDA(cudaFuncSetAttribute(topk_select_kernel<true, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MBRL_CUDA(launch_pdl(topk_select_kernel<true, MODE>, dim3(segments), dim3(kSelectThreads), smem, st, d_costs, n, k, d_idx,
+                         d_cost, d_best, d_best_ever, iteration, sh));
   } else {
-    MBRL_CUDA(launch_pdl(topk_select_kernel<false>, dim3(segments), dim3(kSelectThreads), 0, st, d_costs, n, k, d_idx, d_cost,
-                         d_best, d_best_ever, iteration));
+    const size_t smem = sizeof(uint32_t) * 16 * kSelectThreads;  // compaction buffer of one 16384-key pass
+    MBRL_CUDA(cudaFuncSetAttribute(topk_select_kernel<false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MBRL_CUDA(launch_pdl(topk_select_kernel<false, MODE>, dim3(segments), dim3(kSelectThreads), smem, st, d_costs, n, k, d_idx,
+                         d_cost, d_best, d_best_ever, iteration, sh));
   }
   MBRL_CUDA(cudaGetLastError());
   return MBRL_OK;
+}
+
+static int launch_topk(const float* d_costs, int segments, int n, int k, int* d_idx, float* d_cost,
+                       MbrlPlanInfo* d_best, BestEver* d_best_ever, int iteration, cudaStream_t st) {
+  static const SelShard none{};
+  return launch_topk_mode<kSelPlain>(d_costs, segments, n, k, d_idx, d_cost, d_best, d_best_ever, iteration, none, st);
 }
 
 static int launch_refit(const MbrlPlanner* p, const ActionSource& src, const int* d_elite, int k,
@@ -505,8 +514,13 @@ static int launch_refit(const MbrlPlanner* p, const ActionSource& src, const int
   const int G = (p->A + 3) / 4;
   Shape sh{p->H, p->N, p->E};
   dim3 grid(p->H * G, p->E, (k + kRefitChunk - 1) / kRefitChunk);
-  MBRL_CUDA(launch_pdl(refit_kernel, grid, dim3(refit_threads(k)), 0, st, src, sh, p->A, d_elite, k, d_mu_new, d_sd_new,
-                       p->d_refit_part, p->d_refit_arrive));
+  const int threads = refit_threads(k);
+  if (threads <= kRefitThreads / 2)  // register-capped build: three CTAs per SM
+    MBRL_CUDA(launch_pdl(refit_kernel<kRefitThreads / 2, 3>, grid, dim3(threads), 0, st, src, sh, p->A, d_elite, k, d_mu_new,
+                         d_sd_new, p->d_refit_part, p->d_refit_arrive));
+  else
+    MBRL_CUDA(launch_pdl(refit_kernel<kRefitThreads, 1>, grid, dim3(threads), 0, st, src, sh, p->A, d_elite, k, d_mu_new,
+                         d_sd_new, p->d_refit_part, p->d_refit_arrive));
   MBRL_CUDA(cudaGetLastError());
   return MBRL_OK;
 }
@@ -677,7 +691,7 @@ extern "C" int mbrl_p2p_export(MbrlPlanner* p, int32_t world, uint8_t* h_handle6
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   MBRL_CUDA(cudaSetDevice(p->cfg.device));
   const int slot = std::min(p->cfg.max_elites, p->N);
-  const size_t words = (size_t)2 * world * 2 * slot + world;
+  const size_t words = p2p_total_words(world, slot);
   if (p->d_p2p_local && p->p2p_world != world) {  // another world size: a new buffer
     MBRL_CUDA(cudaDeviceSynchronize());
     cudaFree(p->d_p2p_local); p->d_p2p_local = nullptr;
@@ -851,7 +865,7 @@ static int enqueue_plan(MbrlPlanner* p, const MbrlPlanArgs* a, const float* d_s0
       // redundant refit from GLOBAL indices (cand_offset 0): no second collective
       // Worst case a single shard holds all k global elites (k_full = min(k, N) per rank); the
       // shards are i.i.d., so a rank's share is Binomial(k, 1/world): send the expected share plus
-      // 8 standard deviations (+64) and verify exactness on the device (remap_elites_kernel); a
+      // 8 standard deviations (+64) and verify exactness on the device (the merge select); a
       // flagged plan -- probability ~1e-15 per iteration -- is redone with full-size gathers.
       const int k_full = std::min(k, p->N);
       const int share = (k + p->world - 1) / p->world;
@@ -860,27 +874,30 @@ static int enqueue_plan(MbrlPlanner* p, const MbrlPlanArgs* a, const float* d_s0
         // expected share), which the exactness check must flag so that the redo path is exercised
         if (!p->full_gather && p->world > 1 && force[0] == 'm') kl = std::min(k_full, (k + p->world - 1) / p->world);
       }
-      rc = launch_topk(p->d_costs, 1, p->N, kl, p->d_elite, p->d_ecost, nullptr, nullptr, it, st);
-      if (rc) return rc;
       const int ng = kl * p->world;
       if (p->p2p_attached) {
-        // peer-memory exchange: one kernel stores our elites into every rank's buffer and publishes
-        // the sequence flag; the consumer acquires all ranks' flags, then unpacks
-        const uint32_t seq = ++p->p2p_seq;
-        MBRL_CUDA(launch_pdl(p2p_scatter_kernel, dim3((kl + 255) / 256), dim3(256), 0, st, p->d_ecost, p->d_elite, kl,
-                             (int)cand_offset, p->p2p_peers, p->rank, p->world, p->p2p_slot, (int)(seq & 1), seq,
-                             p->d_p2p_counter));
-        MBRL_CUDA(launch_pdl(p2p_wait_unpack_kernel, dim3((ng + 255) / 256), dim3(256), 0, st, p->d_p2p_local, p->world,
-                             p->p2p_slot, kl, (int)(seq & 1), seq, p->d_gcost, p->d_gidx, p->d_p2p_error, p2p_timeout_ns()));
+        // peer-memory exchange, two launches: the local select stores its elites straight into every
+        // rank's buffer and publishes the sequence flag; the merge select acquires all ranks' flags,
+        // selects among the gathered candidates in place and emits global indices
+        SelShard sh{};
+        sh.peers = p->p2p_peers; sh.local = p->d_p2p_local; sh.rank = p->rank; sh.world = p->world;
+        sh.slot = p->p2p_slot; sh.seq = ++p->p2p_seq; sh.parity = (int)(sh.seq & 1); sh.idx_offset = (int)cand_offset;
+        sh.k_full = k_full; sh.trunc = p->d_trunc; sh.error = p->d_p2p_error; sh.timeout_ns = p2p_timeout_ns();
+        rc = launch_topk_mode<kSelScatter>(p->d_costs, 1, p->N, kl, nullptr, nullptr, nullptr, nullptr, it, sh, st);
+        if (rc) return rc;
+        rc = launch_topk_mode<kSelMerge>(nullptr, 1, ng, k, p->d_elite, nullptr, nullptr, p->d_best_ever, it, sh, st);
+        if (rc) return rc;
       } else {
+        rc = launch_topk(p->d_costs, 1, p->N, kl, p->d_elite, p->d_ecost, nullptr, nullptr, it, st);
+        if (rc) return rc;
         pack_elites_kernel<<<(kl + 255) / 256, 256, 0, st>>>(p->d_ecost, p->d_elite, kl, (int)cand_offset, p->d_send);
         MBRL_NCCL(g_nccl.AllGather(p->d_send, p->d_recv, (size_t)2 * kl, kNcclUint32, p->comm, st));
         unpack_gathered_kernel<<<(ng + 255) / 256, 256, 0, st>>>(p->d_recv, p->world, kl, p->d_gcost, p->d_gidx);
+        rc = launch_topk(p->d_gcost, 1, ng, k, p->d_pos, nullptr, p->d_best_now, nullptr, it, st);
+        if (rc) return rc;
+        MBRL_CUDA(launch_pdl(remap_elites_kernel, dim3((std::max(k, p->world) + 255) / 256), dim3(256), 0, st, p->d_pos,
+                             p->d_gidx, k, p->d_elite, p->d_best_now, p->d_best_ever, it, p->world, kl, k_full, p->d_trunc));
       }
-      rc = launch_topk(p->d_gcost, 1, ng, k, p->d_pos, nullptr, p->d_best_now, nullptr, it, st);
-      if (rc) return rc;
-      MBRL_CUDA(launch_pdl(remap_elites_kernel, dim3((std::max(k, p->world) + 255) / 256), dim3(256), 0, st, p->d_pos,
-                           p->d_gidx, k, p->d_elite, p->d_best_now, p->d_best_ever, it, p->world, kl, k_full, p->d_trunc));
       MBRL_CUDA(cudaGetLastError());
       if (it + 1 < I || need_final_dist) {
         ActionSource gsrc = src;

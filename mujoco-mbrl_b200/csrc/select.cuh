@@ -19,6 +19,55 @@ __device__ __forceinline__ uint32_t cost_key(float c) {
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+// ---- peer-memory (NVLink P2P) elite exchange ---------------------------------------------------
+// (mbrl_p2p_export / mbrl_p2p_attach).  Every rank exports one buffer of uint32 words:
+//   2 parities x { costs [world*slot] | global indices [world*slot] | local thresholds [world] }
+//   then [world] sequence flags (one per source rank).
+// slot = capacity per rank; a launch that sends k_l <= slot elites per rank packs them
+// CONTIGUOUSLY (rank r's at [r*k_l, (r+1)*k_l)), so that the gathered costs / indices are plain
+// arrays of world*k_l entries in ascending global index order and the merge select reads them in place.
+// Layout of every rank's exported buffer: [2 parities][world][2*slot] uint32 data, then
+// [world] uint32 sequence flags (one per source rank).  slot = k_l capacity.
+struct P2pPeers {
+  uint32_t* base[64];  // peer r's exported buffer (own rank: the local pointer)
+};
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__host__ __device__ inline size_t p2p_parity_words(int world, int slot) { return (size_t)world * (2 * (size_t)slot + 1); }
+__host__ __device__ inline size_t p2p_total_words(int world, int slot) { return 2 * p2p_parity_words(world, slot) + (size_t)world; }
+
+// Sharded roles of the top-k kernel (template parameter MODE):
+//   kSelPlain    the ordinary segmented top-k
+//   kSelScatter  local top-k_l whose compaction stores (cost bits, global index) straight into every
+//                rank's exported buffer over NVLink and then publishes this rank's sequence flag
+//   kSelMerge    waits for every rank's flag, selects the global top-k among the world*k_l gathered
+//                candidates in place, emits GLOBAL candidate indices, keeps the best-ever record in
+//                global indices and checks that the reduced-size gather was exact
+enum { kSelPlain = 0, kSelScatter = 1, kSelMerge = 2 };
+__device__ __forceinline__ bool k_per_rank_lt(int n, int world, int k_full) { return n / world < k_full; }
+struct SelShard {
+  P2pPeers peers;          // kSelScatter: every rank's buffer (own rank: the local pointer)
+  const uint32_t* local;   // kSelMerge: this rank's buffer
+  int rank, world, slot, parity;
+  int idx_offset;          // kSelScatter: global index of local candidate 0
+  int k_full;              // kSelMerge: min(k, N) -- a gather of k_full per rank is exact by construction
+  uint32_t seq;
+  int* trunc;              // kSelMerge: set when the reduced gather cannot be proven exact
+  int* error;              // kSelMerge: set when a rank's flag never arrived
+  unsigned long long timeout_ns;
+};
+
 constexpr int kSelectThreads = 1024;
 #ifdef MBRL_TOPK_PROFILE
 __device__ long long g_topk_stamps[32];
@@ -60,31 +109,58 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
   return v;
 }
 
-template <bool STAGED>
+template <bool STAGED, int MODE>
 __global__ void __launch_bounds__(kSelectThreads)
 topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restrict__ elite_idx,
                    float* __restrict__ elite_cost, MbrlPlanInfo* __restrict__ best,
-                   BestEver* __restrict__ best_ever, int iteration) {
+                   BestEver* __restrict__ best_ever, int iteration, const SelShard sh) {
   extern __shared__ __align__(16) uint32_t sel_smem[];
   uint32_t* keys = sel_smem;  // [round4(n)] when STAGED
   __shared__ uint32_t hist[kSelectBins];
-  __shared__ uint32_t wtot[2][4][32];  // per-warp totals (double buffered; 4 trips per pass)
-  __shared__ uint32_t wtot2[2][4][32];
+  __shared__ uint32_t wtot[2][2][32];  // per-warp totals (double buffered)
   __shared__ uint32_t s_sel[2];        // winning bin, remaining rank
-  __shared__ unsigned long long warp_min[32];
+  __shared__ int warp_first[32];
+  __shared__ int s_ok;
 
   const int seg = blockIdx.x;
-  const float* c = costs + (long long)seg * n;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int n4 = (n + 3) & ~3;
+  // kSelMerge: the gathered candidates live in this rank's exported buffer (written by the peers)
+  const size_t par_off = MODE == kSelPlain ? 0 : (size_t)sh.parity * p2p_parity_words(sh.world, sh.slot);
+  const float* c = MODE == kSelMerge ? reinterpret_cast<const float*>(sh.local + par_off) : costs + (long long)seg * n;
+  const uint32_t* gidx = MODE == kSelMerge ? sh.local + par_off + (size_t)sh.world * sh.slot : nullptr;
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(c) & 15) == 0);
   pdl_trigger();
-  pdl_wait();  // the costs come from the preceding rollout / unpack kernel
+  pdl_wait();  // the costs come from the preceding rollout kernel
   TOPK_STAMP(0);
+  bool bad = false;
+  if (MODE == kSelMerge) {
+    // acquire every rank's sequence flag.  A rank that never shows up within timeout_ns (wall clock,
+    // default 120 s, MBRL_P2P_TIMEOUT_S) trips the timeout: *error = 1 and every gathered candidate
+    // reads as (+inf, -1) instead of the previous iteration's data, so that whatever runs next is
+    // deterministic garbage that the plan reports (info.reserved bit 1), not a plausible wrong plan.
+    if (t == 0) s_ok = 1;
+    __syncthreads();
+    if (t < sh.world) {
+      const uint32_t* flag = sh.local + 2 * p2p_parity_words(sh.world, sh.slot) + t;
+      const unsigned long long t0 = globaltimer_ns();
+      unsigned int spins = 0;
+      while ((int)(ld_acquire_sys(flag) - sh.seq) < 0) {
+        if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > sh.timeout_ns) { s_ok = 0; break; }
+      }
+    }
+    __syncthreads();
+    bad = !s_ok;
+    if (bad && t == 0) *sh.error = 1;
+  }
+  constexpr uint32_t kInfKey = 0x7F800000u | 0x80000000u;  // cost_key(+inf)
 
   // four keys of indices i4..i4+3 (i4 multiple of 4); out-of-range -> 0xFFFFFFFF (masked by index)
   auto load4 = [&](int i4, uint32_t (&kk)[4]) {
-    if (vec_ok && i4 + 3 < n) {
+    if (MODE == kSelMerge && bad) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) kk[j] = i4 + j < n ? kInfKey : 0xFFFFFFFFu;
+    } else if (vec_ok && i4 + 3 < n) {
       const float4 q = dep_load(reinterpret_cast<const float4*>(c + i4));
       kk[0] = cost_key(q.x); kk[1] = cost_key(q.y); kk[2] = cost_key(q.z); kk[3] = cost_key(q.w);
     } else {
@@ -126,6 +202,7 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
     kmin = min(kmin, __shfl_xor_sync(0xFFFFFFFFu, kmin, d));
     kmax = max(kmax, __shfl_xor_sync(0xFFFFFFFFu, kmax, d));
   }
+  const uint32_t key_min = kmin;  // the argmin is the lowest index holding this key
   uint32_t lo = kmin, hi = kmax, rem = (uint32_t)k;
   TOPK_STAMP(1);
 
@@ -171,83 +248,112 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
   const uint32_t take_eq = rem;   // how many keys == T belong to the elite set
   TOPK_STAMP(20);
 
+  if (MODE == kSelScatter && t < sh.world)  // this rank's threshold: the merge proves exactness with it
+    sh.peers.base[t][par_off + 2 * (size_t)sh.world * sh.slot + sh.rank] = T;
+  if (MODE == kSelMerge && t < sh.world && k_per_rank_lt(n, sh.world, sh.k_full)) {
+    // Reduced gather: rank t sent only its k_s = n/world cheapest; its k_s-th key is tl.  tl > T: every
+    // candidate it kept back is above the global threshold -> exact.  tl <= T: cheaper-than-threshold
+    // candidates of that rank may be missing -> flag, the caller redoes the plan with full-size gathers.
+    const uint32_t tl = bad ? 0xFFFFFFFFu : dep_load(sh.local + par_off + 2 * (size_t)sh.world * sh.slot + t);
+    if (tl <= T) atomicOr(sh.trunc, 1);
+  }
+
   // ---- index-ordered compaction + argmin ----
-  // A pass covers 4 trips of 4096 indices (thread t owns indices trip*4096 + 4t .. +3); the per-warp
-  // counts of all 4 trips meet in shared memory once, every warp scans them itself, and the
-  // running base lives in registers: one barrier per 16384 keys.
-  unsigned long long my_min = ~0ull;
+  // Thread t owns 16 CONSECUTIVE indices of every 16384-key pass: one (less, equal) count pair per
+  // thread, one block scan (a single barrier) per pass, the running base in registers.
+  int first_min = 0x7FFFFFFF;
   uint32_t base_less = 0, base_eq = 0;
   int pass = 0;
   for (int p0 = 0; p0 < n4; p0 += 16 * kSelectThreads, ++pass) {
-    uint32_t kk[4][4], il[4], ie[4], nl[4], ne[4];
+    const int i0 = p0 + 16 * t;
+    uint32_t kk[16], nl = 0, ne = 0;
 #pragma unroll
-    for (int tr = 0; tr < 4; ++tr) {
-      const int i4 = p0 + tr * 4 * kSelectThreads + 4 * t;
-      nl[tr] = 0; ne[tr] = 0;
-      if (i4 < n4) {
-        key4_at(i4, kk[tr]);
+    for (int q = 0; q < 4; ++q) {
+      uint32_t k4[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+      if (i0 + 4 * q < n4) key4_at(i0 + 4 * q, k4);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (i4 + j < n) {
-            nl[tr] += kk[tr][j] < T;
-            ne[tr] += kk[tr][j] == T;
-            const unsigned long long packed = ((unsigned long long)kk[tr][j] << 32) | (uint32_t)(i4 + j);
-            my_min = packed < my_min ? packed : my_min;
-          }
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + 4 * q + j;
+        kk[4 * q + j] = k4[j];
+        if (i < n) {
+          nl += k4[j] < T;
+          ne += k4[j] == T;
+          if (k4[j] == key_min) first_min = min(first_min, i);
         }
       }
-      il[tr] = warp_incl_scan(nl[tr], lane);
-      ie[tr] = warp_incl_scan(ne[tr], lane);
-      if (lane == 31) { wtot[pass & 1][tr][warp] = il[tr]; wtot2[pass & 1][tr][warp] = ie[tr]; }
+    }
+    const uint32_t il = warp_incl_scan(nl, lane), ie = warp_incl_scan(ne, lane);
+    if (lane == 31) { wtot[pass & 1][0][warp] = il; wtot[pass & 1][1][warp] = ie; }
+    __syncthreads();
+    const uint32_t tl = wtot[pass & 1][0][lane], te = wtot[pass & 1][1][lane];
+    const uint32_t sl = warp_incl_scan(tl, lane), se = warp_incl_scan(te, lane);
+    uint32_t less_before = base_less + __shfl_sync(0xFFFFFFFFu, sl - tl, warp) + il - nl;
+    uint32_t eq_before = base_eq + __shfl_sync(0xFFFFFFFFu, se - te, warp) + ie - ne;
+    // this pass's elites occupy the output positions [out0, out0 + cnt): positions rise with the index
+    const uint32_t out0 = base_less + min(base_eq, take_eq);
+    base_less += __shfl_sync(0xFFFFFFFFu, sl, 31);
+    base_eq += __shfl_sync(0xFFFFFFFFu, se, 31);
+    const uint32_t cnt = base_less + min(base_eq, take_eq) - out0;
+    // Compact the pass's elite indices in shared memory first (over the pass's own key slice, which
+    // every thread holds in registers by now), then write them out coalesced: a thread's 16 keys map
+    // to 16 scattered positions, and direct stores cost one 32-byte sector per lane.
+    uint32_t* outbuf = STAGED ? keys + p0 : keys;
+    if (nl | ne) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int i = i0 + j;
+        if (i < n) {
+          const bool less = kk[j] < T, eq = kk[j] == T;
+          if (less || (eq && eq_before < take_eq))
+            outbuf[less_before + (eq_before < take_eq ? eq_before : take_eq) - out0] = (uint32_t)i;
+          less_before += less;
+          eq_before += eq;
+        }
+      }
     }
     __syncthreads();
-#pragma unroll
-    for (int tr = 0; tr < 4; ++tr) {
-      const int i4 = p0 + tr * 4 * kSelectThreads + 4 * t;
-      const uint32_t tl = wtot[pass & 1][tr][lane], te = wtot2[pass & 1][tr][lane];
-      const uint32_t sl = warp_incl_scan(tl, lane), se = warp_incl_scan(te, lane);
-      uint32_t less_before = base_less + __shfl_sync(0xFFFFFFFFu, sl - tl, warp) + il[tr] - nl[tr];
-      uint32_t eq_before = base_eq + __shfl_sync(0xFFFFFFFFu, se - te, warp) + ie[tr] - ne[tr];
-      base_less += __shfl_sync(0xFFFFFFFFu, sl, 31);
-      base_eq += __shfl_sync(0xFFFFFFFFu, se, 31);
-      if (i4 < n4) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int i = i4 + j;
-          if (i < n) {
-            const bool less = kk[tr][j] < T, eq = kk[tr][j] == T;
-            if (less || (eq && eq_before < take_eq)) {
-              const uint32_t pos = less_before + (eq_before < take_eq ? eq_before : take_eq);
-              elite_idx[(long long)seg * k + pos] = i;
-              if (elite_cost) elite_cost[(long long)seg * k + pos] = dep_load(c + i);
-            }
-            less_before += less;
-            eq_before += eq;
-          }
+    for (uint32_t j = t; j < cnt; j += kSelectThreads) {
+      const int i = (int)outbuf[j];
+      const uint32_t pos = out0 + j;
+      if (MODE == kSelScatter) {
+        // peer stores over NVLink: (cost bits | global index) into every rank's gathered arrays
+        const uint32_t cb = __float_as_uint(dep_load(c + i));
+        const size_t at = par_off + (size_t)sh.rank * k + pos;
+        for (int r = 0; r < sh.world; ++r) {
+          uint32_t* dst = sh.peers.base[r];
+          dst[at] = cb;
+          dst[at + (size_t)sh.world * sh.slot] = (uint32_t)(i + sh.idx_offset);
         }
+      } else if (MODE == kSelMerge) {
+        elite_idx[pos] = bad ? -1 : (int)dep_load(gidx + i);
+      } else {
+        elite_idx[(long long)seg * k + pos] = i;
+        if (elite_cost) elite_cost[(long long)seg * k + pos] = dep_load(c + i);
       }
     }
   }
   TOPK_STAMP(21);
 
-  // ---- block argmin (lowest index among equal minima) ----
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, my_min, d);
-    my_min = o < my_min ? o : my_min;
+  if (MODE == kSelScatter) {
+    // publish: every thread's peer stores are ordered before the flag at system scope
+    __threadfence_system();
+    __syncthreads();
+    if (t < sh.world) st_release_sys(sh.peers.base[t] + 2 * p2p_parity_words(sh.world, sh.slot) + sh.rank, sh.seq);
+    return;
   }
-  if (lane == 0) warp_min[warp] = my_min;
+
+  // ---- block argmin: the lowest index holding the minimum key ----
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) first_min = min(first_min, __shfl_xor_sync(0xFFFFFFFFu, first_min, d));
+  if (lane == 0) warp_first[warp] = first_min;
   __syncthreads();
   if (warp == 0) {
-    unsigned long long v = warp_min[lane];
+    int v = warp_first[lane];
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, v, d);
-      v = o < v ? o : v;
-    }
+    for (int d = 16; d > 0; d >>= 1) v = min(v, __shfl_xor_sync(0xFFFFFFFFu, v, d));
     if (lane == 0 && n > 0) {
-      const int idx = (int)(uint32_t)(v & 0xFFFFFFFFull);
-      const float cmin = dep_load(c + idx);
+      const float cmin = (MODE == kSelMerge && bad) ? __int_as_float(0x7f800000) : dep_load(c + v);
+      const int idx = MODE == kSelMerge ? (bad ? -1 : (int)dep_load(gidx + v)) : v;
       if (best) { best[seg].best_cost = cmin; best[seg].best_iteration = iteration; best[seg].best_index = idx; best[seg].reserved = 0; }
       if (best_ever) {
         BestEver b = best_ever[seg];
@@ -265,7 +371,12 @@ constexpr int kRefitChunk = 2 * kRefitThreads;  // elites per CTA
 // order -- and with it the bit pattern of the refit -- does not depend on how the population is
 // sharded).  Small elite sets (k = 204 at the cfg-5 shard) would otherwise pay for 1024-thread CTAs
 // that are 80 % idle: 38 400 of them took 0.8 ms per iteration.
-inline int refit_threads(int k) { return k >= kRefitThreads ? kRefitThreads : (k < 1 ? 1 : k + 31) / 32 * 32; }
+// Several chunks (k > 2048): 512-thread CTAs, four elites per thread -- three to four CTAs fit an SM,
+// so that the H*G*chunks CTAs of a large elite set (420 at the 8-way sharded cfg 3) run as one wave.
+inline int refit_threads(int k) {
+  if (k > kRefitChunk) return kRefitThreads / 2;
+  return k >= kRefitThreads ? kRefitThreads : (k < 1 ? 1 : k + 31) / 32 * 32;
+}
 
 // grid = (H * G, E, chunks): one CTA per (step, 4-wide action group, env, chunk of 2048 elites).
 // Each thread regenerates (or gathers) the 4 actions of its elites and accumulates shifted sums
@@ -276,7 +387,8 @@ inline int refit_threads(int k) { return k >= kRefitThreads ? kRefitThreads : (k
 // idle SMs, park their partial sums, and the last one to arrive adds them IN CHUNK ORDER -- the
 // result depends only on the elite list (ascending index), never on timing or on the sharding,
 // which is what keeps every rank's refit bit-identical to the unsharded one.
-__global__ void __launch_bounds__(kRefitThreads)
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 refit_kernel(ActionSource src, Shape sh, int A, const int* __restrict__ elite_idx, int k,
              float* __restrict__ mu_new, float* __restrict__ sd_new, float* __restrict__ part,
              unsigned int* __restrict__ arrive) {
@@ -390,92 +502,6 @@ __global__ void pack_elites_kernel(const float* __restrict__ elite_cost, const i
     send[k_l + i] = (uint32_t)(dep_load(elite_idx + i) + idx_offset);
   }
 }
-// ---- peer-memory (NVLink P2P) elite exchange ---------------------------------------------------
-// Layout of every rank's exported buffer: [2 parities][world][2*slot] uint32 data, then
-// [world] uint32 sequence flags (one per source rank).  slot = k_l capacity.
-struct P2pPeers {
-  uint32_t* base[64];  // peer r's exported buffer (own rank: the local pointer)
-};
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-// One launch per iteration: writes this rank's k_l (cost bits | global index) pairs into slot
-// [parity][rank] of EVERY rank's buffer (peer stores over NVLink), then -- after a system-scope
-// fence and a grid-wide arrival count -- the last block publishes `seq` in flag[rank] of every peer.
-__global__ void p2p_scatter_kernel(const float* __restrict__ elite_cost, const int* __restrict__ elite_idx,
-                                   int k_l, int idx_offset, P2pPeers peers, int rank, int world, int slot,
-                                   int parity, uint32_t seq, unsigned int* __restrict__ arrive_counter) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  pdl_trigger();
-  pdl_wait();
-  if (i < k_l) {
-    const uint32_t c = __float_as_uint(dep_load(elite_cost + i));
-    const uint32_t g = (uint32_t)(dep_load(elite_idx + i) + idx_offset);
-    const size_t off = ((size_t)parity * world + rank) * 2 * slot;
-    for (int r = 0; r < world; ++r) {
-      uint32_t* dst = peers.base[r] + off;
-      dst[i] = c;
-      dst[k_l + i] = g;
-    }
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int done = atomicAdd(arrive_counter, 1u) + 1u;
-    if (done == gridDim.x) {
-      *arrive_counter = 0;  // ready for the next launch (stream order)
-      __threadfence_system();
-      const size_t flags = (size_t)2 * world * 2 * slot;
-      for (int r = 0; r < world; ++r) st_release_sys(peers.base[r] + flags + rank, seq);
-    }
-  }
-}
-// Consumer: acquire every rank's flag (>= seq), then unpack [parity][r][..] into contiguous costs /
-// global indices in rank order.  A rank that never shows up within `timeout_ns` (wall clock, default
-// 120 s, MBRL_P2P_TIMEOUT_S) trips the timeout: *error = 1 and the gathered arrays are filled with
-// (+inf, -1) sentinels instead of the previous iteration's data, so that whatever runs next is
-// deterministic garbage that the plan reports (info.reserved bit 1) rather than a plausible wrong plan.
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-__global__ void p2p_wait_unpack_kernel(const uint32_t* __restrict__ local, int world, int slot, int k_l, int parity,
-                                       uint32_t seq, float* __restrict__ gcost, int* __restrict__ gidx,
-                                       int* __restrict__ error, unsigned long long timeout_ns) {
-  __shared__ int s_ok;
-  pdl_trigger();
-  pdl_wait();
-  if (threadIdx.x == 0) s_ok = 1;
-  __syncthreads();
-  if (threadIdx.x < world) {
-    const uint32_t* flag = local + (size_t)2 * world * 2 * slot + threadIdx.x;
-    const unsigned long long t0 = globaltimer_ns();
-    unsigned int spins = 0;
-    while ((int)(ld_acquire_sys(flag) - seq) < 0) {
-      if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > timeout_ns) { s_ok = 0; break; }
-    }
-  }
-  __syncthreads();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (!s_ok) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) *error = 1;
-    if (i < world * k_l) { gcost[i] = __int_as_float(0x7f800000); gidx[i] = -1; }
-    return;
-  }
-  if (i < world * k_l) {
-    const int r = i / k_l, j = i - r * k_l;
-    const uint32_t* src = local + ((size_t)parity * world + r) * 2 * slot;
-    gcost[i] = __uint_as_float(__ldcg(src + j));
-    gidx[i] = (int)__ldcg(src + k_l + j);
-  }
-}
-
 // End of a sharded plan: info.reserved = (reduced-gather-not-provably-exact) | (exchange timed out) << 1;
 // the truncation flag is reset for the next plan whether or not the caller passed an info buffer.
 __global__ void shard_flags_kernel(MbrlPlanInfo* __restrict__ info, int* __restrict__ trunc, const int* __restrict__ p2p_error) {

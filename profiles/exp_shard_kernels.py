@@ -19,14 +19,20 @@ mu = torch.zeros(1, H, A, device="cuda"); sd = torch.ones(1, H, A, device="cuda"
 elite_big = torch.sort(torch.randperm(N * world, device="cuda", generator=g)[:k]).values.int().view(1, -1)
 elite_small = torch.sort(torch.randperm(N, device="cuda", generator=g)[:1638]).values.int().view(1, -1)
 
-def timed(fn, n=30):
-    for _ in range(5): fn()
+def timed(fn, n=15, batch=40):
+    """GPU time per launch: `batch` back-to-back launches captured in a CUDA graph (no host launch
+    cost in the timed region; launch gaps between dependent kernels included), median of n replays."""
+    for _ in range(3): fn()
     torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(batch): fn()
+    g.replay(); torch.cuda.synchronize()
     ts = []
     for _ in range(n):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); fn(); b.record(); torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b) * 1e3)
+        a.record(); g.replay(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3 / batch)
     ts.sort()
     return ts[len(ts) // 2]
 

@@ -12,8 +12,8 @@ int main() {
   float* dc; int* di; cudaMalloc(&dc, n * 4); cudaMalloc(&di, k * 4);
   cudaMemcpy(dc, h.data(), n * 4, cudaMemcpyHostToDevice);
   const size_t smem = 4 * n;
-  cudaFuncSetAttribute(topk_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  for (int rep = 0; rep < 3; ++rep) topk_select_kernel<true><<<1, kSelectThreads, smem>>>(dc, n, k, di, nullptr, nullptr, nullptr, 0);
+  cudaFuncSetAttribute(topk_select_kernel<true, kSelPlain>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  for (int rep = 0; rep < 3; ++rep) topk_select_kernel<true, kSelPlain><<<1, kSelectThreads, smem>>>(dc, n, k, di, nullptr, nullptr, nullptr, 0, SelShard{});
   cudaError_t e = cudaDeviceSynchronize(); if (e != cudaSuccess) { printf("%s\n", cudaGetErrorString(e)); return 1; }
   long long st[32]; cudaMemcpyFromSymbol(st, g_topk_stamps, sizeof(st));
   const char* names[32] = {};
