@@ -488,7 +488,7 @@ static int launch_topk_mode(const float* d_costs, int segments, int n, int k, in
   MBRL_REQUIRE(segments >= 1 && n >= 1, "topk: empty input");
   MBRL_REQUIRE(k >= 1 && k <= n, "topk: k out of range [1,n]");
   if (n <= kSelectStageMax) {
-    const size_t smem = sizeof(uint32_t) * (size_t)((n + 3) & ~3);
+    const size_t smem = sizeof(uint32_t) * (size_t)select_padded(n);
     MBRL_CUDA(cudaFuncSetAttribute(topk_select_kernel<true, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MBRL_CUDA(launch_pdl(topk_select_kernel<true, MODE>, dim3(segments), dim3(kSelectThreads), smem, st, d_costs, n, k, d_idx,
                          d_cost, d_best, d_best_ever, iteration, sh));

@@ -86,18 +86,27 @@ struct BestEver {  // per environment, device resident
 // One CTA per segment (environment).  The float costs are mapped to monotone uint32 keys and
 // staged once in shared memory (coalesced, loads in flight together) while the block min/max is
 // reduced.  The k-th smallest key T is then found by an ADAPTIVE radix select: every round
-// histograms the keys that are still in range into 1024 equal-width buckets of the CURRENT key
+// histograms the keys that are still in range into 4096 equal-width buckets of the CURRENT key
 // range [lo, hi] (power-of-two width; the candidates spread over the bins instead of piling onto
 // the few leading bit patterns that the costs of one population share), a block scan locates the
-// bucket holding the k-th key, and the range shrinks >= 512x; it ends when the width is 1.
-// A final index-ordered compaction (ballot + warp-shuffle scans) emits every key < T plus the
-// first `take_eq` keys == T.
+// bucket holding the k-th key, and the range shrinks >= 2048x; it ends when the width is 1
+// (two rounds for costs within a binade or two, three for arbitrary floats).
+// A final index-ordered compaction emits every key < T plus the first `take_eq` keys == T:
+// thread t owns 16 consecutive indices of each 16384-key pass (selection bit masks, one packed
+// block scan), the pass's elite indices are compacted in shared memory and written out coalesced.
+// The staged keys are stored with an XOR swizzle of the 16-byte unit index so that both access
+// patterns -- thread-strided units (staging, histogram rounds, where the index is irrelevant) and
+// four consecutive units per thread (compaction) -- are free of bank conflicts.  Padding keys
+// (0xFFFFFFFF up to a multiple of 32) sort after every real key, ties included (highest indices),
+// so the rounds and the compaction need no index mask.
 //   best (nullable):      (min cost, ., argmin) of this launch per segment
 //   best_ever (nullable): updated when this launch's minimum is strictly smaller
 //                         (earlier iteration wins ties)
 // STAGED=false re-reads the costs from global memory (segments too long for shared memory).
 constexpr int kSelectStageMax = 49152;  // keys staged in shared memory: 192 KB
-constexpr int kSelectBins = 1024;
+constexpr int kSelectBins = 4096;
+constexpr int kSelectBinBits = 12;
+__host__ __device__ inline int select_padded(int n) { return (n + 31) & ~31; }
 
 // inclusive warp scan
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
@@ -115,8 +124,8 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
                    float* __restrict__ elite_cost, MbrlPlanInfo* __restrict__ best,
                    BestEver* __restrict__ best_ever, int iteration, const SelShard sh) {
   extern __shared__ __align__(16) uint32_t sel_smem[];
-  uint32_t* keys = sel_smem;  // [round4(n)] when STAGED
-  __shared__ uint32_t hist[kSelectBins];
+  uint32_t* keys = sel_smem;  // [select_padded(n)] when STAGED, else the 16384-entry compaction buffer
+  __shared__ __align__(16) uint32_t hist[kSelectBins];
   __shared__ uint32_t wtot[2][2][32];  // per-warp totals (double buffered)
   __shared__ uint32_t s_sel[2];        // winning bin, remaining rank
   __shared__ int warp_first[32];
@@ -124,7 +133,7 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
 
   const int seg = blockIdx.x;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int n4 = (n + 3) & ~3;
+  const int n32 = select_padded(n);
   // kSelMerge: the gathered candidates live in this rank's exported buffer (written by the peers)
   const size_t par_off = MODE == kSelPlain ? 0 : (size_t)sh.parity * p2p_parity_words(sh.world, sh.slot);
   const float* c = MODE == kSelMerge ? reinterpret_cast<const float*>(sh.local + par_off) : costs + (long long)seg * n;
@@ -155,7 +164,7 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
   }
   constexpr uint32_t kInfKey = 0x7F800000u | 0x80000000u;  // cost_key(+inf)
 
-  // four keys of indices i4..i4+3 (i4 multiple of 4); out-of-range -> 0xFFFFFFFF (masked by index)
+  // four keys of indices i4..i4+3 (i4 multiple of 4); out-of-range -> 0xFFFFFFFF padding
   auto load4 = [&](int i4, uint32_t (&kk)[4]) {
     if (MODE == kSelMerge && bad) {
 #pragma unroll
@@ -168,7 +177,17 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
       for (int j = 0; j < 4; ++j) kk[j] = i4 + j < n ? cost_key(dep_load(c + i4 + j)) : 0xFFFFFFFFu;
     }
   };
-  auto key4_at = [&](int i4, uint32_t (&kk)[4]) {
+  // staged key of index i lives in unit swz(i / 4): the swizzle permutes units within aligned groups of 8
+  auto swz = [](int unit) { return unit ^ ((unit >> 3) & 7); };
+  auto key4_at = [&](int i4, uint32_t (&kk)[4]) {  // the four keys of INDICES i4..i4+3
+    if (STAGED) {
+      const uint4 q = *reinterpret_cast<const uint4*>(keys + 4 * swz(i4 >> 2));
+      kk[0] = q.x; kk[1] = q.y; kk[2] = q.z; kk[3] = q.w;
+    } else {
+      load4(i4, kk);
+    }
+  };
+  auto key4_any = [&](int i4, uint32_t (&kk)[4]) {  // four keys of SOME indices: every unit visited once
     if (STAGED) {
       const uint4 q = *reinterpret_cast<const uint4*>(keys + i4);
       kk[0] = q.x; kk[1] = q.y; kk[2] = q.z; kk[3] = q.w;
@@ -180,15 +199,15 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
   // ---- stage + min/max (16-byte loads, all in flight together) ----
   uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
 #pragma unroll 4
-  for (int i4 = 4 * t; i4 < n4; i4 += 4 * kSelectThreads) {
+  for (int i4 = 4 * t; i4 < n32; i4 += 4 * kSelectThreads) {
     uint32_t kk[4];
     load4(i4, kk);
-    if (STAGED) *reinterpret_cast<uint4*>(keys + i4) = make_uint4(kk[0], kk[1], kk[2], kk[3]);
+    if (STAGED) *reinterpret_cast<uint4*>(keys + 4 * swz(i4 >> 2)) = make_uint4(kk[0], kk[1], kk[2], kk[3]);
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       if (i4 + j < n) { kmin = min(kmin, kk[j]); kmax = max(kmax, kk[j]); }
   }
-  hist[t] = 0;
+  *reinterpret_cast<uint4*>(hist + 4 * t) = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
     kmin = min(kmin, __shfl_xor_sync(0xFFFFFFFFu, kmin, d));
@@ -206,26 +225,27 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
   uint32_t lo = kmin, hi = kmax, rem = (uint32_t)k;
   TOPK_STAMP(1);
 
-  // ---- adaptive radix select: power-of-two bucket width, <= 1024 buckets over [lo, hi] ----
-  for (int round = 0; round < 6; ++round) {
+  // ---- adaptive radix select: power-of-two bucket width, <= 4096 buckets over [lo, hi] ----
+  for (int round = 0; round < 5; ++round) {
     const uint32_t span = hi - lo;                              // in-range test: key - lo <= span
-    const int shift = span < (uint32_t)kSelectBins ? 0 : 32 - __clz(span) - 10;  // span >> shift < 1024
+    const int shift = span < (uint32_t)kSelectBins ? 0 : 32 - __clz(span) - kSelectBinBits;  // span >> shift < 4096
     TOPK_STAMP(2 + 3 * round);
-    for (int i4 = 4 * t; i4 < n4; i4 += 4 * kSelectThreads) {
+    for (int i4 = 4 * t; i4 < n32; i4 += 4 * kSelectThreads) {
       uint32_t kk[4];
-      key4_at(i4, kk);
+      key4_any(i4, kk);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint32_t d = kk[j] - lo;
-        if (d <= span && i4 + j < n) atomicAdd(&hist[d >> shift], 1u);
+        if (d <= span) atomicAdd(&hist[d >> shift], 1u);
       }
     }
     __syncthreads();
     TOPK_STAMP(3 + 3 * round);
-    // block-wide scan of the 1024 bins: one bin per thread, warp totals through shared memory,
-    // every warp scans the 32 totals itself (no single-warp phase)
-    const uint32_t mine = hist[t];
-    hist[t] = 0;  // ready for the next round
+    // block-wide scan of the 4096 bins: four consecutive bins per thread, warp totals through shared
+    // memory, every warp scans the 32 totals itself (no single-warp phase)
+    const uint4 m4 = *reinterpret_cast<const uint4*>(hist + 4 * t);
+    *reinterpret_cast<uint4*>(hist + 4 * t) = make_uint4(0u, 0u, 0u, 0u);  // ready for the next round
+    const uint32_t mine = m4.x + m4.y + m4.z + m4.w;
     const uint32_t incl_w = warp_incl_scan(mine, lane);
     const int buf = round & 1;
     if (lane == 31) wtot[buf][0][warp] = incl_w;
@@ -234,7 +254,11 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
     const uint32_t tot_incl = warp_incl_scan(tot, lane);
     const uint32_t base = __shfl_sync(0xFFFFFFFFu, tot_incl - tot, warp);
     const uint32_t incl = base + incl_w, excl = incl - mine;
-    if (rem > excl && rem <= incl) { s_sel[0] = (uint32_t)t; s_sel[1] = rem - excl; }  // exactly one bin
+    if (rem > excl && rem <= incl) {  // exactly one thread: the k-th key is in one of its four bins
+      uint32_t r = rem - excl, b = 0;
+      if (r > m4.x) { r -= m4.x; b = 1; if (r > m4.y) { r -= m4.y; b = 2; if (r > m4.z) { r -= m4.z; b = 3; } } }
+      s_sel[0] = 4u * t + b; s_sel[1] = r;
+    }
     __syncthreads();
     const uint32_t bin = s_sel[0];
     rem = s_sel[1];
@@ -259,76 +283,103 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
   }
 
   // ---- index-ordered compaction + argmin ----
-  // Thread t owns 16 CONSECUTIVE indices of every 16384-key pass: one (less, equal) count pair per
-  // thread, one block scan (a single barrier) per pass, the running base in registers.
   int first_min = 0x7FFFFFFF;
   uint32_t base_less = 0, base_eq = 0;
   int pass = 0;
-  for (int p0 = 0; p0 < n4; p0 += 16 * kSelectThreads, ++pass) {
+  for (int p0 = 0; p0 < n32; p0 += 16 * kSelectThreads, ++pass) {
     const int i0 = p0 + 16 * t;
-    uint32_t kk[16], nl = 0, ne = 0;
+    uint32_t m_less = 0, m_eq = 0, m_min = 0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       uint32_t k4[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-      if (i0 + 4 * q < n4) key4_at(i0 + 4 * q, k4);
+      if (i0 + 4 * q < n32) key4_at(i0 + 4 * q, k4);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int i = i0 + 4 * q + j;
-        kk[4 * q + j] = k4[j];
-        if (i < n) {
-          nl += k4[j] < T;
-          ne += k4[j] == T;
-          if (k4[j] == key_min) first_min = min(first_min, i);
-        }
+        const uint32_t bit = 1u << (4 * q + j);
+        if (k4[j] < T) m_less |= bit;
+        if (k4[j] == T) m_eq |= bit;
+        if (k4[j] == key_min) m_min |= bit;
       }
     }
-    const uint32_t il = warp_incl_scan(nl, lane), ie = warp_incl_scan(ne, lane);
-    if (lane == 31) { wtot[pass & 1][0][warp] = il; wtot[pass & 1][1][warp] = ie; }
+    if (m_min) first_min = min(first_min, i0 + __ffs(m_min) - 1);
+    TOPK_STAMP(23);
+    // one block scan of the packed (less, equal) counts: at most 16384 of either per pass
+    const uint32_t nl = __popc(m_less), ne = __popc(m_eq);
+    const uint32_t mine = nl | (ne << 16);
+    const uint32_t incl_w = warp_incl_scan(mine, lane);
+    if (lane == 31) wtot[pass & 1][0][warp] = incl_w;
     __syncthreads();
-    const uint32_t tl = wtot[pass & 1][0][lane], te = wtot[pass & 1][1][lane];
-    const uint32_t sl = warp_incl_scan(tl, lane), se = warp_incl_scan(te, lane);
-    uint32_t less_before = base_less + __shfl_sync(0xFFFFFFFFu, sl - tl, warp) + il - nl;
-    uint32_t eq_before = base_eq + __shfl_sync(0xFFFFFFFFu, se - te, warp) + ie - ne;
+    const uint32_t tot = wtot[pass & 1][0][lane];
+    const uint32_t tot_incl = warp_incl_scan(tot, lane);
+    const uint32_t before = __shfl_sync(0xFFFFFFFFu, tot_incl - tot, warp) + incl_w - mine;
+    const uint32_t all = __shfl_sync(0xFFFFFFFFu, tot_incl, 31);
+    uint32_t eq_before = base_eq + (before >> 16);
     // this pass's elites occupy the output positions [out0, out0 + cnt): positions rise with the index
     const uint32_t out0 = base_less + min(base_eq, take_eq);
-    base_less += __shfl_sync(0xFFFFFFFFu, sl, 31);
-    base_eq += __shfl_sync(0xFFFFFFFFu, se, 31);
+    uint32_t p = base_less + (before & 0xFFFFu) + min(eq_before, take_eq) - out0;  // this thread's first position
+    base_less += all & 0xFFFFu;
+    base_eq += all >> 16;
     const uint32_t cnt = base_less + min(base_eq, take_eq) - out0;
+    TOPK_STAMP(24);
     // Compact the pass's elite indices in shared memory first (over the pass's own key slice, which
-    // every thread holds in registers by now), then write them out coalesced: a thread's 16 keys map
-    // to 16 scattered positions, and direct stores cost one 32-byte sector per lane.
+    // every thread has consumed by now), then write them out coalesced: a thread's 16 keys map to
+    // scattered positions, and direct stores would cost one 32-byte sector per lane.
     uint32_t* outbuf = STAGED ? keys + p0 : keys;
-    if (nl | ne) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int i = i0 + j;
-        if (i < n) {
-          const bool less = kk[j] < T, eq = kk[j] == T;
-          if (less || (eq && eq_before < take_eq))
-            outbuf[less_before + (eq_before < take_eq ? eq_before : take_eq) - out0] = (uint32_t)i;
-          less_before += less;
-          eq_before += eq;
-        }
+    if (m_eq == 0) {
+      while (m_less) {
+        const int j = __ffs(m_less) - 1;
+        m_less &= m_less - 1;
+        outbuf[p++] = (uint32_t)(i0 + j);
+      }
+    } else {  // ties at the threshold: the first take_eq of them (by index) belong to the elite set
+      uint32_t m = m_less | m_eq;
+      while (m) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        const bool e = (m_eq >> j) & 1u;
+        if (!e || eq_before < take_eq) outbuf[p++] = (uint32_t)(i0 + j);
+        eq_before += e;
       }
     }
+    TOPK_STAMP(25);
     __syncthreads();
-    for (uint32_t j = t; j < cnt; j += kSelectThreads) {
-      const int i = (int)outbuf[j];
-      const uint32_t pos = out0 + j;
-      if (MODE == kSelScatter) {
-        // peer stores over NVLink: (cost bits | global index) into every rank's gathered arrays
-        const uint32_t cb = __float_as_uint(dep_load(c + i));
-        const size_t at = par_off + (size_t)sh.rank * k + pos;
-        for (int r = 0; r < sh.world; ++r) {
-          uint32_t* dst = sh.peers.base[r];
-          dst[at] = cb;
-          dst[at + (size_t)sh.world * sh.slot] = (uint32_t)(i + sh.idx_offset);
+    TOPK_STAMP(26);
+    // four outputs per thread and trip: the gathers (cost / global index of elite i) are in flight together
+    for (uint32_t j0 = t; j0 < cnt; j0 += 4 * kSelectThreads) {
+      int i[4];
+      uint32_t g[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t j = j0 + u * kSelectThreads;
+        i[u] = j < cnt ? (int)outbuf[j] : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        g[u] = 0;
+        if (i[u] >= 0) {
+          if (MODE == kSelScatter) g[u] = __float_as_uint(dep_load(c + i[u]));
+          else if (MODE == kSelMerge) g[u] = bad ? 0xFFFFFFFFu : dep_load(gidx + i[u]);
+          else if (elite_cost) g[u] = __float_as_uint(dep_load(c + i[u]));
         }
-      } else if (MODE == kSelMerge) {
-        elite_idx[pos] = bad ? -1 : (int)dep_load(gidx + i);
-      } else {
-        elite_idx[(long long)seg * k + pos] = i;
-        if (elite_cost) elite_cost[(long long)seg * k + pos] = dep_load(c + i);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (i[u] < 0) continue;
+        const uint32_t pos = out0 + j0 + u * kSelectThreads;
+        if (MODE == kSelScatter) {
+          // peer stores over NVLink: (cost bits | global index) into every rank's gathered arrays
+          const size_t at = par_off + (size_t)sh.rank * k + pos;
+          for (int r = 0; r < sh.world; ++r) {
+            uint32_t* dst = sh.peers.base[r];
+            dst[at] = g[u];
+            dst[at + (size_t)sh.world * sh.slot] = (uint32_t)(i[u] + sh.idx_offset);
+          }
+        } else if (MODE == kSelMerge) {
+          elite_idx[pos] = (int)g[u];
+        } else {
+          elite_idx[(long long)seg * k + pos] = i[u];
+          if (elite_cost) elite_cost[(long long)seg * k + pos] = __uint_as_float(g[u]);
+        }
       }
     }
   }
