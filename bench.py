@@ -522,6 +522,7 @@ def main():
         if rank == 0:
             full = native.NativePlanner(O, A, U, H, n_total, 1, I, k, engine, local_rank)
             full.load_problem(prob)
+            full.set_refit_segments(world)  # same summation order as the sharded refit (per-rank partials, rank order)
             want = full.plan(s0, I, k, native.SAMPLE_GAUSSIAN, seed=12345, want_dist=True)
             eq = all(np.array_equal(out[key].view(np.int32), want[key].view(np.int32)) for key in ("actions", "states", "mu", "sd"))
             eq = eq and all(np.array_equal(out["info"][key], want["info"][key]) for key in ("best_cost", "best_index", "best_iteration"))

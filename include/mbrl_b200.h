@@ -264,17 +264,25 @@ int mbrl_emit(MbrlPlanner* p, int32_t sample_mode, uint64_t seed, uint32_t cand_
  *   mbrl_nccl_unique_id: rank 0 fills 128 bytes, the host broadcasts them to all ranks.        */
 /* Peer-memory transport for the same sharded loop (NVLink P2P through CUDA IPC instead of the
  * ncclAllGather): every rank exports one gather buffer (mbrl_p2p_export: 64-byte IPC handle),
- * the host all-gathers the handles, mbrl_p2p_attach opens the peers' buffers.  Per iteration a
- * single kernel then stores this rank's (cost, global index) elites straight into every peer's
- * buffer and publishes a sequence flag (st.release.sys); the consumer kernel acquires the flags
- * of all ranks before it reads.  Buffers are double-buffered by iteration parity; a writer can
- * never be two iterations ahead of a reader because its own merge needs every rank's flag.
- * Falls back to NCCL when no peer buffers are attached.                                        */
+ * the host all-gathers the handles, mbrl_p2p_attach opens the peers' buffers.  Per iteration
+ * three kernels run: the local select stores this rank's (cost, global index) elites straight
+ * into every peer's buffer and publishes a sequence flag (st.release.sys); the merge select
+ * acquires the flags of all ranks, finds the global threshold among the gathered candidates and
+ * keeps this rank's own elites; the refit sums them, exchanges the H*ceil(A/4)*8 partial sums
+ * the same way and adds the ranks' partials in rank order.  Buffers are double-buffered by
+ * iteration parity; a writer can never be two iterations ahead of a reader because its own merge
+ * needs every rank's flag.  Falls back to NCCL when no peer buffers are attached.              */
 int mbrl_p2p_export(MbrlPlanner* p, int32_t world, uint8_t* h_handle64);
 int mbrl_p2p_attach(MbrlPlanner* p, const uint8_t* h_handles, int32_t rank, int32_t world);
 /* Closes whatever peer buffers were opened (also after a failed attach) so that the handle can
  * take the NCCL transport instead; the exported buffer stays allocated.  Idempotent. */
 int mbrl_p2p_detach(MbrlPlanner* p);
+/* Summation order of the refit.  A plan sharded over W ranks adds W per-rank partial sums
+ * (rank r: the elites among candidates [r*N, (r+1)*N)) in rank order; an UNSHARDED planner over
+ * the W*N candidates reproduces it bit for bit after mbrl_set_refit_segments(p, W) (W must divide
+ * its population; single-environment planners, W <= 64).  1 (the default) = the plain order.
+ * Test / verification knob: the result is the same mean and std up to fp32 rounding.           */
+int mbrl_set_refit_segments(MbrlPlanner* p, int32_t segments);
 int mbrl_nccl_unique_id(uint8_t* h_id128);
 int mbrl_comm_init(MbrlPlanner* p, const uint8_t* h_id128, int32_t rank, int32_t world);
 int mbrl_comm_destroy(MbrlPlanner* p);

@@ -134,6 +134,9 @@ struct MbrlPlanner {
   int* d_trunc = nullptr;       // truncation flag of the reduced-size elite gather
   float* d_refit_part = nullptr;           // [E][H*G][chunks][8] partial sums of the chunked refit
   unsigned int* d_refit_arrive = nullptr;  // [E][H*G] arrival counters (self-resetting)
+  int refit_parts_cap = 0;                 // partial sums per slot that d_refit_part holds
+  int refit_segments = 1;                  // mbrl_set_refit_segments: canonical summation order of the refit
+  int* d_own_count = nullptr;              // population sharding: number of this rank's elites
   bool full_gather = false;     // force worst-case-size gathers (while a flagged plan is redone)
   int scratch_world = 0;        // world size the sharding scratch buffers were allocated for (0 = none)
   // peer-memory transport (mbrl_p2p_export / mbrl_p2p_attach)
@@ -188,6 +191,7 @@ extern "C" int mbrl_destroy(MbrlPlanner* p) {
   if (p->W4) cudaFree(p->W4);
   if (p->d_refit_part) cudaFree(p->d_refit_part);
   if (p->d_refit_arrive) cudaFree(p->d_refit_arrive);
+  if (p->d_own_count) cudaFree(p->d_own_count);
   if (p->d_best_ever) cudaFree(p->d_best_ever);
   if (p->d_info) cudaFree(p->d_info);
   if (p->comm && g_nccl.ok) g_nccl.CommDestroy(p->comm);
@@ -258,7 +262,13 @@ extern "C" int mbrl_create(const MbrlConfig* cfg, MbrlPlanner** out) {
   A_(dev_alloc(&p->d_mu_last, EHA));
   A_(dev_alloc(&p->d_elite, (size_t)E * cfg->max_elites));
   {
-    const size_t slots = (size_t)E * H * ((A + 3) / 4), chunks = (size_t)(cfg->max_elites + kRefitChunk - 1) / kRefitChunk;
+    // per slot: one partial sum per 2048-elite chunk, or -- single-environment planners, which may be
+    // population-sharded -- per rank / refit segment (up to 64)
+    const size_t slots = (size_t)E * H * ((A + 3) / 4);
+    size_t chunks = (size_t)(cfg->max_elites + kRefitChunk - 1) / kRefitChunk;
+    if (E == 1 && chunks < 64) chunks = 64;
+    p->refit_parts_cap = (int)chunks;
+    A_(dev_alloc(&p->d_own_count, 1));
     A_(dev_alloc(&p->d_refit_part, slots * chunks * 8));
     A_(dev_alloc(&p->d_refit_arrive, slots));
     if (ok) A_(cudaMemset(p->d_refit_arrive, 0, sizeof(unsigned int) * slots));
@@ -525,6 +535,19 @@ static int launch_refit(const MbrlPlanner* p, const ActionSource& src, const int
   return MBRL_OK;
 }
 
+// Segment-canonical refit from the global elite list (see refit_seg_kernel): nseg segments of seg_size candidates.
+static int launch_refit_seg(const MbrlPlanner* p, const ActionSource& src, const int* d_elite, int k, int nseg, int seg_size,
+                            float* d_mu_new, float* d_sd_new, cudaStream_t st) {
+  MBRL_REQUIRE(k >= 1 && k <= p->cfg.max_elites, "refit: k out of range [1, max_elites]");
+  MBRL_REQUIRE(nseg >= 1 && nseg <= p->refit_parts_cap, "refit: too many segments");
+  const int G = (p->A + 3) / 4;
+  Shape sh{p->H, p->N, p->E};
+  MBRL_CUDA(launch_pdl(refit_seg_kernel, dim3(p->H * G, p->E, nseg), dim3(kRefitThreads), 0, st, src, sh, p->A, d_elite, k,
+                       seg_size, d_mu_new, d_sd_new, p->d_refit_part, p->d_refit_arrive));
+  MBRL_CUDA(cudaGetLastError());
+  return MBRL_OK;
+}
+
 static int launch_replay(MbrlPlanner* p, int mode, uint64_t seed, uint32_t cand_offset, uint32_t env_offset,
                          const float* d_s0, const float* d_injected, const float* d_mu_hist,
                          const float* d_sd_hist, int iterations, int return_mean, int actions_only,
@@ -691,7 +714,7 @@ extern "C" int mbrl_p2p_export(MbrlPlanner* p, int32_t world, uint8_t* h_handle6
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   MBRL_CUDA(cudaSetDevice(p->cfg.device));
   const int slot = std::min(p->cfg.max_elites, p->N);
-  const size_t words = p2p_total_words(world, slot);
+  const size_t words = p2p_total_words(world, slot, p->H * ((p->A + 3) / 4));
   if (p->d_p2p_local && p->p2p_world != world) {  // another world size: a new buffer
     MBRL_CUDA(cudaDeviceSynchronize());
     cudaFree(p->d_p2p_local); p->d_p2p_local = nullptr;
@@ -744,6 +767,15 @@ extern "C" int mbrl_p2p_attach(MbrlPlanner* p, const uint8_t* h_handles, int32_t
   }
   p->p2p_attached = true;
   return alloc_shard_scratch(p, world);
+}
+
+extern "C" int mbrl_set_refit_segments(MbrlPlanner* p, int32_t segments) {
+  if (!p) return fail(MBRL_E_INVALID, "null planner");
+  MBRL_REQUIRE(segments >= 1 && segments <= p->refit_parts_cap, "refit segments out of range [1, 64]");
+  MBRL_REQUIRE(p->N % segments == 0, "refit segments must divide the population");
+  MBRL_REQUIRE(p->comm == nullptr && !p->p2p_attached, "a population shard takes its segments from the world size");
+  p->refit_segments = segments;
+  return MBRL_OK;
 }
 
 extern "C" int mbrl_p2p_detach(MbrlPlanner* p) {
@@ -861,8 +893,10 @@ static int enqueue_plan(MbrlPlanner* p, const MbrlPlanArgs* a, const float* d_s0
     int rc = launch_rollout(p, src, d_s0, p->d_costs, nullptr, nullptr, st);
     if (rc) return rc;
     if (sharded) {
-      // local elites -> all-gather (cost, global index) -> same global top-k on every rank ->
-      // redundant refit from GLOBAL indices (cand_offset 0): no second collective
+      // local elites -> all-gather (cost, global index) -> same global top-k threshold on every rank ->
+      // refit from GLOBAL indices (cand_offset 0) as per-rank partial sums added in rank order: over
+      // peer memory every rank sums its own elites and the partials are exchanged, over NCCL every rank
+      // holds the whole list and computes all partials itself (no second collective) -- same bits
       // Worst case a single shard holds all k global elites (k_full = min(k, N) per rank); the
       // shards are i.i.d., so a rank's share is Binomial(k, 1/world): send the expected share plus
       // 8 standard deviations (+64) and verify exactness on the device (the merge select); a
@@ -881,12 +915,33 @@ static int enqueue_plan(MbrlPlanner* p, const MbrlPlanArgs* a, const float* d_s0
         // selects among the gathered candidates in place and emits global indices
         SelShard sh{};
         sh.peers = p->p2p_peers; sh.local = p->d_p2p_local; sh.rank = p->rank; sh.world = p->world;
-        sh.slot = p->p2p_slot; sh.seq = ++p->p2p_seq; sh.parity = (int)(sh.seq & 1); sh.idx_offset = (int)cand_offset;
-        sh.k_full = k_full; sh.trunc = p->d_trunc; sh.error = p->d_p2p_error; sh.timeout_ns = p2p_timeout_ns();
+        sh.slot = p->p2p_slot; sh.pslots = p->H * ((p->A + 3) / 4); sh.seq = ++p->p2p_seq; sh.parity = (int)(sh.seq & 1);
+        sh.idx_offset = (int)cand_offset; sh.k_full = k_full; sh.trunc = p->d_trunc; sh.error = p->d_p2p_error;
+        sh.own_count = p->d_own_count; sh.timeout_ns = p2p_timeout_ns();
         rc = launch_topk_mode<kSelScatter>(p->d_costs, 1, p->N, kl, nullptr, nullptr, nullptr, nullptr, it, sh, st);
         if (rc) return rc;
         rc = launch_topk_mode<kSelMerge>(nullptr, 1, ng, k, p->d_elite, nullptr, nullptr, p->d_best_ever, it, sh, st);
         if (rc) return rc;
+        if (it + 1 < I || need_final_dist) {
+          // distributed refit: this rank's elites only, partial sums exchanged through peer memory
+          ActionSource gsrc = src;
+          gsrc.cand_offset = 0;  // the merge emitted global candidate indices
+          float* mu_new = p->d_mu_hist + (it + 1) * EHA;
+          float* sd_new = p->d_sd_hist + (it + 1) * EHA;
+          if (p->world == 1) {   // the only rank holds every elite: the plain refit, bit for bit
+            rc = launch_refit(p, gsrc, p->d_elite, k, mu_new, sd_new, st);
+            if (rc) return rc;
+          } else {
+            RefitP2p px{};
+            px.peers = p->p2p_peers; px.local = p->d_p2p_local; px.rank = p->rank; px.world = p->world; px.slot = p->p2p_slot;
+            px.pslots = sh.pslots; px.parity = sh.parity; px.seq = sh.seq; px.error = p->d_p2p_error; px.timeout_ns = sh.timeout_ns;
+            Shape shp{p->H, p->N, p->E};
+            MBRL_CUDA(launch_pdl(refit_p2p_kernel, dim3(sh.pslots), dim3(kRefitThreads), 0, st, gsrc, shp, p->A,
+                                 (const int*)p->d_elite, (const int*)p->d_own_count, k, mu_new, sd_new, px));
+            MBRL_CUDA(cudaGetLastError());
+          }
+        }
+        continue;
       } else {
         rc = launch_topk(p->d_costs, 1, p->N, kl, p->d_elite, p->d_ecost, nullptr, nullptr, it, st);
         if (rc) return rc;
@@ -900,9 +955,12 @@ static int enqueue_plan(MbrlPlanner* p, const MbrlPlanArgs* a, const float* d_s0
       }
       MBRL_CUDA(cudaGetLastError());
       if (it + 1 < I || need_final_dist) {
+        // every rank holds the whole global list: the same per-rank partial sums, added in rank order
         ActionSource gsrc = src;
         gsrc.cand_offset = 0;
-        rc = launch_refit(p, gsrc, p->d_elite, k, p->d_mu_hist + (it + 1) * EHA, p->d_sd_hist + (it + 1) * EHA, st);
+        rc = p->world == 1 ? launch_refit(p, gsrc, p->d_elite, k, p->d_mu_hist + (it + 1) * EHA, p->d_sd_hist + (it + 1) * EHA, st)
+                           : launch_refit_seg(p, gsrc, p->d_elite, k, p->world, p->N, p->d_mu_hist + (it + 1) * EHA,
+                                              p->d_sd_hist + (it + 1) * EHA, st);
         if (rc) return rc;
       }
       continue;
@@ -910,7 +968,9 @@ static int enqueue_plan(MbrlPlanner* p, const MbrlPlanArgs* a, const float* d_s0
     rc = launch_topk(p->d_costs, p->E, p->N, k, p->d_elite, nullptr, nullptr, p->d_best_ever, it, st);
     if (rc) return rc;
     if (it + 1 < I || need_final_dist) {
-      rc = launch_refit(p, src, p->d_elite, k, p->d_mu_hist + (it + 1) * EHA, p->d_sd_hist + (it + 1) * EHA, st);
+      rc = p->refit_segments > 1 ? launch_refit_seg(p, src, p->d_elite, k, p->refit_segments, p->N / p->refit_segments,
+                                                    p->d_mu_hist + (it + 1) * EHA, p->d_sd_hist + (it + 1) * EHA, st)
+                                 : launch_refit(p, src, p->d_elite, k, p->d_mu_hist + (it + 1) * EHA, p->d_sd_hist + (it + 1) * EHA, st);
       if (rc) return rc;
     }
   }

@@ -21,8 +21,10 @@ __device__ __forceinline__ uint32_t cost_key(float c) {
 
 // ---- peer-memory (NVLink P2P) elite exchange ---------------------------------------------------
 // (mbrl_p2p_export / mbrl_p2p_attach).  Every rank exports one buffer of uint32 words:
-//   2 parities x { costs [world*slot] | global indices [world*slot] | local thresholds [world] }
-//   then [world] sequence flags (one per source rank).
+//   2 parities x { costs [world*slot] | global indices [world*slot] | local thresholds [world] |
+//                  refit partial sums [world][pslots*8] }
+//   then [world] elite sequence flags (one per source rank), then [world][pslots] refit sequence flags.
+// pslots = H * ceil(A/4): the (step, action group) slots of the refit.
 // slot = capacity per rank; a launch that sends k_l <= slot elites per rank packs them
 // CONTIGUOUSLY (rank r's at [r*k_l, (r+1)*k_l)), so that the gathered costs / indices are plain
 // arrays of world*k_l entries in ascending global index order and the merge select reads them in place.
@@ -44,27 +46,36 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-__host__ __device__ inline size_t p2p_parity_words(int world, int slot) { return (size_t)world * (2 * (size_t)slot + 1); }
-__host__ __device__ inline size_t p2p_total_words(int world, int slot) { return 2 * p2p_parity_words(world, slot) + (size_t)world; }
+__host__ __device__ inline size_t p2p_part_off(int world, int slot) { return (size_t)world * (2 * (size_t)slot + 1); }
+__host__ __device__ inline size_t p2p_parity_words(int world, int slot, int pslots) {
+  return p2p_part_off(world, slot) + (size_t)world * pslots * 8;
+}
+__host__ __device__ inline size_t p2p_flags_off(int world, int slot, int pslots) { return 2 * p2p_parity_words(world, slot, pslots); }
+__host__ __device__ inline size_t p2p_pflags_off(int world, int slot, int pslots) { return p2p_flags_off(world, slot, pslots) + (size_t)world; }
+__host__ __device__ inline size_t p2p_total_words(int world, int slot, int pslots) {
+  return p2p_pflags_off(world, slot, pslots) + (size_t)world * pslots;
+}
 
 // Sharded roles of the top-k kernel (template parameter MODE):
 //   kSelPlain    the ordinary segmented top-k
 //   kSelScatter  local top-k_l whose compaction stores (cost bits, global index) straight into every
 //                rank's exported buffer over NVLink and then publishes this rank's sequence flag
-//   kSelMerge    waits for every rank's flag, selects the global top-k among the world*k_l gathered
-//                candidates in place, emits GLOBAL candidate indices, keeps the best-ever record in
-//                global indices and checks that the reduced-size gather was exact
+//   kSelMerge    waits for every rank's flag, finds the global top-k threshold among the world*k_l
+//                gathered candidates in place, emits the GLOBAL indices of THIS rank's elites only
+//                (+ their count: the refit is distributed), keeps the best-ever record in global
+//                indices and checks that the reduced-size gather was exact
 enum { kSelPlain = 0, kSelScatter = 1, kSelMerge = 2 };
 __device__ __forceinline__ bool k_per_rank_lt(int n, int world, int k_full) { return n / world < k_full; }
 struct SelShard {
   P2pPeers peers;          // kSelScatter: every rank's buffer (own rank: the local pointer)
   const uint32_t* local;   // kSelMerge: this rank's buffer
-  int rank, world, slot, parity;
+  int rank, world, slot, pslots, parity;
   int idx_offset;          // kSelScatter: global index of local candidate 0
   int k_full;              // kSelMerge: min(k, N) -- a gather of k_full per rank is exact by construction
   uint32_t seq;
   int* trunc;              // kSelMerge: set when the reduced gather cannot be proven exact
   int* error;              // kSelMerge: set when a rank's flag never arrived
+  int* own_count;          // kSelMerge: number of this rank's elites
   unsigned long long timeout_ns;
 };
 
@@ -128,14 +139,15 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
   __shared__ __align__(16) uint32_t hist[kSelectBins];
   __shared__ uint32_t wtot[2][2][32];  // per-warp totals (double buffered)
   __shared__ uint32_t s_sel[2];        // winning bin, remaining rank
-  __shared__ int warp_first[32];
   __shared__ int s_ok;
+  __shared__ int s_first;              // lowest index holding the minimum key
+  __shared__ uint32_t s_eq_tot, s_eq_low;  // keys == T in all / below this rank's slice (kSelMerge)
 
   const int seg = blockIdx.x;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int n32 = select_padded(n);
   // kSelMerge: the gathered candidates live in this rank's exported buffer (written by the peers)
-  const size_t par_off = MODE == kSelPlain ? 0 : (size_t)sh.parity * p2p_parity_words(sh.world, sh.slot);
+  const size_t par_off = MODE == kSelPlain ? 0 : (size_t)sh.parity * p2p_parity_words(sh.world, sh.slot, sh.pslots);
   const float* c = MODE == kSelMerge ? reinterpret_cast<const float*>(sh.local + par_off) : costs + (long long)seg * n;
   const uint32_t* gidx = MODE == kSelMerge ? sh.local + par_off + (size_t)sh.world * sh.slot : nullptr;
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(c) & 15) == 0);
@@ -151,7 +163,7 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
     if (t == 0) s_ok = 1;
     __syncthreads();
     if (t < sh.world) {
-      const uint32_t* flag = sh.local + 2 * p2p_parity_words(sh.world, sh.slot) + t;
+      const uint32_t* flag = sh.local + p2p_flags_off(sh.world, sh.slot, sh.pslots) + t;
       const unsigned long long t0 = globaltimer_ns();
       unsigned int spins = 0;
       while ((int)(ld_acquire_sys(flag) - sh.seq) < 0) {
@@ -214,6 +226,7 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
     kmax = max(kmax, __shfl_xor_sync(0xFFFFFFFFu, kmax, d));
   }
   if (lane == 0) { wtot[0][0][warp] = kmin; wtot[0][1][warp] = kmax; }
+  if (t == 0) { s_first = 0x7FFFFFFF; s_eq_low = 0; }
   __syncthreads();
   kmin = wtot[0][0][lane]; kmax = wtot[0][1][lane];  // every warp finishes the reduction itself
 #pragma unroll
@@ -237,6 +250,8 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
       for (int j = 0; j < 4; ++j) {
         const uint32_t d = kk[j] - lo;
         if (d <= span) atomicAdd(&hist[d >> shift], 1u);
+        // the argmin rides on the first round: d == 0 <=> the minimum key (padding never is: n >= 1)
+        if (round == 0 && d == 0) atomicMin(&s_first, (STAGED ? 4 * swz(i4 >> 2) : i4) + j);
       }
     }
     __syncthreads();
@@ -258,6 +273,7 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
       uint32_t r = rem - excl, b = 0;
       if (r > m4.x) { r -= m4.x; b = 1; if (r > m4.y) { r -= m4.y; b = 2; if (r > m4.z) { r -= m4.z; b = 3; } } }
       s_sel[0] = 4u * t + b; s_sel[1] = r;
+      s_eq_tot = b == 0 ? m4.x : b == 1 ? m4.y : b == 2 ? m4.z : m4.w;  // == #keys equal to T once the width is 1
     }
     __syncthreads();
     const uint32_t bin = s_sel[0];
@@ -282,13 +298,31 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
     if (tl <= T) atomicOr(sh.trunc, 1);
   }
 
-  // ---- index-ordered compaction + argmin ----
-  int first_min = 0x7FFFFFFF;
-  uint32_t base_less = 0, base_eq = 0;
+  // ---- index-ordered compaction ----
+  // kSelMerge compacts only this rank's slice [own_lo, own_hi) of the gathered candidates: the refit is
+  // distributed, every rank needs its own elites alone.  Ties at the threshold are taken in global
+  // index order, so the slice must know how many keys == T lie below it -- unless every tied key is an
+  // elite anyway (s_eq_tot == take_eq: always, but for exact cost ties straddling the cut).
+  const int k_s = MODE == kSelMerge ? n / sh.world : 0;
+  const int own_lo = MODE == kSelMerge ? sh.rank * k_s : 0;
+  const int own_hi = MODE == kSelMerge ? own_lo + k_s : n32;
+  if (MODE == kSelMerge && s_eq_tot != take_eq && own_lo > 0) {  // block-uniform; rare
+    uint32_t cnt_low = 0;
+    for (int i4 = 4 * t; i4 < n32; i4 += 4 * kSelectThreads) {
+      uint32_t kk[4];
+      key4_at(i4, kk);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cnt_low += (kk[j] == T && i4 + j < own_lo);
+    }
+    if (cnt_low) atomicAdd(&s_eq_low, cnt_low);
+    __syncthreads();
+  }
+  uint32_t base_less = 0, base_eq = MODE == kSelMerge ? s_eq_low : 0u;
   int pass = 0;
-  for (int p0 = 0; p0 < n32; p0 += 16 * kSelectThreads, ++pass) {
+  const int c0 = own_lo & ~31;  // whole swizzle groups: the compaction buffer reuses the consumed key slice
+  for (int p0 = c0; p0 < own_hi; p0 += 16 * kSelectThreads, ++pass) {
     const int i0 = p0 + 16 * t;
-    uint32_t m_less = 0, m_eq = 0, m_min = 0;
+    uint32_t m_less = 0, m_eq = 0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       uint32_t k4[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
@@ -298,10 +332,14 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
         const uint32_t bit = 1u << (4 * q + j);
         if (k4[j] < T) m_less |= bit;
         if (k4[j] == T) m_eq |= bit;
-        if (k4[j] == key_min) m_min |= bit;
       }
     }
-    if (m_min) first_min = min(first_min, i0 + __ffs(m_min) - 1);
+    if (MODE == kSelMerge) {  // clip to the slice
+      uint32_t in = 0xFFFFu;
+      if (i0 < own_lo) in &= own_lo - i0 >= 16 ? 0u : 0xFFFFu << (own_lo - i0);
+      if (i0 + 16 > own_hi) in &= own_hi - i0 <= 0 ? 0u : 0xFFFFu >> (16 - (own_hi - i0));
+      m_less &= in; m_eq &= in;
+    }
     TOPK_STAMP(23);
     // one block scan of the packed (less, equal) counts: at most 16384 of either per pass
     const uint32_t nl = __popc(m_less), ne = __popc(m_eq);
@@ -315,11 +353,12 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
     const uint32_t all = __shfl_sync(0xFFFFFFFFu, tot_incl, 31);
     uint32_t eq_before = base_eq + (before >> 16);
     // this pass's elites occupy the output positions [out0, out0 + cnt): positions rise with the index
-    const uint32_t out0 = base_less + min(base_eq, take_eq);
-    uint32_t p = base_less + (before & 0xFFFFu) + min(eq_before, take_eq) - out0;  // this thread's first position
+    const uint32_t eq0 = MODE == kSelMerge ? min(s_eq_low, take_eq) : 0u;  // ties taken below the slice hold no position here
+    const uint32_t out0 = base_less + min(base_eq, take_eq) - eq0;
+    uint32_t p = base_less + (before & 0xFFFFu) + min(eq_before, take_eq) - eq0 - out0;  // this thread's first position
     base_less += all & 0xFFFFu;
     base_eq += all >> 16;
-    const uint32_t cnt = base_less + min(base_eq, take_eq) - out0;
+    const uint32_t cnt = base_less + min(base_eq, take_eq) - eq0 - out0;
     TOPK_STAMP(24);
     // Compact the pass's elite indices in shared memory first (over the pass's own key slice, which
     // every thread has consumed by now), then write them out coalesced: a thread's 16 keys map to
@@ -389,28 +428,21 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
     // publish: every thread's peer stores are ordered before the flag at system scope
     __threadfence_system();
     __syncthreads();
-    if (t < sh.world) st_release_sys(sh.peers.base[t] + 2 * p2p_parity_words(sh.world, sh.slot) + sh.rank, sh.seq);
+    if (t < sh.world) st_release_sys(sh.peers.base[t] + p2p_flags_off(sh.world, sh.slot, sh.pslots) + sh.rank, sh.seq);
     return;
   }
 
-  // ---- block argmin: the lowest index holding the minimum key ----
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) first_min = min(first_min, __shfl_xor_sync(0xFFFFFFFFu, first_min, d));
-  if (lane == 0) warp_first[warp] = first_min;
-  __syncthreads();
-  if (warp == 0) {
-    int v = warp_first[lane];
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v = min(v, __shfl_xor_sync(0xFFFFFFFFu, v, d));
-    if (lane == 0 && n > 0) {
-      const float cmin = (MODE == kSelMerge && bad) ? __int_as_float(0x7f800000) : dep_load(c + v);
-      const int idx = MODE == kSelMerge ? (bad ? -1 : (int)dep_load(gidx + v)) : v;
-      if (best) { best[seg].best_cost = cmin; best[seg].best_iteration = iteration; best[seg].best_index = idx; best[seg].reserved = 0; }
-      if (best_ever) {
-        BestEver b = best_ever[seg];
-        if (b.iteration < 0 || cmin < b.cost) { b.cost = cmin; b.iteration = iteration; b.index = idx; best_ever[seg] = b; }
-      }
+  // ---- the minimum: the lowest index holding the minimum key (found in the first round) ----
+  if (t == 0 && n > 0) {
+    const int v = s_first;
+    const float cmin = (MODE == kSelMerge && bad) ? __int_as_float(0x7f800000) : dep_load(c + v);
+    const int idx = MODE == kSelMerge ? (bad ? -1 : (int)dep_load(gidx + v)) : v;
+    if (best) { best[seg].best_cost = cmin; best[seg].best_iteration = iteration; best[seg].best_index = idx; best[seg].reserved = 0; }
+    if (best_ever) {
+      BestEver b = best_ever[seg];
+      if (b.iteration < 0 || cmin < b.cost) { b.cost = cmin; b.iteration = iteration; b.index = idx; best_ever[seg] = b; }
     }
+    if (MODE == kSelMerge) *sh.own_count = (int)(base_less + min(base_eq, take_eq) - min(s_eq_low, take_eq));
   }
   TOPK_STAMP(22);
 }
@@ -429,35 +461,22 @@ inline int refit_threads(int k) {
   return k >= kRefitThreads ? kRefitThreads : (k < 1 ? 1 : k + 31) / 32 * 32;
 }
 
-// grid = (H * G, E, chunks): one CTA per (step, 4-wide action group, env, chunk of 2048 elites).
-// Each thread regenerates (or gathers) the 4 actions of its elites and accumulates shifted sums
+// Shifted sums over the elites list[e_begin + t], list[e_begin + t + blockDim.x], ... (< e_end) of the
+// 4 actions (h, 4g .. 4g+3): each thread regenerates (or gathers) its elites' actions and accumulates
 // sum(d), sum(d^2) with d = a - c, c = the old mean of that (h, a) (the draws are centred there, so
-// the shifted second moment does not cancel); a fixed shuffle tree + one shared-memory stage
-// reduces them.  mean = c + sum(d)/k, std = sqrt(sum(d^2)/k - (sum(d)/k)^2)   (population std).
-// k > 2048 (large or population-sharded elite sets): the chunk CTAs run in parallel on otherwise
-// idle SMs, park their partial sums, and the last one to arrive adds them IN CHUNK ORDER -- the
-// result depends only on the elite list (ascending index), never on timing or on the sharding,
-// which is what keeps every rank's refit bit-identical to the unsharded one.
-template <int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB)
-refit_kernel(ActionSource src, Shape sh, int A, const int* __restrict__ elite_idx, int k,
-             float* __restrict__ mu_new, float* __restrict__ sd_new, float* __restrict__ part,
-             unsigned int* __restrict__ arrive) {
-  __shared__ float red[kRefitThreads / 32][8];
-  __shared__ bool s_last;
+// the shifted second moment does not cancel); a fixed shuffle tree + one shared-memory stage reduce
+// them.  Threads 0..3 return the sums of action 4g + t in (a1, a2); mu_old is returned for all.
+// The order of the additions depends on (the list slice, blockDim.x) only.
+__device__ __forceinline__ void refit_accumulate(const ActionSource& src, const Shape& sh, int A, int h, int g, int env_l,
+                                                 const int* __restrict__ list, int e_begin, int e_end,
+                                                 float (*red)[8], float (&mu_old)[4], float& a1, float& a2) {
   const int G = (A + 3) >> 2;
-  const int h = blockIdx.x / G, g = blockIdx.x % G;
-  const int env_l = blockIdx.y;
-  const int chunk = blockIdx.z, nchunks = gridDim.z;
-  const int e_end = min(k, (chunk + 1) * kRefitChunk);
   const long long R = sh.rows();
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nthreads = blockDim.x;
   const long long ms = ((long long)env_l * sh.H + h) * A;
   const bool inject = src.mode == MBRL_SAMPLE_INJECT_ACTIONS || src.mode == MBRL_SAMPLE_INJECT_NOISE;
   const bool affine = src.mode == MBRL_SAMPLE_INJECT_NOISE || src.mode == MBRL_SAMPLE_GAUSSIAN;
-  float mu_old[4], sd_old[4], s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-  pdl_trigger();
-  pdl_wait();  // elite indices (top-k / remap) and the old mean/std (previous refit)
+  float sd_old[4], s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int ac = min(4 * g + j, A - 1);
@@ -465,8 +484,8 @@ refit_kernel(ActionSource src, Shape sh, int A, const int* __restrict__ elite_id
     sd_old[j] = affine ? dep_load(src.sd + ms + ac) : 0.f;
   }
   const uint2 key = make_uint2(src.seed_lo, src.seed_hi);
-  for (int e = chunk * kRefitChunk + t; e < e_end; e += nthreads) {
-    const int cand_l = dep_load(elite_idx + (long long)env_l * k + e);
+  for (int e = e_begin + t; e < e_end; e += nthreads) {
+    const int cand_l = dep_load(list + e);
     float z[4];
     if (inject) {
       const long long row = (long long)env_l * sh.N + cand_l;
@@ -505,31 +524,15 @@ refit_kernel(ActionSource src, Shape sh, int A, const int* __restrict__ elite_id
     if (lane == 0) { red[warp][j] = s1[j]; red[warp][4 + j] = s2[j]; }
   }
   __syncthreads();
-  float a1 = 0.f, a2 = 0.f;
+  a1 = 0.f; a2 = 0.f;
   if (t < 4)
     for (int w = 0; w < nthreads / 32; ++w) { a1 += red[w][t]; a2 += red[w][4 + t]; }
-  if (nchunks > 1) {
-    const long long slot = (long long)env_l * gridDim.x + blockIdx.x;
-    float* mine = part + (slot * nchunks + chunk) * 8;
-    if (t < 4) { mine[t] = a1; mine[4 + t] = a2; }
-    __threadfence();
-    __syncthreads();
-    if (t == 0) {
-      const unsigned int n = atomicAdd(arrive + slot, 1u);
-      s_last = n == (unsigned int)nchunks - 1;
-      if (s_last) arrive[slot] = 0;  // ready for the next launch (stream order)
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    if (t < 4) {
-      a1 = 0.f; a2 = 0.f;
-      for (int c = 0; c < nchunks; ++c) {
-        a1 += __ldcg(part + (slot * nchunks + c) * 8 + t);
-        a2 += __ldcg(part + (slot * nchunks + c) * 8 + 4 + t);
-      }
-    }
-  }
+}
+
+// mean = c + sum(d)/k, std = sqrt(sum(d^2)/k - (sum(d)/k)^2)   (population std); threads 0..3
+__device__ __forceinline__ void refit_finish(int A, int g, long long ms, const float (&mu_old)[4], float a1, float a2, int k,
+                                             float* __restrict__ mu_new, float* __restrict__ sd_new) {
+  const int t = threadIdx.x;
   if (t < 4) {
     const int a = 4 * g + t;
     const float c = t == 0 ? mu_old[0] : t == 1 ? mu_old[1] : t == 2 ? mu_old[2] : mu_old[3];
@@ -539,6 +542,155 @@ refit_kernel(ActionSource src, Shape sh, int A, const int* __restrict__ elite_id
       sd_new[ms + a] = __fsqrt_rn(fmaxf(fmaf(-m1, m1, a2 * inv), 0.f));
     }
   }
+}
+
+// Parks this CTA's partial sums, counts arrivals; in the last CTA to arrive threads 0..3 return the sum
+// of all `nparts` partials IN PART ORDER (-> true), the others return false.
+__device__ __forceinline__ bool refit_combine(float* __restrict__ part, unsigned int* __restrict__ arrive, long long slot,
+                                              int my_part, int nparts, bool* s_last, float& a1, float& a2) {
+  const int t = threadIdx.x;
+  float* mine = part + (slot * nparts + my_part) * 8;
+  if (t < 4) { mine[t] = a1; mine[4 + t] = a2; }
+  __threadfence();
+  __syncthreads();
+  if (t == 0) {
+    const unsigned int n = atomicAdd(arrive + slot, 1u);
+    *s_last = n == (unsigned int)nparts - 1;
+    if (*s_last) arrive[slot] = 0;  // ready for the next launch (stream order)
+  }
+  __syncthreads();
+  if (!*s_last) return false;
+  __threadfence();
+  if (t < 4) {
+    a1 = 0.f; a2 = 0.f;
+    for (int c = 0; c < nparts; ++c) {
+      a1 += __ldcg(part + (slot * nparts + c) * 8 + t);
+      a2 += __ldcg(part + (slot * nparts + c) * 8 + 4 + t);
+    }
+  }
+  return true;
+}
+
+// grid = (H * G, E, chunks): one CTA per (step, 4-wide action group, env, chunk of 2048 elites).
+// k > 2048 (large elite sets): the chunk CTAs run in parallel on otherwise idle SMs, park their
+// partial sums, and the last one to arrive adds them IN CHUNK ORDER -- the result depends only on
+// the elite list (ascending index), never on timing.
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+refit_kernel(ActionSource src, Shape sh, int A, const int* __restrict__ elite_idx, int k,
+             float* __restrict__ mu_new, float* __restrict__ sd_new, float* __restrict__ part,
+             unsigned int* __restrict__ arrive) {
+  __shared__ float red[kRefitThreads / 32][8];
+  __shared__ bool s_last;
+  const int G = (A + 3) >> 2;
+  const int h = blockIdx.x / G, g = blockIdx.x % G;
+  const int env_l = blockIdx.y;
+  const int chunk = blockIdx.z, nchunks = gridDim.z;
+  const long long ms = ((long long)env_l * sh.H + h) * A;
+  float mu_old[4], a1, a2;
+  pdl_trigger();
+  pdl_wait();  // elite indices (top-k / remap) and the old mean/std (previous refit)
+  refit_accumulate(src, sh, A, h, g, env_l, elite_idx + (long long)env_l * k, chunk * kRefitChunk,
+                   min(k, (chunk + 1) * kRefitChunk), red, mu_old, a1, a2);
+  if (nchunks > 1 && !refit_combine(part, arrive, (long long)env_l * gridDim.x + blockIdx.x, chunk, nchunks, &s_last, a1, a2)) return;
+  refit_finish(A, g, ms, mu_old, a1, a2, k, mu_new, sd_new);
+}
+
+// ---- segment-canonical refit: what a population-sharded run computes ---------------------------
+// Population sharding over W ranks distributes the refit: rank r sums ITS OWN elites (candidates
+// [r*S, (r+1)*S), S = candidates per rank) with 1024 threads, the W partial sums are exchanged and
+// added in rank order.  refit_seg_kernel computes exactly that from the global elite list on one GPU
+// (grid.z = W CTAs per slot, segment bounds by binary search in the ascending list): it is the
+// refit of the NCCL transport (every rank holds the whole list) and of an UNSHARDED plan asked to
+// reproduce a W-way sharded one bit for bit (mbrl_set_refit_segments).
+__global__ void __launch_bounds__(kRefitThreads, 1)
+refit_seg_kernel(ActionSource src, Shape sh, int A, const int* __restrict__ elite_idx, int k, int seg_size,
+                 float* __restrict__ mu_new, float* __restrict__ sd_new, float* __restrict__ part,
+                 unsigned int* __restrict__ arrive) {
+  __shared__ float red[kRefitThreads / 32][8];
+  __shared__ bool s_last;
+  __shared__ int s_bound[2];
+  const int G = (A + 3) >> 2;
+  const int h = blockIdx.x / G, g = blockIdx.x % G;
+  const int env_l = blockIdx.y;
+  const int s = blockIdx.z, nseg = gridDim.z;
+  const long long ms = ((long long)env_l * sh.H + h) * A;
+  const int* list = elite_idx + (long long)env_l * k;
+  float mu_old[4], a1, a2;
+  pdl_trigger();
+  pdl_wait();
+  if (threadIdx.x < 2) {  // first list position whose candidate index is >= (s + threadIdx.x) * seg_size
+    const long long v = (long long)(s + (int)threadIdx.x) * seg_size;
+    int lo = 0, hi = k;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if ((long long)dep_load(list + mid) < v) lo = mid + 1; else hi = mid; }
+    s_bound[threadIdx.x] = lo;
+  }
+  __syncthreads();
+  refit_accumulate(src, sh, A, h, g, env_l, list, s_bound[0], s_bound[1], red, mu_old, a1, a2);
+  if (!refit_combine(part, arrive, (long long)env_l * gridDim.x + blockIdx.x, s, nseg, &s_last, a1, a2)) return;
+  refit_finish(A, g, ms, mu_old, a1, a2, k, mu_new, sd_new);
+}
+
+// The distributed form over peer memory: grid = H * G CTAs.  Each sums this rank's own elites (list,
+// *own_count entries, global candidate indices), stores the 8 partial sums of its slot into every
+// rank's buffer and publishes a per-slot sequence flag; then it acquires the same slot's flag of
+// every rank and adds the W partials in rank order.  A CTA only ever waits for remote CTAs that
+// publish before they wait, so the kernels of different ranks cannot deadlock each other.
+struct RefitP2p {
+  P2pPeers peers;
+  const uint32_t* local;
+  int rank, world, slot, pslots, parity;
+  uint32_t seq;
+  int* error;
+  unsigned long long timeout_ns;
+};
+__global__ void __launch_bounds__(kRefitThreads, 1)
+refit_p2p_kernel(ActionSource src, Shape sh, int A, const int* __restrict__ own_list, const int* __restrict__ own_count,
+                 int k, float* __restrict__ mu_new, float* __restrict__ sd_new, const RefitP2p px) {
+  __shared__ float red[kRefitThreads / 32][8];
+  const int G = (A + 3) >> 2;
+  const int h = blockIdx.x / G, g = blockIdx.x % G;
+  const long long ms = (long long)h * A;
+  const int t = threadIdx.x, lane = t & 31;
+  float mu_old[4], a1, a2;
+  pdl_trigger();
+  pdl_wait();
+  const int kc = dep_load(own_count);
+  refit_accumulate(src, sh, A, h, g, 0, own_list, 0, kc, red, mu_old, a1, a2);
+  if (t >= 32) return;
+  const size_t part = (size_t)px.parity * p2p_parity_words(px.world, px.slot, px.pslots) + p2p_part_off(px.world, px.slot);
+  const size_t pflags = p2p_pflags_off(px.world, px.slot, px.pslots);
+  if (t < 4) {
+    const size_t at = part + ((size_t)px.rank * px.pslots + blockIdx.x) * 8;
+    for (int r = 0; r < px.world; ++r) {
+      px.peers.base[r][at + t] = __float_as_uint(a1);
+      px.peers.base[r][at + 4 + t] = __float_as_uint(a2);
+    }
+    __threadfence_system();
+  }
+  __syncwarp();
+  for (int r = lane; r < px.world; r += 32)
+    st_release_sys(px.peers.base[r] + pflags + (size_t)px.rank * px.pslots + blockIdx.x, px.seq);
+  bool ok = true;
+  for (int r = lane; r < px.world; r += 32) {
+    const uint32_t* flag = px.local + pflags + (size_t)r * px.pslots + blockIdx.x;
+    const unsigned long long t0 = globaltimer_ns();
+    unsigned int spins = 0;
+    while ((int)(ld_acquire_sys(flag) - px.seq) < 0) {
+      if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > px.timeout_ns) { ok = false; break; }
+    }
+  }
+  ok = __all_sync(0xFFFFFFFFu, ok);
+  if (!ok && t == 0) *px.error = 1;  // the plan reports it (info.reserved bit 1); the sums below are garbage then
+  if (t < 4) {
+    a1 = 0.f; a2 = 0.f;
+    for (int r = 0; r < px.world; ++r) {
+      const uint32_t* src_r = px.local + part + ((size_t)r * px.pslots + blockIdx.x) * 8;
+      a1 += __uint_as_float(__ldcg(src_r + t));
+      a2 += __uint_as_float(__ldcg(src_r + 4 + t));
+    }
+  }
+  refit_finish(A, g, ms, mu_old, a1, a2, k, mu_new, sd_new);
 }
 
 // ---- population-sharded elite merge (see mbrl_comm_init) ---------------------------------------

@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "mbrl_set_norm", "mbrl_set_cost", "mbrl_set_action_bounds", "mbrl_set_reward_head", "mbrl_plan", "mbrl_plan_device",
     "mbrl_rollout", "mbrl_sample", "mbrl_philox_raw", "mbrl_topk", "mbrl_refit", "mbrl_emit",
     "mbrl_tc_debug", "mbrl_nccl_unique_id", "mbrl_comm_init", "mbrl_comm_destroy",
-    "mbrl_p2p_export", "mbrl_p2p_attach", "mbrl_p2p_detach", "mbrl_plan_gd",
+    "mbrl_p2p_export", "mbrl_p2p_attach", "mbrl_p2p_detach", "mbrl_plan_gd", "mbrl_set_refit_segments",
 ]
 
 
@@ -111,6 +111,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         "mbrl_p2p_export": [p, i32, vp],
         "mbrl_p2p_attach": [p, vp, i32, i32],
         "mbrl_p2p_detach": [p],
+        "mbrl_set_refit_segments": [p, i32],
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)
@@ -364,6 +365,11 @@ class NativePlanner:
             return False
         self.rank, self.world = rank, world
         return True
+
+    def set_refit_segments(self, segments):
+        """mbrl_set_refit_segments: make this UNSHARDED planner add the refit's sums the way a plan
+        sharded over `segments` ranks does (per-rank partial sums in rank order) -- bit-identical to it."""
+        _check(self.lib.mbrl_set_refit_segments(self._h, int(segments)))
 
     def tc_debug(self, enable=True, fetch=False):
         """Diagnostic: arm / fetch the raw accumulator dump of tile 0, step 0 ([3,128,512]: three

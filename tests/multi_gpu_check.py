@@ -4,7 +4,9 @@
 
 Every rank plans on its shard; all ranks must return the same plan, and it must equal the
 UNSHARDED plan over the whole population (bit for bit: Philox counters carry global indices,
-the merge keeps the lower-global-index tie rule, the refit regenerates elites from global indices)."""
+the merge keeps the lower-global-index tie rule, the refit regenerates elites from global indices and
+adds per-rank partial sums in rank order -- the unsharded plan is asked for the same order with
+set_refit_segments(world))."""
 import os
 import sys
 
@@ -55,6 +57,7 @@ def main():
         if rank == 0:
             full = native.NativePlanner(O, A, U, H, n_total, 1, I, k, engine, local)
             full.load_problem(prob)
+            full.set_refit_segments(world)  # the sharded refit adds per-rank partial sums in rank order
             want = full.plan(s0, I, k, native.SAMPLE_GAUSSIAN, seed=21, want_dist=True)
             for key in ("actions", "states", "mu", "sd"):
                 np.testing.assert_array_equal(out[key], want[key], err_msg=f"{engine} {key}")

@@ -106,6 +106,34 @@ def test_in_library_nccl_world1_equals_plain_plan(native):
         np.testing.assert_array_equal(got["info"][key], want["info"][key])
 
 
+def test_refit_segments_change_only_the_rounding(native):
+    """mbrl_set_refit_segments(W): the refit adds W per-segment partial sums in segment order -- the
+    arithmetic of a W-way sharded plan (tests/multi_gpu_check.py proves that identity on >= 2 GPUs).
+    Against the plain order the mean / std move by fp32 rounding only (tolerance 2e-6 absolute on
+    values in [-1, 1]), one segment IS the plain order, and the setter validates its argument."""
+    p = po.synthetic_params(17, 6, 200)
+    H, N, I, k = 30, 8192, 3, 819
+    s0 = po.synthetic_state(p, 5).numpy()
+    plain = _planner(native, p, H, N, 1, I, engine="fp32")
+    want = plain.plan(s0, I, k, native.SAMPLE_GAUSSIAN, seed=9, want_dist=True)
+    seg = _planner(native, p, H, N, 1, I, engine="fp32")
+    seg.set_refit_segments(1)
+    one = seg.plan(s0, I, k, native.SAMPLE_GAUSSIAN, seed=9, want_dist=True)
+    for key in ("actions", "mu", "sd"):
+        np.testing.assert_array_equal(one[key], want[key])
+    for w in (2, 8, 64):
+        seg.set_refit_segments(w)
+        got = seg.plan(s0, 1, k, native.SAMPLE_GAUSSIAN, seed=9, want_dist=True)  # one iteration: same elites for sure
+        ref = plain.plan(s0, 1, k, native.SAMPLE_GAUSSIAN, seed=9, want_dist=True)
+        np.testing.assert_allclose(got["mu"], ref["mu"], rtol=0, atol=2e-6)
+        np.testing.assert_allclose(got["sd"], ref["sd"], rtol=0, atol=2e-6)
+        assert got["info"]["best_index"][0] == ref["info"]["best_index"][0]
+    with pytest.raises(RuntimeError):
+        seg.set_refit_segments(3)      # does not divide the population
+    with pytest.raises(RuntimeError):
+        seg.set_refit_segments(128)    # more than 64
+
+
 def test_multi_gpu_population_sharding_is_bit_identical():
     """Runs tests/multi_gpu_check.py under torchrun when this box has >= 2 GPUs (skipped on the
     single-GPU test box): every rank's plan == the unsharded plan, both transports, incl. the full
@@ -121,4 +149,4 @@ def test_multi_gpu_population_sharding_is_bit_identical():
            "--master-addr", "127.0.0.1", "--master-port", "29533", script]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
-    assert res.stdout.count("multi_gpu_check[") == 6, res.stdout[-2000:]
+    assert res.stdout.count("multi_gpu_check[") == 8, res.stdout[-2000:]
