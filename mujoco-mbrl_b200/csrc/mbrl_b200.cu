@@ -137,6 +137,7 @@ struct MbrlPlanner {
   int refit_parts_cap = 0;                 // partial sums per slot that d_refit_part holds
   int refit_segments = 1;                  // mbrl_set_refit_segments: canonical summation order of the refit
   int* d_own_count = nullptr;              // population sharding: number of this rank's elites
+  long long* d_shard_stamps = nullptr;     // MBRL_SHARD_TIMELINE diagnostic: [max_iterations][16] globaltimer stamps
   bool full_gather = false;     // force worst-case-size gathers (while a flagged plan is redone)
   int scratch_world = 0;        // world size the sharding scratch buffers were allocated for (0 = none)
   // peer-memory transport (mbrl_p2p_export / mbrl_p2p_attach)
@@ -180,9 +181,34 @@ static cudaError_t dev_alloc(T** ptr, size_t count) {
 extern "C" int mbrl_abi_version(void) { return MBRL_ABI_VERSION; }
 extern "C" const char* mbrl_last_error(void) { return g_err.c_str(); }
 
+// MBRL_SHARD_TIMELINE=<prefix> (diagnostic): the sharded kernels of the last plan left globaltimer
+// stamps per iteration; write them, in ns relative to the first, to <prefix>.rank<r>.txt:
+//   select: start, published | merge: start, flags acquired, end | refit (CTA 0): start, published, acquired, end
+static void dump_shard_timeline(MbrlPlanner* p) {
+  const char* prefix = getenv("MBRL_SHARD_TIMELINE");
+  if (!prefix || !p->d_shard_stamps) return;
+  const int I = p->cfg.max_iterations;
+  std::vector<long long> h((size_t)16 * I);
+  if (cudaDeviceSynchronize() != cudaSuccess ||
+      cudaMemcpy(h.data(), p->d_shard_stamps, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return;
+  const std::string path = std::string(prefix) + ".rank" + std::to_string(p->rank) + ".txt";
+  if (FILE* f = std::fopen(path.c_str(), "w")) {
+    std::fprintf(f, "# iteration: sel_start sel_pub | mrg_start mrg_acq mrg_end | rft_start rft_pub rft_acq rft_end   (ns since iteration 0 sel_start; absolute t0 %lld)\n", h[0]);
+    for (int it = 0; it < I; ++it) {
+      if (!h[(size_t)16 * it]) break;
+      std::fprintf(f, "%d:", it);
+      for (int j = 0; j < 9; ++j) std::fprintf(f, " %lld%s", h[(size_t)16 * it + j] ? h[(size_t)16 * it + j] - h[0] : -1, (j == 1 || j == 4) ? " |" : "");
+      std::fprintf(f, "\n");
+    }
+    std::fclose(f);
+  }
+}
+
 extern "C" int mbrl_destroy(MbrlPlanner* p) {
   if (!p) return MBRL_OK;
   cudaSetDevice(p->cfg.device);
+  dump_shard_timeline(p);
+  if (p->d_shard_stamps) cudaFree(p->d_shard_stamps);
   float* dev[] = {p->W1t, p->b1, p->W2t, p->b2, p->W3t, p->b3, p->mu_s, p->sd_s, p->mu_a, p->sd_a,
                   p->cost_w, p->goal, p->d_s0, p->d_costs, p->d_mu_hist, p->d_sd_hist, p->d_mu_last,
                   p->d_out_states, p->d_out_actions, p->d_injected};
@@ -766,6 +792,11 @@ extern "C" int mbrl_p2p_attach(MbrlPlanner* p, const uint8_t* h_handles, int32_t
     p->p2p_peers.base[r] = (uint32_t*)ptr;
   }
   p->p2p_attached = true;
+  if (getenv("MBRL_SHARD_TIMELINE") && !p->d_shard_stamps) {
+    const size_t n = (size_t)16 * p->cfg.max_iterations;
+    if (cudaMalloc((void**)&p->d_shard_stamps, sizeof(long long) * n) == cudaSuccess) cudaMemset(p->d_shard_stamps, 0, sizeof(long long) * n);
+    else { p->d_shard_stamps = nullptr; cudaGetLastError(); }
+  }
   return alloc_shard_scratch(p, world);
 }
 
@@ -918,6 +949,7 @@ static int enqueue_plan(MbrlPlanner* p, const MbrlPlanArgs* a, const float* d_s0
         sh.slot = p->p2p_slot; sh.pslots = p->H * ((p->A + 3) / 4); sh.seq = ++p->p2p_seq; sh.parity = (int)(sh.seq & 1);
         sh.idx_offset = (int)cand_offset; sh.k_full = k_full; sh.trunc = p->d_trunc; sh.error = p->d_p2p_error;
         sh.own_count = p->d_own_count; sh.timeout_ns = p2p_timeout_ns();
+        sh.stamps = p->d_shard_stamps ? p->d_shard_stamps + 16 * it : nullptr;
         rc = launch_topk_mode<kSelScatter>(p->d_costs, 1, p->N, kl, nullptr, nullptr, nullptr, nullptr, it, sh, st);
         if (rc) return rc;
         rc = launch_topk_mode<kSelMerge>(nullptr, 1, ng, k, p->d_elite, nullptr, nullptr, p->d_best_ever, it, sh, st);
@@ -935,6 +967,7 @@ static int enqueue_plan(MbrlPlanner* p, const MbrlPlanArgs* a, const float* d_s0
             RefitP2p px{};
             px.peers = p->p2p_peers; px.local = p->d_p2p_local; px.rank = p->rank; px.world = p->world; px.slot = p->p2p_slot;
             px.pslots = sh.pslots; px.parity = sh.parity; px.seq = sh.seq; px.error = p->d_p2p_error; px.timeout_ns = sh.timeout_ns;
+            px.stamps = sh.stamps;
             Shape shp{p->H, p->N, p->E};
             MBRL_CUDA(launch_pdl(refit_p2p_kernel, dim3(sh.pslots), dim3(kRefitThreads), 0, st, gsrc, shp, p->A,
                                  (const int*)p->d_elite, (const int*)p->d_own_count, k, mu_new, sd_new, px));

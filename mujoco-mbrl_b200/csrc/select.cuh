@@ -22,8 +22,8 @@ __device__ __forceinline__ uint32_t cost_key(float c) {
 // ---- peer-memory (NVLink P2P) elite exchange ---------------------------------------------------
 // (mbrl_p2p_export / mbrl_p2p_attach).  Every rank exports one buffer of uint32 words:
 //   2 parities x { costs [world*slot] | global indices [world*slot] | local thresholds [world] |
-//                  refit partial sums [world][pslots*8] }
-//   then [world] elite sequence flags (one per source rank), then [world][pslots] refit sequence flags.
+//                  refit partial sums [world][pslots][8] as {value bits, sequence} pairs }
+//   then [world] elite sequence flags (one per source rank).
 // pslots = H * ceil(A/4): the (step, action group) slots of the refit.
 // slot = capacity per rank; a launch that sends k_l <= slot elites per rank packs them
 // CONTIGUOUSLY (rank r's at [r*k_l, (r+1)*k_l)), so that the gathered costs / indices are plain
@@ -36,6 +36,17 @@ struct P2pPeers {
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// one naturally aligned 64-bit SCALAR access (vector accesses carry no single-copy atomicity in the
+// PTX memory model): a {value, sequence tag} packet is never seen torn
+__device__ __forceinline__ void st_packet(uint32_t* p, uint32_t v, uint32_t tag) {
+  const unsigned long long w = (unsigned long long)v | ((unsigned long long)tag << 32);
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ uint2 ld_packet(const uint32_t* p) {
+  unsigned long long w;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+  return make_uint2((uint32_t)w, (uint32_t)(w >> 32));
+}
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -46,14 +57,13 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-__host__ __device__ inline size_t p2p_part_off(int world, int slot) { return (size_t)world * (2 * (size_t)slot + 1); }
+__host__ __device__ inline size_t p2p_part_off(int world, int slot) { return ((size_t)world * (2 * (size_t)slot + 1) + 1) & ~(size_t)1; }  // even: 8-byte packets
 __host__ __device__ inline size_t p2p_parity_words(int world, int slot, int pslots) {
-  return p2p_part_off(world, slot) + (size_t)world * pslots * 8;
+  return p2p_part_off(world, slot) + (size_t)world * pslots * 16;
 }
 __host__ __device__ inline size_t p2p_flags_off(int world, int slot, int pslots) { return 2 * p2p_parity_words(world, slot, pslots); }
-__host__ __device__ inline size_t p2p_pflags_off(int world, int slot, int pslots) { return p2p_flags_off(world, slot, pslots) + (size_t)world; }
 __host__ __device__ inline size_t p2p_total_words(int world, int slot, int pslots) {
-  return p2p_pflags_off(world, slot, pslots) + (size_t)world * pslots;
+  return p2p_flags_off(world, slot, pslots) + (size_t)world;
 }
 
 // Sharded roles of the top-k kernel (template parameter MODE):
@@ -77,7 +87,9 @@ struct SelShard {
   int* error;              // kSelMerge: set when a rank's flag never arrived
   int* own_count;          // kSelMerge: number of this rank's elites
   unsigned long long timeout_ns;
+  long long* stamps;       // diagnostic (MBRL_SHARD_TIMELINE): globaltimer stamps of this iteration, or null
 };
+#define SHARD_STAMP(ptr, i) do { if ((ptr) && threadIdx.x == 0 && blockIdx.x == 0) (ptr)[i] = (long long)globaltimer_ns(); } while (0)
 
 constexpr int kSelectThreads = 1024;
 #ifdef MBRL_TOPK_PROFILE
@@ -152,8 +164,13 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
   const uint32_t* gidx = MODE == kSelMerge ? sh.local + par_off + (size_t)sh.world * sh.slot : nullptr;
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(c) & 15) == 0);
   pdl_trigger();
-  pdl_wait();  // the costs come from the preceding rollout kernel
+  // kSelMerge does not wait for the preceding (local select) kernel to drain: everything it consumes
+  // is ordered by the sequence flags it acquires -- its own rank's included, which the select publishes
+  // after its last store -- and it writes nothing before it holds them.  It starts polling while the
+  // select still runs, so the launch gap and the select's kernel-end flush leave the critical path.
+  if (MODE != kSelMerge) pdl_wait();  // the costs come from the preceding rollout kernel
   TOPK_STAMP(0);
+  if (MODE != kSelPlain) SHARD_STAMP(sh.stamps, MODE == kSelScatter ? 0 : 2);
   bool bad = false;
   if (MODE == kSelMerge) {
     // acquire every rank's sequence flag.  A rank that never shows up within timeout_ns (wall clock,
@@ -173,6 +190,7 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
     __syncthreads();
     bad = !s_ok;
     if (bad && t == 0) *sh.error = 1;
+    SHARD_STAMP(sh.stamps, 3);
   }
   constexpr uint32_t kInfKey = 0x7F800000u | 0x80000000u;  // cost_key(+inf)
 
@@ -425,9 +443,10 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
   TOPK_STAMP(21);
 
   if (MODE == kSelScatter) {
-    // publish: every thread's peer stores are ordered before the flag at system scope
-    __threadfence_system();
+    // publish: the barrier orders every thread's peer stores before the flag threads, whose
+    // st.release.sys is cumulative over them (one system-scope fence instead of one per warp + one)
     __syncthreads();
+    SHARD_STAMP(sh.stamps, 1);
     if (t < sh.world) st_release_sys(sh.peers.base[t] + p2p_flags_off(sh.world, sh.slot, sh.pslots) + sh.rank, sh.seq);
     return;
   }
@@ -443,6 +462,7 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
       if (b.iteration < 0 || cmin < b.cost) { b.cost = cmin; b.iteration = iteration; b.index = idx; best_ever[seg] = b; }
     }
     if (MODE == kSelMerge) *sh.own_count = (int)(base_less + min(base_eq, take_eq) - min(s_eq_low, take_eq));
+    if (MODE == kSelMerge) SHARD_STAMP(sh.stamps, 4);
   }
   TOPK_STAMP(22);
 }
@@ -633,9 +653,9 @@ refit_seg_kernel(ActionSource src, Shape sh, int A, const int* __restrict__ elit
 
 // The distributed form over peer memory: grid = H * G CTAs.  Each sums this rank's own elites (list,
 // *own_count entries, global candidate indices), stores the 8 partial sums of its slot into every
-// rank's buffer and publishes a per-slot sequence flag; then it acquires the same slot's flag of
-// every rank and adds the W partials in rank order.  A CTA only ever waits for remote CTAs that
-// publish before they wait, so the kernels of different ranks cannot deadlock each other.
+// rank's buffer as sequence-tagged packets, then polls the same slot's packets of every rank and
+// adds the W partials in rank order.  A CTA only ever waits for remote CTAs that publish before
+// they wait, so the kernels of different ranks cannot deadlock each other.
 struct RefitP2p {
   P2pPeers peers;
   const uint32_t* local;
@@ -643,11 +663,13 @@ struct RefitP2p {
   uint32_t seq;
   int* error;
   unsigned long long timeout_ns;
+  long long* stamps;
 };
 __global__ void __launch_bounds__(kRefitThreads, 1)
 refit_p2p_kernel(ActionSource src, Shape sh, int A, const int* __restrict__ own_list, const int* __restrict__ own_count,
                  int k, float* __restrict__ mu_new, float* __restrict__ sd_new, const RefitP2p px) {
   __shared__ float red[kRefitThreads / 32][8];
+  __shared__ float s_pk[64 * 8];  // every rank's 8 partial sums of this slot
   const int G = (A + 3) >> 2;
   const int h = blockIdx.x / G, g = blockIdx.x % G;
   const long long ms = (long long)h * A;
@@ -655,42 +677,45 @@ refit_p2p_kernel(ActionSource src, Shape sh, int A, const int* __restrict__ own_
   float mu_old[4], a1, a2;
   pdl_trigger();
   pdl_wait();
+  SHARD_STAMP(px.stamps, 5);
   const int kc = dep_load(own_count);
   refit_accumulate(src, sh, A, h, g, 0, own_list, 0, kc, red, mu_old, a1, a2);
   if (t >= 32) return;
+  // Each of the slot's 8 partial sums travels as one naturally aligned 8-byte store {value bits, seq}:
+  // the tag arrives with the value, so no system-scope fence and no separate flag are needed.  The
+  // parity half that seq selects was last read two iterations ago (see the double-buffering argument
+  // in mbrl_b200.h), so a reader can only ever see this iteration's tag or an older one.
   const size_t part = (size_t)px.parity * p2p_parity_words(px.world, px.slot, px.pslots) + p2p_part_off(px.world, px.slot);
-  const size_t pflags = p2p_pflags_off(px.world, px.slot, px.pslots);
-  if (t < 4) {
-    const size_t at = part + ((size_t)px.rank * px.pslots + blockIdx.x) * 8;
-    for (int r = 0; r < px.world; ++r) {
-      px.peers.base[r][at + t] = __float_as_uint(a1);
-      px.peers.base[r][at + 4 + t] = __float_as_uint(a2);
-    }
-    __threadfence_system();
+  if (t < 8) {
+    const float v1 = __shfl_sync(0xFFu, a1, t & 3), v2 = __shfl_sync(0xFFu, a2, t & 3);
+    const size_t at = part + ((size_t)px.rank * px.pslots + blockIdx.x) * 16 + 2 * t;  // packet t: sum(d) of action t, or sum(d^2) of action t - 4
+    for (int r = 0; r < px.world; ++r) st_packet(px.peers.base[r] + at, __float_as_uint(t < 4 ? v1 : v2), px.seq);
   }
-  __syncwarp();
-  for (int r = lane; r < px.world; r += 32)
-    st_release_sys(px.peers.base[r] + pflags + (size_t)px.rank * px.pslots + blockIdx.x, px.seq);
+  SHARD_STAMP(px.stamps, 6);
+  // the lanes poll the world * 8 packets of this slot (packet q = rank * 8 + j)
   bool ok = true;
-  for (int r = lane; r < px.world; r += 32) {
-    const uint32_t* flag = px.local + pflags + (size_t)r * px.pslots + blockIdx.x;
-    const unsigned long long t0 = globaltimer_ns();
+  const int npk = px.world * 8;
+  const unsigned long long t0 = globaltimer_ns();
+  for (int q = lane; q < npk; q += 32) {
+    const uint32_t* src_q = px.local + part + ((size_t)(q >> 3) * px.pslots + blockIdx.x) * 16 + 2 * (q & 7);
+    uint2 pkt = ld_packet(src_q);
     unsigned int spins = 0;
-    while ((int)(ld_acquire_sys(flag) - px.seq) < 0) {
+    while (pkt.y != px.seq) {
       if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > px.timeout_ns) { ok = false; break; }
+      pkt = ld_packet(src_q);
     }
+    s_pk[q] = __uint_as_float(pkt.x);
   }
   ok = __all_sync(0xFFFFFFFFu, ok);
+  __syncwarp();
+  SHARD_STAMP(px.stamps, 7);
   if (!ok && t == 0) *px.error = 1;  // the plan reports it (info.reserved bit 1); the sums below are garbage then
   if (t < 4) {
     a1 = 0.f; a2 = 0.f;
-    for (int r = 0; r < px.world; ++r) {
-      const uint32_t* src_r = px.local + part + ((size_t)r * px.pslots + blockIdx.x) * 8;
-      a1 += __uint_as_float(__ldcg(src_r + t));
-      a2 += __uint_as_float(__ldcg(src_r + 4 + t));
-    }
+    for (int r = 0; r < px.world; ++r) { a1 += s_pk[r * 8 + t]; a2 += s_pk[r * 8 + 4 + t]; }
   }
   refit_finish(A, g, ms, mu_old, a1, a2, k, mu_new, sd_new);
+  SHARD_STAMP(px.stamps, 8);
 }
 
 // ---- population-sharded elite merge (see mbrl_comm_init) ---------------------------------------
