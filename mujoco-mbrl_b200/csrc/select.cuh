@@ -20,16 +20,19 @@ __device__ __forceinline__ uint32_t cost_key(float c) {
 }
 
 // ---- peer-memory (NVLink P2P) elite exchange ---------------------------------------------------
-// (mbrl_p2p_export / mbrl_p2p_attach).  Every rank exports one buffer of uint32 words:
-//   2 parities x { costs [world*slot] | global indices [world*slot] | local thresholds [world] |
-//                  refit partial sums [world][pslots][8] as {value bits, sequence} pairs }
-//   then [world] elite sequence flags (one per source rank).
-// pslots = H * ceil(A/4): the (step, action group) slots of the refit.
-// slot = capacity per rank; a launch that sends k_l <= slot elites per rank packs them
-// CONTIGUOUSLY (rank r's at [r*k_l, (r+1)*k_l)), so that the gathered costs / indices are plain
-// arrays of world*k_l entries in ascending global index order and the merge select reads them in place.
-// Layout of every rank's exported buffer: [2 parities][world][2*slot] uint32 data, then
-// [world] uint32 sequence flags (one per source rank).  slot = k_l capacity.
+// (mbrl_p2p_export / mbrl_p2p_attach).  Every rank exports one buffer made of PACKETS: 64-bit words
+// {value (32 bits), sequence tag (32 bits)} written with one scalar store each, so a reader that
+// finds this iteration's tag holds this iteration's value -- no flags and no system-scope fences;
+// data is consumed as it lands.  Per iteration parity (double buffering):
+//   cost packets  [world][k_l]   rank r's k_l cheapest costs in ascending candidate order, packed
+//                                contiguously (k_l <= slot): the gathered costs are one array of
+//                                world*k_l entries in ascending GLOBAL index order
+//   index packets [k_l]          the global indices of THIS rank's entries (written locally)
+//   rank packets  [world][3]     rank r's local threshold key, minimum cost, argmin (global index)
+//   refit packets [world][pslots][8]  partial sums; pslots = H * ceil(A/4) (step, action group) slots
+// The parity half that a sequence number selects was last read two iterations earlier (a writer
+// cannot be two iterations ahead of a reader: its own merge needs every rank's packets of the
+// iteration in between), so a reader sees this iteration's tag or an older one, never a newer one.
 struct P2pPeers {
   uint32_t* base[64];  // peer r's exported buffer (own rank: the local pointer)
 };
@@ -57,23 +60,34 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-__host__ __device__ inline size_t p2p_part_off(int world, int slot) { return ((size_t)world * (2 * (size_t)slot + 1) + 1) & ~(size_t)1; }  // even: 8-byte packets
+__host__ __device__ inline size_t p2p_idx_off(int world, int slot) { return 2 * (size_t)world * slot; }
+__host__ __device__ inline size_t p2p_rank_off(int world, int slot) { return p2p_idx_off(world, slot) + 2 * (size_t)slot; }
+__host__ __device__ inline size_t p2p_part_off(int world, int slot) { return p2p_rank_off(world, slot) + 6 * (size_t)world; }
 __host__ __device__ inline size_t p2p_parity_words(int world, int slot, int pslots) {
-  return p2p_part_off(world, slot) + (size_t)world * pslots * 16;
+  return (p2p_part_off(world, slot) + 16 * (size_t)world * pslots + 3) & ~(size_t)3;  // 16-byte multiple
 }
-__host__ __device__ inline size_t p2p_flags_off(int world, int slot, int pslots) { return 2 * p2p_parity_words(world, slot, pslots); }
-__host__ __device__ inline size_t p2p_total_words(int world, int slot, int pslots) {
-  return p2p_flags_off(world, slot, pslots) + (size_t)world;
+__host__ __device__ inline size_t p2p_total_words(int world, int slot, int pslots) { return 2 * p2p_parity_words(world, slot, pslots); }
+// Spin until the packet carries `seq`; false (and the stale value) once timeout_ns of wall clock have passed since t0.
+__device__ __forceinline__ bool wait_packet(const uint32_t* p, uint32_t seq, unsigned long long t0,
+                                            unsigned long long timeout_ns, uint32_t& value) {
+  uint2 pkt = ld_packet(p);
+  unsigned int spins = 0;
+  while (pkt.y != seq) {
+    if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > timeout_ns) { value = pkt.x; return false; }
+    pkt = ld_packet(p);
+  }
+  value = pkt.x;
+  return true;
 }
 
 // Sharded roles of the top-k kernel (template parameter MODE):
 //   kSelPlain    the ordinary segmented top-k
-//   kSelScatter  local top-k_l whose compaction stores (cost bits, global index) straight into every
-//                rank's exported buffer over NVLink and then publishes this rank's sequence flag
-//   kSelMerge    waits for every rank's flag, finds the global top-k threshold among the world*k_l
-//                gathered candidates in place, emits the GLOBAL indices of THIS rank's elites only
-//                (+ their count: the refit is distributed), keeps the best-ever record in global
-//                indices and checks that the reduced-size gather was exact
+//   kSelScatter  local top-k_l whose compaction stores cost packets straight into every rank's
+//                exported buffer over NVLink (+ its own index packets, threshold and minimum)
+//   kSelMerge    stages the world*k_l gathered cost packets as they arrive, finds the global top-k
+//                threshold, emits the GLOBAL indices of THIS rank's elites only (+ their count: the
+//                refit is distributed), keeps the best-ever record in global indices and checks
+//                that the reduced-size gather was exact
 enum { kSelPlain = 0, kSelScatter = 1, kSelMerge = 2 };
 __device__ __forceinline__ bool k_per_rank_lt(int n, int world, int k_full) { return n / world < k_full; }
 struct SelShard {
@@ -84,7 +98,7 @@ struct SelShard {
   int k_full;              // kSelMerge: min(k, N) -- a gather of k_full per rank is exact by construction
   uint32_t seq;
   int* trunc;              // kSelMerge: set when the reduced gather cannot be proven exact
-  int* error;              // kSelMerge: set when a rank's flag never arrived
+  int* error;              // kSelMerge: set when a rank's packets never arrived
   int* own_count;          // kSelMerge: number of this rank's elites
   unsigned long long timeout_ns;
   long long* stamps;       // diagnostic (MBRL_SHARD_TIMELINE): globaltimer stamps of this iteration, or null
@@ -160,9 +174,9 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
   const int n32 = select_padded(n);
   // kSelMerge: the gathered candidates live in this rank's exported buffer (written by the peers)
   const size_t par_off = MODE == kSelPlain ? 0 : (size_t)sh.parity * p2p_parity_words(sh.world, sh.slot, sh.pslots);
-  const float* c = MODE == kSelMerge ? reinterpret_cast<const float*>(sh.local + par_off) : costs + (long long)seg * n;
-  const uint32_t* gidx = MODE == kSelMerge ? sh.local + par_off + (size_t)sh.world * sh.slot : nullptr;
+  const float* c = costs + (long long)seg * n;  // unused by kSelMerge: its costs are packets in sh.local
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(c) & 15) == 0);
+  const unsigned long long t_start = MODE == kSelMerge ? globaltimer_ns() : 0ull;
   pdl_trigger();
   // kSelMerge does not wait for the preceding (local select) kernel to drain: everything it consumes
   // is ordered by the sequence flags it acquires -- its own rank's included, which the select publishes
@@ -171,34 +185,33 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
   if (MODE != kSelMerge) pdl_wait();  // the costs come from the preceding rollout kernel
   TOPK_STAMP(0);
   if (MODE != kSelPlain) SHARD_STAMP(sh.stamps, MODE == kSelScatter ? 0 : 2);
+  // kSelMerge: a rank whose packets never show up within timeout_ns (wall clock, default 120 s,
+  // MBRL_P2P_TIMEOUT_S) trips the timeout: *error = 1 and every gathered candidate reads as
+  // (+inf, -1) instead of stale data, so that whatever runs next is deterministic garbage that the
+  // plan reports (info.reserved bit 1), not a plausible wrong plan.
   bool bad = false;
   if (MODE == kSelMerge) {
-    // acquire every rank's sequence flag.  A rank that never shows up within timeout_ns (wall clock,
-    // default 120 s, MBRL_P2P_TIMEOUT_S) trips the timeout: *error = 1 and every gathered candidate
-    // reads as (+inf, -1) instead of the previous iteration's data, so that whatever runs next is
-    // deterministic garbage that the plan reports (info.reserved bit 1), not a plausible wrong plan.
     if (t == 0) s_ok = 1;
     __syncthreads();
-    if (t < sh.world) {
-      const uint32_t* flag = sh.local + p2p_flags_off(sh.world, sh.slot, sh.pslots) + t;
-      const unsigned long long t0 = globaltimer_ns();
-      unsigned int spins = 0;
-      while ((int)(ld_acquire_sys(flag) - sh.seq) < 0) {
-        if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > sh.timeout_ns) { s_ok = 0; break; }
-      }
-    }
-    __syncthreads();
-    bad = !s_ok;
-    if (bad && t == 0) *sh.error = 1;
-    SHARD_STAMP(sh.stamps, 3);
   }
   constexpr uint32_t kInfKey = 0x7F800000u | 0x80000000u;  // cost_key(+inf)
 
   // four keys of indices i4..i4+3 (i4 multiple of 4); out-of-range -> 0xFFFFFFFF padding
   auto load4 = [&](int i4, uint32_t (&kk)[4]) {
-    if (MODE == kSelMerge && bad) {
+    if (MODE == kSelMerge) {
+      const uint32_t* pk = sh.local + par_off + 2 * (size_t)i4;  // cost packets of the gathered indices i4..i4+3
+      uint2 q[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) kk[j] = i4 + j < n ? kInfKey : 0xFFFFFFFFu;
+      for (int j = 0; j < 4; ++j) q[j] = (i4 + j < n && !bad) ? ld_packet(pk + 2 * j) : make_uint2(0u, sh.seq);  // in flight together
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        kk[j] = 0xFFFFFFFFu;
+        if (i4 + j < n) {
+          uint32_t v = q[j].x;
+          if (bad || (q[j].y != sh.seq && !wait_packet(pk + 2 * j, sh.seq, t_start, sh.timeout_ns, v))) { s_ok = 0; kk[j] = kInfKey; }
+          else kk[j] = cost_key(__uint_as_float(v));
+        }
+      }
     } else if (vec_ok && i4 + 3 < n) {
       const float4 q = dep_load(reinterpret_cast<const float4*>(c + i4));
       kk[0] = cost_key(q.x); kk[1] = cost_key(q.y); kk[2] = cost_key(q.z); kk[3] = cost_key(q.w);
@@ -228,14 +241,50 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
 
   // ---- stage + min/max (16-byte loads, all in flight together) ----
   uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
-#pragma unroll 4
-  for (int i4 = 4 * t; i4 < n32; i4 += 4 * kSelectThreads) {
-    uint32_t kk[4];
-    load4(i4, kk);
-    if (STAGED) *reinterpret_cast<uint4*>(keys + 4 * swz(i4 >> 2)) = make_uint4(kk[0], kk[1], kk[2], kk[3]);
+  if (MODE == kSelMerge) {
+    // packets of four units per thread (16 loads) in flight, then validated: whatever has not landed
+    // yet is polled, so the slice of an early rank is staged while a late rank is still sending
+    for (int b4 = 4 * t; b4 < n32; b4 += 16 * kSelectThreads) {
+      uint2 q[4][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (i4 + j < n) { kmin = min(kmin, kk[j]); kmax = max(kmax, kk[j]); }
+      for (int m = 0; m < 4; ++m) {
+        const int i4 = b4 + m * 4 * kSelectThreads;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          q[m][j] = i4 + j < n ? ld_packet(sh.local + par_off + 2 * (size_t)(i4 + j)) : make_uint2(0u, sh.seq);
+      }
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int i4 = b4 + m * 4 * kSelectThreads;
+        if (i4 >= n32) break;
+        uint32_t kk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          kk[j] = 0xFFFFFFFFu;
+          if (i4 + j < n) {
+            uint32_t v = q[m][j].x;
+            if (q[m][j].y != sh.seq && !wait_packet(sh.local + par_off + 2 * (size_t)(i4 + j), sh.seq, t_start, sh.timeout_ns, v)) {
+              s_ok = 0;
+              kk[j] = kInfKey;
+            } else {
+              kk[j] = cost_key(__uint_as_float(v));
+            }
+            kmin = min(kmin, kk[j]); kmax = max(kmax, kk[j]);
+          }
+        }
+        if (STAGED) *reinterpret_cast<uint4*>(keys + 4 * swz(i4 >> 2)) = make_uint4(kk[0], kk[1], kk[2], kk[3]);
+      }
+    }
+  } else {
+#pragma unroll 4
+    for (int i4 = 4 * t; i4 < n32; i4 += 4 * kSelectThreads) {
+      uint32_t kk[4];
+      load4(i4, kk);
+      if (STAGED) *reinterpret_cast<uint4*>(keys + 4 * swz(i4 >> 2)) = make_uint4(kk[0], kk[1], kk[2], kk[3]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (i4 + j < n) { kmin = min(kmin, kk[j]); kmax = max(kmax, kk[j]); }
+    }
   }
   *reinterpret_cast<uint4*>(hist + 4 * t) = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
@@ -246,6 +295,11 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
   if (lane == 0) { wtot[0][0][warp] = kmin; wtot[0][1][warp] = kmax; }
   if (t == 0) { s_first = 0x7FFFFFFF; s_eq_low = 0; }
   __syncthreads();
+  if (MODE == kSelMerge) {
+    bad = !s_ok;  // block-uniform from here on
+    if (bad && t == 0) *sh.error = 1;
+    SHARD_STAMP(sh.stamps, 3);
+  }
   kmin = wtot[0][0][lane]; kmax = wtot[0][1][lane];  // every warp finishes the reduction itself
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
@@ -269,7 +323,7 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
         const uint32_t d = kk[j] - lo;
         if (d <= span) atomicAdd(&hist[d >> shift], 1u);
         // the argmin rides on the first round: d == 0 <=> the minimum key (padding never is: n >= 1)
-        if (round == 0 && d == 0) atomicMin(&s_first, (STAGED ? 4 * swz(i4 >> 2) : i4) + j);
+        if (MODE != kSelMerge && round == 0 && d == 0) atomicMin(&s_first, (STAGED ? 4 * swz(i4 >> 2) : i4) + j);
       }
     }
     __syncthreads();
@@ -307,12 +361,14 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
   TOPK_STAMP(20);
 
   if (MODE == kSelScatter && t < sh.world)  // this rank's threshold: the merge proves exactness with it
-    sh.peers.base[t][par_off + 2 * (size_t)sh.world * sh.slot + sh.rank] = T;
+    st_packet(sh.peers.base[t] + par_off + p2p_rank_off(sh.world, sh.slot) + 6 * (size_t)sh.rank, T, sh.seq);
   if (MODE == kSelMerge && t < sh.world && k_per_rank_lt(n, sh.world, sh.k_full)) {
     // Reduced gather: rank t sent only its k_s = n/world cheapest; its k_s-th key is tl.  tl > T: every
     // candidate it kept back is above the global threshold -> exact.  tl <= T: cheaper-than-threshold
     // candidates of that rank may be missing -> flag, the caller redoes the plan with full-size gathers.
-    const uint32_t tl = bad ? 0xFFFFFFFFu : dep_load(sh.local + par_off + 2 * (size_t)sh.world * sh.slot + t);
+    uint32_t tl = 0;
+    if (!bad && !wait_packet(sh.local + par_off + p2p_rank_off(sh.world, sh.slot) + 6 * (size_t)t, sh.seq, t_start, sh.timeout_ns, tl))
+      *sh.error = 1;
     if (tl <= T) atomicOr(sh.trunc, 1);
   }
 
@@ -415,7 +471,11 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
         g[u] = 0;
         if (i[u] >= 0) {
           if (MODE == kSelScatter) g[u] = __float_as_uint(dep_load(c + i[u]));
-          else if (MODE == kSelMerge) g[u] = bad ? 0xFFFFFFFFu : dep_load(gidx + i[u]);
+          else if (MODE == kSelMerge) {  // this rank's own index packets (written by the local select)
+            g[u] = 0xFFFFFFFFu;
+            if (!bad && !wait_packet(sh.local + par_off + p2p_idx_off(sh.world, sh.slot) + 2 * (size_t)(i[u] - own_lo), sh.seq, t_start,
+                                     sh.timeout_ns, g[u])) { *sh.error = 1; g[u] = 0xFFFFFFFFu; }
+          }
           else if (elite_cost) g[u] = __float_as_uint(dep_load(c + i[u]));
         }
       }
@@ -424,13 +484,11 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
         if (i[u] < 0) continue;
         const uint32_t pos = out0 + j0 + u * kSelectThreads;
         if (MODE == kSelScatter) {
-          // peer stores over NVLink: (cost bits | global index) into every rank's gathered arrays
-          const size_t at = par_off + (size_t)sh.rank * k + pos;
-          for (int r = 0; r < sh.world; ++r) {
-            uint32_t* dst = sh.peers.base[r];
-            dst[at] = g[u];
-            dst[at + (size_t)sh.world * sh.slot] = (uint32_t)(i[u] + sh.idx_offset);
-          }
+          // peer stores over NVLink: the cost packet into every rank's gathered array, the index packet locally
+          const size_t at = par_off + 2 * ((size_t)sh.rank * k + pos);
+          for (int r = 0; r < sh.world; ++r) st_packet(sh.peers.base[r] + at, g[u], sh.seq);
+          st_packet(sh.peers.base[sh.rank] + par_off + p2p_idx_off(sh.world, sh.slot) + 2 * (size_t)pos,
+                    (uint32_t)(i[u] + sh.idx_offset), sh.seq);
         } else if (MODE == kSelMerge) {
           elite_idx[pos] = (int)g[u];
         } else {
@@ -443,26 +501,53 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
   TOPK_STAMP(21);
 
   if (MODE == kSelScatter) {
-    // publish: the barrier orders every thread's peer stores before the flag threads, whose
-    // st.release.sys is cumulative over them (one system-scope fence instead of one per warp + one)
-    __syncthreads();
+    // this rank's minimum (cost, global index) for the best-ever record, two more packets per peer
+    if (t < sh.world) {
+      const int v = s_first;
+      uint32_t* dst = sh.peers.base[t] + par_off + p2p_rank_off(sh.world, sh.slot) + 6 * (size_t)sh.rank;
+      st_packet(dst + 2, __float_as_uint(dep_load(c + v)), sh.seq);
+      st_packet(dst + 4, (uint32_t)(v + sh.idx_offset), sh.seq);
+    }
     SHARD_STAMP(sh.stamps, 1);
-    if (t < sh.world) st_release_sys(sh.peers.base[t] + p2p_flags_off(sh.world, sh.slot, sh.pslots) + sh.rank, sh.seq);
+    return;
+  }
+  if (MODE == kSelMerge) {
+    // global minimum = the best of the ranks' minima; equal costs -> the lower rank == the lower global index
+    if (t < sh.world) {
+      const uint32_t* src_r = sh.local + par_off + p2p_rank_off(sh.world, sh.slot) + 6 * (size_t)t;
+      uint32_t cb = 0x7F800000u, gi = 0xFFFFFFFFu;
+      if (!bad && !(wait_packet(src_r + 2, sh.seq, t_start, sh.timeout_ns, cb) && wait_packet(src_r + 4, sh.seq, t_start, sh.timeout_ns, gi))) {
+        *sh.error = 1; cb = 0x7F800000u; gi = 0xFFFFFFFFu;
+      }
+      hist[2 * t] = cb; hist[2 * t + 1] = gi;  // the histogram is idle by now
+    }
+    __syncthreads();
+    if (t == 0) {
+      uint32_t kb = 0xFFFFFFFFu, cb = 0x7F800000u, gi = 0xFFFFFFFFu;
+      for (int r = 0; r < sh.world; ++r) {
+        const uint32_t kr = cost_key(__uint_as_float(hist[2 * r]));
+        if (r == 0 || kr < kb) { kb = kr; cb = hist[2 * r]; gi = hist[2 * r + 1]; }
+      }
+      const float cmin = __uint_as_float(cb);
+      if (best_ever) {
+        BestEver b = best_ever[0];
+        if (b.iteration < 0 || cmin < b.cost) { b.cost = cmin; b.iteration = iteration; b.index = (int)gi; best_ever[0] = b; }
+      }
+      *sh.own_count = (int)(base_less + min(base_eq, take_eq) - min(s_eq_low, take_eq));
+      SHARD_STAMP(sh.stamps, 4);
+    }
     return;
   }
 
   // ---- the minimum: the lowest index holding the minimum key (found in the first round) ----
   if (t == 0 && n > 0) {
     const int v = s_first;
-    const float cmin = (MODE == kSelMerge && bad) ? __int_as_float(0x7f800000) : dep_load(c + v);
-    const int idx = MODE == kSelMerge ? (bad ? -1 : (int)dep_load(gidx + v)) : v;
-    if (best) { best[seg].best_cost = cmin; best[seg].best_iteration = iteration; best[seg].best_index = idx; best[seg].reserved = 0; }
+    const float cmin = dep_load(c + v);
+    if (best) { best[seg].best_cost = cmin; best[seg].best_iteration = iteration; best[seg].best_index = v; best[seg].reserved = 0; }
     if (best_ever) {
       BestEver b = best_ever[seg];
-      if (b.iteration < 0 || cmin < b.cost) { b.cost = cmin; b.iteration = iteration; b.index = idx; best_ever[seg] = b; }
+      if (b.iteration < 0 || cmin < b.cost) { b.cost = cmin; b.iteration = iteration; b.index = v; best_ever[seg] = b; }
     }
-    if (MODE == kSelMerge) *sh.own_count = (int)(base_less + min(base_eq, take_eq) - min(s_eq_low, take_eq));
-    if (MODE == kSelMerge) SHARD_STAMP(sh.stamps, 4);
   }
   TOPK_STAMP(22);
 }
