@@ -242,17 +242,35 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
   // ---- stage + min/max (16-byte loads, all in flight together) ----
   uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
   if (MODE == kSelMerge) {
-    // packets of four units per thread (16 loads) in flight, then validated: whatever has not landed
-    // yet is polled, so the slice of an early rank is staged while a late rank is still sending
+    // Four units per thread (16 packets) are loaded together and the whole batch is re-read until every
+    // tag is current: one L2 round trip per attempt, so staging ends within a round trip of the last
+    // packet landing.  This kernel is resident long before the data exists (it does not wait for the
+    // preceding grids), so until its first packet shows up a thread polls that one packet only.
     for (int b4 = 4 * t; b4 < n32; b4 += 16 * kSelectThreads) {
       uint2 q[4][4];
-#pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        const int i4 = b4 + m * 4 * kSelectThreads;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          q[m][j] = i4 + j < n ? ld_packet(sh.local + par_off + 2 * (size_t)(i4 + j)) : make_uint2(0u, sh.seq);
+      bool timed_out = false;
+      if (b4 < n) {
+        uint32_t v;
+        timed_out = !wait_packet(sh.local + par_off + 2 * (size_t)b4, sh.seq, t_start, sh.timeout_ns, v);
       }
+      unsigned int spins = 0;
+      while (!timed_out) {
+        bool all = true;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const int i4 = b4 + m * 4 * kSelectThreads;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            q[m][j] = i4 + j < n ? ld_packet(sh.local + par_off + 2 * (size_t)(i4 + j)) : make_uint2(0u, sh.seq);
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) all = all && q[m][j].y == sh.seq;
+        if (all) break;
+        if ((++spins & 255u) == 0 && globaltimer_ns() - t_start > sh.timeout_ns) timed_out = true;
+      }
+      if (timed_out) s_ok = 0;
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
         const int i4 = b4 + m * 4 * kSelectThreads;
@@ -262,13 +280,7 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
         for (int j = 0; j < 4; ++j) {
           kk[j] = 0xFFFFFFFFu;
           if (i4 + j < n) {
-            uint32_t v = q[m][j].x;
-            if (q[m][j].y != sh.seq && !wait_packet(sh.local + par_off + 2 * (size_t)(i4 + j), sh.seq, t_start, sh.timeout_ns, v)) {
-              s_ok = 0;
-              kk[j] = kInfKey;
-            } else {
-              kk[j] = cost_key(__uint_as_float(v));
-            }
+            kk[j] = timed_out ? kInfKey : cost_key(__uint_as_float(q[m][j].x));
             kmin = min(kmin, kk[j]); kmax = max(kmax, kk[j]);
           }
         }

@@ -22,6 +22,7 @@ from mbrl_b200.synthetic import synthetic_problem, synthetic_state  # noqa: E402
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    os.environ["MBRL_P2P_TIMEOUT_S"] = "2"   # for the last case; microseconds are what every other case needs
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     O, A, U, H, I = 24, 6, 200, 30, 4  # walker-walk shape (BASELINE config 4)
@@ -97,6 +98,23 @@ def main():
                   f"argmin {out['info']['best_index'][0]} cost {out['info']['best_cost'][0]:.4f}")
         dist.barrier()
         h.close()
+    # A rank that never shows up: the survivor must get an error (deterministic sentinels inside, never a
+    # plausible plan built from the previous iteration's packets).  MBRL_P2P_TIMEOUT_S is read once per
+    # process, before the first sharded plan -- main() set it to 2 s.
+    h = native.NativePlanner(O, A, U, H, 2048, 1, 2, 204, "fp16", local)
+    h.load_problem(prob)
+    assert h.p2p_init(rank, world)
+    h.plan(s0, 2, 204, native.SAMPLE_GAUSSIAN, seed=40)   # everybody: fine
+    dist.barrier()
+    if rank == 0:
+        try:
+            h.plan(s0, 1, 204, native.SAMPLE_GAUSSIAN, seed=41, want_dist=True)  # alone
+            raise AssertionError("a plan whose peers never sent anything returned normally")
+        except native.MbrlError as e:
+            assert "timed out" in str(e), str(e)
+            print(f"multi_gpu_check[timeout]: rank 0 alone -> {str(e)[:60]}...")
+    dist.barrier()
+    h.close()
     dist.destroy_process_group()
 
 
