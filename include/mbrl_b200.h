@@ -264,14 +264,18 @@ int mbrl_emit(MbrlPlanner* p, int32_t sample_mode, uint64_t seed, uint32_t cand_
  *   mbrl_nccl_unique_id: rank 0 fills 128 bytes, the host broadcasts them to all ranks.        */
 /* Peer-memory transport for the same sharded loop (NVLink P2P through CUDA IPC instead of the
  * ncclAllGather): every rank exports one gather buffer (mbrl_p2p_export: 64-byte IPC handle),
- * the host all-gathers the handles, mbrl_p2p_attach opens the peers' buffers.  Per iteration
- * three kernels run: the local select stores this rank's (cost, global index) elites straight
- * into every peer's buffer and publishes a sequence flag (st.release.sys); the merge select
- * acquires the flags of all ranks, finds the global threshold among the gathered candidates and
- * keeps this rank's own elites; the refit sums them, exchanges the H*ceil(A/4)*8 partial sums
- * the same way and adds the ranks' partials in rank order.  Buffers are double-buffered by
- * iteration parity; a writer can never be two iterations ahead of a reader because its own merge
- * needs every rank's flag.  Falls back to NCCL when no peer buffers are attached.              */
+ * the host all-gathers the handles, mbrl_p2p_attach opens the peers' buffers.  Everything in a
+ * buffer is a packet -- a 64-bit {value, sequence tag} word written with one scalar store -- so
+ * data is consumed as it lands, without flags or system-scope fences.  Per iteration three
+ * kernels run: the local select stores this rank's cheapest costs straight into every peer's
+ * buffer; the merge select (resident and polling while the rollout still runs) stages the
+ * gathered costs, finds the global threshold and keeps this rank's own elites; the refit sums
+ * them, exchanges the H*ceil(A/4)*8 partial sums the same way and adds the ranks' partials in
+ * rank order.  Buffers are double-buffered by iteration parity; a writer can never be two
+ * iterations ahead of a reader because its own merge needs every rank's packets of the iteration
+ * in between.  Every wait gives up after MBRL_P2P_TIMEOUT_S (default 120) seconds of wall clock:
+ * the plan then fails instead of using stale data.  Falls back to NCCL when no peer buffers are
+ * attached.                                                                                     */
 int mbrl_p2p_export(MbrlPlanner* p, int32_t world, uint8_t* h_handle64);
 int mbrl_p2p_attach(MbrlPlanner* p, const uint8_t* h_handles, int32_t rank, int32_t world);
 /* Closes whatever peer buffers were opened (also after a failed attach) so that the handle can

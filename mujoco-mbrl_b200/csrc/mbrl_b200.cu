@@ -141,11 +141,10 @@ struct MbrlPlanner {
   bool full_gather = false;     // force worst-case-size gathers (while a flagged plan is redone)
   int scratch_world = 0;        // world size the sharding scratch buffers were allocated for (0 = none)
   // peer-memory transport (mbrl_p2p_export / mbrl_p2p_attach)
-  uint32_t* d_p2p_local = nullptr;  // exported: [2][world][2*slot] data + [world] flags
+  uint32_t* d_p2p_local = nullptr;  // exported packet buffer (layout: select.cuh, p2p_*_off)
   int p2p_slot = 0, p2p_world = 0;
   bool p2p_attached = false;
   P2pPeers p2p_peers{};
-  unsigned int* d_p2p_counter = nullptr;
   int* d_p2p_error = nullptr;
   uint32_t p2p_seq = 0;
 };
@@ -225,7 +224,6 @@ extern "C" int mbrl_destroy(MbrlPlanner* p) {
     for (int r = 0; r < p->world; ++r)
       if (r != p->rank && p->p2p_peers.base[r]) cudaIpcCloseMemHandle(p->p2p_peers.base[r]);
   if (p->d_p2p_local) cudaFree(p->d_p2p_local);
-  if (p->d_p2p_counter) cudaFree(p->d_p2p_counter);
   if (p->d_p2p_error) cudaFree(p->d_p2p_error);
   void* shard[] = {p->d_ecost, p->d_send, p->d_recv, p->d_gcost, p->d_gidx, p->d_pos, p->d_best_now, p->d_trunc};
   for (void* q : shard) if (q) cudaFree(q);
@@ -747,25 +745,21 @@ extern "C" int mbrl_p2p_export(MbrlPlanner* p, int32_t world, uint8_t* h_handle6
   }
   if (!p->d_p2p_local) {
     uint32_t* buf = nullptr;
-    unsigned int* counter = p->d_p2p_counter;
     int* err = p->d_p2p_error;
-    bool ok = dev_alloc(&buf, words) == cudaSuccess && (counter || dev_alloc(&counter, 1) == cudaSuccess) &&
-              (err || dev_alloc(&err, 1) == cudaSuccess);
+    bool ok = dev_alloc(&buf, words) == cudaSuccess && (err || dev_alloc(&err, 1) == cudaSuccess);
     if (!ok) {  // nothing half-initialised is left behind: a retry starts from scratch
       if (buf) cudaFree(buf);
-      if (counter && counter != p->d_p2p_counter) cudaFree(counter);
       if (err && err != p->d_p2p_error) cudaFree(err);
       cudaGetLastError();
       return fail(MBRL_E_CUDA, "out of device memory allocating the peer-memory gather buffer");
     }
-    p->d_p2p_local = buf; p->d_p2p_counter = counter; p->d_p2p_error = err;
+    p->d_p2p_local = buf; p->d_p2p_error = err;
   }
-  // (re-)export: flags, sequence number and arrival counter restart from zero on every rank
+  // (re-)export: packet tags and the sequence number restart from zero on every rank
   p->p2p_slot = slot;
   p->p2p_world = world;
   p->p2p_seq = 0;
   MBRL_CUDA(cudaMemset(p->d_p2p_local, 0, sizeof(uint32_t) * words));
-  MBRL_CUDA(cudaMemset(p->d_p2p_counter, 0, sizeof(unsigned int)));
   MBRL_CUDA(cudaMemset(p->d_p2p_error, 0, sizeof(int)));
   cudaIpcMemHandle_t hdl;
   MBRL_CUDA(cudaIpcGetMemHandle(&hdl, p->d_p2p_local));

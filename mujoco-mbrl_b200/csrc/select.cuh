@@ -36,9 +36,6 @@ __device__ __forceinline__ uint32_t cost_key(float c) {
 struct P2pPeers {
   uint32_t* base[64];  // peer r's exported buffer (own rank: the local pointer)
 };
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 // one naturally aligned 64-bit SCALAR access (vector accesses carry no single-copy atomicity in the
 // PTX memory model): a {value, sequence tag} packet is never seen torn
 __device__ __forceinline__ void st_packet(uint32_t* p, uint32_t v, uint32_t tag) {
@@ -49,11 +46,6 @@ __device__ __forceinline__ uint2 ld_packet(const uint32_t* p) {
   unsigned long long w;
   asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
   return make_uint2((uint32_t)w, (uint32_t)(w >> 32));
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
 }
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
