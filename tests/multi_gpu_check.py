@@ -98,6 +98,37 @@ def main():
                   f"argmin {out['info']['best_index'][0]} cost {out['info']['best_cost'][0]:.4f}")
         dist.barrier()
         h.close()
+    # Every candidate costs the same (zero state weights, a flat action term): the elite set is decided by
+    # the tie rule alone -- the k lowest GLOBAL indices, all of them on rank 0.  Exercises ties straddling
+    # the cut inside the merge's own-slice compaction, ranks without a single elite (an empty partial sum),
+    # and the exactness flag + full-size redo (a rank's threshold equals the global one).
+    import dataclasses
+    flat = dataclasses.replace(prob, cost_w=torch.zeros(O), beta=1e30)
+    for transport in ("nccl", "p2p"):
+        n_local, k = 2048, int(0.1 * 2048 * world)
+        h = native.NativePlanner(O, A, U, H, n_local, 1, I, k, "fp16", local)
+        h.load_problem(flat)
+        if transport == "p2p":
+            assert h.p2p_init(rank, world)
+        else:
+            h.comm_init(rank, world)
+        out = h.plan(s0, I, k, native.SAMPLE_GAUSSIAN, seed=50, want_dist=True)
+        mine = torch.from_numpy(np.concatenate([out["actions"].ravel(), out["mu"].ravel(), out["sd"].ravel(),
+                                                out["info"]["best_index"].astype(np.float32)])).cuda()
+        ref = mine.clone()
+        dist.broadcast(ref, src=0)
+        assert torch.equal(mine, ref), f"rank {rank}: all-ties plan differs from rank 0 ({transport})"
+        if rank == 0:
+            full = native.NativePlanner(O, A, U, H, n_local * world, 1, I, k, "fp16", local)
+            full.load_problem(flat)
+            full.set_refit_segments(world)
+            want = full.plan(s0, I, k, native.SAMPLE_GAUSSIAN, seed=50, want_dist=True)
+            for key in ("actions", "states", "mu", "sd"):
+                np.testing.assert_array_equal(out[key], want[key], err_msg=f"ties {transport} {key}")
+            assert out["info"]["best_index"][0] == want["info"]["best_index"][0] == 0
+            print(f"multi_gpu_check[all costs tie, {transport}]: {world} ranks == unsharded, elites = the {k} lowest global indices")
+        dist.barrier()
+        h.close()
     # A rank that never shows up: the survivor must get an error (deterministic sentinels inside, never a
     # plausible plan built from the previous iteration's packets).  MBRL_P2P_TIMEOUT_S is read once per
     # process, before the first sharded plan -- main() set it to 2 s.

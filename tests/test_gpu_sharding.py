@@ -149,4 +149,4 @@ def test_multi_gpu_population_sharding_is_bit_identical():
            "--master-addr", "127.0.0.1", "--master-port", "29533", script]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
-    assert res.stdout.count("multi_gpu_check[") == 9, res.stdout[-2000:]
+    assert res.stdout.count("multi_gpu_check[") == 11, res.stdout[-2000:]
