@@ -138,6 +138,8 @@ struct MbrlPlanner {
   int refit_segments = 1;                  // mbrl_set_refit_segments: canonical summation order of the refit
   int* d_own_count = nullptr;              // population sharding: number of this rank's elites
   long long* d_shard_stamps = nullptr;     // MBRL_SHARD_TIMELINE diagnostic: [max_iterations][16] globaltimer stamps
+  long long* d_plan_stamps = nullptr;      // MBRL_PLAN_TIMELINE diagnostic: [max_iterations][kPlanStampStride]
+  long long* cur_stamps = nullptr;         // the current iteration's slice of d_plan_stamps (null: off)
   bool full_gather = false;     // force worst-case-size gathers (while a flagged plan is redone)
   int scratch_world = 0;        // world size the sharding scratch buffers were allocated for (0 = none)
   // peer-memory transport (mbrl_p2p_export / mbrl_p2p_attach)
@@ -183,6 +185,40 @@ extern "C" const char* mbrl_last_error(void) { return g_err.c_str(); }
 // MBRL_SHARD_TIMELINE=<prefix> (diagnostic): the sharded kernels of the last plan left globaltimer
 // stamps per iteration; write them, in ns relative to the first, to <prefix>.rank<r>.txt:
 //   select: start, published | merge: start, flags acquired, end | refit (CTA 0): start, published, acquired, end
+constexpr int kPlanStampCtas = 256;
+constexpr int kPlanStampStride = 8 + 3 * kPlanStampCtas;
+// MBRL_PLAN_TIMELINE=<path> (diagnostic, unsharded fused tcgen05 engine, <= 256 row tiles): globaltimer
+// stamps of the last plan's kernels per iteration, in ns relative to the first:
+//   top-k start (inputs ready), end | refit (CTA 0) start, end | rollout CTAs: entry, upstream data ready, exit
+static void dump_plan_timeline(MbrlPlanner* p) {
+  const char* path = getenv("MBRL_PLAN_TIMELINE");
+  if (!path || !p->d_plan_stamps) return;
+  const int I = p->cfg.max_iterations;
+  std::vector<long long> h((size_t)kPlanStampStride * I);
+  if (cudaDeviceSynchronize() != cudaSuccess ||
+      cudaMemcpy(h.data(), p->d_plan_stamps, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return;
+  FILE* f = std::fopen(path, "w");
+  if (!f) return;
+  long long t0 = 0;
+  for (long long v : h) if (v && (!t0 || v < t0)) t0 = v;
+  std::fprintf(f, "# ns since the first stamp; rollout columns: min / median / max over the CTAs\n");
+  std::fprintf(f, "# it | rollout entry | rollout data-ready | rollout exit | topk start end | refit start end\n");
+  for (int it = 0; it < I; ++it) {
+    const long long* s = h.data() + (size_t)kPlanStampStride * it;
+    if (!s[0]) break;
+    std::fprintf(f, "%d |", it);
+    for (int j = 0; j < 3; ++j) {
+      std::vector<long long> v;
+      for (int c = 0; c < kPlanStampCtas; ++c) if (s[8 + 3 * c + j]) v.push_back(s[8 + 3 * c + j] - t0);
+      std::sort(v.begin(), v.end());
+      if (v.empty()) std::fprintf(f, " - - - |");
+      else std::fprintf(f, " %lld %lld %lld |", v.front(), v[v.size() / 2], v.back());
+    }
+    std::fprintf(f, " %lld %lld | %lld %lld\n", s[0] - t0, s[1] ? s[1] - t0 : -1, s[2] ? s[2] - t0 : -1, s[3] ? s[3] - t0 : -1);
+  }
+  std::fclose(f);
+}
+
 static void dump_shard_timeline(MbrlPlanner* p) {
   const char* prefix = getenv("MBRL_SHARD_TIMELINE");
   if (!prefix || !p->d_shard_stamps) return;
@@ -207,7 +243,9 @@ extern "C" int mbrl_destroy(MbrlPlanner* p) {
   if (!p) return MBRL_OK;
   cudaSetDevice(p->cfg.device);
   dump_shard_timeline(p);
+  dump_plan_timeline(p);
   if (p->d_shard_stamps) cudaFree(p->d_shard_stamps);
+  if (p->d_plan_stamps) cudaFree(p->d_plan_stamps);
   float* dev[] = {p->W1t, p->b1, p->W2t, p->b2, p->W3t, p->b3, p->mu_s, p->sd_s, p->mu_a, p->sd_a,
                   p->cost_w, p->goal, p->d_s0, p->d_costs, p->d_mu_hist, p->d_sd_hist, p->d_mu_last,
                   p->d_out_states, p->d_out_actions, p->d_injected};
@@ -306,6 +344,11 @@ extern "C" int mbrl_create(const MbrlConfig* cfg, MbrlPlanner** out) {
   A_(cudaMallocHost((void**)&p->h_sd, sizeof(float) * EHA));
   A_(cudaMallocHost((void**)&p->h_info, sizeof(MbrlPlanInfo) * E));
   A_(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  if (ok && getenv("MBRL_PLAN_TIMELINE") && (p->R + kTcRows - 1) / kTcRows <= kPlanStampCtas) {
+    const size_t n = (size_t)kPlanStampStride * cfg->max_iterations;
+    if (cudaMalloc((void**)&p->d_plan_stamps, sizeof(long long) * n) == cudaSuccess) cudaMemset(p->d_plan_stamps, 0, sizeof(long long) * n);
+    else { p->d_plan_stamps = nullptr; cudaGetLastError(); }
+  }
   if (ok) {
     // identity normalisers until mbrl_set_norm is called
     std::vector<float> zeros(kMaxObs, 0.f), ones(kMaxObs, 1.f);
@@ -537,8 +580,9 @@ static int launch_topk_mode(const float* d_costs, int segments, int n, int k, in
 }
 
 static int launch_topk(const float* d_costs, int segments, int n, int k, int* d_idx, float* d_cost,
-                       MbrlPlanInfo* d_best, BestEver* d_best_ever, int iteration, cudaStream_t st) {
-  static const SelShard none{};
+                       MbrlPlanInfo* d_best, BestEver* d_best_ever, int iteration, cudaStream_t st, long long* stamps = nullptr) {
+  SelShard none{};
+  none.stamps = stamps;
   return launch_topk_mode<kSelPlain>(d_costs, segments, n, k, d_idx, d_cost, d_best, d_best_ever, iteration, none, st);
 }
 
@@ -551,10 +595,10 @@ static int launch_refit(const MbrlPlanner* p, const ActionSource& src, const int
   const int threads = refit_threads(k);
   if (threads <= kRefitThreads / 2)  // register-capped build: three CTAs per SM
     MBRL_CUDA(launch_pdl(refit_kernel<kRefitThreads / 2, 3>, grid, dim3(threads), 0, st, src, sh, p->A, d_elite, k, d_mu_new,
-                         d_sd_new, p->d_refit_part, p->d_refit_arrive));
+                         d_sd_new, p->d_refit_part, p->d_refit_arrive, p->cur_stamps));
   else
     MBRL_CUDA(launch_pdl(refit_kernel<kRefitThreads, 1>, grid, dim3(threads), 0, st, src, sh, p->A, d_elite, k, d_mu_new,
-                         d_sd_new, p->d_refit_part, p->d_refit_arrive));
+                         d_sd_new, p->d_refit_part, p->d_refit_arrive, p->cur_stamps));
   MBRL_CUDA(cudaGetLastError());
   return MBRL_OK;
 }
@@ -915,6 +959,8 @@ static int enqueue_plan(MbrlPlanner* p, const MbrlPlanArgs* a, const float* d_s0
     const float* inj = d_injected ? d_injected + (long long)it * HRA : nullptr;
     ActionSource src = action_source(p, a->sample_mode, a->seed, (uint32_t)it, cand_offset, a->env_offset, inj,
                                      p->d_mu_hist + it * EHA, p->d_sd_hist + it * EHA);
+    p->cur_stamps = (p->d_plan_stamps && !sharded) ? p->d_plan_stamps + (size_t)kPlanStampStride * it : nullptr;
+    p->tc.fg.stamps = p->cur_stamps ? p->cur_stamps + 8 : nullptr;
     int rc = launch_rollout(p, src, d_s0, p->d_costs, nullptr, nullptr, st);
     if (rc) return rc;
     if (sharded) {
@@ -992,7 +1038,7 @@ static int enqueue_plan(MbrlPlanner* p, const MbrlPlanArgs* a, const float* d_s0
       }
       continue;
     }
-    rc = launch_topk(p->d_costs, p->E, p->N, k, p->d_elite, nullptr, nullptr, p->d_best_ever, it, st);
+    rc = launch_topk(p->d_costs, p->E, p->N, k, p->d_elite, nullptr, nullptr, p->d_best_ever, it, st, p->cur_stamps);
     if (rc) return rc;
     if (it + 1 < I || need_final_dist) {
       rc = p->refit_segments > 1 ? launch_refit_seg(p, src, p->d_elite, k, p->refit_segments, p->N / p->refit_segments,
@@ -1001,6 +1047,8 @@ static int enqueue_plan(MbrlPlanner* p, const MbrlPlanArgs* a, const float* d_s0
       if (rc) return rc;
     }
   }
+  p->cur_stamps = nullptr;
+  p->tc.fg.stamps = nullptr;
   int rc = launch_replay(p, a->sample_mode, a->seed, sharded ? 0u : a->cand_offset, a->env_offset, d_s0, d_injected,
                          p->d_mu_hist, p->d_sd_hist, I, a->return_mean, a->actions_only, p->d_best_ever, d_out_states,
                          d_out_actions, d_info, st);

@@ -48,6 +48,7 @@ struct TcfGeom {
   int ms_off, ms_floats;  // staging area for the sampling mean/std rows of the tile's environments
   int exp;      // profiling experiments (MBRL_TCF_EXP bit mask)
   int xch_off;  // task costs: per-step control terms (a0, ctl_mean) handed from the sampler to the cost threads; -1 = no room
+  long long* stamps;  // diagnostic (MBRL_PLAN_TIMELINE): per CTA globaltimer at entry / upstream data ready / exit, or null
 };
 
 constexpr int kTcfSlots = 3;  // action tiles in flight: the sampler runs up to 3 steps ahead
@@ -133,9 +134,9 @@ inline void tcf_pack(const TcfGeom& g, bool fp16, const float* W1, const float* 
 // SPEC: the geometry class of BASELINE cfgs 3 and 4 (cheetah-run O=17 / walker-walk O=24, A=6, hidden 200:
 // Np = 208, Oy = 32, Ka = 16, Ks = 32) as compile-time constants, so that the single MMA-issuing thread
 // runs straight-line code with immediate operand offsets (see rollout_tcw.cuh for the measurements).
-constexpr int kTcfSpecNp = 208, kTcfSpecOy = 32, kTcfSpecKa = 16, kTcfSpecKs = 32;
+constexpr int kTcfSpecNp = 208, kTcfSpecOy = 32, kTcfSpecKa = 16, kTcfSpecKs = 32, kTcfSpecA = 6;
 inline bool tcf_matches_spec(const TcfGeom& g) {
-  return g.Np == kTcfSpecNp && g.Oy == kTcfSpecOy && g.Ka == kTcfSpecKa && g.Ks == kTcfSpecKs;
+  return g.Np == kTcfSpecNp && g.Oy == kTcfSpecOy && g.Ka == kTcfSpecKa && g.Ks == kTcfSpecKs && g.A == kTcfSpecA;
 }
 
 // TASK: a dm_control task cost instead of SmoothAbs + Cosh (compiled out of the default-cost kernel: the
@@ -153,6 +154,7 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
   // cost write follows a block barrier that those threads have passed.
   pdl_trigger();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (g.stamps && tid == 0) g.stamps[3 * blockIdx.x] = (long long)globaltimer_ns();
   const int O = g.O, A = g.A, H = sh.H;
   const int NpC = SPEC ? kTcfSpecNp : g.Np, OyC = SPEC ? kTcfSpecOy : g.Oy, NaC = NpC + OyC;
   constexpr bool smooth = !TASK;
@@ -267,10 +269,13 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
           for (int i = 0; i < 4; ++i)
             if (ks + i < KS_H) mma_ts(tm_b, tm_a + 16 * (ks + i), d64(lo_w2 + (ks + i) * step_h), idesc_h, (ks + i) > 0);
         }
+        if (DBG) tc_stamp(dbg, h, 8);
         tc_commit(bar_dB);
+        if (DBG) tc_stamp(dbg, h, 9);
         // ---- GEMM-A(h+1) (or, after the last step, only the y columns) ----
         const bool last = h + 1 == H;
         if (h >= 1) mbar_wait(bar_y, (h - 1) & 1);  // y(h-1) in D_A has been consumed
+        if (DBG) tc_stamp(dbg, h, 10);
         uint32_t acc = 0;
         if (!last) {
           if (++slot == kTcfSlots) { slot = 0; slot_ph ^= 1; }  // slot (h+1) % kTcfSlots, phase ((h+1) / kTcfSlots) & 1
@@ -310,11 +315,15 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
     const bool valid = row < R;
     const int env_l = valid ? (int)(row / sh.N) : 0;
     const int cand_l = valid ? (int)(row - (long long)env_l * sh.N) : 0;
-    const float inv_beta = 1.0f / m.beta, cscale = (valid && smooth) ? m.beta2 / (float)A : 0.f;
-    const int QA = (A + 8) >> 3;  // 8-wide chunks holding the actions and the constant 1
+    // The sampler warps are the kernel's critical path (one row per thread, everything serial): with the
+    // action count a compile-time constant the index clamps, masks and padding lanes fold away.
+    const int AC = SPEC ? kTcfSpecA : A;
+    const float inv_beta = 1.0f / m.beta, cscale = (valid && smooth) ? m.beta2 / (float)AC : 0.f;
+    const int QA = (AC + 8) >> 3;  // 8-wide chunks holding the actions and the constant 1
     float act_total = 0.f;
     // (Drawing step 0's noise before this wait was tried: -2 % -- the extra live registers spill.)
     pdl_wait();
+    if (g.stamps && srow == 0) g.stamps[3 * blockIdx.x + 1] = (long long)globaltimer_ns();
 
     // The mean/std of the sampling distribution (written by the preceding refit) are re-read every
     // step by every row: copy the rows of this tile's environments into shared memory once
@@ -331,45 +340,46 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
       for (int i = srow; i < ms_n; i += kTcRows) { ms_mu[i] = dep_load(src.mu + base + i); ms_sd[i] = dep_load(src.sd + base + i); }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
-    const int ms_env = (env_l - env_lo) * H * A;
+    const int ms_env = (env_l - env_lo) * H * AC;
 
     auto stage_actions = [&](int hs) {
       float acc = 0.f;
-      float* aout = (actions_out && valid) ? actions_out + ((long long)hs * R + row) * A : nullptr;
+      float* aout = (actions_out && valid) ? actions_out + ((long long)hs * R + row) * AC : nullptr;
       uint8_t* xt = xa + (hs % kTcfSlots) * xa_bytes;
       for (int q = 0; q < QA; ++q) {
         float v[8];
         {
           float t4[4], u4[4];
-          const float* pm = staged ? ms_mu + ms_env + hs * A : nullptr;
-          const float* ps = staged ? ms_sd + ms_env + hs * A : nullptr;
-          raw_action4(src, A, H, hs, env_l, cand_l, row, R, 2 * q, t4, pm, ps);
-          if (8 * q + 4 < A) raw_action4(src, A, H, hs, env_l, cand_l, row, R, 2 * q + 1, u4, pm, ps);
+          const float* pm = staged ? ms_mu + ms_env + hs * AC : nullptr;
+          const float* ps = staged ? ms_sd + ms_env + hs * AC : nullptr;
+          raw_action4(src, AC, H, hs, env_l, cand_l, row, R, 2 * q, t4, pm, ps);
+          if (8 * q + 4 < AC) raw_action4(src, AC, H, hs, env_l, cand_l, row, R, 2 * q + 1, u4, pm, ps);
           else { u4[0] = u4[1] = u4[2] = u4[3] = 0.f; }
           v[0] = t4[0]; v[1] = t4[1]; v[2] = t4[2]; v[3] = t4[3];
           v[4] = u4[0]; v[5] = u4[1]; v[6] = u4[2]; v[7] = u4[3];
         }
-        // branch-free: raw_action4 returns 0 beyond A (cosh(0) - 1 == 0), tables are zero-padded
+        // raw_action4 returns 0 beyond A (cosh(0) - 1 == 0), tables are zero-padded: lanes beyond a
+        // compile-time A are dropped, a run-time A runs all 8 branch-free
         if (xch && !smooth) {
           // task costs: this step's first control and mean_a(quadratic tolerance of the control), accumulated
           // in the step's exchange slot (no live registers on the default-cost path)
           float c8 = 0.f;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) c8 += (8 * q + i < A && fabsf(v[i]) < 1.0f) ? 1.0f - v[i] * v[i] : 0.0f;
+          for (int i = 0; i < 8; ++i) c8 += (8 * q + i < AC && fabsf(v[i]) < 1.0f) ? 1.0f - v[i] * v[i] : 0.0f;
           float* slot = xch + ((hs % kTcfXchSlots) * 2) * kTcRows + srow;
-          if (q == 0) { slot[0] = v[0]; slot[kTcRows] = c8 / (float)A; }
-          else slot[kTcRows] += c8 / (float)A;
+          if (q == 0) { slot[0] = v[0]; slot[kTcRows] = c8 / (float)AC; }
+          else slot[kTcRows] += c8 / (float)AC;
         }
         float xn[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          acc += cosh_m1_fast(v[i] * inv_beta);
-          xn[i] = fmaf(v[i], t_ainv[8 * q + i], -t_aoff[8 * q + i]);
+          if (!SPEC || 8 * q + i < AC) acc += cosh_m1_fast(v[i] * inv_beta);
+          xn[i] = fmaf(v[i], t_ainv[8 * q + i], -t_aoff[8 * q + i]);  // the lane after the last action holds the constant 1
         }
         if (aout) {
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            if (8 * q + i < A) aout[8 * q + i] = v[i];
+            if (8 * q + i < AC) aout[8 * q + i] = v[i];
         }
         uint4 pk;
         pk.x = pack2<FP16>(xn[0], xn[1]); pk.y = pack2<FP16>(xn[2], xn[3]);
@@ -555,6 +565,7 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
     const long long row = (long long)blockIdx.x * kTcRows + tid;
     if (row < R) costs[row] = costp[tid] + costp[kTcRows + tid];
   }
+  if (g.stamps && tid == 0) g.stamps[3 * blockIdx.x + 2] = (long long)globaltimer_ns();
   if (warp == kTcfMmaWarp) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
   }

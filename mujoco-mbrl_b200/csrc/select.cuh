@@ -47,11 +47,6 @@ __device__ __forceinline__ uint2 ld_packet(const uint32_t* p) {
   asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
   return make_uint2((uint32_t)w, (uint32_t)(w >> 32));
 }
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
 __host__ __device__ inline size_t p2p_idx_off(int world, int slot) { return 2 * (size_t)world * slot; }
 __host__ __device__ inline size_t p2p_rank_off(int world, int slot) { return p2p_idx_off(world, slot) + 2 * (size_t)slot; }
 __host__ __device__ inline size_t p2p_part_off(int world, int slot) { return p2p_rank_off(world, slot) + 6 * (size_t)world; }
@@ -176,7 +171,7 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
   // select still runs, so the launch gap and the select's kernel-end flush leave the critical path.
   if (MODE != kSelMerge) pdl_wait();  // the costs come from the preceding rollout kernel
   TOPK_STAMP(0);
-  if (MODE != kSelPlain) SHARD_STAMP(sh.stamps, MODE == kSelScatter ? 0 : 2);
+  SHARD_STAMP(sh.stamps, MODE == kSelMerge ? 2 : 0);
   // kSelMerge: a rank whose packets never show up within timeout_ns (wall clock, default 120 s,
   // MBRL_P2P_TIMEOUT_S) trips the timeout: *error = 1 and every gathered candidate reads as
   // (+inf, -1) instead of stale data, so that whatever runs next is deterministic garbage that the
@@ -553,6 +548,7 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
       if (b.iteration < 0 || cmin < b.cost) { b.cost = cmin; b.iteration = iteration; b.index = v; best_ever[seg] = b; }
     }
   }
+  SHARD_STAMP(sh.stamps, 1);
   TOPK_STAMP(22);
 }
 
@@ -688,7 +684,7 @@ template <int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 refit_kernel(ActionSource src, Shape sh, int A, const int* __restrict__ elite_idx, int k,
              float* __restrict__ mu_new, float* __restrict__ sd_new, float* __restrict__ part,
-             unsigned int* __restrict__ arrive) {
+             unsigned int* __restrict__ arrive, long long* stamps) {
   __shared__ float red[kRefitThreads / 32][8];
   __shared__ bool s_last;
   const int G = (A + 3) >> 2;
@@ -699,10 +695,12 @@ refit_kernel(ActionSource src, Shape sh, int A, const int* __restrict__ elite_id
   float mu_old[4], a1, a2;
   pdl_trigger();
   pdl_wait();  // elite indices (top-k / remap) and the old mean/std (previous refit)
+  if (stamps && threadIdx.x == 0 && blockIdx.x + blockIdx.y + blockIdx.z == 0) stamps[2] = (long long)globaltimer_ns();
   refit_accumulate(src, sh, A, h, g, env_l, elite_idx + (long long)env_l * k, chunk * kRefitChunk,
                    min(k, (chunk + 1) * kRefitChunk), red, mu_old, a1, a2);
   if (nchunks > 1 && !refit_combine(part, arrive, (long long)env_l * gridDim.x + blockIdx.x, chunk, nchunks, &s_last, a1, a2)) return;
   refit_finish(A, g, ms, mu_old, a1, a2, k, mu_new, sd_new);
+  if (stamps && threadIdx.x == 0 && blockIdx.x + blockIdx.y + blockIdx.z == 0) stamps[3] = (long long)globaltimer_ns();
 }
 
 // ---- segment-canonical refit: what a population-sharded run computes ---------------------------

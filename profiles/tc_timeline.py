@@ -22,7 +22,7 @@ h.rollout(s0, native.SAMPLE_GAUSSIAN, 1, 0, d_mu=mu, d_sd=sd)
 torch.cuda.synchronize()
 h.tc_debug(True, fetch=True)
 t = h.tc_timeline[:H].astype(np.float64)
-names = {0: "mma:step start (dA committed)", 1: "mma:GEMM-B chunk0 released", 2: "mma:GEMM-B last chunk released", 3: "mma:GEMM-A y+xa ready",
+names = {8: "mma:GEMM-B all issued", 9: "mma:dB commit issued", 10: "mma:y(h-1) consumed seen", 0: "mma:step start (dA committed)", 1: "mma:GEMM-B chunk0 released", 2: "mma:GEMM-B last chunk released", 3: "mma:GEMM-A y+xa ready",
          16: "mma:GEMM-A chunk0 released", 17: "mma:GEMM-A last chunk released", 4: "epi:dA ready", 5: "epi:epiA done",
          6: "epi:dB ready", 7: "epi:epiB done", 18: "mma:before wait GEMM-A chunk0", 19: "epi:warp0 first unit A", 20: "epi:warp0 first unit B", 21: "epi:warp15 first unit A", 22: "epi:warp15 first unit B", 23: "epi:slowest warp first unit A", 24: "epi:slowest warp first unit B", 12: "smp:dA ready", 13: "smp:actions(h+1) arrived", 14: "cost:dA ready", 15: "cost:y consumed"}
 base = t[:, 0:1]
