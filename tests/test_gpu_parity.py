@@ -75,7 +75,7 @@ def test_sampler_matches_oracle(native, act_dim, n, envs):
     ref_z = np.concatenate(
         [ophilox.standard_normal(seed, it, H, n, act_dim, coff, eoff + e).reshape(H, n, act_dim) for e in range(envs)],
         axis=1).reshape(H * n * envs, act_dim)
-    # log / sincospi differ from numpy's libm in the last ulps only
+    # Box-Muller runs on the SFU (lg2 / sqrt / sin / cos approx, csrc/philox.cuh): <= 4e-6 from numpy's libm
     np.testing.assert_allclose(z, ref_z, rtol=0, atol=4e-6)
     # clip + affine
     mu2 = torch.rand(envs, H, act_dim, device="cuda") - 0.5
