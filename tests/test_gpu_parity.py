@@ -263,6 +263,27 @@ def test_topk_bit_exact_with_ties(native, n, k, segments):
         assert best[s, 0].view(np.float32) == costs[s].min()
 
 
+@pytest.mark.parametrize("n", [31, 33, 16383, 16384, 16385, 16400, 32768, 32801, 49151, 49152, 49153, 65537])
+def test_topk_size_boundaries(native, n):
+    """Sizes around the kernel's internal boundaries: the 32-key padding / swizzle groups, the 16384-key
+    compaction pass (whose output buffer reuses the pass's own key slice), the 49152-key staging limit
+    (beyond it the costs are re-read from global memory), with k = 1, ~10 %, n - 1 and n, on continuous
+    costs (two or three radix rounds), heavily tied costs, all-equal costs and all-NaN costs."""
+    rng = np.random.default_rng(n)
+    cases = {"continuous": (300.0 + 40.0 * rng.standard_normal(n)).astype(np.float32),
+             "wide": np.exp(rng.uniform(-30, 30, n)).astype(np.float32) * rng.choice([-1.0, 1.0], n).astype(np.float32),
+             "tied": np.round(rng.normal(size=n) * 3).astype(np.float32),
+             "equal": np.full(n, 7.25, np.float32),
+             "nan": np.full(n, np.nan, np.float32)}
+    for name, c in cases.items():
+        for k in sorted({1, max(1, n // 10), max(1, n - 1), n}):
+            idx, cost, best = native.topk(_cuda(c[None]), k, 1)
+            want = np.sort(po.topk_stable(c, k))
+            np.testing.assert_array_equal(idx.cpu().numpy()[0], want, err_msg=f"{name} n={n} k={k}")
+            np.testing.assert_array_equal(cost.cpu().numpy()[0], c[want], err_msg=f"{name} n={n} k={k}")
+            assert best.cpu().numpy()[0, 2] == (0 if name in ("equal", "nan") else np.argmin(c)), f"{name} n={n} k={k}"
+
+
 def test_topk_special_values(native):
     c = np.array([[3.0, -0.0, 0.0, np.inf, -np.inf, np.nan, 1e-45, -1e-45, 2.0, np.nan, -np.inf, 0.0]], np.float32)
     for k in range(1, c.shape[1] + 1):
