@@ -131,17 +131,27 @@ inline void tcf_pack(const TcfGeom& g, bool fp16, const float* W1, const float* 
 
 // DBG: accumulator dump + clock64 timeline instrumentation (tests / profiling only); the
 // production instantiation carries none of it.
-// SPEC: the geometry class of BASELINE cfgs 3 and 4 (cheetah-run O=17 / walker-walk O=24, A=6, hidden 200:
-// Np = 208, Oy = 32, Ka = 16, Ks = 32) as compile-time constants, so that the single MMA-issuing thread
-// runs straight-line code with immediate operand offsets (see rollout_tcw.cuh for the measurements).
-constexpr int kTcfSpecNp = 208, kTcfSpecOy = 32, kTcfSpecKa = 16, kTcfSpecKs = 32, kTcfSpecA = 6;
-inline bool tcf_matches_spec(const TcfGeom& g) {
-  return g.Np == kTcfSpecNp && g.Oy == kTcfSpecOy && g.Ka == kTcfSpecKa && g.Ks == kTcfSpecKs && g.A == kTcfSpecA;
+// SPEC: a geometry class as compile-time constants, so that the single MMA-issuing thread runs
+// straight-line code with immediate operand offsets (see rollout_tcw.cuh for the measurements) and the
+// sampler's per-action clamps and masks fold away.  0 = run-time geometry;
+//   1 = BASELINE cfgs 3 and 4 (cheetah-run O=17 / walker-walk O=24, A=6, hidden 200): Np 208, Oy 32, Ka 16, Ks 32
+//   2 = BASELINE cfgs 1 and 2 (cartpole-swingup O=5, A=1, hidden 50):                 Np  64, Oy 16, Ka 16, Ks 16
+constexpr int kTcfSpecs = 2;
+__host__ __device__ constexpr int tcf_spec_np(int s) { return s == 1 ? 208 : 64; }
+__host__ __device__ constexpr int tcf_spec_oy(int s) { return s == 1 ? 32 : 16; }
+__host__ __device__ constexpr int tcf_spec_ka(int s) { return 16; }
+__host__ __device__ constexpr int tcf_spec_ks(int s) { return s == 1 ? 32 : 16; }
+__host__ __device__ constexpr int tcf_spec_a(int s) { return s == 1 ? 6 : 1; }
+inline int tcf_matches_spec(const TcfGeom& g) {  // the matching class, 0 = none
+  for (int s = 1; s <= kTcfSpecs; ++s)
+    if (g.Np == tcf_spec_np(s) && g.Oy == tcf_spec_oy(s) && g.Ka == tcf_spec_ka(s) && g.Ks == tcf_spec_ks(s) && g.A == tcf_spec_a(s))
+      return s;
+  return 0;
 }
 
 // TASK: a dm_control task cost instead of SmoothAbs + Cosh (compiled out of the default-cost kernel: the
 // extra registers and branches in the sampler / cost threads cost the default path 12 % when left in).
-template <bool FP16, bool DBG, bool SPEC, bool TASK>
+template <bool FP16, bool DBG, int SPEC, bool TASK>
 __global__ void __launch_bounds__(kTcfThreads, 1)
 rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, ActionSource src, Shape sh,
                    const float* __restrict__ s0, float* __restrict__ costs, float* __restrict__ states_out,
@@ -156,11 +166,11 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (g.stamps && tid == 0) g.stamps[3 * blockIdx.x] = (long long)globaltimer_ns();
   const int O = g.O, A = g.A, H = sh.H;
-  const int NpC = SPEC ? kTcfSpecNp : g.Np, OyC = SPEC ? kTcfSpecOy : g.Oy, NaC = NpC + OyC;
+  const int NpC = SPEC ? tcf_spec_np(SPEC) : g.Np, OyC = SPEC ? tcf_spec_oy(SPEC) : g.Oy, NaC = NpC + OyC;
   constexpr bool smooth = !TASK;
   float* const xch = (TASK && g.xch_off >= 0) ? reinterpret_cast<float*>(smem + g.xch_off) : nullptr;  // [slot][a0, ctl][row]
   const int KS_H = NpC >> 4;        // K-steps over a hidden operand
-  const int KS_A = SPEC ? kTcfSpecKa >> 4 : g.Ka >> 4, KS_S = SPEC ? kTcfSpecKs >> 4 : g.Ks >> 4;
+  const int KS_A = SPEC ? tcf_spec_ka(SPEC) >> 4 : g.Ka >> 4, KS_S = SPEC ? tcf_spec_ks(SPEC) >> 4 : g.Ks >> 4;
 
   float* tab = reinterpret_cast<float*>(smem + g.tab_off);
   float *t_b3 = tab, *t_P = tab + g.Oy, *t_Q = tab + 2 * g.Oy, *t_sd = tab + 3 * g.Oy, *t_mu = tab + 4 * g.Oy;
@@ -317,7 +327,7 @@ rollout_tcf_kernel(TcfGeom g, const uint8_t* __restrict__ wimg, ModelDev m, Acti
     const int cand_l = valid ? (int)(row - (long long)env_l * sh.N) : 0;
     // The sampler warps are the kernel's critical path (one row per thread, everything serial): with the
     // action count a compile-time constant the index clamps, masks and padding lanes fold away.
-    const int AC = SPEC ? kTcfSpecA : A;
+    const int AC = SPEC ? tcf_spec_a(SPEC) : A;
     const float inv_beta = 1.0f / m.beta, cscale = (valid && smooth) ? m.beta2 / (float)AC : 0.f;
     const int QA = (AC + 8) >> 3;  // 8-wide chunks holding the actions and the constant 1
     float act_total = 0.f;
@@ -693,24 +703,30 @@ inline cudaError_t tc_launch_rollout(TcModel* t, const ModelDev& m, const Action
   return tc_launch_one(KERN, GEOM, (GEOM).smem_bytes, THREADS, t, m, src, sh, d_s0, d_costs, d_states, d_actions, st, \
                        t->kind == kTcWide ? t->wg.cluster : 1)
   if (t->kind == kTcFused) {
-    const bool spec = tcf_matches_spec(t->fg) && !getenv("MBRL_TCF_NO_SPEC");
+    const int spec = getenv("MBRL_TCF_NO_SPEC") ? 0 : tcf_matches_spec(t->fg);
     if (m.cost_kind != MBRL_COST_SMOOTHABS_COSH) {  // dm_control task cost (no debug-dump variant)
       if (dbg) return cudaErrorNotSupported;
-      if (spec && t->fp16) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, false, true, true>), t->fg, kTcfThreads);
-      if (spec) MBRL_TC_LAUNCH((rollout_tcf_kernel<false, false, true, true>), t->fg, kTcfThreads);
-      if (t->fp16) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, false, false, true>), t->fg, kTcfThreads);
-      MBRL_TC_LAUNCH((rollout_tcf_kernel<false, false, false, true>), t->fg, kTcfThreads);
+      if (spec == 1 && t->fp16) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, false, 1, true>), t->fg, kTcfThreads);
+      if (spec == 1) MBRL_TC_LAUNCH((rollout_tcf_kernel<false, false, 1, true>), t->fg, kTcfThreads);
+      if (spec == 2 && t->fp16) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, false, 2, true>), t->fg, kTcfThreads);
+      if (spec == 2) MBRL_TC_LAUNCH((rollout_tcf_kernel<false, false, 2, true>), t->fg, kTcfThreads);
+      if (t->fp16) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, false, 0, true>), t->fg, kTcfThreads);
+      MBRL_TC_LAUNCH((rollout_tcf_kernel<false, false, 0, true>), t->fg, kTcfThreads);
     }
-    if (spec) {
-      if (t->fp16 && !dbg) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, false, true, false>), t->fg, kTcfThreads);
-      if (t->fp16) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, true, true, false>), t->fg, kTcfThreads);
-      if (!dbg) MBRL_TC_LAUNCH((rollout_tcf_kernel<false, false, true, false>), t->fg, kTcfThreads);
-      MBRL_TC_LAUNCH((rollout_tcf_kernel<false, true, true, false>), t->fg, kTcfThreads);
+    if (spec == 1) {
+      if (t->fp16 && !dbg) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, false, 1, false>), t->fg, kTcfThreads);
+      if (t->fp16) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, true, 1, false>), t->fg, kTcfThreads);
+      if (!dbg) MBRL_TC_LAUNCH((rollout_tcf_kernel<false, false, 1, false>), t->fg, kTcfThreads);
+      MBRL_TC_LAUNCH((rollout_tcf_kernel<false, true, 1, false>), t->fg, kTcfThreads);
     }
-    if (t->fp16 && !dbg) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, false, false, false>), t->fg, kTcfThreads);
-    if (t->fp16) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, true, false, false>), t->fg, kTcfThreads);
-    if (!dbg) MBRL_TC_LAUNCH((rollout_tcf_kernel<false, false, false, false>), t->fg, kTcfThreads);
-    MBRL_TC_LAUNCH((rollout_tcf_kernel<false, true, false, false>), t->fg, kTcfThreads);
+    if (spec == 2 && !dbg) {  // (the debug dump of this class runs on the run-time-geometry instantiation)
+      if (t->fp16) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, false, 2, false>), t->fg, kTcfThreads);
+      MBRL_TC_LAUNCH((rollout_tcf_kernel<false, false, 2, false>), t->fg, kTcfThreads);
+    }
+    if (t->fp16 && !dbg) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, false, 0, false>), t->fg, kTcfThreads);
+    if (t->fp16) MBRL_TC_LAUNCH((rollout_tcf_kernel<true, true, 0, false>), t->fg, kTcfThreads);
+    if (!dbg) MBRL_TC_LAUNCH((rollout_tcf_kernel<false, false, 0, false>), t->fg, kTcfThreads);
+    MBRL_TC_LAUNCH((rollout_tcf_kernel<false, true, 0, false>), t->fg, kTcfThreads);
   }
   if (t->kind == kTcWide) {
     const bool spec = tcw_matches_spec(t->wg) && !getenv("MBRL_TCW_NO_SPEC");
