@@ -321,3 +321,25 @@ def test_reward_head_at_cfg5_shape_matches_fp32_engine(native):
     print(f"reward head hidden 512: fp16 vs fp32 engine max abs err {err:.3e} (scale {scale:.3f}, spread {outs['fp32'].std():.3f})")
     assert outs["fp32"].std() > 1e-3
     assert err <= 2e-3 * scale + 2e-3
+
+
+@pytest.mark.parametrize("engine", ["fp16", "bf16"])
+@pytest.mark.parametrize("dims,knob", [((17, 6, 200), "MBRL_TCF_NO_SPEC"), ((24, 6, 200), "MBRL_TCF_NO_SPEC"),
+                                       ((5, 1, 50), "MBRL_TCF_NO_SPEC"), ((67, 21, 512), "MBRL_TCW_NO_SPEC")])
+def test_compile_time_geometry_classes_are_bit_identical_to_runtime_geometry(native, engine, dims, knob, monkeypatch):
+    """The specialised instantiations (fused kernel: cheetah / walker class and cartpole class; weight-streaming
+    kernel: humanoid class) only turn geometry and the action count into compile-time constants: costs, states
+    and actions must equal the run-time-geometry instantiation bit for bit (the knob is read at every launch)."""
+    O, A, U = dims
+    p = po.synthetic_params(O, A, U)
+    H, n = (12, 512) if U > 255 else (30, 1024)
+    h = _planner(native, p, H, n, engine=engine)
+    s0 = po.synthetic_state(p, 3)[None].cuda()
+    mu = 0.1 * torch.ones(1, H, A, device="cuda")
+    sd = 0.7 * torch.ones(1, H, A, device="cuda")
+    monkeypatch.delenv(knob, raising=False)
+    c1, st1, a1 = h.rollout(s0, native.SAMPLE_GAUSSIAN, 5, 1, d_mu=mu, d_sd=sd, want_states=True, want_actions=True)
+    monkeypatch.setenv(knob, "1")
+    c0, st0, a0 = h.rollout(s0, native.SAMPLE_GAUSSIAN, 5, 1, d_mu=mu, d_sd=sd, want_states=True, want_actions=True)
+    assert torch.equal(c1, c0) and torch.equal(st1, st0) and torch.equal(a1, a0)
+    assert torch.isfinite(c1).all() and c1.std() > 0
