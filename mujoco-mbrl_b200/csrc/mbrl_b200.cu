@@ -920,8 +920,8 @@ static int enqueue_plan(MbrlPlanner* p, const MbrlPlanArgs* a, const float* d_s0
   const int I = a->iterations;
   MBRL_REQUIRE(I >= 1 && I <= p->cfg.max_iterations, "iterations out of range [1, max_iterations]");
   need_final_dist = need_final_dist || (a->warm_start & MBRL_WARM_KEEP) != 0;  // the kept mean is the refit after the last iteration
-  const int k = (I == 1 && !need_final_dist) ? 1 : a->elites;
-  MBRL_REQUIRE(k >= 1 && k <= p->cfg.max_elites, "elites out of range [1, max_elites]");
+  const int k_all = (I == 1 && !need_final_dist) ? 1 : a->elites;
+  MBRL_REQUIRE(k_all >= 1 && k_all <= p->cfg.max_elites, "elites out of range [1, max_elites]");
   const size_t EHA = (size_t)p->E * p->H * p->A;
   const long long HRA = (long long)p->H * p->R * p->A;
 
@@ -950,12 +950,14 @@ static int enqueue_plan(MbrlPlanner* p, const MbrlPlanArgs* a, const float* d_s0
   if (sharded) {
     MBRL_REQUIRE(a->sample_mode == MBRL_SAMPLE_GAUSSIAN || a->sample_mode == MBRL_SAMPLE_UNIFORM,
                  "population sharding supports the Philox sample modes only");
-    MBRL_REQUIRE((long long)k <= (long long)p->world * p->N, "elites exceed the global population");
+    MBRL_REQUIRE((long long)k_all <= (long long)p->world * p->N, "elites exceed the global population");
   } else {
-    MBRL_REQUIRE(k <= p->N, "elites exceed the population");
+    MBRL_REQUIRE(k_all <= p->N, "elites exceed the population");
   }
   const uint32_t cand_offset = sharded ? (uint32_t)((long long)p->rank * p->N) : a->cand_offset;
   for (int it = 0; it < I; ++it) {
+    // the last iteration of a plan that keeps no distribution only needs its best candidate: a k = 1 select
+    const int k = (it + 1 == I && !need_final_dist) ? 1 : k_all;
     const float* inj = d_injected ? d_injected + (long long)it * HRA : nullptr;
     ActionSource src = action_source(p, a->sample_mode, a->seed, (uint32_t)it, cand_offset, a->env_offset, inj,
                                      p->d_mu_hist + it * EHA, p->d_sd_hist + it * EHA);

@@ -309,8 +309,24 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
   uint32_t lo = kmin, hi = kmax, rem = (uint32_t)k;
   TOPK_STAMP(1);
 
+  // k == 1 (random shooting; the last CEM iteration of a plan that keeps no distribution): the threshold is
+  // the minimum key itself, no histogram round is needed -- one pass finds the lowest index holding it
+  if (k == 1) {
+    if (MODE != kSelMerge) {
+      for (int i4 = 4 * t; i4 < n32; i4 += 4 * kSelectThreads) {
+        uint32_t kk[4];
+        key4_any(i4, kk);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (kk[j] == key_min) atomicMin(&s_first, (STAGED ? 4 * swz(i4 >> 2) : i4) + j);
+      }
+    }
+    if (t == 0) s_eq_tot = 0xFFFFFFFFu;  // kSelMerge: always count the ties below this rank's slice
+    __syncthreads();
+    hi = lo;
+  }
   // ---- adaptive radix select: power-of-two bucket width, <= 4096 buckets over [lo, hi] ----
-  for (int round = 0; round < 5; ++round) {
+  for (int round = 0; round < (k == 1 ? 0 : 5); ++round) {
     const uint32_t span = hi - lo;                              // in-range test: key - lo <= span
     const int shift = span < (uint32_t)kSelectBins ? 0 : 32 - __clz(span) - kSelectBinBits;  // span >> shift < 4096
     TOPK_STAMP(2 + 3 * round);
