@@ -627,7 +627,9 @@ def main():
                           f"oracle port of planners.py:189-216 incl. autograd + Python list build; {sec * 1e3:.0f} ms/plan",
                    ms_per_plan=sec * 1e3)
 
-    launches_per_plan = (1 + 2 * I + (I - 1) + 1) if (world == 1 or env_mode) else (1 + 6 * I + (I - 1) + 1)
+    # init + I x (rollout, select) + (I-1) refits + replay; population-sharded: init + I x (rollout, local select,
+    # merge select) + (I-1) distributed refits + replay + the flag kernel
+    launches_per_plan = (1 + 2 * I + (I - 1) + 1) if (world == 1 or env_mode) else (1 + 3 * I + (I - 1) + 2)
     cfg = dict(workload=w["name"] + (f" x{world} GPUs population-sharded, N_total={n_total}" if (world > 1 and not env_mode) else "")
                + (f" x{world} GPUs environment-sharded" if (world > 1 and env_mode) else ""),
                engine=engine, elites=k, l2="flushed between timed plans (256 MiB write)",
