@@ -650,7 +650,10 @@ def main():
                  latency_ms_p50_actions_only=(statistics.median(e2e_lat_actions) * 1e3 if e2e_lat_actions else None),
                  python_api_first_action_latency_ms_p50=(py_api[0] if py_api else None),
                  python_api_calls=(py_api[1] if py_api else None),
-                 api="mbrl_plan (host buffers)" + ("" if world == 1 or env_mode else ", population-sharded (in-library elite exchange: %s)" % transport)),
+                 api="mbrl_plan (host buffers)" + ("" if world == 1 or env_mode else ", population-sharded (in-library elite exchange: %s)" % transport),
+                 transfer="host buffers -> the handle's pinned, device-mapped staging buffers; the plan's first kernel reads s0 from "
+                          "there and its last kernels store the plan there (PCIe reads / posted writes inside the timed region; "
+                          "copy-engine transfers above 256 KB)"),
         gpu_launches=launches_per_plan * args.steps,
         roofline=roofline, hbm_kernels=hbm_kernels, cpu_baseline=cpu,
         sharded_equals_unsharded=(None if equal is None else bool(equal.get("ranks_identical") and equal.get("rank0_equals_unsharded_plan"))),

@@ -140,6 +140,7 @@ struct MbrlPlanner {
   long long* d_shard_stamps = nullptr;     // MBRL_SHARD_TIMELINE diagnostic: [max_iterations][16] globaltimer stamps
   long long* d_plan_stamps = nullptr;      // MBRL_PLAN_TIMELINE diagnostic: [max_iterations][kPlanStampStride]
   long long* cur_stamps = nullptr;         // the current iteration's slice of d_plan_stamps (null: off)
+  StageS0 stage_s0{nullptr, nullptr, 0};   // mbrl_plan: initial states staged by the plan's first kernel
   bool full_gather = false;     // force worst-case-size gathers (while a flagged plan is redone)
   int scratch_world = 0;        // world size the sharding scratch buffers were allocated for (0 = none)
   // peer-memory transport (mbrl_p2p_export / mbrl_p2p_attach)
@@ -930,18 +931,18 @@ static int enqueue_plan(MbrlPlanner* p, const MbrlPlanArgs* a, const float* d_s0
   if (a->h_mu0 && a->h_sd0) {
     MBRL_CUDA(cudaMemcpyAsync(p->d_mu_hist, a->h_mu0, sizeof(float) * EHA, cudaMemcpyHostToDevice, st));
     MBRL_CUDA(cudaMemcpyAsync(p->d_sd_hist, a->h_sd0, sizeof(float) * EHA, cudaMemcpyHostToDevice, st));
-    init_plan_kernel<<<(unsigned)((p->E + 255) / 256), 256, 0, st>>>(nullptr, nullptr, 0, p->lo, p->hi, p->d_best_ever, p->E);
+    init_plan_kernel<<<(unsigned)((p->E + 255) / 256), 256, 0, st>>>(nullptr, nullptr, 0, p->lo, p->hi, p->d_best_ever, p->E, p->stage_s0);
   } else if ((a->warm_start & MBRL_WARM_USE) && p->have_last) {
     // device-resident warm start: no host round trip of the mean between MPC steps
     MBRL_REQUIRE(!a->h_mu0 && !a->h_sd0, "mu0 and sd0 must be given together");
     const float std = a->warm_std > 0.f ? a->warm_std : 0.5f * (p->hi - p->lo);
     const long long n = (long long)EHA > p->E ? (long long)EHA : p->E;
     warm_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p->d_mu_hist, p->d_sd_hist, p->d_mu_last, p->E, p->H, p->A, std,
-                                                                  p->lo, p->hi, p->d_best_ever);
+                                                                  p->lo, p->hi, p->d_best_ever, p->stage_s0);
   } else {
     MBRL_REQUIRE(!a->h_mu0 && !a->h_sd0, "mu0 and sd0 must be given together");
     const long long n = (long long)EHA > p->E ? (long long)EHA : p->E;
-    init_plan_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p->d_mu_hist, p->d_sd_hist, (long long)EHA, p->lo, p->hi, p->d_best_ever, p->E);
+    init_plan_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p->d_mu_hist, p->d_sd_hist, (long long)EHA, p->lo, p->hi, p->d_best_ever, p->E, p->stage_s0);
   }
   MBRL_CUDA(cudaGetLastError());
 
@@ -1152,13 +1153,36 @@ extern "C" int mbrl_plan(MbrlPlanner* p, const MbrlPlanArgs* args, const float* 
     d_inj = p->d_injected;
   }
   std::memcpy(p->h_s0, h_s0, sizeof(float) * E * O);
-  MBRL_CUDA(cudaMemcpyAsync(p->d_s0, p->h_s0, sizeof(float) * E * O, cudaMemcpyHostToDevice, st));
   const bool need_dist = h_out_mu != nullptr || args->return_mean != 0;
-  int rc = enqueue_plan(p, args, p->d_s0, d_inj, p->d_out_states, p->d_out_actions, p->d_info, need_dist, st);
+  // The plan (a few KB) goes straight into the handle's pinned, device-mapped host buffers: the last kernels
+  // store it there with posted PCIe writes, so no copy engine has to be started after them (three
+  // device-to-host copies cost ~10 us of latency at the end of a 0.5 ms plan).  MBRL_NO_ZERO_COPY=1: copies.
+  static const bool zero_copy_ok = getenv("MBRL_NO_ZERO_COPY") == nullptr;
+  float *m_states = nullptr, *m_actions = nullptr;
+  MbrlPlanInfo* m_info = nullptr;
+  const bool small = sizeof(float) * ((size_t)E * H * O + EHA) <= (256u << 10);  // big batches: the copy engine's bursts win
+  const bool zc = zero_copy_ok && small && cudaHostGetDevicePointer((void**)&m_states, p->h_out_states, 0) == cudaSuccess &&
+                  cudaHostGetDevicePointer((void**)&m_actions, p->h_out_actions, 0) == cudaSuccess &&
+                  cudaHostGetDevicePointer((void**)&m_info, p->h_info, 0) == cudaSuccess;
+  if (!zc) cudaGetLastError();
+  // ... and the initial states come the same way: the plan's first kernel reads them from the pinned buffer
+  float* m_s0 = nullptr;
+  const bool zs = zero_copy_ok && sizeof(float) * (size_t)E * O <= (64u << 10) &&
+                  cudaHostGetDevicePointer((void**)&m_s0, p->h_s0, 0) == cudaSuccess;
+  if (!zs) {
+    cudaGetLastError();
+    MBRL_CUDA(cudaMemcpyAsync(p->d_s0, p->h_s0, sizeof(float) * E * O, cudaMemcpyHostToDevice, st));
+  }
+  p->stage_s0 = zs ? StageS0{m_s0, p->d_s0, E * O} : StageS0{nullptr, nullptr, 0};
+  struct Unstage { MbrlPlanner* q; ~Unstage() { q->stage_s0 = StageS0{nullptr, nullptr, 0}; } } unstage{p};
+  int rc = enqueue_plan(p, args, p->d_s0, d_inj, zc ? m_states : p->d_out_states, zc ? m_actions : p->d_out_actions,
+                        zc ? m_info : p->d_info, need_dist, st);
   if (rc) return rc;
-  MBRL_CUDA(cudaMemcpyAsync(p->h_out_actions, p->d_out_actions, sizeof(float) * EHA, cudaMemcpyDeviceToHost, st));
-  MBRL_CUDA(cudaMemcpyAsync(p->h_out_states, p->d_out_states, sizeof(float) * E * H * O, cudaMemcpyDeviceToHost, st));
-  MBRL_CUDA(cudaMemcpyAsync(p->h_info, p->d_info, sizeof(MbrlPlanInfo) * E, cudaMemcpyDeviceToHost, st));
+  if (!zc) {
+    MBRL_CUDA(cudaMemcpyAsync(p->h_out_actions, p->d_out_actions, sizeof(float) * EHA, cudaMemcpyDeviceToHost, st));
+    MBRL_CUDA(cudaMemcpyAsync(p->h_out_states, p->d_out_states, sizeof(float) * E * H * O, cudaMemcpyDeviceToHost, st));
+    MBRL_CUDA(cudaMemcpyAsync(p->h_info, p->d_info, sizeof(MbrlPlanInfo) * E, cudaMemcpyDeviceToHost, st));
+  }
   if (h_out_mu) {
     MBRL_CUDA(cudaMemcpyAsync(p->h_mu, p->d_mu_hist + (size_t)args->iterations * EHA, sizeof(float) * EHA, cudaMemcpyDeviceToHost, st));
     MBRL_CUDA(cudaMemcpyAsync(p->h_sd, p->d_sd_hist + (size_t)args->iterations * EHA, sizeof(float) * EHA, cudaMemcpyDeviceToHost, st));

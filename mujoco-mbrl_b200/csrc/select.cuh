@@ -889,12 +889,27 @@ __global__ void remap_elites_kernel(const int* __restrict__ pos, const int* __re
   }
 }
 
+// The initial states of a host-buffer plan: read from the handle's pinned, device-mapped host buffer by
+// the first kernel of the plan instead of a host-to-device copy in front of it (one PCIe read round).
+struct StageS0 {
+  const float* src;  // null: nothing to stage
+  float* dst;
+  int n;
+};
+__device__ __forceinline__ void stage_s0(const StageS0& s) {
+  if (!s.src) return;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < s.n; i += stride)
+    s.dst[i] = *reinterpret_cast<const volatile float*>(s.src + i);
+}
+
 // mu/sd initialisation: (lo+hi)/2 and (hi-lo)/2 per (env, h, a); best-ever reset.
 __global__ void init_plan_kernel(float* __restrict__ mu, float* __restrict__ sd, long long n,
-                                 float lo, float hi, BestEver* __restrict__ best_ever, int E) {
+                                 float lo, float hi, BestEver* __restrict__ best_ever, int E, const StageS0 s0) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   pdl_trigger();
   pdl_wait();
+  stage_s0(s0);
   if (mu && i < n) { mu[i] = 0.5f * (lo + hi); sd[i] = 0.5f * (hi - lo); }
   if (best_ever && i < E) best_ever[i] = BestEver{0.f, -1, -1, 0};
 }
@@ -903,10 +918,12 @@ __global__ void init_plan_kernel(float* __restrict__ mu, float* __restrict__ sd,
 // shifted by one step with the last step repeated (the MPC receding-horizon shift of
 // MPCPolicy's hand-over, src/mbrl/agents.py:41-47), std = `std`; best-ever reset.
 __global__ void warm_init_kernel(float* __restrict__ mu, float* __restrict__ sd, const float* __restrict__ last_mu,
-                                 int E, int H, int A, float std, float lo, float hi, BestEver* __restrict__ best_ever) {
+                                 int E, int H, int A, float std, float lo, float hi, BestEver* __restrict__ best_ever,
+                                 const StageS0 s0) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   pdl_trigger();
   pdl_wait();
+  stage_s0(s0);
   const long long n = (long long)E * H * A;
   if (i < n) {
     const int a = (int)(i % A), h = (int)((i / A) % H);
