@@ -8,6 +8,10 @@
   redundantly by regenerating the elite actions from their global indices -- the refit needs
   no second collective and is bit-identical on all ranks (the north_star's "broadcast the
   refit mean/std" is available as `broadcast_refit=True`, e.g. to assert that equality).
+  This module is the readable, gloo-tested statement of that host logic.  The production loop
+  runs inside the library (native.NativePlanner.p2p_init / comm_init + plan): same elites, but
+  over peer memory the refit is distributed -- per-rank partial sums added in rank order -- so
+  its mean/std equal this module's up to fp32 rounding (and exactly at world size 1).
 * Environment sharding (config 5): independent environments, no collective at all --
   `env_shard()` just computes each rank's slice; the caller runs a plain NativePlanner on it.
 

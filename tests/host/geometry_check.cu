@@ -7,6 +7,7 @@
 #include <string>
 #include "../../mujoco-mbrl_b200/csrc/rollout_tcf.cuh"
 #include "../../mujoco-mbrl_b200/csrc/replay.cuh"
+#include "../../mujoco-mbrl_b200/csrc/select.cuh"
 using namespace mbrl;
 
 #define CHECK(cond, ...) do { if (!(cond)) { std::printf("FAIL %s:%d " #cond " ", __FILE__, __LINE__); std::printf(__VA_ARGS__); std::printf("\n"); ++fails; } } while (0)
@@ -124,6 +125,38 @@ int main() {
           CHECK(L.total > 0 && L.w1 % 4 == 0 && L.part % 4 == 0, "smem-weight replay layout");
         }
       }
+  // ---- peer-memory packet buffer (select.cuh): regions in order, 8-byte packets, 16-byte parity halves ----
+  int layouts = 0;
+  for (int world : {1, 2, 3, 4, 8, 16, 64})
+    for (int slot : {1, 7, 73, 409, 2026, 13107, 16384})
+      for (int pslots : {1, 30, 60, 300}) {
+        ++layouts;
+        const size_t idx = p2p_idx_off(world, slot), rank = p2p_rank_off(world, slot), part = p2p_part_off(world, slot);
+        const size_t par = p2p_parity_words(world, slot, pslots), total = p2p_total_words(world, slot, pslots);
+        CHECK(idx == 2 * (size_t)world * slot && rank == idx + 2 * (size_t)slot && part == rank + 6 * (size_t)world, "region order");
+        CHECK(idx % 2 == 0 && rank % 2 == 0 && part % 2 == 0, "8-byte packets world=%d slot=%d", world, slot);
+        CHECK(par >= part + 16 * (size_t)world * pslots && par % 4 == 0 && total == 2 * par, "parity halves world=%d slot=%d pslots=%d", world, slot, pslots);
+      }
+  // ---- select / refit launch helpers ----
+  for (int n : {1, 31, 32, 33, 16384, 16385, 49152}) CHECK(select_padded(n) >= n && select_padded(n) % 32 == 0 && select_padded(n) < n + 32, "select_padded(%d)", n);
+  CHECK(sizeof(uint32_t) * (size_t)select_padded(kSelectStageMax) + sizeof(uint32_t) * kSelectBins + 2048 <= max_smem, "top-k staging + histogram fit in shared memory");
+  for (int k : {1, 31, 32, 33, 204, 1023, 1024, 1638, 2048, 2049, 13107, 131072}) {
+    const int t = refit_threads(k);
+    CHECK(t % 32 == 0 && t >= 32 && t <= kRefitThreads && (k > kRefitChunk || t >= std::min(k, kRefitThreads)), "refit_threads(%d) = %d", k, t);
+  }
+  for (int s = 1; s <= kTcfSpecs; ++s) {  // every compile-time geometry class is a geometry the run-time function produces
+    const int O = s == 1 ? 17 : 5, A = tcf_spec_a(s), U = s == 1 ? 200 : 50;
+    TcfGeom g{};
+    std::string why;
+    CHECK(tcf_geometry(O, A, U, max_smem, &g, &why) && tcf_matches_spec(g) == s, "geometry class %d", s);
+  }
+  {
+    TcfGeom g{};
+    std::string why;
+    CHECK(tcf_geometry(24, 6, 200, max_smem, &g, &why) && tcf_matches_spec(g) == 1, "walker shape is class 1");
+    CHECK(tcf_geometry(17, 7, 200, max_smem, &g, &why) && tcf_matches_spec(g) == 0, "another action count is no class");
+  }
+  std::printf("packet layouts checked: %d\n", layouts);
   std::printf("geometry sweep: %d shapes, fused tensor-core geometry accepted %d, weight-streaming geometry accepted %d, register replay accepted %d, failures %d\n",
               total, fused_ok, wide_ok, reg_ok, fails);
   return fails ? 1 : 0;
