@@ -15,10 +15,14 @@
 //             dL/da_h = (W1^T g)[O:] / sd_a + (beta/A) sinh(a_h / beta);  carried = (W1^T g)[:O] / sd_s
 //   Adam      torch.optim.Adam defaults (betas 0.9 / 0.999, eps 1e-8, bias correction), fp32
 //
-// fp32 CUDA cores throughout: batch-1 matrix-vector chains have nothing for tensor cores to do.  The
-// weights stay in L2 (K-major fp32 copies of the handle); a forward matvec splits K over the 16 warps
-// (coalesced 128-byte rows, 16 partial sums reduced through shared memory), a transposed matvec gives
-// every warp whole rows (coalesced, shuffle reduction).
+// fp32 CUDA cores throughout: batch-1 matrix-vector chains have nothing for tensor cores to do.  W2 (the
+// bulk of the weights) is copied into shared memory when it fits next to the activations (hidden 200 at
+// H = 30: 232,208 of 232,448 bytes), W1 / W3 (and W2 otherwise) are read from L2 (K-major fp32 copies of
+// the handle).  A forward matvec splits K over the 16 warps (coalesced 128-byte rows, 16 partial sums
+// reduced through shared memory), a transposed matvec gives every warp whole rows (coalesced, shuffle
+// reduction).  Both issue their loads in batches of up to 8 independent rows / column blocks before the
+// dependent FMA chain: the first version paid one L2 round trip per element (25 us per step) -- the order
+// of the additions, and with it every result bit, is unchanged.
 #pragma once
 #include "common.cuh"
 
@@ -53,16 +57,29 @@ __host__ __device__ inline GdLayout gd_layout(int O, int A, int U, int H) {
   return L;
 }
 
-// out[j] = act(bias[j] + sum_k Wt[k][j] x[k]),  Wt K-major [K][N]
+template <bool GLOBAL>
+__device__ __forceinline__ float gd_ld(const float* p) { return GLOBAL ? __ldg(p) : *p; }
+
+// out[j] = act(bias[j] + sum_k Wt[k][j] x[k]),  Wt K-major [K][N].  GLOBAL: Wt in global memory (else shared).
+template <bool GLOBAL>
 __device__ __forceinline__ void gd_matvec_fwd(const float* __restrict__ Wt, const float* __restrict__ bias, const float* x,
                                               float* out, int K, int N, bool relu, float* part, int Npad) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int cb = 0; cb < N; cb += 32) {
-    const int j = cb + lane;
-    float acc = 0.f;
-    if (j < N)
-      for (int k = warp; k < K; k += kGdWarps) acc = fmaf(__ldg(Wt + (size_t)k * N + j), x[k], acc);
-    part[warp * Npad + j] = acc;
+  for (int cs = 0; cs < N; cs += 256) {  // 8 column blocks of 32 at a time: 8 independent accumulators per lane
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+    for (int k = warp; k < K; k += kGdWarps) {
+      const float xk = x[k];
+      const float* row = Wt + (size_t)k * N + cs + lane;
+      float w[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) w[c] = cs + 32 * c + lane < N ? gd_ld<GLOBAL>(row + 32 * c) : 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c] = fmaf(w[c], xk, acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (cs + 32 * c < N) part[warp * Npad + cs + 32 * c + lane] = acc[c];  // Npad is a multiple of 32 >= N
   }
   __syncthreads();
   for (int j = threadIdx.x; j < N; j += kGdThreads) {
@@ -75,17 +92,98 @@ __device__ __forceinline__ void gd_matvec_fwd(const float* __restrict__ Wt, cons
 }
 
 // out[k] = (sum_j Wt[k][j] g[j]) * (mask ? mask[k] > 0 : 1)
+template <bool GLOBAL>
 __device__ __forceinline__ void gd_matvec_bwd(const float* __restrict__ Wt, const float* g, float* out, int K, int N,
                                               const float* mask) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll 2
   for (int k = warp; k < K; k += kGdWarps) {
     float acc = 0.f;
-    for (int j = lane; j < N; j += 32) acc = fmaf(__ldg(Wt + (size_t)k * N + j), g[j], acc);
+    for (int js = 0; js < N; js += 256) {
+      const float* row = Wt + (size_t)k * N + js + lane;
+      float w[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) w[c] = js + 32 * c + lane < N ? gd_ld<GLOBAL>(row + 32 * c) : 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (js + 32 * c + lane < N) acc = fmaf(w[c], g[js + 32 * c + lane], acc);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) out[k] = (mask == nullptr || mask[k] > 0.f) ? acc : 0.f;
   }
   __syncthreads();
+}
+
+// Register-resident variants for the two small matrices.  Both matvec directions touch element
+// Wt[k][j] from the SAME thread -- warp = k mod 16, lane = j mod 32 -- so a thread loads its RI x RC
+// elements (k = warp + 16 i, j = lane + 32 c; zero beyond K / N) once per plan and no step reads W1 or W3
+// from memory again.  The additions run in the order of the memory-based functions above: same bits.
+template <int RI, int RC>
+__device__ __forceinline__ void gd_load_regs(const float* __restrict__ Wt, int K, int N, float (&w)[RI][RC]) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < RI; ++i)
+#pragma unroll
+    for (int c = 0; c < RC; ++c) {
+      const int k = warp + kGdWarps * i, j = lane + 32 * c;
+      w[i][c] = (k < K && j < N) ? __ldg(Wt + (size_t)k * N + j) : 0.f;
+    }
+}
+template <int RI, int RC>
+__device__ __forceinline__ void gd_matvec_fwd_regs(const float (&w)[RI][RC], const float* __restrict__ bias, const float* x,
+                                                   float* out, int K, int N, bool relu, float* part, int Npad) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc[RC];
+#pragma unroll
+  for (int c = 0; c < RC; ++c) acc[c] = 0.f;
+#pragma unroll
+  for (int i = 0; i < RI; ++i) {
+    const int k = warp + kGdWarps * i;
+    if (k < K) {
+      const float xk = x[k];
+#pragma unroll
+      for (int c = 0; c < RC; ++c) acc[c] = fmaf(w[i][c], xk, acc[c]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < RC; ++c)
+    if (32 * c < N) part[warp * Npad + 32 * c + lane] = acc[c];
+  __syncthreads();
+  for (int j = threadIdx.x; j < N; j += kGdThreads) {
+    float s = __ldg(bias + j);
+#pragma unroll
+    for (int ww = 0; ww < kGdWarps; ++ww) s += part[ww * Npad + j];
+    out[j] = relu ? fmaxf(s, 0.f) : s;
+  }
+  __syncthreads();
+}
+template <int RI, int RC>
+__device__ __forceinline__ void gd_matvec_bwd_regs(const float (&w)[RI][RC], const float* g, float* out, int K, int N,
+                                                   const float* mask) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float gl[RC];
+#pragma unroll
+  for (int c = 0; c < RC; ++c) gl[c] = lane + 32 * c < N ? g[lane + 32 * c] : 0.f;
+#pragma unroll
+  for (int i = 0; i < RI; ++i) {
+    const int k = warp + kGdWarps * i;
+    if (k < K) {  // warp-uniform
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < RC; ++c)
+        if (lane + 32 * c < N) acc = fmaf(w[i][c], gl[c], acc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) out[k] = (mask == nullptr || mask[k] > 0.f) ? acc : 0.f;
+    }
+  }
+  __syncthreads();
+}
+// shapes whose W1 / W3 fit the register budget: D <= 32, hidden <= 208, O <= 32 (cartpole, cheetah, walker)
+constexpr int kGdR1I = 2, kGdR1C = 7, kGdR3I = 13, kGdR3C = 1;
+__host__ __device__ inline bool gd_small_in_regs(int O, int A, int U) {
+  return O + A <= kGdWarps * kGdR1I && U <= 32 * kGdR1C && U <= kGdWarps * kGdR3I && O <= 32 * kGdR3C;
 }
 
 __device__ __forceinline__ float gd_block_sum(float v, float* red) {
@@ -110,10 +208,12 @@ __device__ __forceinline__ float gd_block_sum(float v, float* red) {
 // grid = restarts; s0 [O] is shared by all restarts; init_actions [B][H][A];
 // out_states [B][H+1][O] (s_0 first, as the reference returns them), out_actions [B][H][A],
 // out_cost [B] = the loss of the last forward pass, out_iters [B] = iterations run.
+template <bool W2_SMEM, bool REGW>
 __global__ void __launch_bounds__(kGdThreads, 1)
 gd_plan_kernel(ModelDev m, GdParams gp, const float* __restrict__ s0, const float* __restrict__ init_actions,
                float* __restrict__ out_states, float* __restrict__ out_actions, float* __restrict__ out_cost,
                int* __restrict__ out_iters) {
+  constexpr bool W2S = W2_SMEM;
   extern __shared__ __align__(16) float gd_smem[];
   const int O = m.O, A = m.A, D = m.D, U = m.U, H = gp.H;
   const GdLayout L = gd_layout(O, A, U, H);
@@ -124,6 +224,19 @@ gd_plan_kernel(ModelDev m, GdParams gp, const float* __restrict__ s0, const floa
   const int tid = threadIdx.x, b = blockIdx.x;
   const int HA = H * A;
 
+  const float* W2 = m.W2t;
+  if (W2S) {  // 16-byte copies: U*U floats right after the activations (gd_layout keeps total a multiple of 4)
+    float* w2s = gd_smem + L.total;
+    const int n = U * U;
+    if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(m.W2t) & 15) == 0) {
+      for (int i = tid; i < n / 4; i += kGdThreads) reinterpret_cast<float4*>(w2s)[i] = __ldg(reinterpret_cast<const float4*>(m.W2t) + i);
+    } else {
+      for (int i = tid; i < n; i += kGdThreads) w2s[i] = __ldg(m.W2t + i);
+    }
+    W2 = w2s;
+  }
+  float w1r[REGW ? kGdR1I : 1][REGW ? kGdR1C : 1], w3r[REGW ? kGdR3I : 1][REGW ? kGdR3C : 1];
+  if (REGW) { gd_load_regs(m.W1t, D, U, w1r); gd_load_regs(m.W3t, U, O, w3r); }
   for (int i = tid; i < O; i += kGdThreads) S[i] = s0[i];
   for (int i = tid; i < HA; i += kGdThreads) { Aa[i] = init_actions[(size_t)b * HA + i]; M[i] = 0.f; V[i] = 0.f; }
   __syncthreads();
@@ -141,9 +254,11 @@ gd_plan_kernel(ModelDev m, GdParams gp, const float* __restrict__ s0, const floa
         x[d] = d < O ? __fdiv_rn(__fsub_rn(S[h * O + d], __ldg(m.mu_s + d)), __ldg(m.sd_s + d))
                      : __fdiv_rn(__fsub_rn(Aa[h * A + d - O], __ldg(m.mu_a + d - O)), __ldg(m.sd_a + d - O));
       __syncthreads();
-      gd_matvec_fwd(m.W1t, m.b1, x, H1 + h * U, D, U, true, part, L.Npad);
-      gd_matvec_fwd(m.W2t, m.b2, H1 + h * U, H2 + h * U, U, U, true, part, L.Npad);
-      gd_matvec_fwd(m.W3t, m.b3, H2 + h * U, gy, U, O, false, part, L.Npad);  // gy doubles as the y buffer
+      if (REGW) gd_matvec_fwd_regs(w1r, m.b1, x, H1 + h * U, D, U, true, part, L.Npad);
+      else gd_matvec_fwd<true>(m.W1t, m.b1, x, H1 + h * U, D, U, true, part, L.Npad);
+      gd_matvec_fwd<!W2S>(W2, m.b2, H1 + h * U, H2 + h * U, U, U, true, part, L.Npad);
+      if (REGW) gd_matvec_fwd_regs(w3r, m.b3, H2 + h * U, gy, U, O, false, part, L.Npad);  // gy doubles as the y buffer
+      else gd_matvec_fwd<true>(m.W3t, m.b3, H2 + h * U, gy, U, O, false, part, L.Npad);
       for (int o = tid; o < O; o += kGdThreads) {
         const float s = __fadd_rn(__fmul_rn(gy[o], __ldg(m.sd_s + o)), __ldg(m.mu_s + o));  // unnormalize_field
         S[(h + 1) * O + o] = s;
@@ -165,9 +280,11 @@ gd_plan_kernel(ModelDev m, GdParams gp, const float* __restrict__ s0, const floa
         gy[o] = (gs[o] + dcost) * __ldg(m.sd_s + o);
       }
       __syncthreads();
-      gd_matvec_bwd(m.W3t, gy, gh2, U, O, H2 + h * U);   // W3^T g, relu'(z2)
-      gd_matvec_bwd(m.W2t, gh2, gh1, U, U, H1 + h * U);  // W2^T g, relu'(z1)
-      gd_matvec_bwd(m.W1t, gh1, gx, D, U, nullptr);      // W1^T g
+      if (REGW) gd_matvec_bwd_regs(w3r, gy, gh2, U, O, H2 + h * U);  // W3^T g, relu'(z2)
+      else gd_matvec_bwd<true>(m.W3t, gy, gh2, U, O, H2 + h * U);
+      gd_matvec_bwd<!W2S>(W2, gh2, gh1, U, U, H1 + h * U);           // W2^T g, relu'(z1)
+      if (REGW) gd_matvec_bwd_regs(w1r, gh1, gx, D, U, nullptr);     // W1^T g
+      else gd_matvec_bwd<true>(m.W1t, gh1, gx, D, U, nullptr);
       for (int d = tid; d < D; d += kGdThreads) {
         if (d < O) gs[d] = gx[d] / __ldg(m.sd_s + d);
         else {

@@ -1084,7 +1084,7 @@ extern "C" int mbrl_plan_gd(MbrlPlanner* p, const MbrlGdArgs* a, const float* h_
     return fail(MBRL_E_UNSUPPORTED, "the gradient planner differentiates the SmoothAbs + Cosh cost only");
   MBRL_CUDA(cudaSetDevice(p->cfg.device));
   const GdLayout L = gd_layout(p->O, p->A, p->U, p->H);
-  const size_t smem = sizeof(float) * (size_t)L.total;
+  size_t smem = sizeof(float) * (size_t)L.total;
   if (smem > p->max_smem)
     return fail(MBRL_E_UNSUPPORTED, "horizon x hidden too large for the gradient planner: it keeps every step's activations "
                                     "(H*(O+A+2*hidden) floats) in shared memory");
@@ -1100,11 +1100,17 @@ extern "C" int mbrl_plan_gd(MbrlPlanner* p, const MbrlGdArgs* a, const float* h_
   if (e == cudaSuccess) {
     ok(cudaMemcpyAsync(d_s0, h_s0, sizeof(float) * p->O, cudaMemcpyHostToDevice, st));
     ok(cudaMemcpyAsync(d_init, h_init_actions, sizeof(float) * (size_t)B * HA, cudaMemcpyHostToDevice, st));
-    ok(cudaFuncSetAttribute(gd_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
+  // W2 rides in shared memory when it fits next to the activations (hidden 200, H = 30: to the byte, almost)
+  const bool w2_smem = smem + sizeof(float) * (size_t)p->U * p->U <= p->max_smem;
+  if (w2_smem) smem += sizeof(float) * (size_t)p->U * p->U;
+  const bool regw = gd_small_in_regs(p->O, p->A, p->U);  // W1 / W3 in registers
+  auto kern = w2_smem ? (regw ? gd_plan_kernel<true, true> : gd_plan_kernel<true, false>)
+                      : (regw ? gd_plan_kernel<false, true> : gd_plan_kernel<false, false>);
+  if (e == cudaSuccess) ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (e == cudaSuccess) {
     GdParams gp{p->H, a->iterations, a->lr, a->stop_condition, a->beta1, a->beta2, a->eps};
-    gd_plan_kernel<<<B, kGdThreads, smem, st>>>(model_view(p), gp, d_s0, d_init, d_st, d_ac, d_cost, d_it);
+    kern<<<B, kGdThreads, smem, st>>>(model_view(p), gp, d_s0, d_init, d_st, d_ac, d_cost, d_it);
     ok(cudaGetLastError());
     ok(cudaMemcpyAsync(h_out_states, d_st, sizeof(float) * (size_t)B * HO1, cudaMemcpyDeviceToHost, st));
     ok(cudaMemcpyAsync(h_out_actions, d_ac, sizeof(float) * (size_t)B * HA, cudaMemcpyDeviceToHost, st));
