@@ -185,7 +185,7 @@ extern "C" const char* mbrl_last_error(void) { return g_err.c_str(); }
 
 // MBRL_SHARD_TIMELINE=<prefix> (diagnostic): the sharded kernels of the last plan left globaltimer
 // stamps per iteration; write them, in ns relative to the first, to <prefix>.rank<r>.txt:
-//   select: start, published | merge: start, flags acquired, end | refit (CTA 0): start, published, acquired, end
+//   select: start, packets sent | merge: start, all packets staged, end | refit (CTA 0): start, partial sums sent, all ranks' sums in, end
 constexpr int kPlanStampCtas = 256;
 constexpr int kPlanStampStride = 8 + 3 * kPlanStampCtas;
 // MBRL_PLAN_TIMELINE=<path> (diagnostic, unsharded fused tcgen05 engine, <= 256 row tiles): globaltimer
@@ -984,9 +984,9 @@ static int enqueue_plan(MbrlPlanner* p, const MbrlPlanArgs* a, const float* d_s0
       }
       const int ng = kl * p->world;
       if (p->p2p_attached) {
-        // peer-memory exchange, two launches: the local select stores its elites straight into every
-        // rank's buffer and publishes the sequence flag; the merge select acquires all ranks' flags,
-        // selects among the gathered candidates in place and emits global indices
+        // peer-memory exchange: the local select stores its elites as sequence-tagged packets straight into
+        // every rank's buffer; the merge select (resident and polling already) stages them as they land,
+        // finds the global threshold and keeps this rank's own elites; the refit below is distributed
         SelShard sh{};
         sh.peers = p->p2p_peers; sh.local = p->d_p2p_local; sh.rank = p->rank; sh.world = p->world;
         sh.slot = p->p2p_slot; sh.pslots = p->H * ((p->A + 3) / 4); sh.seq = ++p->p2p_seq; sh.parity = (int)(sh.seq & 1);

@@ -166,9 +166,9 @@ topk_select_kernel(const float* __restrict__ costs, int n, int k, int* __restric
   const unsigned long long t_start = MODE == kSelMerge ? globaltimer_ns() : 0ull;
   pdl_trigger();
   // kSelMerge does not wait for the preceding (local select) kernel to drain: everything it consumes
-  // is ordered by the sequence flags it acquires -- its own rank's included, which the select publishes
-  // after its last store -- and it writes nothing before it holds them.  It starts polling while the
-  // select still runs, so the launch gap and the select's kernel-end flush leave the critical path.
+  // arrives as sequence-tagged packets -- its own rank's included, which the local select writes like
+  // any other rank's -- and it writes nothing before it holds them.  It is resident and polling while the
+  // rollout and the select still run, so the launch gap and the select's kernel end leave the critical path.
   if (MODE != kSelMerge) pdl_wait();  // the costs come from the preceding rollout kernel
   TOPK_STAMP(0);
   SHARD_STAMP(sh.stamps, MODE == kSelMerge ? 2 : 0);
